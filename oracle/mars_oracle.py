@@ -1,0 +1,485 @@
+"""CPU oracle for the MARS proposal scoring / ranking / merging stage.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product:
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this file, and only as the checker or the
+timed CPU baseline.  The shipped path (the ``marsb200`` package) never imports
+it and fails loudly when its CUDA library is missing.
+
+Every function restates, in plain torch/numpy on the CPU, one piece of the
+reference's algorithm and cites the reference ``file:line`` it follows
+(paths relative to the reference checkout).  Where the reference has no code
+(mask-vs-mask intersection/union, mask NMS — SURVEY.md §0 D2) the function is
+a builder-defined specification and says so.
+
+Pinning: ``tests/golden/make_golden.py`` runs the *reference's own modules*
+(imported from the reference checkout with three import shims) on seeded
+inputs and commits inputs+outputs under ``tests/golden/``; the CPU test-suite
+checks this oracle against those vectors.  The builder-defined pieces
+(`pairwise_intersections`, `mask_nms`) and the exact-EMD stand-in (POT is not
+installed anywhere we can run) have no reference output to pin against:
+**parity unpinned** for those three, pinned for everything else.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-7  # the reference's min-max / ratio epsilon (FilteringMergingModule.py:108-132)
+
+
+# --------------------------------------------------------------------------
+# A1 / A2 / A3: features -> similarity -> visual-visual prior
+# --------------------------------------------------------------------------
+def normalize_rows(x: torch.Tensor) -> torch.Tensor:
+    """Row-wise L2 normalisation, ``x / max(||x||, 1e-12)``.
+
+    Follows mars/components/VisualVisualAlignmentModule.py:124-125 and
+    matcher/Matcher.py:297-298.
+    """
+    x = x.reshape(-1, x.shape[-1]).float()
+    return F.normalize(x, p=2, dim=1)
+
+
+def similarity_and_cost(fs_n: torch.Tensor, fq_n: torch.Tensor):
+    """``S = Fs @ Fq^T`` and the transport cost ``(1 - S) / 2``.
+
+    Follows VisualVisualAlignmentModule.py:69-70 and matcher/Matcher.py:437-440.
+    """
+    sim = torch.matmul(fs_n, fq_n.T)
+    return sim, (1 - sim) / 2
+
+
+def pool_mask(mask: torch.Tensor, g: int) -> torch.Tensor:
+    """Adaptive max pool of ``[..., H, W]`` masks to ``[..., g, g]`` booleans.
+
+    Bin ``i`` spans ``[floor(i*H/g), ceil((i+1)*H/g))`` (PyTorch's adaptive
+    pooling rule).  Follows FilteringMergingModule.py:73-76,
+    104-107 and VisualVisualAlignmentModule.py:72-75.  The reference tests the
+    pooled value with ``> 0`` (proposals) or ``.bool()`` (support mask); both
+    agree for the non-negative masks the pipeline carries.
+    """
+    lead = mask.shape[:-2]
+    m = mask.reshape(-1, 1, mask.shape[-2], mask.shape[-1]).float()
+    pooled = F.adaptive_max_pool2d(m, (g, g))
+    return (pooled > 0).reshape(*lead, g, g)
+
+
+def minmax(x):
+    """``(x - min) / (1e-7 + max - min)`` (VisualVisualAlignmentModule.py:102, mars/MARS.py:82)."""
+    return (x - x.min()) / (EPS + x.max() - x.min())
+
+
+def vva_prior(fs_n: torch.Tensor, fq_n: torch.Tensor, support_bits: torch.Tensor, g: int) -> torch.Tensor:
+    """Foreground-minus-background ``mean * max`` prior over support rows, min-max scaled.
+
+    ``support_bits`` is the shot-major flattened pooled support mask
+    ``[ns*N]`` (bool).  Follows VisualVisualAlignmentModule.py:76-102: the
+    products are recomputed on the fg / bg row subsets exactly as the reference
+    does, the bg term is skipped when there are no bg rows.
+    """
+    sel = support_bits.reshape(-1).bool()
+    s_fg = torch.matmul(fs_n[sel], fq_n.T)
+    s_bg = torch.matmul(fs_n[~sel], fq_n.T)
+    vva = s_fg.mean(dim=0) * s_fg.max(dim=0).values
+    if s_bg.shape[0] != 0:
+        vva = vva - s_bg.mean(dim=0) * s_bg.max(dim=0).values
+    vva = vva.reshape(g, g)
+    return minmax(vva)
+
+
+# --------------------------------------------------------------------------
+# A4: prior-information refinement (PIR)
+# --------------------------------------------------------------------------
+def attention_mean(attn_maps: Sequence[torch.Tensor], last_n: int, num_regs: int) -> torch.Tensor:
+    """Mean over the last ``last_n`` layers and all heads of the patch-to-patch attention.
+
+    Accepts ``[1,h,T,T]`` or ``[h,T,T]`` maps; drops the cls + register rows
+    and columns.  Follows PriorInformationRefinementModule.py:31-45.
+    """
+    r = 1 + num_regs
+    if attn_maps[0].dim() == 4:
+        stack = torch.stack([a[0, :, r:, r:] for a in attn_maps], dim=0)[-last_n:]
+    else:
+        stack = torch.stack([a[:, r:, r:] for a in attn_maps], dim=0)[-last_n:]
+    return torch.mean(stack, dim=(0, 1)).float()
+
+
+def _components_8(fg: np.ndarray):
+    """Bounding boxes (x, y, w, h) of the 8-connected components of a boolean image.
+
+    Pure-numpy flood fill; stands in for cv2.findContours + cv2.boundingRect
+    (PriorInformationRefinementModule.py:103-116).  Hole contours returned by
+    RETR_TREE lie inside their component's box and never change the box union
+    (SURVEY.md A.1-4), so components are sufficient.
+    """
+    h, w = fg.shape
+    seen = np.zeros_like(fg, dtype=bool)
+    boxes = []
+    for y in range(h):
+        for x in range(w):
+            if not fg[y, x] or seen[y, x]:
+                continue
+            stack = [(y, x)]
+            seen[y, x] = True
+            x0 = x1 = x
+            y0 = y1 = y
+            while stack:
+                cy, cx = stack.pop()
+                x0, x1 = min(x0, cx), max(x1, cx)
+                y0, y1 = min(y0, cy), max(y1, cy)
+                for dy in (-1, 0, 1):
+                    for dx in (-1, 0, 1):
+                        ny, nx = cy + dy, cx + dx
+                        if 0 <= ny < h and 0 <= nx < w and fg[ny, nx] and not seen[ny, nx]:
+                            seen[ny, nx] = True
+                            stack.append((ny, nx))
+            boxes.append((x0, y0, x1 - x0 + 1, y1 - y0 + 1))
+    return boxes
+
+
+def box_mask(prior: np.ndarray, threshold: float, use_cv2: bool = False) -> np.ndarray:
+    """The 0/1 box mask ``B`` of PIR, ``[h, w]`` float32.
+
+    ``img = uint8(prior * 255)`` (truncation), ``thr = int(threshold * max(img))``,
+    keep ``img > thr``, one box per connected component with the reference's
+    clipping quirk ``x1 = min(x + w, W - 1)`` and *exclusive* fill
+    (PriorInformationRefinementModule.py:56-63, 91-122).  ``use_cv2=True`` runs
+    the same OpenCV calls as the reference (for cross-checking the flood fill).
+    """
+    height, width = prior.shape
+    img = (prior * 255).astype(np.uint8)
+    thr = int(threshold * np.max(img))
+    fg = img > thr
+    if use_cv2:
+        import cv2
+
+        _, binary = cv2.threshold(src=np.expand_dims(img, 2), thresh=thr, maxval=255, type=cv2.THRESH_BINARY)
+        contours = cv2.findContours(image=binary, mode=cv2.RETR_TREE, method=cv2.CHAIN_APPROX_SIMPLE)[0]
+        rects = [cv2.boundingRect(c) for c in contours]
+    else:
+        rects = _components_8(fg)
+    out = np.zeros((height, width), dtype=np.float32)
+    for (x, y, w, h) in rects:
+        x1 = min(x + w, width - 1)
+        y1 = min(y + h, height - 1)
+        out[y:y1, x:x1] = 1
+    return out
+
+
+def pir_refine(prior: torch.Tensor, attn_mean: torch.Tensor, threshold: float, use_cv2: bool = False) -> torch.Tensor:
+    """Refine a ``[g,g]`` prior with the attention-derived matrix ``R``.
+
+    ``D = A / colsum; D = D / rowsum; R = max(D, D D^T); R = R R;
+    out = (R * B) @ prior``.  Follows PriorInformationRefinementModule.py:47-89.
+    """
+    shape = prior.shape
+    p_np = prior.detach().cpu().numpy().astype(np.float32)
+    b = torch.from_numpy(box_mask(p_np, threshold, use_cv2=use_cv2)).reshape(1, -1)
+    a = attn_mean.float()
+    d = a / torch.sum(a, dim=0, keepdim=True)
+    d = d / torch.sum(d, dim=1, keepdim=True)
+    r = torch.max(d, d @ d.t())
+    r = torch.matmul(r, r)
+    out = torch.matmul(r * b, torch.from_numpy(p_np).reshape(-1, 1))
+    return out.reshape(shape)
+
+
+def nearest_resize(x: torch.Tensor, size) -> torch.Tensor:
+    """``F.interpolate(mode='nearest')`` of a 2-D map (mars/MARS.py:77-81)."""
+    return F.interpolate(x[None, None].float(), size, mode="nearest")[0, 0]
+
+
+# --------------------------------------------------------------------------
+# A7: exact EMD (stand-in for POT's ot.emd2; parity unpinned)
+# --------------------------------------------------------------------------
+def emd_exact(cost: np.ndarray) -> float:
+    """Exact optimal-transport cost with uniform marginals ``1/T`` and ``1/M``.
+
+    The reference calls ``ot.emd2`` (POT 0.9.4, network simplex) at
+    FilteringMergingModule.py:160-166 / matcher/Matcher.py:1187-1193; POT is
+    not installed here, so this solves the same transportation LP with HiGHS.
+    An empty marginal (all-zero proposal) is defined as cost 0.
+    """
+    from scipy.optimize import linprog
+    from scipy.sparse import lil_matrix
+
+    c = np.asarray(cost, dtype=np.float64)
+    t, m = c.shape
+    if t == 0 or m == 0:
+        return 0.0
+    a_eq = lil_matrix((t + m, t * m))
+    for i in range(t):
+        a_eq[i, i * m:(i + 1) * m] = 1
+    for j in range(m):
+        a_eq[t + j, j::m] = 1
+    b_eq = np.concatenate([np.full(t, 1.0 / t), np.full(m, 1.0 / m)])
+    res = linprog(c.reshape(-1), A_eq=a_eq.tocsr(), b_eq=b_eq, bounds=(0, None), method="highs")
+    if res.status != 0:
+        raise RuntimeError(f"transport LP failed: {res.message}")
+    return float(res.fun)
+
+
+def emd_score(pooled_support: torch.Tensor, pooled_proposal: torch.Tensor, cost_matrix: torch.Tensor) -> float:
+    """``1 - emd`` on the cost sub-matrix (FilteringMergingModule.py:142-169)."""
+    sub = cost_matrix[pooled_support.reshape(-1).bool(), :][:, pooled_proposal.reshape(-1).bool()]
+    return 1.0 - emd_exact(sub.cpu().numpy())
+
+
+# --------------------------------------------------------------------------
+# A6 / A8 / A11: per-proposal region scores, fusion, ranking, merge
+# --------------------------------------------------------------------------
+def region_scores(masks: torch.Tensor, vva: np.ndarray, vta: np.ndarray, g: int):
+    """Per-proposal pooled bitmap, coverage and the two alignment means.
+
+    Loops over the proposals exactly like the reference hot loop
+    (FilteringMergingModule.py:77-81, 103-110); quotients come out float64 as
+    in the reference (numpy float32 / float64).
+    Returns ``pooled [P,g,g] bool, coverage [P], pvv_align [P], pvt_align [P]``.
+    """
+    union = (torch.sum(masks, dim=0) > 0).float()
+    pooled_union = F.adaptive_max_pool2d(union.unsqueeze(0), (g, g)).squeeze(0).numpy() > 0
+    pooled, cov, avv, avt = [], [], [], []
+    for m_p in masks:
+        pm = F.adaptive_max_pool2d(m_p.unsqueeze(0).float(), (g, g)).squeeze(0).numpy() > 0
+        n = np.sum(pm)
+        cov.append(n / (EPS + np.sum(pooled_union)))
+        avv.append(np.sum(vva[pm]) / (EPS + n))
+        avt.append(np.sum(vta[pm]) / (EPS + n))
+        pooled.append(pm)
+    return np.stack(pooled), np.asarray(cov, dtype=np.float64), np.asarray(avv, dtype=np.float64), np.asarray(avt, dtype=np.float64)
+
+
+def fuse_scores(emd_scores, clip_scores, coverage, pvv_align, pvt_align, alpha: float) -> np.ndarray:
+    """Fused proposal score, ``[P]`` float64.
+
+    ``pvv = a*align + (1-a)*coverage`` (FilteringMergingModule.py:118-119),
+    min-max of the EMD and AlphaCLIP scores over the proposals (:126-132; the
+    AlphaCLIP min-max is evaluated in the feature dtype, float32 in this
+    oracle), mean of the four (:136).
+    """
+    emd = np.asarray(emd_scores, dtype=np.float64)
+    clip = np.asarray(clip_scores, dtype=np.float32).reshape(-1)
+    pvv = alpha * np.asarray(pvv_align) + (1 - alpha) * np.asarray(coverage)
+    pvt = alpha * np.asarray(pvt_align) + (1 - alpha) * np.asarray(coverage)
+    emd_n = (emd - emd.min()) / (EPS + emd.max() - emd.min())
+    clip_n = (clip - clip.min()) / (np.float32(EPS) + clip.max() - clip.min())
+    return (emd_n + clip_n.astype(np.float64) + pvv + pvt) / 4
+
+
+def stable_rank(scores: np.ndarray) -> np.ndarray:
+    """Descending order that keeps the original order among equal scores.
+
+    Python's ``sorted(key=score, reverse=True)`` (FilteringMergingModule.py:138)
+    is stable, SURVEY.md A.1-7.
+    """
+    return np.argsort(-np.asarray(scores, dtype=np.float64), kind="stable")
+
+
+def merge_select(ranked_scores: np.ndarray, static_threshold: float, dynamic_threshold: float) -> np.ndarray:
+    """Boolean selection over the ranked list (FilteringMergingModule.py:213-217)."""
+    top = ranked_scores[0]
+    if top < static_threshold:
+        return ranked_scores >= dynamic_threshold * top
+    return ranked_scores >= static_threshold
+
+
+def merge_masks(masks: torch.Tensor, selected_indices) -> torch.Tensor:
+    """OR of the selected masks as a float32 ``[H,W]`` map (FilteringMergingModule.py:219)."""
+    sel = torch.as_tensor(np.asarray(selected_indices), dtype=torch.long)
+    return (torch.sum(masks[sel].float(), dim=0) > 0).float()
+
+
+def clip_scores(img_feats: torch.Tensor, text_feat: torch.Tensor) -> np.ndarray:
+    """``img_feats @ text_feats.T`` (FilteringMergingModule.py:97), ``[P]``."""
+    return (img_feats @ text_feat.reshape(1, -1).T).reshape(-1).numpy()
+
+
+# --------------------------------------------------------------------------
+# A9 / A10: builder-defined (no reference code; parity unpinned)
+# --------------------------------------------------------------------------
+def pairwise_intersections(masks: torch.Tensor):
+    """``inter[i,j] = sum(m_i & m_j)``, ``area_i = inter[i,i]`` as int32.
+
+    Builder-defined.  Union follows the formula the
+    reference's evaluator uses, ``area_a + area_b - inter``
+    (mars/utils/evaluation.py:36).  Computed blockwise as an exact integer
+    contraction.
+    """
+    mb = (masks.reshape(masks.shape[0], -1) > 0)
+    p, hw = mb.shape
+    inter = torch.zeros((p, p), dtype=torch.float64)
+    step = 1 << 18
+    for s in range(0, hw, step):
+        blk = mb[:, s:s + step].float()
+        inter += (blk @ blk.T).double()  # exact: each block sum < 2**24
+    inter = inter.to(torch.int32)
+    area = torch.diagonal(inter).clone()
+    return inter, area
+
+
+def iou_matrix(inter: torch.Tensor, area: torch.Tensor) -> torch.Tensor:
+    """float32 IoU with ``union == 0 -> 0``."""
+    union = area[:, None] + area[None, :] - inter
+    iou = inter.float() / union.float()
+    return torch.where(union > 0, iou, torch.zeros_like(iou))
+
+
+def mask_nms(order: np.ndarray, inter: torch.Tensor, area: torch.Tensor, iou_threshold: float) -> np.ndarray:
+    """Greedy score-ordered suppression; returns a keep flag per proposal index.
+
+    Builder-defined, with the semantics of torchvision's ``nms`` as used at
+    segment_anything/automatic_mask_generator.py:370-376: walk the proposals in
+    rank order, drop one iff its IoU with an already-kept higher-ranked
+    proposal is ``> iou_threshold``.
+    """
+    iou = iou_matrix(inter, area).numpy()
+    p = len(order)
+    keep = np.zeros(p, dtype=bool)
+    kept = []
+    for idx in order:
+        if all(not (iou[idx, k] > np.float32(iou_threshold)) for k in kept):
+            keep[idx] = True
+            kept.append(idx)
+    return keep
+
+
+# --------------------------------------------------------------------------
+# A12: Matcher-derived scoring and merging
+# --------------------------------------------------------------------------
+def matcher_mask_scores(masks: np.ndarray, all_points: np.ndarray, g: int):
+    """Purity and coverage of every mask from the matched points.
+
+    ``masks`` is ``[n,H,W]`` bool, ``all_points`` ``[K,2]`` (x, y) pixel
+    coordinates.  Follows matcher/Matcher.py:1163-1209: pooled area by
+    any-pixel pooling (``cv2.resize(INTER_AREA) > 0`` is the same predicate at
+    the native 518/14 geometry, SURVEY.md A.2 probe4), ``purity = in/max(area,1)
+    + 1e-6``, ``coverage = in/K + 1e-6`` as float32 tensors.
+    """
+    n, h, w = masks.shape
+    pts = all_points.astype(np.int64)[:, ::-1]
+    pts = np.clip(pts, 0, [h - 1, w - 1])
+    pooled = pool_mask(torch.from_numpy(masks), g).numpy()
+    purity = torch.zeros(n)
+    coverage = torch.zeros(n)
+    for i in range(n):
+        inside = int(masks[i][pts[:, 0], pts[:, 1]].sum())
+        area = max(float(pooled[i].sum()), 1.0)
+        purity[i] = (torch.tensor([inside / area]) + 1e-6)[0]
+        coverage[i] = (torch.tensor([inside / all_points.shape[0]]) + 1e-6)[0]
+    return purity, coverage
+
+
+def matcher_fuse(emd: torch.Tensor, purity: torch.Tensor, coverage: torch.Tensor, alpha: float, beta: float, exp: float):
+    """``alpha*emd + beta*purity*coverage**exp`` (matcher/Matcher.py:719-720)."""
+    return alpha * emd + beta * purity * coverage ** exp
+
+
+def matcher_metric_filter(scores, metrics: dict, cfg: dict):
+    """Index set surviving the coverage/emd/purity filters (matcher/Matcher.py:732-746)."""
+    idx_all = torch.arange(scores.shape[0])
+    metrics = dict(metrics)
+    for metric in ["coverage", "emd", "purity"]:
+        if cfg.get(metric, 0) > 0:
+            thres = min(cfg[metric], metrics[metric].max())
+            idx = torch.where(metrics[metric] >= thres)[0]
+            scores = scores[idx]
+            idx_all = idx_all[idx]
+            for key in metrics:
+                metrics[key] = metrics[key][idx]
+    return scores, idx_all
+
+
+def matcher_merge_topk(scores: torch.Tensor, num_merging_mask: int, topk_scores_threshold: float):
+    """Top-k merge selection (matcher/Matcher.py:788-832): indices into ``scores`` and the mean score."""
+    topk = min(num_merging_mask, scores.size(0))
+    topk_idx = scores.topk(topk)[1]
+    topk_scores = scores[topk_idx].numpy()
+    if topk_scores_threshold > 0:
+        topk_scores = topk_scores / topk_scores.max()
+    sel = topk_scores > topk_scores_threshold
+    return topk_idx.numpy()[sel], topk_scores[sel].mean()
+
+
+def matcher_merge_score_filter(scores: torch.Tensor, num_merging_mask: int, score: float, score_norm: float):
+    """Score-filter merge selection (matcher/Matcher.py:749-787): indices and the mean score."""
+    distances = 1 - scores
+    distances, rank = torch.sort(distances, descending=False)
+    distances_norm = distances - distances.min()
+    distances_norm = distances_norm / (distances.max() + 1e-6)
+    keep = distances < score
+    keep[..., 0] = True
+    keep = keep * (distances_norm < score_norm)
+    idx = rank[keep][:num_merging_mask]
+    return idx.numpy(), scores[idx].mean()
+
+
+# --------------------------------------------------------------------------
+# 8f-3: evaluator (the step after the path)
+# --------------------------------------------------------------------------
+def evaluator_areas(pred_mask: torch.Tensor, gt_mask: torch.Tensor, ignore: Optional[torch.Tensor] = None):
+    """Per-sample ``[bg, fg]`` intersection and union areas (mars/utils/evaluation.py:12-38)."""
+    pred_mask = pred_mask.clone().float()
+    gt_mask = gt_mask.clone().float()
+    if ignore is not None:
+        gt_mask = gt_mask + ignore.float() * 255
+        pred_mask[gt_mask == 255] = 255
+    inter, pred_a, gt_a = [], [], []
+    for p, g_ in zip(pred_mask, gt_mask):
+        same = p[p == g_]
+        inter.append(torch.histc(same, bins=2, min=0, max=1) if same.numel() else torch.zeros(2))
+        pred_a.append(torch.histc(p, bins=2, min=0, max=1))
+        gt_a.append(torch.histc(g_, bins=2, min=0, max=1))
+    inter = torch.stack(inter).t()
+    union = torch.stack(pred_a).t() + torch.stack(gt_a).t() - inter
+    return inter, union
+
+
+# --------------------------------------------------------------------------
+# Whole-episode restatement (what bench.py times as the CPU baseline)
+# --------------------------------------------------------------------------
+def run_episode(ep: dict, cfg: dict, emd_fn: Optional[Callable] = None) -> dict:
+    """The full ranking stage on one episode of already-computed backbone tensors.
+
+    ``ep`` keys: feat_s [ns,N,C], feat_q [N,C], support_mask [ns,H,W],
+    attn_vva [N,N], vta_raw [gt,gt], attn_vta [Nt,Nt], masks [P,H,W],
+    clip_img [P,D], clip_txt [D], emd [P] (used when ``emd_fn`` is None).
+    Order of operations follows mars/MARS.py:62-101.  Returns every
+    intermediate the parity tests compare.
+    """
+    g = cfg["g"]
+    fs = normalize_rows(ep["feat_s"])
+    fq = normalize_rows(ep["feat_q"])
+    sim, cost = similarity_and_cost(fs, fq)
+    sup_bits = pool_mask(ep["support_mask"], g).reshape(-1)
+    prior = vva_prior(fs, fq, sup_bits, g)
+    vva = minmax(pir_refine(prior, ep["attn_vva"], cfg["vva_box_threshold"]))
+    vta = pir_refine(ep["vta_raw"], ep["attn_vta"], cfg["vta_box_threshold"])
+    vta = minmax(nearest_resize(vta, (g, g)))
+
+    masks = ep["masks"]
+    pooled, cov, avv, avt = region_scores(masks, vva.numpy(), vta.numpy(), g)
+    if emd_fn is not None:
+        emd = np.asarray([emd_fn(sup_bits, torch.from_numpy(pm), cost) for pm in pooled])
+    else:
+        emd = ep["emd"].numpy().astype(np.float64)
+    clip = clip_scores(ep["clip_img"], ep["clip_txt"])
+    scores = fuse_scores(emd, clip, cov, avv, avt, cfg["alpha"])
+    order = stable_rank(scores)
+    out = dict(sim=sim, cost=cost, support_bits=sup_bits, prior=prior, vva=vva, vta=vta,
+               pooled=pooled, coverage=cov, pvv_align=avv, pvt_align=avt, clip=clip,
+               scores=scores, order=order)
+    nms_thr = cfg.get("nms_iou_threshold")
+    sel = merge_select(scores[order], cfg["static_threshold"], cfg["dynamic_threshold"])
+    if nms_thr is not None:
+        inter, area = pairwise_intersections(masks)
+        keep = mask_nms(order, inter, area, nms_thr)
+        sel = sel & keep[order]
+        out.update(inter=inter, area=area, keep=keep)
+    out["selected"] = order[sel]
+    out["merged"] = merge_masks(masks, order[sel])
+    return out

@@ -1,0 +1,165 @@
+"""Seeded inputs for the golden fixtures (shared by make_golden.py and the tests).
+
+Everything is generated with CPU generators of fixed seed so the tests can
+rebuild the exact inputs the reference saw; each fixture stores a checksum of
+its inputs so a generator drift is detected instead of silently compared.
+Do not edit a case after its fixture has been generated - add a new one.
+"""
+import hashlib
+
+import numpy as np
+import torch
+
+
+def _gen(seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+def checksum(case: dict) -> np.ndarray:
+    h = hashlib.sha256()
+    for k in sorted(case):
+        v = case[k]
+        if isinstance(v, (list, tuple)):
+            for t in v:
+                h.update(t.contiguous().numpy().tobytes())
+        else:
+            h.update(v.contiguous().numpy().tobytes())
+    return np.asarray(h.hexdigest())
+
+
+def blob_masks(n, h, w, seed, min_frac=0.01, max_frac=0.35, dup_every=0):
+    """``[n,h,w]`` float32 0/1 masks: unions of 1-3 rectangles / ellipses; never empty."""
+    rs = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    out = np.zeros((n, h, w), dtype=np.float32)
+    for i in range(n):
+        if dup_every and i and i % dup_every == 0:
+            src = out[rs.randint(0, i)]
+            out[i] = np.roll(src, 1, axis=1) if (i // dup_every) % 2 else src
+            continue
+        m = np.zeros((h, w), dtype=bool)
+        for _ in range(rs.randint(1, 4)):
+            frac = rs.uniform(min_frac, max_frac)
+            aspect = rs.uniform(0.5, 2.0)
+            bh = max(1, min(h, int(round(np.sqrt(frac * h * w * aspect)))))
+            bw = max(1, min(w, int(round(np.sqrt(frac * h * w / aspect)))))
+            y0 = rs.randint(0, h - bh + 1)
+            x0 = rs.randint(0, w - bw + 1)
+            if rs.rand() < 0.5:
+                m[y0:y0 + bh, x0:x0 + bw] = True
+            else:
+                cy, cx = y0 + bh / 2.0, x0 + bw / 2.0
+                m |= ((yy - cy) / (bh / 2.0 + 1e-6)) ** 2 + ((xx - cx) / (bw / 2.0 + 1e-6)) ** 2 <= 1.0
+        if not m.any():
+            m[h // 2, w // 2] = True
+        out[i] = m
+    return torch.from_numpy(out)
+
+
+def proto_features(rows, c, seed, n_proto=8):
+    """Features with shared prototypes so cosine similarities span a wide range."""
+    g = _gen(seed)
+    protos = torch.randn(n_proto, c, generator=_gen(seed + 7919))
+    k = torch.randint(0, n_proto, (rows,), generator=g)
+    return 0.6 * protos[k] + 0.8 * torch.randn(rows, c, generator=g)
+
+
+def attention_stack(layers, heads, tokens, seed, four_d=True):
+    g = _gen(seed)
+    maps = []
+    for _ in range(layers):
+        a = torch.softmax(2.0 * torch.randn(heads, tokens, tokens, generator=g), dim=-1)
+        maps.append(a[None] if four_d else a)
+    return maps
+
+
+# ---------------------------------------------------------------- VVA cases
+VVA_CASES = {
+    # g=10 (H=140): tiny, 2-shot, register tokens, only the last 2 of 3 attention layers used
+    "g10_2shot": dict(seed=11, g=10, H=140, ns=2, C=32, regs=4, layers=3, heads=2, last_n=2, thr=0.8),
+    # native geometry 518/14 = 37, 1-shot
+    "g37_1shot": dict(seed=12, g=37, H=518, ns=1, C=64, regs=4, layers=2, heads=2, last_n=24, thr=0.8),
+    # support mask covering every patch: the reference skips the background term
+    "g10_allfg": dict(seed=13, g=10, H=140, ns=1, C=32, regs=0, layers=1, heads=1, last_n=1, thr=0.5, all_fg=True),
+}
+
+
+def vva_inputs(spec):
+    g, h, ns, c = spec["g"], spec["H"], spec["ns"], spec["C"]
+    n = g * g
+    seed = spec["seed"]
+    feats = proto_features((ns + 1) * n, c, seed)
+    support = blob_masks(ns, h, h, seed + 1, 0.05, 0.3)
+    if spec.get("all_fg"):
+        support = torch.ones_like(support)
+    tokens = 1 + spec["regs"] + n
+    return dict(feat_s=feats[:ns * n].reshape(ns, n, c).contiguous(), feat_q=feats[ns * n:].contiguous(),
+                support_mask=support, attn_maps=attention_stack(spec["layers"], spec["heads"], tokens, seed + 2))
+
+
+# ---------------------------------------------------------------- PIR cases
+PIR_CASES = {
+    "g12_multi": dict(seed=21, g=12, regs=0, layers=2, heads=3, last_n=8, thr=0.4, kind="blobs", four_d=True),
+    "g33_border": dict(seed=22, g=33, regs=0, layers=1, heads=2, last_n=8, thr=0.4, kind="border", four_d=False),
+    "g9_flat": dict(seed=23, g=9, regs=2, layers=1, heads=1, last_n=1, thr=0.8, kind="flat", four_d=True),
+    "g16_rand": dict(seed=24, g=16, regs=1, layers=3, heads=2, last_n=2, thr=0.6, kind="rand", four_d=True),
+}
+
+
+def pir_inputs(spec):
+    g = spec["g"]
+    seed = spec["seed"]
+    rs = np.random.RandomState(seed)
+    if spec["kind"] == "blobs":
+        prior = 0.2 * rs.rand(g, g)
+        prior[1:4, 1:5] += 0.7
+        prior[7:11, 6:12] += 0.6      # touches the right border
+        prior[5, 0] = 0.95            # isolated single pixel on the left border
+        prior[9:12, 0:2] += 0.65      # touches the bottom border
+    elif spec["kind"] == "border":
+        prior = 0.1 * rs.rand(g, g)
+        prior[g - 6:, g - 6:] = 0.9   # component touching the bottom-right corner
+        prior[0:3, 0:3] = 0.8
+        prior[10:20, 10:20] = 0.7
+        prior[13:17, 13:17] = 0.05    # a hole inside a component
+        prior[14:16, 14:16] = 0.75    # an island inside the hole
+    elif spec["kind"] == "flat":
+        prior = np.zeros((g, g))      # no pixel above the threshold -> no contour -> B == 0
+    else:
+        prior = rs.rand(g, g)
+    prior = torch.from_numpy(np.clip(prior, 0, 1).astype(np.float32))
+    tokens = 1 + spec["regs"] + g * g
+    return dict(prior=prior, attn_maps=attention_stack(spec["layers"], spec["heads"], tokens, seed + 2, spec["four_d"]))
+
+
+# ---------------------------------------------------------------- FM cases
+FM_CASES = {
+    # tiny geometry with overlapping pooling bins (H=100, g=7: 100/7 is not an integer)
+    "g7_overlap": dict(seed=31, g=7, H=100, ns=1, P=9, D=32, alpha=0.85, static=0.55, dynamic=0.95, dup_every=4),
+    # native geometry, 2-shot support (shot-major cost rows)
+    "g37_native": dict(seed=32, g=37, H=518, ns=2, P=6, D=48, alpha=0.85, static=0.55, dynamic=0.95, dup_every=0, small_support=True),
+    # high static threshold -> the dynamic branch of the merge is taken
+    "g10_dynamic": dict(seed=33, g=10, H=140, ns=1, P=12, D=16, alpha=0.7, static=0.99, dynamic=0.8, dup_every=5),
+}
+
+
+def fm_inputs(spec):
+    g, h, ns, p, d = spec["g"], spec["H"], spec["ns"], spec["P"], spec["D"]
+    n = g * g
+    seed = spec["seed"]
+    gen = _gen(seed)
+    masks = blob_masks(p, h, h, seed + 1, 0.01, 0.2, spec["dup_every"])
+    if spec.get("small_support"):
+        support = blob_masks(ns, h, h, seed + 2, 0.01, 0.03)
+    else:
+        support = blob_masks(ns, h, h, seed + 2, 0.05, 0.25)
+    fs = torch.nn.functional.normalize(proto_features(ns * n, 24, seed + 3), dim=1)
+    fq = torch.nn.functional.normalize(proto_features(n, 24, seed + 4), dim=1)
+    cost = (1 - fs @ fq.T) / 2
+    img = torch.nn.functional.normalize(torch.randn(p, d, generator=gen), dim=1)
+    txt = torch.nn.functional.normalize(torch.randn(d, generator=gen), dim=0)
+    vva = torch.rand(g, g, generator=gen)
+    vta = torch.rand(g, g, generator=gen)
+    return dict(masks=masks, support_mask=support, cost=cost.contiguous(), clip_img=img, clip_txt=txt, vva=vva, vta=vta)

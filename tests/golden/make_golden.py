@@ -1,0 +1,162 @@
+"""Generate the golden vectors under tests/golden/ by running the REFERENCE's own modules.
+
+Run in the build container only (the reference checkout does not exist on the
+GPU box):
+
+    python tests/golden/make_golden.py [/root/reference]
+
+The reference's hot-path modules import three things that are not installed
+here (POT ``ot``, ``alpha_clip``, ``utils.backbone_loader`` -> loralib); they
+are shimmed in ``sys.modules`` exactly as SURVEY.md A.2 describes.  ``ot.emd2``
+is replaced by the exact transport LP of ``oracle/mars_oracle.emd_exact``
+(POT itself is unavailable: EMD parity is unpinned).  Backbones are fakes that
+return seeded tensors, so the vectors pin everything the reference computes
+*after* the backbones.
+
+Outputs (small, committed): ``vva_*.npz``, ``pir_*.npz``, ``fm_*.npz``.
+Inputs that would be large are regenerated from the recorded seed by
+``tests/golden/cases.py`` and guarded by a checksum stored in the fixture.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+sys.dont_write_bytecode = True
+
+from oracle import mars_oracle as orc  # noqa: E402
+import cases  # noqa: E402
+
+
+def install_shims(ref_root):
+    sys.path.insert(0, ref_root)
+    ot = types.ModuleType("ot")
+    ot.emd2 = lambda a, b, M: np.float64(orc.emd_exact(np.asarray(M)))
+    ac = types.ModuleType("alpha_clip")
+    ac.tokenize = lambda t: torch.zeros(len(t), 77, dtype=torch.long)
+    ub = types.ModuleType("utils.backbone_loader")
+    ub.BackboneLoader = object
+    sys.modules.update({"ot": ot, "alpha_clip": ac, "utils.backbone_loader": ub})
+
+
+class FakeDino(torch.nn.Module):
+    """Returns the seeded x_prenorm tensors in call order (support first, then query)."""
+
+    def __init__(self, feats_in_call_order, attn_maps, embed_dim):
+        super().__init__()
+        self._feats = list(feats_in_call_order)
+        self._attn = attn_maps
+        self.embed_dim = embed_dim
+
+    def forward_features(self, imgs):
+        return {"x_prenorm": self._feats.pop(0)}
+
+    def get_last_self_attention(self, img):
+        return tuple(self._attn)
+
+
+class FakeAlphaClip:
+    def __init__(self, img_feats, text_feat):
+        self._img = img_feats
+        self._txt = text_feat
+        self._cursor = 0
+        self.visual = self._visual
+
+    def _visual(self, image, alpha):
+        n = alpha.shape[0]
+        out = self._img[self._cursor:self._cursor + n]
+        self._cursor += n
+        return out
+
+    def encode_text(self, tok):
+        return self._txt.reshape(1, -1)
+
+
+def gen_vva(name, spec):
+    from mars.components.VisualVisualAlignmentModule import VisualVisualAlignmentModule
+
+    c = cases.vva_inputs(spec)
+    regs = spec["regs"]
+    ns, n, cdim = c["feat_s"].shape
+    pad = lambda f: torch.cat([torch.full((f.shape[0], 1 + regs, cdim), 7.0), f], dim=1)
+    model = FakeDino([pad(c["feat_s"]), pad(c["feat_q"][None])], c["attn_maps"], cdim)
+    mod = VisualVisualAlignmentModule(
+        model=model, model_transforms=lambda x: x, model_patch_size=14,
+        model_embedding_spatial_dimensions=spec["g"], model_num_regs=regs,
+        vva_refinement_box_threshold=spec["thr"],
+        last_n_attention_maps_for_refinement=spec["last_n"], device="cpu")
+    h = spec["H"]
+    out = mod.compute(torch.zeros(1, ns, 3, h, h), c["support_mask"][None], torch.zeros(1, 3, h, h))
+    st = 1 if n <= 200 else 11  # keep the fixture small: strided sample of the big matrices
+    np.savez_compressed(
+        os.path.join(HERE, f"vva_{name}.npz"), spec=np.asarray(repr(spec)), stride=st,
+        checksum=cases.checksum(c), sim=mod.similarity_matrix.numpy()[::st, ::st],
+        cost=mod.cost_matrix.numpy()[::st, ::st], vva_refined=out.numpy())
+    print("vva", name, out.shape, float(out.max()))
+
+
+def gen_pir(name, spec):
+    from mars.components.PriorInformationRefinementModule import PriorInformationRefinementModule
+
+    c = cases.pir_inputs(spec)
+    mod = PriorInformationRefinementModule(box_threshold=spec["thr"],
+                                           last_n_attention_maps_for_refinement=spec["last_n"],
+                                           device="cpu", num_regs=spec["regs"])
+    out = mod.compute(prior=c["prior"], attn_maps=c["attn_maps"])
+    box, cnt = mod._scoremap2bbox(c["prior"].numpy(), multi_contour_eval=True)
+    np.savez_compressed(os.path.join(HERE, f"pir_{name}.npz"), spec=np.asarray(repr(spec)),
+                        checksum=cases.checksum(c), refined=out.numpy(), boxes=np.asarray(box), cnt=cnt)
+    print("pir", name, out.shape, cnt)
+
+
+def gen_fm(name, spec):
+    from mars.components.FilteringMergingModule import FilteringMergingModule
+
+    c = cases.fm_inputs(spec)
+    model = FakeAlphaClip(c["clip_img"], c["clip_txt"])
+    mod = FilteringMergingModule(
+        alpha_clip_model=model, img_transforms=lambda x: torch.zeros(3, 8, 8),
+        mask_transforms=lambda m: torch.from_numpy(m)[None].float(),
+        alpha=spec["alpha"], static_threshold=spec["static"], dynamic_threshold=spec["dynamic"], device="cpu")
+    h = spec["H"]
+    ranked = mod._score_proposals(
+        query_img=torch.zeros(1, 3, h, h), mask_proposals=c["masks"], support_mask=c["support_mask"][None],
+        cost_matrix=c["cost"], patch_features_spatial_dimension=spec["g"], vva=c["vva"], vta=c["vta"], text=["a thing."])
+    merged = mod._merge_masks(ranked)
+    order = []
+    for m, _ in ranked:
+        order.append([i for i in range(c["masks"].shape[0]) if m.data_ptr() == c["masks"][i].data_ptr()][0])
+    scores = np.asarray([float(np.asarray(s).reshape(-1)[0]) for _, s in ranked], dtype=np.float64)
+    # the emd scores the reference saw (1 - emd), recomputed through its own method
+    pooled_sup = torch.nn.functional.adaptive_max_pool2d(c["support_mask"][:, None].float(), (spec["g"], spec["g"]))
+    emd = []
+    for m_p in c["masks"]:
+        pm = torch.nn.functional.adaptive_max_pool2d(m_p[None].float(), (spec["g"], spec["g"]))[0]
+        emd.append(mod._compute_emd(pooled_sup, pm, c["cost"]))
+    np.savez_compressed(os.path.join(HERE, f"fm_{name}.npz"), spec=np.asarray(repr(spec)),
+                        checksum=cases.checksum(c), order=np.asarray(order), scores=scores,
+                        emd=np.asarray(emd, dtype=np.float64),
+                        merged_bits=np.packbits(merged.numpy() > 0), merged_shape=np.asarray(merged.shape))
+    print("fm", name, order[:8], scores[:4])
+
+
+def main():
+    ref_root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    install_shims(ref_root)
+    torch.set_num_threads(1)  # deterministic reductions in the fixtures
+    for name, spec in cases.VVA_CASES.items():
+        gen_vva(name, spec)
+    for name, spec in cases.PIR_CASES.items():
+        gen_pir(name, spec)
+    for name, spec in cases.FM_CASES.items():
+        gen_fm(name, spec)
+
+
+if __name__ == "__main__":
+    main()

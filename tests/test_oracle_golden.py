@@ -1,0 +1,96 @@
+"""The CPU oracle against the golden vectors produced by the reference's own modules."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import mars_oracle as orc
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(kind, name):
+    z = np.load(os.path.join(GOLD, f"{kind}_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    return z, spec
+
+
+@pytest.mark.parametrize("name", list(cases.VVA_CASES))
+def test_vva_matches_reference(name):
+    z, spec = load("vva", name)
+    c = cases.vva_inputs(spec)
+    assert str(cases.checksum(c)) == str(z["checksum"]), "input generator drifted"
+    g = spec["g"]
+    fs, fq = orc.normalize_rows(c["feat_s"]), orc.normalize_rows(c["feat_q"])
+    sim, cost = orc.similarity_and_cost(fs, fq)
+    st = int(z["stride"])
+    np.testing.assert_allclose(sim.numpy()[::st, ::st], z["sim"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(cost.numpy()[::st, ::st], z["cost"], rtol=0, atol=2e-6)
+    bits = orc.pool_mask(c["support_mask"], g).reshape(-1)
+    prior = orc.vva_prior(fs, fq, bits, g)
+    a = orc.attention_mean(c["attn_maps"], spec["last_n"], spec["regs"])
+    out = orc.minmax(orc.pir_refine(prior, a, spec["thr"]))
+    np.testing.assert_allclose(out.numpy(), z["vva_refined"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", list(cases.PIR_CASES))
+@pytest.mark.parametrize("use_cv2", [False, True])
+def test_pir_matches_reference(name, use_cv2):
+    z, spec = load("pir", name)
+    c = cases.pir_inputs(spec)
+    assert str(cases.checksum(c)) == str(z["checksum"])
+    a = orc.attention_mean(c["attn_maps"], spec["last_n"], spec["regs"])
+    out = orc.pir_refine(c["prior"], a, spec["thr"], use_cv2=use_cv2)
+    np.testing.assert_allclose(out.numpy(), z["refined"], rtol=1e-5, atol=1e-7)
+    # the box union the reference built
+    b_ref = np.zeros((spec["g"], spec["g"]), dtype=np.float32)
+    for x0, y0, x1, y1 in z["boxes"][: int(z["cnt"])]:
+        b_ref[y0:y1, x0:x1] = 1
+    np.testing.assert_array_equal(orc.box_mask(c["prior"].numpy(), spec["thr"], use_cv2=use_cv2), b_ref)
+
+
+@pytest.mark.parametrize("name", list(cases.FM_CASES))
+def test_filtering_merging_matches_reference(name):
+    z, spec = load("fm", name)
+    c = cases.fm_inputs(spec)
+    assert str(cases.checksum(c)) == str(z["checksum"])
+    g = spec["g"]
+    pooled, cov, avv, avt = orc.region_scores(c["masks"], c["vva"].numpy(), c["vta"].numpy(), g)
+    sup = orc.pool_mask(c["support_mask"], g).reshape(-1)
+    emd = np.asarray([orc.emd_score(sup, torch.from_numpy(pm), c["cost"]) for pm in pooled])
+    np.testing.assert_allclose(emd, z["emd"], rtol=0, atol=1e-9)
+    clip = orc.clip_scores(c["clip_img"], c["clip_txt"])
+    scores = orc.fuse_scores(z["emd"], clip, cov, avv, avt, spec["alpha"])
+    order = orc.stable_rank(scores)
+    np.testing.assert_array_equal(order, z["order"])
+    np.testing.assert_allclose(scores[order], z["scores"], rtol=1e-6, atol=1e-7)
+    sel = orc.merge_select(scores[order], spec["static"], spec["dynamic"])
+    merged = orc.merge_masks(c["masks"], order[sel])
+    ref = np.unpackbits(z["merged_bits"])[: merged.numel()].reshape(tuple(z["merged_shape"]))
+    np.testing.assert_array_equal(merged.numpy() > 0, ref > 0)
+
+
+def test_run_episode_consistency():
+    """run_episode chains the same pieces (used as the checker for the CUDA episode path)."""
+    spec = cases.FM_CASES["g10_dynamic"]
+    c = cases.fm_inputs(spec)
+    vs = cases.VVA_CASES["g10_2shot"]
+    v = cases.vva_inputs(vs)
+    g = 10
+    ep = dict(feat_s=v["feat_s"][:1], feat_q=v["feat_q"], support_mask=c["support_mask"],
+              attn_vva=orc.attention_mean(v["attn_maps"], 2, 4), vta_raw=torch.rand(8, 8),
+              attn_vta=torch.softmax(torch.randn(64, 64), -1), masks=c["masks"],
+              clip_img=c["clip_img"], clip_txt=c["clip_txt"], emd=torch.rand(spec["P"]))
+    cfg = dict(g=g, vva_box_threshold=0.8, vta_box_threshold=0.4, alpha=0.85, static_threshold=0.55,
+               dynamic_threshold=0.95, nms_iou_threshold=0.7)
+    out = orc.run_episode(ep, cfg)
+    assert out["merged"].shape == (140, 140)
+    assert out["keep"][out["order"][0]]
+    assert set(out["selected"]) <= set(np.nonzero(out["keep"])[0])
+    inter, area = out["inter"], out["area"]
+    mb = c["masks"].reshape(spec["P"], -1) > 0
+    assert torch.equal(area, mb.sum(1).to(torch.int32))
+    assert torch.equal(inter, (mb.float() @ mb.float().T).to(torch.int32))
