@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the MARS ranking stage (BASELINE.json metric: episodes/s, config c2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+A *step* is one pass of the whole hot path over one batch of `--episodes-per-step` synthetic
+episodes per GPU (inputs resident in HBM for `value`; pinned host buffers + H2D/D2H inside the
+timed region for `e2e`).  Under torchrun (N > 1) every rank processes its own shard of episodes and
+the per-episode result records are all-gathered over NCCL each step; the time is the max over
+ranks, measured with CUDA events between barrier + synchronize.
+
+`--impl reference` times the reference's algorithm on the host CPU (the oracle port: the reference
+is Python and cannot travel to the GPU box), on the same workload, one episode per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--episodes-per-step", type=int, default=8)
+    ap.add_argument("--e2e-episodes-per-step", type=int, default=2)
+    ap.add_argument("--mask-dtype", default="f32", choices=["f32", "u8"])
+    ap.add_argument("--nms", type=float, default=0.7)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-episodes", type=int, default=2)
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_description(shape, args):
+    return (f"{args.workload}: {shape.ns}-shot episode, N={shape.N} patches x C={shape.C}, P={shape.P} proposals at "
+            f"{shape.H}x{shape.W} ({args.mask_dtype} masks), vva+PIR, vta PIR, region scores, AlphaCLIP cosine, "
+            f"pairwise intersections + IoU-NMS {args.nms}, fuse/rank, merge; EMD scores are an input")
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_episodes(shape, args, n_episodes, device_for_generation):
+    """Run the oracle port on `n_episodes` episodes with all host threads; returns (seconds per episode list)."""
+    import marsb200
+    from oracle import mars_oracle as orc
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = dict(g=shape.g, vva_box_threshold=0.8, vta_box_threshold=0.4, alpha=0.85, static_threshold=0.55,
+               dynamic_threshold=0.95, nms_iou_threshold=args.nms)
+    md = torch.float32 if args.mask_dtype == "f32" else torch.uint8
+    times = []
+    for i in range(n_episodes):
+        ep = marsb200.make_episode(shape, 10_000 + i, device_for_generation, md)
+        ep = {k: v.cpu() for k, v in ep.items()}
+        ep["masks"] = ep["masks"].float()  # the reference's wire format
+        t0 = time.perf_counter()
+        orc.run_episode(ep, cfg)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import marsb200
+
+    shape = marsb200.CONFIGS[args.workload]
+    gen_dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    cpu_reference_episodes(shape, args, min(args.warmup, 1), gen_dev)  # one warm-up episode is enough on the CPU
+    times = cpu_reference_episodes(shape, args, args.steps, gen_dev)
+    total = sum(times)
+    value = len(times) / total
+    cores = os.cpu_count() or 1
+    sample = f"{len(times)} episodes of {args.workload}, one per step, torch CPU with {cores} threads, EMD excluded"
+    print(json.dumps({
+        "impl": "reference", "metric": "episodes_per_sec", "value": value, "unit": "episodes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": workload_description(shape, args)},
+        "cpu_baseline": {"value": value, "unit": "episodes/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    import marsb200
+    from marsb200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (marsb200 has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    shape = marsb200.CONFIGS[args.workload]
+    md = torch.float32 if args.mask_dtype == "f32" else torch.uint8
+    cfg = marsb200.RankingConfig(nms_iou_threshold=args.nms)
+    E = args.episodes_per_step
+    eng = marsb200.RankingEngine(shape, E, cfg, dev, md)
+
+    # two distinct resident batches, alternated: every step reads inputs far larger than the 126 MB L2
+    n_batches = 2
+    batches = []
+    for b in range(n_batches):
+        eps = [marsb200.make_episode(shape, (rank * n_batches + b) * E + i, dev, md) for i in range(E)]
+        batches.append(marsb200.stack_episodes(eps))
+        del eps
+    bytes_per_step = sum(v.numel() * v.element_size() for v in batches[0].values())
+    total_episodes = world * E
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        out = eng.run(batches[i % n_batches])
+        if world > 1:
+            marsb200.gather_records(eng.records(), total_episodes)
+        return out
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for i in range(args.steps):
+        step(i)
+    stop.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = start.elapsed_time(stop)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = total_episodes * args.steps / (elapsed_ms / 1e3)
+
+    # ---- per-kernel timing of the dominant kernels with CUDA events on the launching stream
+    def time_kernel(fn, iters):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for i, (a, b) in enumerate(evs):
+            a.record()
+            fn(i)
+            b.record()
+        torch.cuda.synchronize()
+        return statistics.mean(a.elapsed_time(b) for a, b in evs)
+
+    iters = max(4, min(args.steps, 20))
+    pack_ms = time_kernel(lambda i: ops.pack_masks(batches[i % n_batches]["masks"], out=eng.bits), iters)
+    pair_ms = time_kernel(lambda i: ops.pairwise_inter(eng.bits, backend=cfg.pair_backend, out=eng.inter), iters)
+    hw = shape.H * shape.W
+    wpm = ops.words_per_mask(hw)
+    pack_bytes = E * shape.P * (hw * (4 if md == torch.float32 else 1) + wpm * 4)
+    peak, peak_kind = measured_peak_gbs()
+    achieved = pack_bytes / (pack_ms / 1e3) / 1e9
+    pairs = E * shape.P * (shape.P + 1) // 2
+    roofline = {"kernel": "pack_masks (mask ingest -> packed bits)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": pack_bytes, "ms_per_launch": pack_ms}
+    pairwise = {"kernel": "pairwise_inter", "unordered_pairs_per_s": pairs / (pair_ms / 1e3), "ms_per_launch": pair_ms,
+                "word_ops_per_s": pairs * wpm / (pair_ms / 1e3)}
+
+    # ---- end to end: pinned host inputs -> H2D -> ranking -> D2H of the result records, every step
+    e2e = None
+    if not args.no_e2e:
+        Ee = args.e2e_episodes_per_step
+        eng2 = marsb200.RankingEngine(shape, Ee, cfg, dev, md)
+        host = {k: v[:Ee].cpu().pin_memory() for k, v in batches[0].items()}
+        dev_in = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+        rec_host = torch.empty((Ee, eng2.record_bytes()), dtype=torch.uint8).pin_memory()
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = rec_host.numel()
+
+        def e2e_step():
+            for k in host:
+                dev_in[k].copy_(host[k], non_blocking=True)
+            eng2.run(dev_in)
+            rec_host.copy_(eng2.records(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller reads the result on the host
+
+        for _ in range(args.warmup):
+            e2e_step()
+        barrier()
+        s2, t2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(args.steps):
+            e2e_step()
+        t2.record()
+        barrier()
+        ms2 = s2.elapsed_time(t2)
+        if world > 1:
+            t = torch.tensor([ms2], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t.item())
+        e2e = {"value": world * Ee * args.steps / (ms2 / 1e3), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "episodes_per_step": Ee, "ms_per_step": ms2 / args.steps}
+        del eng2, host, dev_in
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times = cpu_reference_episodes(shape, args, args.cpu_sample_episodes, dev)
+        cores = os.cpu_count() or 1
+        cpu_baseline = {"value": len(times) / sum(times), "unit": "episodes/s", "cores": cores, "kind": "port",
+                        "sample": f"{len(times)} episodes of {args.workload} through oracle.run_episode "
+                                  f"(torch CPU, {cores} threads, EMD excluded)"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "episodes_per_sec", "value": value, "unit": "episodes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+fp32(3xtf32)",
+            "data": "synthetic",
+            "config": {"workload": workload_description(shape, args), "episodes_per_step_per_gpu": E,
+                       "input_bytes_per_step_per_gpu": bytes_per_step,
+                       "l2": "two resident batches alternate; each step's inputs exceed the 126 MB L2",
+                       "gemm_backend": "tcgen05" if ops.DEFAULT_GEMM == ops.GEMM_TCGEN05 else "simt",
+                       "pair_backend": "popc" if ops.DEFAULT_PAIR == ops.PAIR_POPC else "mma"},
+            "clocks": clocks, "e2e": e2e,
+            "gpu_launches": marsb200.kernel_launches_per_run(cfg) * args.steps * world,
+            "roofline": roofline, "pairwise": pairwise, "cpu_baseline": cpu_baseline,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,178 @@
+/* marsb200 - C ABI of the B200-native MARS proposal scoring / ranking / merging stage.
+ *
+ * The reference (a pure-Python/PyTorch repo) has no FFI; the surface a
+ * maintainer would bind is the arithmetic inside its Python classes.  Every
+ * entry point below names the reference code it replaces (paths relative to
+ * the reference checkout).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - the caller owns every buffer (inputs, outputs, workspaces); the library
+ *    never allocates, frees or synchronises, and enqueues work only on
+ *    `stream` (a cudaStream_t passed as void*), so a whole episode batch can
+ *    be captured into a CUDA graph;
+ *  - all arrays are dense row-major; a leading E is the episode batch;
+ *  - return value: 0 on success, a negative MARSB200_ERR_* otherwise, with a
+ *    thread-local message available from marsb200_last_error();
+ *  - there is no CPU fallback: every call needs an sm_100a device.
+ */
+#ifndef MARSB200_H
+#define MARSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MARSB200_OK 0
+#define MARSB200_ERR_ARG (-1)
+#define MARSB200_ERR_CUDA (-2)
+#define MARSB200_ERR_UNSUPPORTED (-3)
+
+/* mask element types accepted by the ingest kernels */
+#define MARSB200_MASK_F32 0 /* reference-native float32 0/1 (main_MARS.py:62, Matcher.py:728-729) */
+#define MARSB200_MASK_U8 1  /* uint8 / bool, 1 byte per pixel */
+
+/* contraction back ends of marsb200_sim_contract / marsb200_pir_refine */
+#define MARSB200_GEMM_TCGEN05 0 /* TMA + tcgen05 3xTF32 (error-compensated), fp32 accumulate in TMEM */
+#define MARSB200_GEMM_SIMT 1    /* fp32 FFMA tiles; validation path for the tensor-core kernel */
+
+/* pairwise-intersection back ends */
+#define MARSB200_PAIR_POPC 0 /* shared-memory tiled AND + popcount */
+#define MARSB200_PAIR_MMA 1  /* bits expanded to int8 in shared memory, tcgen05 kind::i8 into TMEM */
+
+int marsb200_version(void);
+const char* marsb200_last_error(void);
+/* words (uint32) per packed mask row for an H*W mask: ceil(HW/32) rounded up to 32 words (128 B) */
+int64_t marsb200_words_per_mask(int64_t hw);
+/* padded extents used by the contraction operands */
+int64_t marsb200_pad_rows(int64_t rows);  /* -> multiple of 128 */
+int64_t marsb200_pad_k(int64_t k);        /* -> multiple of 32  */
+
+/* ---- A1: row L2-normalise + TF32 hi/lo split -------------------------------------------
+ * Replaces F.normalize(feats, p=2, dim=1): VisualVisualAlignmentModule.py:124-125,
+ * matcher/Matcher.py:297-298.  x [E, rows, k] fp32 -> xn [E, rows_pad, k_pad] fp32 normalised,
+ * hi/lo [E, rows_pad, k_pad] with hi = tf32(xn), lo = xn - hi; padding is zero-filled.
+ * If `normalize` is 0 the rows are only split (used for the PIR matrix D). */
+int marsb200_normalize_split(const float* x, int64_t ld_x, int E, int64_t rows, int64_t k, int normalize,
+                             float* hi, float* lo, void* stream);
+
+/* ---- A3/A6: adaptive max pool of masks to the patch grid ---------------------------------
+ * Replaces F.adaptive_max_pool2d(mask, (g, g)) > 0: VisualVisualAlignmentModule.py:72-76,
+ * FilteringMergingModule.py:73-76.  masks [n, H, W] -> out [n, g*g] uint8 0/1. */
+int marsb200_pool_mask(const void* masks, int mask_dtype, int64_t n, int H, int W, int g, uint8_t* out, void* stream);
+
+/* ---- A2 + A3: S = Fs Fq^T with fused masked column statistics -----------------------------
+ * Replaces torch.matmul at VisualVisualAlignmentModule.py:69 and the two recomputed products
+ * + max/mean reductions at :78-102, and matcher/Matcher.py:437-440.
+ * a_hi/a_lo [E, pad_rows(M), pad_k(K)], b_hi/b_lo [E, pad_rows(N), pad_k(K)] from normalize_split.
+ * sim_out / cost_out [E, M, N] are optional (NULL to skip); cost = (1 - S) / 2.
+ * row_fg [E, M] uint8 (pooled support mask, shot-major) and colstats [E, tiles_m, 4, N] are optional
+ * (both or neither): per 128-row tile, the per-column {max over fg rows, sum over fg rows,
+ * max over bg rows, sum over bg rows}; -inf / 0 when a tile has no such row. tiles_m = pad_rows(M)/128. */
+int marsb200_sim_contract(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int E,
+                          int64_t M, int64_t N, int64_t K, float* sim_out, float* cost_out,
+                          const uint8_t* row_fg, float* colstats, int backend, void* stream);
+
+/* vva = mean_fg*max_fg - mean_bg*max_bg (bg skipped when there is no bg row), then min-max with eps 1e-7.
+ * Replaces VisualVisualAlignmentModule.py:82-102.  out [E, N].  Returns an error when an episode has no fg row
+ * only at the Python level (the kernel writes NaN for such an episode). */
+int marsb200_vva_finalize(const float* colstats, const uint8_t* row_fg, int E, int64_t M, int64_t N, float* out,
+                          void* stream);
+
+/* ---- A4: prior-information refinement ------------------------------------------------------
+ * Mean over layers and heads of the patch-to-patch attention, dropping `skip` leading tokens
+ * (cls + registers).  Replaces PriorInformationRefinementModule.py:31-45.
+ * maps_host: host array of n_maps device pointers, each [heads, T, T] of fp32 (dtype 0) or fp16 (dtype 1);
+ * out [N, ld_out] fp32 with N = T - skip. */
+int marsb200_attn_mean(const void* const* maps_host, int n_maps, int dtype, int heads, int T, int skip,
+                       float* out, int64_t ld_out, void* stream);
+
+/* Bytes of workspace marsb200_pir_refine needs for E episodes of an N x N attention matrix. */
+int64_t marsb200_pir_workspace_bytes(int E, int64_t N);
+
+/* Full PIR: box mask from the prior (uint8 quantise, threshold, 8-connected components, clipped
+ * boxes), D = A/colsum, D = D/rowsum, R = max(D, D D^T), out = R (R (B*prior)) [== ((R R)*B) prior],
+ * optional min-max.  Replaces PriorInformationRefinementModule.py:47-89 and :91-122.
+ * prior [E, g*g]; attn [E, N, ld_attn] with N = g*g; out [E, N]; box_out [E, N] uint8 optional. */
+int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, int E, int g, double box_threshold,
+                        int apply_minmax, float* out, uint8_t* box_out, void* workspace, int64_t workspace_bytes,
+                        int backend, void* stream);
+
+/* Nearest-neighbour resize of [E, gs, gs] maps to [E, gd, gd] followed by min-max (eps 1e-7).
+ * Replaces mars/MARS.py:77-82. */
+int marsb200_resize_minmax(const float* src, int E, int gs, int gd, int apply_minmax, float* out, void* stream);
+
+/* ---- A6/A9 ingest: bit-pack the proposal masks ---------------------------------------------
+ * masks [n, HW] (float32 or uint8, pixel set iff value > 0) -> bits [n, words_per_mask(HW)] uint32,
+ * bit k of word w = pixel 32*w + k; padding words are zero.  Replaces the per-proposal `m_p > 0`
+ * views of FilteringMergingModule.py:77,104-108 and feeds every later mask kernel. */
+int marsb200_pack_masks(const void* masks, int mask_dtype, int64_t n, int64_t HW, uint32_t* bits, void* stream);
+
+/* Pooled patch bitmap, pixel area and pooled count of every packed mask.
+ * Replaces F.adaptive_max_pool2d(m_p, (g, g)) > 0 in the hot loop, FilteringMergingModule.py:104-108.
+ * bits [n, wpm] -> pooled [n, ceil(g*g/32)] uint32, area [n] int32, pooled_count [n] int32. */
+int marsb200_pool_packed(const uint32_t* bits, int64_t n, int H, int W, int g, uint32_t* pooled, int32_t* area,
+                         int32_t* pooled_count, void* stream);
+
+/* Per-proposal sums of the vva / vta maps under the pooled bitmap and the pooled size of the
+ * proposal union.  Replaces FilteringMergingModule.py:77-81,108-110.
+ * pooled [E, P, npw]; vva, vta [E, N]; sum_vva, sum_vta [E, P] fp32; union_count [E] int32. */
+int marsb200_region_sums(const uint32_t* pooled, int E, int P, int N, const float* vva, const float* vta,
+                         float* sum_vva, float* sum_vta, int32_t* union_count, void* stream);
+
+/* ---- A9: pairwise intersection matrix (builder-defined; no reference code) -----------------
+ * inter[e,i,j] = popcount(bits[e,i] & bits[e,j]) as int32 [E, P, P]; the diagonal is the area. */
+int marsb200_pairwise_inter(const uint32_t* bits, int E, int P, int64_t words_per_mask, int32_t* inter,
+                            int backend, void* stream);
+
+/* ---- A8: AlphaCLIP cosine scores -----------------------------------------------------------
+ * clip[e,p] = img[e,p,:] . txt[e,:].  Replaces img_feats @ text_feats.T, FilteringMergingModule.py:97. */
+int marsb200_clip_scores(const float* img, const float* txt, int E, int P, int D, float* out, void* stream);
+
+/* ---- A8 + A10 + A11: fuse, rank, NMS, select ------------------------------------------------
+ * score = (minmax(emd) + minmax(clip) + a*pvv+(1-a)*cov + a*pvt+(1-a)*cov) / 4, stable descending
+ * rank, optional greedy IoU-NMS over `inter` (skipped when inter is NULL or nms_iou_threshold < 0),
+ * static/dynamic threshold selection.  Replaces FilteringMergingModule.py:118-138 and :213-217; the NMS is
+ * builder-defined with the semantics of torchvision nms (segment_anything/automatic_mask_generator.py:370-376).
+ * emd is fp64 (the reference's 1 - ot.emd2 is a float64) and alpha / thresholds are doubles (Python floats in
+ * the reference); the AlphaCLIP min-max is evaluated in fp32 exactly as the reference's numpy does.
+ * Outputs: scores [E,P] fp64 by proposal index; order [E,P] int32 (rank -> index);
+ * flags [E,P] uint8 by proposal index (bit0 = kept by NMS, bit1 = selected for the merge);
+ * summary [E,4] int32 = {n_kept, n_selected, top_index, 0}. */
+int marsb200_fuse_rank(const double* emd, const float* clip, const int32_t* pooled_count, const float* sum_vva,
+                       const float* sum_vta, const int32_t* union_count, const int32_t* inter, int E, int P,
+                       double alpha, double static_threshold, double dynamic_threshold, float nms_iou_threshold,
+                       double* scores, int32_t* order, uint8_t* flags, int32_t* summary, void* stream);
+
+/* OR of the selected packed masks and expansion to the float32 [H,W] map the reference returns.
+ * Replaces (torch.sum(torch.stack(ranked_masks), 0) > 0).float(), FilteringMergingModule.py:219, and the
+ * merges at matcher/Matcher.py:776,823.  merged_bits [E, wpm] and merged_f32 [E, HW] are each optional. */
+int marsb200_merge_masks(const uint32_t* bits, const uint8_t* flags, int E, int P, int64_t HW,
+                         uint32_t* merged_bits, float* merged_f32, void* stream);
+
+/* ---- A12: Matcher-derived scoring ---------------------------------------------------------
+ * Number of matched points falling inside every packed mask (is_in_mask, matcher/Matcher.py:1166-1173,
+ * 1198-1199).  points [K,2] int32 (x, y), clipped to the image; out [n] int32. */
+int marsb200_points_in_masks(const uint32_t* bits, int64_t n, int H, int W, const int32_t* points, int K,
+                             int32_t* out, void* stream);
+
+/* purity = in/max(pooled,1) + 1e-6, coverage = in/K + 1e-6, score = alpha*emd + beta*purity*coverage^exp.
+ * Replaces matcher/Matcher.py:1203-1209 and :719-720.  All arrays [n] fp32. */
+int marsb200_matcher_scores(const int32_t* points_in, const int32_t* pooled_count, const float* emd, int64_t n, int K,
+                            float alpha, float beta, float exp, float* purity, float* coverage, float* scores,
+                            void* stream);
+
+/* ---- 8f-3: evaluator -------------------------------------------------------------------------
+ * Per-sample foreground/background intersection and union areas of a prediction against the
+ * ground truth with an optional ignore mask.  Replaces Evaluator.classify_prediction,
+ * mars/utils/evaluation.py:12-38.  pred, gt, ignore: [n, HW] fp32; out [n, 4] int32 =
+ * {inter_bg, inter_fg, union_bg, union_fg}. */
+int marsb200_eval_areas(const float* pred, const float* gt, const float* ignore, int64_t n, int64_t HW, int32_t* out,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARSB200_H */

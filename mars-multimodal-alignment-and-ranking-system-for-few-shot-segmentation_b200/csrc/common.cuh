@@ -1,0 +1,85 @@
+// Shared helpers for the marsb200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/marsb200.h"
+
+namespace marsb200 {
+
+// thread-local message returned by marsb200_last_error()
+char* last_error_buffer();
+
+inline int fail(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
+    snprintf(last_error_buffer(), 512, fmt, a, b, c);
+    return code;
+}
+
+#define MARS_REQUIRE(cond, msg)                                                        \
+    do {                                                                                 \
+        if (!(cond)) return ::marsb200::fail(MARSB200_ERR_ARG, "%s: requirement failed: " msg " (%lld, %lld)", __func__, 0, 0); \
+    } while (0)
+
+#define MARS_CUDA_OK(expr)                                                             \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            return ::marsb200::fail(MARSB200_ERR_CUDA, "%s: CUDA error %lld at line %lld", cudaGetErrorString(_e), (long long)_e, __LINE__); \
+    } while (0)
+
+#define MARS_LAUNCH_OK() MARS_CUDA_OK(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__host__ __device__ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// adaptive-pool bin i over an axis of length L with g bins: [floor(i*L/g), ceil((i+1)*L/g))
+__host__ __device__ static inline int bin_start(int i, int L, int g) { return (int)(((int64_t)i * L) / g); }
+__host__ __device__ static inline int bin_end(int i, int L, int g) { return (int)((((int64_t)i + 1) * L + g - 1) / g); }
+// bins that contain coordinate x: [floor(x*g/L), ceil((x+1)*g/L) - 1]
+__host__ __device__ static inline int bin_lo_of(int x, int L, int g) { return (int)(((int64_t)x * g) / L); }
+__host__ __device__ static inline int bin_hi_of(int x, int L, int g) { return (int)((((int64_t)x + 1) * g + L - 1) / L) - 1; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// streaming 128-bit load that does not allocate in L1 (inputs are read once)
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// internal back ends shared between translation units
+int pairwise_popc(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s);
+int pairwise_mma(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s);
+
+}  // namespace marsb200

@@ -1,0 +1,224 @@
+// Score fusion, stable ranking, greedy IoU-NMS and merge selection (one CTA per episode), plus
+// the AlphaCLIP cosine scores.
+#include "common.cuh"
+
+namespace marsb200 {
+
+__global__ void clip_scores_kernel(const float* __restrict__ img, const float* __restrict__ txt, int64_t total, int P,
+                                   int D, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wg >= total) return;
+    const int64_t e = wg / P;
+    const float* a = img + wg * D;
+    const float* t = txt + e * D;
+    double acc = 0.0;
+    for (int d = lane; d < D; d += 32) acc += (double)a[d] * (double)t[d];
+    acc = warp_sum(acc);
+    if (lane == 0) out[wg] = (float)acc;
+}
+
+// block-wide reductions through shared memory (blockDim.x == FUSE_THREADS)
+constexpr int FUSE_THREADS = 256;
+
+template <typename T, typename Op>
+__device__ T block_reduce(T v, Op op, T* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    T r = scratch[0];
+    for (int w = 1; w < FUSE_THREADS / 32; ++w) r = op(r, scratch[w]);
+    return r;
+}
+
+// sort key order: higher score first, equal scores keep ascending proposal index (stable sort of the
+// reference's sorted(reverse=True), FilteringMergingModule.py:138)
+__device__ __forceinline__ bool ranks_before(double sa, int ia, double sb, int ib) {
+    return sa > sb || (sa == sb && ia < ib);
+}
+
+__global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
+    const double* __restrict__ emd, const float* __restrict__ clip, const int32_t* __restrict__ pooled_count,
+    const float* __restrict__ sum_vva, const float* __restrict__ sum_vta, const int32_t* __restrict__ union_count,
+    const int32_t* __restrict__ inter, int P, int n2, double alpha, double static_thr, double dynamic_thr,
+    float nms_thr, double* __restrict__ scores, int32_t* __restrict__ order, uint8_t* __restrict__ flags,
+    int32_t* __restrict__ summary) {
+    extern __shared__ unsigned char smem_raw[];
+    double* s_key = reinterpret_cast<double*>(smem_raw);               // n2
+    int* s_idx = reinterpret_cast<int*>(s_key + n2);                   // n2
+    int* s_rank = s_idx + n2;                                          // P: proposal index -> rank
+    int* s_area = s_rank + P;                                          // P
+    unsigned char* s_removed = reinterpret_cast<unsigned char*>(s_area + P);  // P
+    __shared__ double s_scratch_d[FUSE_THREADS / 32];
+    __shared__ float s_scratch_f[FUSE_THREADS / 32];
+    __shared__ int s_counts[2];
+
+    const int64_t e = blockIdx.x;
+    const int tid = threadIdx.x;
+    emd += e * P;
+    clip += e * P;
+    pooled_count += e * P;
+    sum_vva += e * P;
+    sum_vta += e * P;
+
+    // ---- min / max of the two globally normalised scores
+    double emin = INFINITY, emax = -INFINITY;
+    float cmin = INFINITY, cmax = -INFINITY;
+    for (int p = tid; p < P; p += FUSE_THREADS) {
+        const double v = emd[p];
+        const float c = clip[p];
+        emin = fmin(emin, v);
+        emax = fmax(emax, v);
+        cmin = fminf(cmin, c);
+        cmax = fmaxf(cmax, c);
+    }
+    emin = block_reduce(emin, [](double a, double b) { return fmin(a, b); }, s_scratch_d);
+    emax = block_reduce(emax, [](double a, double b) { return fmax(a, b); }, s_scratch_d);
+    cmin = block_reduce(cmin, [](float a, float b) { return fminf(a, b); }, s_scratch_f);
+    cmax = block_reduce(cmax, [](float a, float b) { return fmaxf(a, b); }, s_scratch_f);
+
+    const double e_den = 1e-7 + emax - emin;         // float64, FilteringMergingModule.py:131
+    const float c_den = (1e-7f + cmax) - cmin;       // evaluated in the feature dtype (float32), :132
+    const double u_den = 1e-7 + (double)union_count[e];
+
+    // ---- fused score per proposal
+    for (int p = tid; p < n2; p += FUSE_THREADS) {
+        if (p < P) {
+            const double cnt = (double)pooled_count[p];
+            const double cov = cnt / u_den;
+            const double avv = (double)sum_vva[p] / (1e-7 + cnt);
+            const double avt = (double)sum_vta[p] / (1e-7 + cnt);
+            const double pvv = alpha * avv + (1.0 - alpha) * cov;
+            const double pvt = alpha * avt + (1.0 - alpha) * cov;
+            const double en = (emd[p] - emin) / e_den;
+            const float cn = __fdiv_rn(clip[p] - cmin, c_den);
+            const double sc = (((en + (double)cn) + pvv) + pvt) / 4.0;
+            scores[e * P + p] = sc;
+            s_key[p] = sc;
+            s_idx[p] = p;
+        } else {
+            s_key[p] = -INFINITY;
+            s_idx[p] = 0x7fffffff;
+        }
+    }
+    __syncthreads();
+
+    // ---- bitonic sort of (key, idx) into rank order
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n2; i += FUSE_THREADS) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;  // this sub-sequence ends in rank order
+                    const double ki = s_key[i], kl = s_key[l];
+                    const int ii = s_idx[i], il = s_idx[l];
+                    const bool l_first = ranks_before(kl, il, ki, ii);
+                    if (l_first == up) {
+                        s_key[i] = kl;
+                        s_key[l] = ki;
+                        s_idx[i] = il;
+                        s_idx[l] = ii;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int r = tid; r < P; r += FUSE_THREADS) {
+        const int p = s_idx[r];
+        order[e * P + r] = p;
+        s_rank[p] = r;
+        s_removed[r] = 0;  // indexed by proposal below; cleared for all P entries here
+    }
+    __syncthreads();
+
+    // ---- greedy IoU-NMS in rank order (builder-defined; torchvision nms semantics)
+    const bool do_nms = inter != nullptr && nms_thr >= 0.f;
+    if (do_nms) {
+        const int32_t* im = inter + e * (int64_t)P * P;
+        for (int p = tid; p < P; p += FUSE_THREADS) s_area[p] = im[(int64_t)p * P + p];
+        __syncthreads();
+        for (int r = 0; r < P; ++r) {
+            const int i = s_idx[r];
+            if (s_removed[i]) continue;  // uniform: shared state is stable between barriers
+            const int ai = s_area[i];
+            const int32_t* row = im + (int64_t)i * P;
+            for (int j = tid; j < P; j += FUSE_THREADS) {
+                if (s_rank[j] > r && !s_removed[j]) {
+                    const int in = row[j];
+                    const int un = ai + s_area[j] - in;
+                    const float iou = un > 0 ? __fdiv_rn((float)in, (float)un) : 0.f;
+                    if (iou > nms_thr) s_removed[j] = 1;
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- merge selection (FilteringMergingModule.py:213-217) and outputs
+    if (tid == 0) s_counts[0] = s_counts[1] = 0;
+    __syncthreads();
+    const double top = s_key[0];
+    const double bound = (top < static_thr) ? dynamic_thr * top : static_thr;
+    int kept = 0, selected = 0;
+    for (int p = tid; p < P; p += FUSE_THREADS) {
+        const bool keep = !do_nms || !s_removed[p];
+        const bool sel = keep && (s_key[s_rank[p]] >= bound);
+        flags[e * P + p] = (keep ? 1 : 0) | (sel ? 2 : 0);
+        kept += keep;
+        selected += sel;
+    }
+    kept = warp_sum(kept);
+    selected = warp_sum(selected);
+    if ((tid & 31) == 0) {
+        atomicAdd(&s_counts[0], kept);
+        atomicAdd(&s_counts[1], selected);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        summary[e * 4 + 0] = s_counts[0];
+        summary[e * 4 + 1] = s_counts[1];
+        summary[e * 4 + 2] = s_idx[0];
+        summary[e * 4 + 3] = 0;
+    }
+}
+
+}  // namespace marsb200
+
+using namespace marsb200;
+
+extern "C" {
+
+int marsb200_clip_scores(const float* img, const float* txt, int E, int P, int D, float* out, void* stream) {
+    MARS_REQUIRE(img && txt && out, "null pointer");
+    MARS_REQUIRE(E > 0 && P > 0 && D > 0, "shape");
+    const int64_t total = (int64_t)E * P;
+    clip_scores_kernel<<<(unsigned)ceil_div64(total, 8), 256, 0, as_stream(stream)>>>(img, txt, total, P, D, out);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+int marsb200_fuse_rank(const double* emd, const float* clip, const int32_t* pooled_count, const float* sum_vva,
+                       const float* sum_vta, const int32_t* union_count, const int32_t* inter, int E, int P,
+                       double alpha, double static_threshold, double dynamic_threshold, float nms_iou_threshold,
+                       double* scores, int32_t* order, uint8_t* flags, int32_t* summary, void* stream) {
+    MARS_REQUIRE(emd && clip && pooled_count && sum_vva && sum_vta && union_count, "null input");
+    MARS_REQUIRE(scores && order && flags && summary, "null output");
+    MARS_REQUIRE(E > 0 && P > 0 && P <= 8192, "shape (P <= 8192)");
+    int n2 = 1;
+    while (n2 < P) n2 <<= 1;
+    const size_t smem = (size_t)n2 * (sizeof(double) + sizeof(int)) + (size_t)P * (2 * sizeof(int) + 1) + 16;
+    if (smem > 48 * 1024)
+        MARS_CUDA_OK(cudaFuncSetAttribute(fuse_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fuse_rank_kernel<<<E, FUSE_THREADS, smem, as_stream(stream)>>>(emd, clip, pooled_count, sum_vva, sum_vta,
+                                                                   union_count, inter, P, n2, alpha, static_threshold,
+                                                                   dynamic_threshold, nms_iou_threshold, scores, order,
+                                                                   flags, summary);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+}  // extern "C"

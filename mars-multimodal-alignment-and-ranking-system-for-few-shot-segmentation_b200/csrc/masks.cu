@@ -1,0 +1,580 @@
+// Mask ingest and mask-geometry kernels: bit-pack, patch pooling, region sums, pairwise
+// AND+popcount intersections, OR-merge, point lookups, evaluator areas.
+//
+// HBM layout: a packed proposal is one row of `wpm = words_per_mask(HW)` uint32 words, bit k of
+// word w = pixel 32*w + k of the flattened [H,W] mask; wpm is a multiple of 32 words (128 B) and
+// the tail is zero.  One episode's proposals are P consecutive rows.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace marsb200 {
+
+// --------------------------------------------------------------------------------------------
+// pack: [n, HW] float32 / uint8  ->  [n, wpm] bits.  HBM-bound: reads 4 (or 1) B/pixel once with
+// 128-bit streaming loads, writes 1/32 (1/8) of that.  One warp turns 4 x 512 B into 16 words.
+// --------------------------------------------------------------------------------------------
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_UNROLL = 4;
+
+// f32: a thread's float4 gives a nibble; 8 lanes make a word.
+__global__ void __launch_bounds__(PACK_THREADS) pack_f32_vec_kernel(const float* __restrict__ masks, int64_t n,
+                                                                     int64_t HW, int64_t wpm,
+                                                                     uint32_t* __restrict__ bits, int chunks) {
+    const int64_t blk = blockIdx.x;
+    const int64_t m = blk / chunks;
+    const int chunk = (int)(blk % chunks);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PX_PER_BLOCK = PACK_THREADS * PACK_UNROLL * 4;  // 4096 pixels = 128 words
+    const int64_t px_base = (int64_t)chunk * PX_PER_BLOCK + (int64_t)warp * (PACK_UNROLL * 128);
+    const float* src = masks + m * HW;
+
+    uint4 v[PACK_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL; ++u) {
+        const int64_t px = px_base + u * 128 + lane * 4;
+        v[u] = (px < HW) ? ldg_stream_u4(src + px) : make_uint4(0, 0, 0, 0);  // HW % 4 == 0 on this path
+    }
+    uint32_t word[PACK_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL; ++u) {
+        uint32_t nib = (__uint_as_float(v[u].x) > 0.f ? 1u : 0u) | (__uint_as_float(v[u].y) > 0.f ? 2u : 0u) |
+                       (__uint_as_float(v[u].z) > 0.f ? 4u : 0u) | (__uint_as_float(v[u].w) > 0.f ? 8u : 0u);
+        uint32_t w = nib << (4 * (lane & 7));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        word[u] = w;  // every lane of octet o = lane>>3 holds word (u, o)
+    }
+    // lane t < 16 stores word (u = t>>2, o = t&3): one 64 B store per warp
+    uint32_t out = 0;
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL; ++u) {
+        uint32_t got = __shfl_sync(0xffffffffu, word[u], (lane & 3) * 8);
+        if ((lane >> 2) == u) out = got;
+    }
+    const int64_t w_idx = px_base / 32 + lane;
+    if (lane < PACK_UNROLL * 4 && w_idx < wpm) bits[m * wpm + w_idx] = out;
+}
+
+// u8: a thread's uint4 gives 16 bits; 2 lanes make a word.
+__global__ void __launch_bounds__(PACK_THREADS) pack_u8_vec_kernel(const uint8_t* __restrict__ masks, int64_t n,
+                                                                    int64_t HW, int64_t wpm,
+                                                                    uint32_t* __restrict__ bits, int chunks) {
+    const int64_t blk = blockIdx.x;
+    const int64_t m = blk / chunks;
+    const int chunk = (int)(blk % chunks);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PX_PER_BLOCK = PACK_THREADS * PACK_UNROLL * 16;  // 16384 pixels = 512 words
+    const int64_t px_base = (int64_t)chunk * PX_PER_BLOCK + (int64_t)warp * (PACK_UNROLL * 512);
+    const uint8_t* src = masks + m * HW;
+
+    uint4 v[PACK_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL; ++u) {
+        const int64_t px = px_base + u * 512 + lane * 16;
+        v[u] = (px < HW) ? ldg_stream_u4(src + px) : make_uint4(0, 0, 0, 0);  // HW % 16 == 0 on this path
+    }
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL; ++u) {
+        auto nib = [](uint32_t x) -> uint32_t {
+            // bytes > 0 -> 0xff, keep bit 0 of each byte, gather the four into bits 24..27
+            uint32_t mbits = __vcmpgtu4(x, 0u) & 0x01010101u;
+            return (mbits * 0x01020408u) >> 24 & 0xfu;
+        };
+        uint32_t half = nib(v[u].x) | (nib(v[u].y) << 4) | (nib(v[u].z) << 8) | (nib(v[u].w) << 12);
+        uint32_t w = half << (16 * (lane & 1));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        const int64_t w_idx = px_base / 32 + u * 16 + (lane >> 1);
+        if ((lane & 1) == 0 && w_idx < wpm) bits[m * wpm + w_idx] = w;
+    }
+}
+
+// generic path (any HW / alignment): one pixel per lane, a ballot per word.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_scalar_kernel(const T* __restrict__ masks, int64_t n, int64_t HW,
+                                                          int64_t wpm, uint32_t* __restrict__ bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t total = n * wpm;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp_global; w < total; w += warps) {
+        const int64_t m = w / wpm, wi = w % wpm;
+        const int64_t px = wi * 32 + lane;
+        bool on = false;
+        if (px < HW) on = (float)masks[m * HW + px] > 0.f;
+        const uint32_t word = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) bits[w] = word;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// support-mask pooling: one warp per (mask, bin), any pixel > 0 in the adaptive-pool window.
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pool_mask_kernel(const T* __restrict__ masks, int64_t n, int H, int W, int g,
+                                 uint8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t total = n * g * g;
+    if (warp_global >= total) return;
+    const int64_t m = warp_global / (g * g);
+    const int b = (int)(warp_global % (g * g));
+    const int by = b / g, bx = b % g;
+    const int y0 = bin_start(by, H, g), y1 = bin_end(by, H, g);
+    const int x0 = bin_start(bx, W, g), x1 = bin_end(bx, W, g);
+    const int ww = x1 - x0, cnt = (y1 - y0) * ww;
+    bool any = false;
+    for (int i = lane; i < cnt; i += 32) {
+        const int y = y0 + i / ww, x = x0 + i % ww;
+        any |= (float)masks[(m * H + y) * (int64_t)W + x] > 0.f;
+    }
+    const uint32_t hit = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) out[warp_global] = hit ? 1 : 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// pooled bitmap / area / pooled count of a packed mask: one block per mask, reads the row once.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_packed_kernel(const uint32_t* __restrict__ bits, int64_t n, int H, int W,
+                                                          int g, int64_t wpm, int npw, uint32_t* __restrict__ pooled,
+                                                          int32_t* __restrict__ area,
+                                                          int32_t* __restrict__ pooled_count) {
+    extern __shared__ uint32_t s_pool[];  // npw words + 2 counters
+    int* s_cnt = reinterpret_cast<int*>(s_pool + npw);
+    const int64_t m = blockIdx.x;
+    for (int i = threadIdx.x; i < npw + 2; i += blockDim.x) s_pool[i] = 0;
+    __syncthreads();
+
+    const int64_t HW = (int64_t)H * W;
+    const int64_t words = ceil_div64(HW, 32);
+    const uint32_t* row = bits + m * wpm;
+    int my_area = 0;
+    for (int64_t w = threadIdx.x; w < words; w += blockDim.x) {
+        uint32_t word = row[w];
+        if (word == 0) continue;
+        my_area += __popc(word);
+        int64_t px = w * 32;
+        int y = (int)(px / W), x = (int)(px % W);
+        int consumed = 0;
+        while (consumed < 32 && word != 0 && y < H) {
+            const int len = min(32 - consumed, W - x);
+            const uint32_t seg = (len == 32) ? word : (word & ((1u << len) - 1u));
+            if (seg != 0) {
+                const int first = __ffs(seg) - 1, last = 31 - __clz(seg);
+                const int jy0 = bin_lo_of(y, H, g), jy1 = bin_hi_of(y, H, g);
+                const int jx0 = bin_lo_of(x + first, W, g), jx1 = bin_hi_of(x + last, W, g);
+                for (int jx = jx0; jx <= jx1; ++jx) {
+                    const int lo = max(bin_start(jx, W, g) - x, 0);
+                    const int hi = min(bin_end(jx, W, g) - x, len);  // exclusive
+                    if (hi <= lo) continue;
+                    const uint32_t window = ((hi - lo) == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+                    if ((seg & window) == 0) continue;
+                    for (int jy = jy0; jy <= jy1; ++jy) {
+                        const int b = jy * g + jx;
+                        const uint32_t bit = 1u << (b & 31);
+                        if ((s_pool[b >> 5] & bit) == 0) atomicOr(&s_pool[b >> 5], bit);
+                    }
+                }
+            }
+            word = (len == 32) ? 0u : (word >> len);
+            consumed += len;
+            x = 0;
+            ++y;
+        }
+    }
+    my_area = warp_sum(my_area);
+    if ((threadIdx.x & 31) == 0 && my_area) atomicAdd(&s_cnt[0], my_area);
+    __syncthreads();
+    int pc = 0;
+    for (int i = threadIdx.x; i < npw; i += blockDim.x) {
+        const uint32_t v = s_pool[i];
+        pooled[m * npw + i] = v;
+        pc += __popc(v);
+    }
+    pc = warp_sum(pc);
+    if ((threadIdx.x & 31) == 0 && pc) atomicAdd(&s_cnt[1], pc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        area[m] = s_cnt[0];
+        pooled_count[m] = s_cnt[1];
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// region sums: one warp per proposal; union count: one block per episode.
+// --------------------------------------------------------------------------------------------
+__global__ void region_sums_kernel(const uint32_t* __restrict__ pooled, int64_t total, int P, int N, int npw,
+                                   const float* __restrict__ vva, const float* __restrict__ vta,
+                                   float* __restrict__ sum_vva, float* __restrict__ sum_vta) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wg >= total) return;
+    const int64_t e = wg / P;
+    const uint32_t* row = pooled + wg * npw;
+    const float* a = vva + e * N;
+    const float* t = vta + e * N;
+    double sa = 0.0, st = 0.0;
+    for (int w = 0; w < npw; ++w) {
+        const uint32_t word = row[w];
+        const int b = w * 32 + lane;
+        if (((word >> lane) & 1u) && b < N) {
+            sa += (double)a[b];
+            st += (double)t[b];
+        }
+    }
+    sa = warp_sum(sa);
+    st = warp_sum(st);
+    if (lane == 0) {
+        sum_vva[wg] = (float)sa;
+        sum_vta[wg] = (float)st;
+    }
+}
+
+__global__ void union_count_kernel(const uint32_t* __restrict__ pooled, int P, int npw,
+                                   int32_t* __restrict__ union_count) {
+    __shared__ int s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    const int64_t e = blockIdx.x;
+    int c = 0;
+    for (int w = threadIdx.x; w < npw; w += blockDim.x) {
+        uint32_t acc = 0;
+        for (int p = 0; p < P; ++p) acc |= pooled[(e * P + p) * npw + w];
+        c += __popc(acc);
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_total, c);
+    __syncthreads();
+    if (threadIdx.x == 0) union_count[e] = s_total;
+}
+
+// --------------------------------------------------------------------------------------------
+// pairwise intersections, AND + popcount.  A block owns a 64x64 tile of pairs over a slice of the
+// words; operand slices are staged k-major in shared memory (padded: conflict-free both ways);
+// each thread keeps a 4x4 tile of int32 counters.  Integer atomics make the split-K reduction exact
+// and order independent.
+// --------------------------------------------------------------------------------------------
+constexpr int PW_TILE = 64;
+constexpr int PW_KC = 32;
+
+__global__ void __launch_bounds__(256) pairwise_popc_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm,
+                                                            int tiles, int ksplit, int64_t words_per_split,
+                                                            int32_t* __restrict__ inter) {
+    __shared__ uint32_t sA[PW_KC][PW_TILE + 1];
+    __shared__ uint32_t sB[PW_KC][PW_TILE + 1];
+    // blockIdx.x -> (upper-triangular tile pair), blockIdx.y -> k split, blockIdx.z -> episode
+    int t = blockIdx.x, ti = 0;
+    while (t >= tiles - ti) {
+        t -= tiles - ti;
+        ++ti;
+    }
+    const int tj = ti + t;
+    const int64_t e = blockIdx.z;
+    const int64_t k_begin = (int64_t)blockIdx.y * words_per_split;
+    const int64_t k_end = min(k_begin + words_per_split, wpm);
+    const uint32_t* base = bits + e * P * wpm;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    int acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0;
+
+    const int lk = threadIdx.x & 31;  // word within the chunk
+    const int lr = threadIdx.x >> 5;  // 8 rows per pass
+    for (int64_t k0 = k_begin; k0 < k_end; k0 += PW_KC) {
+#pragma unroll
+        for (int r = 0; r < PW_TILE; r += 8) {
+            const int i = ti * PW_TILE + r + lr, j = tj * PW_TILE + r + lr;
+            const int64_t k = k0 + lk;
+            sA[lk][r + lr] = (i < P && k < k_end) ? base[(int64_t)i * wpm + k] : 0u;
+            sB[lk][r + lr] = (j < P && k < k_end) ? base[(int64_t)j * wpm + k] : 0u;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < PW_KC; ++k) {
+            uint32_t a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[q] = sA[k][ty + 16 * q];
+                b[q] = sB[k][tx + 16 * q];
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] += __popc(a[p] & b[q]);
+        }
+        __syncthreads();
+    }
+    int32_t* out = inter + e * P * (int64_t)P;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = ti * PW_TILE + ty + 16 * p, j = tj * PW_TILE + tx + 16 * q;
+            if (i < P && j < P && acc[p][q] != 0) {
+                if (ti == tj) {
+                    atomicAdd(&out[(int64_t)i * P + j], acc[p][q]);
+                } else {
+                    atomicAdd(&out[(int64_t)i * P + j], acc[p][q]);
+                    atomicAdd(&out[(int64_t)j * P + i], acc[p][q]);
+                }
+            }
+        }
+}
+
+// --------------------------------------------------------------------------------------------
+// merge: OR of the selected rows, optional expansion to float32 0/1.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge_masks_kernel(const uint32_t* __restrict__ bits,
+                                                          const uint8_t* __restrict__ flags, int P, int64_t wpm,
+                                                          int64_t HW, uint32_t* __restrict__ merged_bits,
+                                                          float* __restrict__ merged_f32) {
+    extern __shared__ int s_sel[];  // P indices + 1 counter
+    int* s_n = s_sel + P;
+    const int64_t e = blockIdx.y;
+    if (threadIdx.x == 0) *s_n = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += blockDim.x)
+        if (flags[e * P + p] & 2) s_sel[atomicAdd(s_n, 1)] = p;
+    __syncthreads();
+    const int nsel = *s_n;
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t acc = 0;
+    if (w < wpm) {
+        const uint32_t* base = bits + e * P * wpm + w;
+        for (int k = 0; k < nsel; ++k) acc |= base[(int64_t)s_sel[k] * wpm];
+        if (merged_bits) merged_bits[e * wpm + w] = acc;
+    }
+    if (merged_f32) {
+        const int64_t w_warp = w - lane;  // first word of this warp
+        float* out = merged_f32 + e * HW;
+#pragma unroll 4
+        for (int l = 0; l < 32; ++l) {
+            const uint32_t wv = __shfl_sync(0xffffffffu, acc, l);
+            const int64_t px = (w_warp + l) * 32 + lane;
+            if (px < HW) out[px] = (float)((wv >> lane) & 1u);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Matcher: matched points inside each packed mask (one block per mask).
+// --------------------------------------------------------------------------------------------
+__global__ void points_in_masks_kernel(const uint32_t* __restrict__ bits, int H, int W, int64_t wpm,
+                                       const int32_t* __restrict__ points, int K, int32_t* __restrict__ out) {
+    __shared__ int s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    const int64_t m = blockIdx.x;
+    int c = 0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int x = min(max(points[2 * k], 0), W - 1);
+        const int y = min(max(points[2 * k + 1], 0), H - 1);
+        const int64_t px = (int64_t)y * W + x;
+        c += (bits[m * wpm + (px >> 5)] >> (px & 31)) & 1u;
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_total, c);
+    __syncthreads();
+    if (threadIdx.x == 0) out[m] = s_total;
+}
+
+__global__ void matcher_scores_kernel(const int32_t* __restrict__ points_in, const int32_t* __restrict__ pooled_count,
+                                      const float* __restrict__ emd, int64_t n, int K, float alpha, float beta,
+                                      float expo, float* __restrict__ purity, float* __restrict__ coverage,
+                                      float* __restrict__ scores) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // python float (double) quotient -> float32 tensor -> + 1e-6 in float32 (Matcher.py:1203-1207)
+    const double area = fmax((double)pooled_count[i], 1.0);
+    const float pur = (float)((double)points_in[i] / area) + 1e-6f;
+    const float cov = (float)((double)points_in[i] / (double)K) + 1e-6f;
+    purity[i] = pur;
+    coverage[i] = cov;
+    scores[i] = alpha * emd[i] + beta * pur * powf(cov, expo);
+}
+
+// --------------------------------------------------------------------------------------------
+// evaluator areas: histc(bins=2, min=0, max=1) semantics (values outside [0,1] are not counted).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eval_areas_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                         const float* __restrict__ ignore, int64_t HW,
+                                                         int32_t* __restrict__ out) {
+    __shared__ int s_c[6];
+    if (threadIdx.x < 6) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t m = blockIdx.y;
+    int c[6] = {0, 0, 0, 0, 0, 0};  // inter_bg, inter_fg, pred_bg, pred_fg, gt_bg, gt_fg
+    for (int64_t px = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; px < HW; px += (int64_t)gridDim.x * blockDim.x) {
+        float g = gt[m * HW + px];
+        float p = pred[m * HW + px];
+        if (ignore) {
+            g = g + ignore[m * HW + px] * 255.f;
+            if (g == 255.f) p = 255.f;
+        }
+        auto bin = [](float v) -> int { return (v >= 0.f && v <= 1.f) ? (v >= 0.5f ? 1 : 0) : -1; };
+        const int bp = bin(p), bg = bin(g);
+        if (p == g && bp >= 0) c[bp]++;
+        if (bp >= 0) c[2 + bp]++;
+        if (bg >= 0) c[4 + bg]++;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int v = warp_sum(c[i]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_c[i], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const int inter = s_c[threadIdx.x];
+        atomicAdd(&out[m * 4 + threadIdx.x], inter);
+        atomicAdd(&out[m * 4 + 2 + threadIdx.x], s_c[2 + threadIdx.x] + s_c[4 + threadIdx.x] - inter);
+    }
+}
+
+}  // namespace marsb200
+
+using namespace marsb200;
+
+extern "C" {
+
+int64_t marsb200_words_per_mask(int64_t hw) { return ceil_div64(ceil_div64(hw, 32), 32) * 32; }
+
+int marsb200_pack_masks(const void* masks, int mask_dtype, int64_t n, int64_t HW, uint32_t* bits, void* stream) {
+    MARS_REQUIRE(masks && bits, "null pointer");
+    MARS_REQUIRE(n > 0 && HW > 0, "empty input");
+    MARS_REQUIRE(mask_dtype == MARSB200_MASK_F32 || mask_dtype == MARSB200_MASK_U8, "mask_dtype");
+    const int64_t wpm = marsb200_words_per_mask(HW);
+    cudaStream_t s = as_stream(stream);
+    const bool aligned = (reinterpret_cast<uintptr_t>(masks) & 15) == 0;
+    if (mask_dtype == MARSB200_MASK_F32 && aligned && HW % 4 == 0) {
+        const int chunks = (int)ceil_div64(wpm * 32, PACK_THREADS * PACK_UNROLL * 4);
+        MARS_REQUIRE(n * chunks < (1ll << 31), "grid too large");
+        pack_f32_vec_kernel<<<(unsigned)(n * chunks), PACK_THREADS, 0, s>>>((const float*)masks, n, HW, wpm, bits, chunks);
+    } else if (mask_dtype == MARSB200_MASK_U8 && aligned && HW % 16 == 0) {
+        const int chunks = (int)ceil_div64(wpm * 32, PACK_THREADS * PACK_UNROLL * 16);
+        MARS_REQUIRE(n * chunks < (1ll << 31), "grid too large");
+        pack_u8_vec_kernel<<<(unsigned)(n * chunks), PACK_THREADS, 0, s>>>((const uint8_t*)masks, n, HW, wpm, bits, chunks);
+    } else {
+        const int64_t warps = n * wpm;
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(warps, 8), 148 * 64);
+        if (mask_dtype == MARSB200_MASK_F32)
+            pack_scalar_kernel<float><<<grid, 256, 0, s>>>((const float*)masks, n, HW, wpm, bits);
+        else
+            pack_scalar_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)masks, n, HW, wpm, bits);
+    }
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+int marsb200_pool_mask(const void* masks, int mask_dtype, int64_t n, int H, int W, int g, uint8_t* out, void* stream) {
+    MARS_REQUIRE(masks && out, "null pointer");
+    MARS_REQUIRE(n > 0 && H > 0 && W > 0 && g > 0 && g <= H && g <= W, "shape");
+    const int64_t warps = n * g * g;
+    const unsigned grid = (unsigned)ceil_div64(warps, 8);
+    if (mask_dtype == MARSB200_MASK_F32)
+        pool_mask_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)masks, n, H, W, g, out);
+    else if (mask_dtype == MARSB200_MASK_U8)
+        pool_mask_kernel<uint8_t><<<grid, 256, 0, as_stream(stream)>>>((const uint8_t*)masks, n, H, W, g, out);
+    else
+        MARS_REQUIRE(false, "mask_dtype");
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+int marsb200_pool_packed(const uint32_t* bits, int64_t n, int H, int W, int g, uint32_t* pooled, int32_t* area,
+                         int32_t* pooled_count, void* stream) {
+    MARS_REQUIRE(bits && pooled && area && pooled_count, "null pointer");
+    MARS_REQUIRE(n > 0 && H > 0 && W > 0 && g > 0 && g <= H && g <= W, "shape");
+    const int npw = ceil_div(g * g, 32);
+    const int64_t wpm = marsb200_words_per_mask((int64_t)H * W);
+    MARS_REQUIRE(n < (1ll << 31), "too many masks");
+    pool_packed_kernel<<<(unsigned)n, 256, (npw + 2) * sizeof(uint32_t), as_stream(stream)>>>(
+        bits, n, H, W, g, wpm, npw, pooled, area, pooled_count);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+int marsb200_region_sums(const uint32_t* pooled, int E, int P, int N, const float* vva, const float* vta,
+                         float* sum_vva, float* sum_vta, int32_t* union_count, void* stream) {
+    MARS_REQUIRE(pooled && vva && vta && sum_vva && sum_vta && union_count, "null pointer");
+    MARS_REQUIRE(E > 0 && P > 0 && N > 0, "shape");
+    const int npw = ceil_div(N, 32);
+    const int64_t total = (int64_t)E * P;
+    region_sums_kernel<<<(unsigned)ceil_div64(total, 8), 256, 0, as_stream(stream)>>>(pooled, total, P, N, npw, vva, vta,
+                                                                                      sum_vva, sum_vta);
+    MARS_LAUNCH_OK();
+    union_count_kernel<<<E, 64, 0, as_stream(stream)>>>(pooled, P, npw, union_count);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+}  // extern "C"
+
+namespace marsb200 {
+int pairwise_popc(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s) {
+    const int tiles = ceil_div(P, PW_TILE);
+    const int tile_pairs = tiles * (tiles + 1) / 2;
+    // enough blocks for ~4 waves of 148 SMs x 4 resident blocks, but at least 4 chunks of work per block
+    int ksplit = (int)std::min<int64_t>(std::max<int64_t>(1, (148 * 16) / ((int64_t)tile_pairs * E)), std::max<int64_t>(1, wpm / (4 * PW_KC)));
+    ksplit = min(ksplit, 65535);
+    int64_t words_per_split = ceil_div64(ceil_div64(wpm, ksplit), PW_KC) * PW_KC;
+    ksplit = (int)ceil_div64(wpm, words_per_split);
+    MARS_CUDA_OK(cudaMemsetAsync(inter, 0, sizeof(int32_t) * (size_t)E * P * P, s));
+    dim3 grid(tile_pairs, ksplit, E);
+    pairwise_popc_kernel<<<grid, 256, 0, s>>>(bits, P, wpm, tiles, ksplit, words_per_split, inter);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+}  // namespace marsb200
+
+extern "C" {
+
+int marsb200_merge_masks(const uint32_t* bits, const uint8_t* flags, int E, int P, int64_t HW, uint32_t* merged_bits,
+                         float* merged_f32, void* stream) {
+    MARS_REQUIRE(bits && flags, "null pointer");
+    MARS_REQUIRE(merged_bits || merged_f32, "no output requested");
+    MARS_REQUIRE(E > 0 && P > 0 && HW > 0 && E <= 65535, "shape");
+    const int64_t wpm = marsb200_words_per_mask(HW);
+    dim3 grid((unsigned)ceil_div64(wpm, 256), E);
+    merge_masks_kernel<<<grid, 256, (P + 1) * sizeof(int), as_stream(stream)>>>(bits, flags, P, wpm, HW, merged_bits,
+                                                                                merged_f32);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+int marsb200_points_in_masks(const uint32_t* bits, int64_t n, int H, int W, const int32_t* points, int K, int32_t* out,
+                             void* stream) {
+    MARS_REQUIRE(bits && points && out, "null pointer");
+    MARS_REQUIRE(n > 0 && K > 0 && H > 0 && W > 0, "shape");
+    const int64_t wpm = marsb200_words_per_mask((int64_t)H * W);
+    points_in_masks_kernel<<<(unsigned)n, 128, 0, as_stream(stream)>>>(bits, H, W, wpm, points, K, out);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+int marsb200_matcher_scores(const int32_t* points_in, const int32_t* pooled_count, const float* emd, int64_t n, int K,
+                            float alpha, float beta, float expo, float* purity, float* coverage, float* scores,
+                            void* stream) {
+    MARS_REQUIRE(points_in && pooled_count && emd && purity && coverage && scores, "null pointer");
+    MARS_REQUIRE(n > 0 && K > 0, "shape");
+    matcher_scores_kernel<<<(unsigned)ceil_div64(n, 128), 128, 0, as_stream(stream)>>>(
+        points_in, pooled_count, emd, n, K, alpha, beta, expo, purity, coverage, scores);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+int marsb200_eval_areas(const float* pred, const float* gt, const float* ignore, int64_t n, int64_t HW, int32_t* out,
+                        void* stream) {
+    MARS_REQUIRE(pred && gt && out, "null pointer");
+    MARS_REQUIRE(n > 0 && n <= 65535 && HW > 0, "shape");
+    MARS_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(int32_t) * 4 * (size_t)n, as_stream(stream)));
+    const unsigned gx = (unsigned)std::min<int64_t>(ceil_div64(HW, 256 * 8), 148 * 4);
+    eval_areas_kernel<<<dim3(gx, (unsigned)n), 256, 0, as_stream(stream)>>>(pred, gt, ignore, HW, out);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+}  // extern "C"

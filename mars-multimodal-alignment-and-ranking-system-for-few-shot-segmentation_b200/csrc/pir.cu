@@ -1,0 +1,327 @@
+// Prior-information refinement (A4): attention mean, box mask by 8-connected components,
+// Sinkhorn-1 normalisation, R = max(D, D D^T) through the shared contraction, and the refinement
+// applied as two matrix-vector products, R (R (B * prior)) == ((R R) * B) prior.
+#include <cuda_fp16.h>
+
+#include "gemm_common.cuh"
+
+namespace marsb200 {
+
+int minmax_rows(float* v, int E, int64_t n, cudaStream_t s);  // vva.cu
+
+// --------------------------------------------------------------------------------------------
+// attention mean over (layers, heads); HBM-bound: every map element is read exactly once.
+// --------------------------------------------------------------------------------------------
+constexpr int MAX_ATTN_MAPS = 64;
+struct AttnPtrs {
+    const void* p[MAX_ATTN_MAPS];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_mean_kernel(AttnPtrs maps, int n_maps, int heads, int T_tokens, int skip,
+                                                        float* __restrict__ out, int64_t ld_out) {
+    const int N = T_tokens - skip;
+    const int row = blockIdx.y;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= N) return;
+    float acc = 0.f;
+    for (int l = 0; l < n_maps; ++l) {
+        const T* base = reinterpret_cast<const T*>(maps.p[l]);
+        for (int h = 0; h < heads; ++h)
+            acc += (float)base[((int64_t)h * T_tokens + (row + skip)) * T_tokens + (col + skip)];
+    }
+    float mean = acc / (float)(n_maps * heads);
+    // torch.mean of fp16 maps returns fp16 (fp32 accumulation, rounded once) before the .float()
+    if (sizeof(T) == 2) mean = __half2float(__float2half_rn(mean));
+    out[(int64_t)row * ld_out + col] = mean;
+}
+
+// --------------------------------------------------------------------------------------------
+// box mask: one block per episode.  img = uint8(prior*255); thr = int(threshold * max(img));
+// fg = img > thr; 8-connected components by min-label propagation; per component the box
+// [x0, min(x0+w, W-1)) x [y0, min(y0+h, H-1)) is filled (PriorInformationRefinementModule.py:56-63,
+// 91-122).  Writes B (uint8, optional) and v = B * prior.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) box_mask_kernel(const float* __restrict__ prior, int g, double threshold,
+                                                       uint8_t* __restrict__ box_out, float* __restrict__ v_out) {
+    extern __shared__ int s_mem[];
+    const int n = g * g;
+    int* label = s_mem;          // n
+    int* bx0 = label + n;        // n each
+    int* bx1 = bx0 + n;
+    int* by0 = bx1 + n;
+    int* by1 = by0 + n;
+    int* boxm = by1 + n;         // n
+    __shared__ int s_max;
+    const int64_t e = blockIdx.x;
+    const float* p = prior + e * n;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    int local_max = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float q = p[i] * 255.0f;
+        const int v = (int)fminf(fmaxf(q, 0.f), 255.f);  // astype(uint8) truncation for in-range values
+        label[i] = v;                                     // temporarily holds the quantised value
+        local_max = max(local_max, v);
+    }
+    atomicMax(&s_max, local_max);
+    __syncthreads();
+    const int thr = (int)(threshold * (double)s_max);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        label[i] = (label[i] > thr) ? i : -1;
+        bx0[i] = g;
+        by0[i] = g;
+        bx1[i] = -1;
+        by1[i] = -1;
+        boxm[i] = 0;
+    }
+    __syncthreads();
+    // min-label propagation over the 8-neighbourhood with pointer jumping
+    while (true) {
+        int changed = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            int l = label[i];
+            if (l < 0) continue;
+            const int y = i / g, x = i % g;
+            int best = l;
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int yy = y + dy, xx = x + dx;
+                    if (yy < 0 || yy >= g || xx < 0 || xx >= g) continue;
+                    const int ln = label[yy * g + xx];
+                    if (ln >= 0 && ln < best) best = ln;
+                }
+            const int root = label[best];  // one jump (labels only decrease, always >= 0 for fg)
+            if (root >= 0 && root < best) best = root;
+            if (best < l) {
+                label[i] = best;
+                changed = 1;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = label[i];
+        if (l < 0) continue;
+        const int y = i / g, x = i % g;
+        atomicMin(&bx0[l], x);
+        atomicMax(&bx1[l], x);
+        atomicMin(&by0[l], y);
+        atomicMax(&by1[l], y);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (label[i] != i) continue;  // roots only
+        const int x0 = bx0[i], y0 = by0[i];
+        const int x1 = min(bx1[i] + 1, g - 1), y1 = min(by1[i] + 1, g - 1);  // x0 + w clipped, exclusive
+        for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; ++x) boxm[y * g + x] = 1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (box_out) box_out[e * n + i] = (uint8_t)boxm[i];
+        v_out[e * n + i] = boxm[i] ? p[i] : 0.f;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Sinkhorn-1: column sums in two deterministic stages, then one block per row.
+// --------------------------------------------------------------------------------------------
+constexpr int COLSUM_SPLITS = 16;
+
+__global__ void __launch_bounds__(128) colsum_partial_kernel(const float* __restrict__ attn, int64_t ld, int N,
+                                                             double* __restrict__ partial) {
+    const int64_t e = blockIdx.z;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int split = blockIdx.y;
+    if (col >= N) return;
+    const int rows_per = ceil_div(N, COLSUM_SPLITS);
+    const int r0 = split * rows_per, r1 = min(r0 + rows_per, N);
+    const float* a = attn + e * N * ld;
+    double acc = 0.0;
+    for (int r = r0; r < r1; ++r) acc += (double)a[(int64_t)r * ld + col];
+    partial[(e * COLSUM_SPLITS + split) * N + col] = acc;
+}
+
+__global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restrict__ attn, int64_t ld, int N,
+                                                            const double* __restrict__ partial, int64_t n_pad,
+                                                            int64_t k_pad, float* __restrict__ D,
+                                                            float* __restrict__ hi, float* __restrict__ lo) {
+    __shared__ double s_red[8];
+    const int64_t e = blockIdx.y;
+    const int row = blockIdx.x;
+    float* h = hi + (e * n_pad + row) * k_pad;
+    float* l = lo + (e * n_pad + row) * k_pad;
+    if (row >= N) {  // zero the padding rows of the operands
+        for (int64_t c = threadIdx.x; c < k_pad; c += blockDim.x) {
+            h[c] = 0.f;
+            l[c] = 0.f;
+        }
+        return;
+    }
+    const float* a = attn + (e * N + row) * ld;
+    float* d = D + (e * N + row) * k_pad;
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < N; c += blockDim.x) {
+        double cs = 0.0;
+#pragma unroll
+        for (int s = 0; s < COLSUM_SPLITS; ++s) cs += partial[(e * COLSUM_SPLITS + s) * N + c];
+        const float v = __fdiv_rn(a[c], (float)cs);
+        d[c] = v;
+        acc += (double)v;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    double total = 0.0;
+    for (int w = 0; w < 8; ++w) total += s_red[w];
+    const float rs = (float)total;
+    for (int64_t c = threadIdx.x; c < k_pad; c += blockDim.x) {
+        float v = 0.f;
+        if (c < N) v = __fdiv_rn(d[c], rs);
+        d[c] = v;
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+        const float vh = __uint_as_float(r);
+        h[c] = vh;
+        l[c] = v - vh;
+    }
+}
+
+// y[e, i] = sum_j R[e, i, j] x[e, j]; one warp per row, double accumulation.
+__global__ void __launch_bounds__(256) matvec_kernel(const float* __restrict__ R, int64_t ld, int N,
+                                                     const float* __restrict__ x, float* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t e = blockIdx.y;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const float* r = R + (e * N + row) * ld;
+    const float* xv = x + e * N;
+    double acc = 0.0;
+    for (int j = lane; j < N; j += 32) acc += (double)r[j] * (double)xv[j];
+    acc = warp_sum(acc);
+    if (lane == 0) y[e * N + row] = (float)acc;
+}
+
+struct PirWorkspace {
+    double* partial;  // [E, 16, N]
+    float* D;         // [E, N, k_pad]
+    float* hi;        // [E, n_pad, k_pad]
+    float* lo;        // [E, n_pad, k_pad]
+    float* R;         // [E, N, N]
+    float* v;         // [E, N]
+    float* t;         // [E, N]
+    int64_t bytes;
+};
+
+static PirWorkspace carve(void* base, int E, int64_t N) {
+    const int64_t n_pad = marsb200_pad_rows(N), k_pad = marsb200_pad_k(N);
+    auto align = [](int64_t b) { return (b + 255) / 256 * 256; };
+    char* p = reinterpret_cast<char*>(base);
+    int64_t off = 0;
+    PirWorkspace w;
+    w.partial = reinterpret_cast<double*>(p + off);
+    off += align((int64_t)E * COLSUM_SPLITS * N * 8);
+    w.D = reinterpret_cast<float*>(p + off);
+    off += align((int64_t)E * N * k_pad * 4);
+    w.hi = reinterpret_cast<float*>(p + off);
+    off += align((int64_t)E * n_pad * k_pad * 4);
+    w.lo = reinterpret_cast<float*>(p + off);
+    off += align((int64_t)E * n_pad * k_pad * 4);
+    w.R = reinterpret_cast<float*>(p + off);
+    off += align((int64_t)E * N * N * 4);
+    w.v = reinterpret_cast<float*>(p + off);
+    off += align((int64_t)E * N * 4);
+    w.t = reinterpret_cast<float*>(p + off);
+    off += align((int64_t)E * N * 4);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace marsb200
+
+using namespace marsb200;
+
+extern "C" {
+
+int marsb200_attn_mean(const void* const* maps_host, int n_maps, int dtype, int heads, int T, int skip, float* out,
+                       int64_t ld_out, void* stream) {
+    MARS_REQUIRE(maps_host && out, "null pointer");
+    MARS_REQUIRE(n_maps > 0 && n_maps <= MAX_ATTN_MAPS, "1..64 maps");
+    MARS_REQUIRE(heads > 0 && T > skip && skip >= 0 && ld_out >= T - skip, "shape");
+    MARS_REQUIRE(dtype == 0 || dtype == 1, "dtype (0 fp32, 1 fp16)");
+    AttnPtrs ptrs{};
+    for (int i = 0; i < n_maps; ++i) {
+        MARS_REQUIRE(maps_host[i] != nullptr, "null map");
+        ptrs.p[i] = maps_host[i];
+    }
+    const int N = T - skip;
+    dim3 grid(ceil_div(N, 256), N);
+    if (dtype == 0)
+        attn_mean_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(ptrs, n_maps, heads, T, skip, out, ld_out);
+    else
+        attn_mean_kernel<__half><<<grid, 256, 0, as_stream(stream)>>>(ptrs, n_maps, heads, T, skip, out, ld_out);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+int64_t marsb200_pir_workspace_bytes(int E, int64_t N) {
+    if (E <= 0 || N <= 0) return 0;
+    return carve(nullptr, E, N).bytes;
+}
+
+int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, int E, int g, double box_threshold,
+                        int apply_minmax, float* out, uint8_t* box_out, void* workspace, int64_t workspace_bytes,
+                        int backend, void* stream) {
+    MARS_REQUIRE(prior && attn && out && workspace, "null pointer");
+    MARS_REQUIRE(E > 0 && E <= 65535 && g > 0 && g <= 96, "shape (g <= 96)");
+    const int N = g * g;
+    MARS_REQUIRE(ld_attn >= N, "ld_attn");
+    PirWorkspace w = carve(workspace, E, N);
+    MARS_REQUIRE(workspace_bytes >= w.bytes, "workspace too small");
+    MARS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    cudaStream_t s = as_stream(stream);
+    const int64_t n_pad = marsb200_pad_rows(N), k_pad = marsb200_pad_k(N);
+
+    const size_t smem = (size_t)6 * N * sizeof(int);
+    if (smem > 48 * 1024)
+        MARS_CUDA_OK(cudaFuncSetAttribute(box_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    box_mask_kernel<<<E, 256, smem, s>>>(prior, g, box_threshold, box_out, w.v);
+    MARS_LAUNCH_OK();
+
+    colsum_partial_kernel<<<dim3(ceil_div(N, 128), COLSUM_SPLITS, E), 128, 0, s>>>(attn, ld_attn, N, w.partial);
+    MARS_LAUNCH_OK();
+    row_normalize_kernel<<<dim3((unsigned)n_pad, E), 256, 0, s>>>(attn, ld_attn, N, w.partial, n_pad, k_pad, w.D, w.hi,
+                                                                    w.lo);
+    MARS_LAUNCH_OK();
+
+    GemmEpilogue ep{};
+    ep.out0 = w.R;
+    ep.out1 = nullptr;
+    ep.maxwith = w.D;
+    ep.row_fg = nullptr;
+    ep.colstats = nullptr;
+    ep.M = N;
+    ep.N = N;
+    ep.ld_out = N;
+    ep.ld_max = k_pad;
+    ep.tiles_m = (int)(n_pad / GEMM_BM);
+    int rc;
+    if (backend == MARSB200_GEMM_SIMT)
+        rc = gemm_simt(w.hi, w.lo, w.hi, w.lo, E, N, N, N, ep, s);
+    else if (backend == MARSB200_GEMM_TCGEN05)
+        rc = gemm_tcgen05(w.hi, w.lo, w.hi, w.lo, E, N, N, N, ep, s);
+    else
+        return fail(MARSB200_ERR_ARG, "%s: unknown backend %lld", "marsb200_pir_refine", backend);
+    if (rc != MARSB200_OK) return rc;
+
+    dim3 mv_grid(ceil_div(N, 8), E);
+    matvec_kernel<<<mv_grid, 256, 0, s>>>(w.R, N, N, w.v, w.t);
+    MARS_LAUNCH_OK();
+    matvec_kernel<<<mv_grid, 256, 0, s>>>(w.R, N, N, w.t, out);
+    MARS_LAUNCH_OK();
+    if (apply_minmax) return minmax_rows(out, E, N, s);
+    return MARSB200_OK;
+}
+
+}  // extern "C"

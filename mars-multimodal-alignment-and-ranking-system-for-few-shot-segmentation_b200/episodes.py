@@ -1,0 +1,203 @@
+"""Batched episode engine: the whole ranking stage for E episodes per launch sequence.
+
+One `RankingEngine` owns every intermediate buffer for a fixed episode shape
+(nothing is allocated inside `run`), enqueues the kernel sequence on the
+current stream without a single host synchronisation, and can therefore be
+captured into a CUDA graph (`capture`).  Episodes are independent
+(main_MARS.py:54-94 of the reference processes them one by one), so multi-GPU
+execution shards the episode list across ranks and all-gathers the fixed-size
+result records.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import ops
+from .synthetic import EpisodeShape
+
+
+@dataclass
+class RankingConfig:
+    vva_box_threshold: float = 0.8     # main_MARS.py:151
+    vta_box_threshold: float = 0.4     # main_MARS.py:144
+    alpha: float = 0.85                # main_MARS.py:157 (alpha_coverage)
+    static_threshold: float = 0.55     # main_MARS.py:155
+    dynamic_threshold: float = 0.95    # main_MARS.py:156
+    nms_iou_threshold: Optional[float] = None  # None = the reference's behaviour (no mask NMS)
+    want_sim: bool = False             # export S like VisualVisualAlignmentModule.similarity_matrix
+    want_cost: bool = False            # export (1 - S) / 2 (the EMD cost)
+    want_merged_f32: bool = True       # the float32 [H, W] map the reference returns
+    gemm_backend: Optional[int] = None
+    pair_backend: Optional[int] = None
+
+
+def kernel_launches_per_run(cfg: RankingConfig) -> int:
+    """How many of our kernels one `RankingEngine.run` launches (counted from the sequence below)."""
+    n = 2                      # normalize_split x2
+    n += 1                     # pool_mask
+    n += 1                     # sim_contract
+    n += 1                     # vva_finalize
+    n += 2 * (1 + 2 + 1 + 2)   # two PIR passes: box mask, colsum+rownorm, contraction, two mat-vecs
+    n += 1                     # min-max of the refined vva
+    n += 1                     # resize + min-max of the vta
+    n += 1                     # pack
+    n += 1                     # pool_packed
+    n += 2                     # region sums + union count
+    if cfg.nms_iou_threshold is not None:
+        n += 1                 # pairwise intersections (memset not counted)
+    n += 1                     # clip scores
+    n += 1                     # fuse / rank / nms / select
+    n += 1                     # merge
+    return n
+
+
+class RankingEngine:
+    def __init__(self, shape: EpisodeShape, episodes_per_batch: int, cfg: RankingConfig, device,
+                 mask_dtype=torch.float32):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("RankingEngine needs a CUDA device (marsb200 has no CPU path)")
+        self.shape, self.E, self.cfg, self.device = shape, episodes_per_batch, cfg, torch.device(device)
+        self.mask_dtype = mask_dtype
+        s, e = shape, episodes_per_batch
+        n, m, nt = s.N, s.ns * s.N, s.gt * s.gt
+        dev = self.device
+        f32, i32, u8 = torch.float32, torch.int32, torch.uint8
+        new = lambda shp, dt: torch.empty(shp, device=dev, dtype=dt)
+        self.fs = (new((e, ops.pad_rows(m), ops.pad_k(s.C)), f32), new((e, ops.pad_rows(m), ops.pad_k(s.C)), f32))
+        self.fq = (new((e, ops.pad_rows(n), ops.pad_k(s.C)), f32), new((e, ops.pad_rows(n), ops.pad_k(s.C)), f32))
+        self.row_fg = new((e, s.ns, n), u8)
+        self.gemm_out = dict(colstats=new((e, ops.pad_rows(m) // 128, 4, n), f32))
+        if cfg.want_sim:
+            self.gemm_out["sim"] = new((e, m, n), f32)
+        if cfg.want_cost:
+            self.gemm_out["cost"] = new((e, m, n), f32)
+        self.prior = new((e, n), f32)
+        self.vva = new((e, n), f32)
+        self.vta_ref = new((e, nt), f32)
+        self.vta = new((e, n), f32)
+        self.pir_ws = ops.pir_workspace(e, max(n, nt), dev)
+        wpm = ops.words_per_mask(s.H * s.W)
+        npw = (n + 31) // 32
+        self.bits = new((e, s.P, wpm), i32)
+        self.pool_out = (new((e, s.P, npw), i32), new((e, s.P), i32), new((e, s.P), i32))
+        self.region_out = (new((e, s.P), f32), new((e, s.P), f32), new((e,), i32))
+        self.inter = new((e, s.P, s.P), i32) if cfg.nms_iou_threshold is not None else None
+        self.clip = new((e, s.P), f32)
+        self.rank_out = dict(scores=new((e, s.P), torch.float64), order=new((e, s.P), i32),
+                             flags=new((e, s.P), u8), summary=new((e, 4), i32))
+        self.merge_out = dict(bits=new((e, wpm), i32))
+        if cfg.want_merged_f32:
+            self.merge_out["f32"] = new((e, s.H * s.W), f32)
+        self._graph = None
+        self._static = None
+
+    # ------------------------------------------------------------------ the kernel sequence
+    def run(self, batch: dict) -> dict:
+        s, e, cfg = self.shape, self.E, self.cfg
+        n, m = s.N, s.ns * s.N
+        ops.normalize_split(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
+        ops.normalize_split(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
+        ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
+        ops.sim_contract(self.fs, self.fq, m, n, s.C, want_sim=cfg.want_sim, want_cost=cfg.want_cost,
+                         row_fg=self.row_fg, backend=cfg.gemm_backend, out=self.gemm_out)
+        ops.vva_finalize(self.gemm_out["colstats"], self.row_fg, m, n, out=self.prior)
+        ops.pir_refine(self.prior, batch["attn_vva"], s.g, cfg.vva_box_threshold, apply_minmax=True,
+                       backend=cfg.gemm_backend, workspace=self.pir_ws, out=self.vva)
+        ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
+                       backend=cfg.gemm_backend, workspace=self.pir_ws, out=self.vta_ref)
+        ops.resize_minmax(self.vta_ref.reshape(e, s.gt, s.gt), s.g, True, out=self.vta)
+        ops.pack_masks(batch["masks"], out=self.bits)
+        ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
+        ops.region_sums(self.pool_out[0], self.vva, self.vta, out=self.region_out)
+        if self.inter is not None:
+            ops.pairwise_inter(self.bits, backend=cfg.pair_backend, out=self.inter)
+        ops.clip_scores(batch["clip_img"], batch["clip_txt"], out=self.clip)
+        ops.fuse_rank(batch["emd"], self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
+                      self.region_out[2], self.inter, cfg.alpha, cfg.static_threshold, cfg.dynamic_threshold,
+                      cfg.nms_iou_threshold, out=self.rank_out)
+        ops.merge_masks(self.bits, self.rank_out["flags"], s.H * s.W, want_bits=True,
+                        want_f32=cfg.want_merged_f32, out=self.merge_out)
+        return self.outputs()
+
+    def outputs(self) -> dict:
+        out = dict(row_fg=self.row_fg, prior=self.prior, vva=self.vva, vta=self.vta, bits=self.bits,
+                   pooled=self.pool_out[0], area=self.pool_out[1], pooled_count=self.pool_out[2],
+                   sum_vva=self.region_out[0], sum_vta=self.region_out[1], union_count=self.region_out[2],
+                   inter=self.inter, clip=self.clip, merged_bits=self.merge_out["bits"],
+                   merged=self.merge_out.get("f32"), sim=self.gemm_out.get("sim"), cost=self.gemm_out.get("cost"))
+        out.update(self.rank_out)
+        return out
+
+    # ------------------------------------------------------------------ CUDA graph replay
+    def capture(self, batch: dict):
+        """Capture `run` on static copies of `batch`; `replay(batch)` then refreshes the inputs and replays."""
+        self._static = {k: v.clone() for k, v in batch.items()}
+        stream = torch.cuda.Stream(device=self.device)
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            self.run(self._static)  # warm-up outside the capture (function attributes, lazy module load)
+        torch.cuda.current_stream().wait_stream(stream)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.run(self._static)
+        return self
+
+    def replay(self, batch: Optional[dict] = None) -> dict:
+        if batch is not None:
+            for k, v in batch.items():
+                self._static[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        return self.outputs()
+
+    # ------------------------------------------------------------------ result records
+    def record_bytes(self) -> int:
+        p = self.shape.P
+        return 4 * p + 4 * p + p + 16
+
+    def records(self) -> torch.Tensor:
+        """Fixed-size per-episode result records [E, record_bytes] uint8: order, score (f32), flags, summary."""
+        r = self.rank_out
+        e = self.E
+        return torch.cat([r["order"].view(torch.uint8).reshape(e, -1),
+                          r["scores"].float().view(torch.uint8).reshape(e, -1),
+                          r["flags"].reshape(e, -1),
+                          r["summary"].view(torch.uint8).reshape(e, -1)], dim=1).contiguous()
+
+
+def decode_records(records: torch.Tensor, p: int) -> dict:
+    """Inverse of `RankingEngine.records` (works on CPU or CUDA tensors)."""
+    n = records.shape[0]
+    order = records[:, :4 * p].contiguous().view(torch.int32).reshape(n, p)
+    scores = records[:, 4 * p:8 * p].contiguous().view(torch.float32).reshape(n, p)
+    flags = records[:, 8 * p:9 * p]
+    summary = records[:, 9 * p:9 * p + 16].contiguous().view(torch.int32).reshape(n, 4)
+    return dict(order=order, scores=scores, flags=flags, summary=summary)
+
+
+def shard_range(num_episodes: int, rank: int, world_size: int):
+    """Contiguous block of episode ids owned by `rank`."""
+    per = (num_episodes + world_size - 1) // world_size
+    lo = min(rank * per, num_episodes)
+    return lo, min(lo + per, num_episodes)
+
+
+def gather_records(local: torch.Tensor, num_episodes: int, group=None) -> torch.Tensor:
+    """All-gather per-rank record blocks into the global [num_episodes, record_bytes] table.
+
+    The only collective of the path: one all_gather over NCCL (NVLink/NVSwitch) on GPUs, gloo in the
+    CPU tests.  Ranks own contiguous, equally sized blocks (the last one may be padded).
+    """
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    per = (num_episodes + world - 1) // world
+    if local.shape[0] < per:
+        pad = torch.zeros((per - local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
+        local = torch.cat([local, pad], dim=0)
+    out = torch.empty((world * per, local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out[:num_episodes]

@@ -1,0 +1,324 @@
+"""Thin torch wrappers over the C ABI: one function per entry point of include/marsb200.h.
+
+PyTorch is used only for device memory and streams.  Every wrapper takes CUDA
+tensors, allocates its outputs with torch (so the caching allocator owns
+them), and enqueues on the current torch stream without synchronising.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import GEMM_SIMT, GEMM_TCGEN05, MASK_F32, MASK_U8, PAIR_MMA, PAIR_POPC, check, lib
+
+__all__ = [
+    "words_per_mask", "pad_rows", "pad_k", "normalize_split", "pool_mask", "sim_contract", "vva_finalize",
+    "attn_mean", "pir_refine", "resize_minmax", "pack_masks", "pool_packed", "region_sums", "pairwise_inter",
+    "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas",
+    "GEMM_TCGEN05", "GEMM_SIMT", "PAIR_POPC", "PAIR_MMA",
+]
+
+# default back ends (module-level so tests can pin either one)
+# (MARSB200_GEMM=simt / MARSB200_PAIR=popc|mma select the validation kernels, for debugging only)
+DEFAULT_GEMM = GEMM_SIMT if os.environ.get("MARSB200_GEMM", "") == "simt" else GEMM_TCGEN05
+DEFAULT_PAIR = PAIR_MMA if os.environ.get("MARSB200_PAIR", "") == "mma" else PAIR_POPC
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _cuda(t: torch.Tensor, dtype=None, name="tensor") -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.MarsB200Error(f"{name} must be a CUDA tensor (marsb200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _mask_tensor(m: torch.Tensor):
+    """Masks as the ingest kernels read them: float32 as is, bool/uint8 as bytes, anything else -> float32."""
+    if not m.is_cuda:
+        raise _lib.MarsB200Error("masks must be CUDA tensors (marsb200 has no CPU path)")
+    if m.dtype == torch.float32:
+        return m.contiguous(), MASK_F32
+    if m.dtype == torch.bool:
+        return m.contiguous().view(torch.uint8), MASK_U8
+    if m.dtype == torch.uint8:
+        return m.contiguous(), MASK_U8
+    return m.float().contiguous(), MASK_F32
+
+
+def words_per_mask(hw: int) -> int:
+    return int(lib.marsb200_words_per_mask(hw))
+
+
+def pad_rows(rows: int) -> int:
+    return int(lib.marsb200_pad_rows(rows))
+
+
+def pad_k(k: int) -> int:
+    return int(lib.marsb200_pad_k(k))
+
+
+# ----------------------------------------------------------------------------- A1
+def normalize_split(x: torch.Tensor, normalize: bool = True, out=None):
+    """x [E, rows, k] -> (hi, lo) [E, pad_rows, pad_k]; hi + lo is the (normalised) fp32 row."""
+    x = _cuda(x, torch.float32, "x")
+    if x.dim() == 2:
+        x = x[None]
+    e, rows, k = x.shape
+    if out is None:
+        hi = torch.empty((e, pad_rows(rows), pad_k(k)), device=x.device, dtype=torch.float32)
+        lo = torch.empty_like(hi)
+    else:
+        hi, lo = out
+    check(lib.marsb200_normalize_split(x.data_ptr(), k, e, rows, k, int(normalize), hi.data_ptr(), lo.data_ptr(), _stream()))
+    return hi, lo
+
+
+# ----------------------------------------------------------------------------- A3 / A6
+def pool_mask(masks: torch.Tensor, g: int, out=None) -> torch.Tensor:
+    """masks [..., H, W] -> uint8 [..., g*g] (adaptive max pool > 0)."""
+    m, dt = _mask_tensor(masks)
+    h, w = m.shape[-2:]
+    n = m.numel() // (h * w)
+    if out is None:
+        out = torch.empty(tuple(m.shape[:-2]) + (g * g,), device=m.device, dtype=torch.uint8)
+    check(lib.marsb200_pool_mask(m.data_ptr(), dt, n, h, w, g, out.data_ptr(), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- A2 + A3
+def sim_contract(a, b, m: int, n: int, k: int, want_sim=True, want_cost=False, row_fg=None, backend=None, out=None):
+    """S = A B^T on operands from normalize_split.  Returns dict(sim, cost, colstats)."""
+    a_hi, a_lo = a
+    b_hi, b_lo = b
+    e = a_hi.shape[0]
+    dev = a_hi.device
+    out = out or {}
+    sim = out.get("sim") if want_sim else None
+    cost = out.get("cost") if want_cost else None
+    if want_sim and sim is None:
+        sim = torch.empty((e, m, n), device=dev, dtype=torch.float32)
+    if want_cost and cost is None:
+        cost = torch.empty((e, m, n), device=dev, dtype=torch.float32)
+    colstats = None
+    if row_fg is not None:
+        row_fg = _cuda(row_fg, torch.uint8, "row_fg").reshape(e, m)
+        colstats = out.get("colstats")
+        if colstats is None:
+            colstats = torch.empty((e, pad_rows(m) // 128, 4, n), device=dev, dtype=torch.float32)
+    check(lib.marsb200_sim_contract(a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), e, m, n, k,
+                                    _ptr(sim), _ptr(cost), _ptr(row_fg), _ptr(colstats),
+                                    DEFAULT_GEMM if backend is None else backend, _stream()))
+    return dict(sim=sim, cost=cost, colstats=colstats)
+
+
+def vva_finalize(colstats: torch.Tensor, row_fg: torch.Tensor, m: int, n: int, out=None) -> torch.Tensor:
+    e = colstats.shape[0]
+    row_fg = _cuda(row_fg, torch.uint8, "row_fg").reshape(e, m)
+    if out is None:
+        out = torch.empty((e, n), device=colstats.device, dtype=torch.float32)
+    check(lib.marsb200_vva_finalize(colstats.data_ptr(), row_fg.data_ptr(), e, m, n, out.data_ptr(), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- A4
+def attn_mean(maps: Sequence[torch.Tensor], skip: int, out=None) -> torch.Tensor:
+    """Mean over layers and heads of [heads, T, T] (or [1, heads, T, T]) maps -> [N, N] with N = T - skip."""
+    prepared = []
+    for a in maps:
+        if a.dim() == 4:
+            a = a[0]
+        if a.dtype not in (torch.float32, torch.float16):
+            a = a.float()
+        prepared.append(_cuda(a, None, "attention map"))
+    dt = prepared[0].dtype
+    if any(p.dtype != dt or p.shape != prepared[0].shape for p in prepared):
+        raise _lib.MarsB200Error("attention maps must share dtype and shape")
+    heads, t, _ = prepared[0].shape
+    n = t - skip
+    if out is None:
+        out = torch.empty((n, n), device=prepared[0].device, dtype=torch.float32)
+    arr = (ctypes.c_void_p * len(prepared))(*[p.data_ptr() for p in prepared])
+    check(lib.marsb200_attn_mean(arr, len(prepared), 0 if dt == torch.float32 else 1, heads, t, skip,
+                                 out.data_ptr(), out.stride(0), _stream()))
+    return out
+
+
+def pir_workspace(e: int, n: int, device) -> torch.Tensor:
+    nbytes = int(lib.marsb200_pir_workspace_bytes(e, n))
+    return torch.empty((nbytes + 255) // 256 * 256, device=device, dtype=torch.uint8)
+
+
+def pir_refine(prior: torch.Tensor, attn: torch.Tensor, g: int, box_threshold: float, apply_minmax=False,
+               want_box=False, backend=None, workspace=None, out=None):
+    """prior [E, g*g], attn [E, N, N] -> refined [E, N] (and the uint8 box mask when asked)."""
+    prior = _cuda(prior, torch.float32, "prior").reshape(-1, g * g)
+    e, n = prior.shape
+    attn = _cuda(attn, torch.float32, "attn").reshape(e, n, -1)
+    if workspace is None:
+        workspace = pir_workspace(e, n, prior.device)
+    if out is None:
+        out = torch.empty((e, n), device=prior.device, dtype=torch.float32)
+    box = torch.empty((e, n), device=prior.device, dtype=torch.uint8) if want_box else None
+    check(lib.marsb200_pir_refine(prior.data_ptr(), attn.data_ptr(), attn.stride(1), e, g, float(box_threshold),
+                                  int(apply_minmax), out.data_ptr(), _ptr(box), workspace.data_ptr(),
+                                  workspace.numel(), DEFAULT_GEMM if backend is None else backend, _stream()))
+    return (out, box) if want_box else out
+
+
+def resize_minmax(src: torch.Tensor, gd: int, apply_minmax=True, out=None) -> torch.Tensor:
+    src = _cuda(src, torch.float32, "src")
+    gs = src.shape[-1]
+    e = src.numel() // (gs * gs)
+    if out is None:
+        out = torch.empty((e, gd * gd), device=src.device, dtype=torch.float32)
+    check(lib.marsb200_resize_minmax(src.data_ptr(), e, gs, gd, int(apply_minmax), out.data_ptr(), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- A6 / A9
+def pack_masks(masks: torch.Tensor, out=None) -> torch.Tensor:
+    """masks [..., H, W] -> packed bits [..., words_per_mask(H*W)] (int32 storage of uint32 words)."""
+    m, dt = _mask_tensor(masks)
+    h, w = m.shape[-2:]
+    n = m.numel() // (h * w)
+    wpm = words_per_mask(h * w)
+    if out is None:
+        out = torch.empty(tuple(m.shape[:-2]) + (wpm,), device=m.device, dtype=torch.int32)
+    check(lib.marsb200_pack_masks(m.data_ptr(), dt, n, h * w, out.data_ptr(), _stream()))
+    return out
+
+
+def pool_packed(bits: torch.Tensor, h: int, w: int, g: int, out=None):
+    """bits [..., wpm] -> (pooled [..., ceil(g*g/32)] int32, area [...], pooled_count [...])."""
+    lead = tuple(bits.shape[:-1])
+    n = bits.numel() // bits.shape[-1]
+    npw = (g * g + 31) // 32
+    if out is None:
+        pooled = torch.empty(lead + (npw,), device=bits.device, dtype=torch.int32)
+        area = torch.empty(lead, device=bits.device, dtype=torch.int32)
+        cnt = torch.empty(lead, device=bits.device, dtype=torch.int32)
+    else:
+        pooled, area, cnt = out
+    check(lib.marsb200_pool_packed(bits.data_ptr(), n, h, w, g, pooled.data_ptr(), area.data_ptr(), cnt.data_ptr(), _stream()))
+    return pooled, area, cnt
+
+
+def region_sums(pooled: torch.Tensor, vva: torch.Tensor, vta: torch.Tensor, out=None):
+    """pooled [E, P, npw]; vva/vta [E, N] -> (sum_vva [E,P], sum_vta [E,P], union_count [E])."""
+    e, p, _ = pooled.shape
+    n = vva.shape[-1]
+    vva = _cuda(vva, torch.float32, "vva").reshape(e, n)
+    vta = _cuda(vta, torch.float32, "vta").reshape(e, n)
+    if out is None:
+        sv = torch.empty((e, p), device=pooled.device, dtype=torch.float32)
+        st = torch.empty_like(sv)
+        uc = torch.empty((e,), device=pooled.device, dtype=torch.int32)
+    else:
+        sv, st, uc = out
+    check(lib.marsb200_region_sums(pooled.data_ptr(), e, p, n, vva.data_ptr(), vta.data_ptr(), sv.data_ptr(),
+                                   st.data_ptr(), uc.data_ptr(), _stream()))
+    return sv, st, uc
+
+
+def pairwise_inter(bits: torch.Tensor, backend=None, out=None) -> torch.Tensor:
+    """bits [E, P, wpm] -> int32 intersections [E, P, P] (diagonal = area)."""
+    if bits.dim() == 2:
+        bits = bits[None]
+    e, p, wpm = bits.shape
+    if out is None:
+        out = torch.empty((e, p, p), device=bits.device, dtype=torch.int32)
+    check(lib.marsb200_pairwise_inter(bits.data_ptr(), e, p, wpm, out.data_ptr(),
+                                      DEFAULT_PAIR if backend is None else backend, _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- A8 / A10 / A11
+def clip_scores(img: torch.Tensor, txt: torch.Tensor, out=None) -> torch.Tensor:
+    img = _cuda(img, torch.float32, "img")
+    if img.dim() == 2:
+        img = img[None]
+    e, p, d = img.shape
+    txt = _cuda(txt, torch.float32, "txt").reshape(e, d)
+    if out is None:
+        out = torch.empty((e, p), device=img.device, dtype=torch.float32)
+    check(lib.marsb200_clip_scores(img.data_ptr(), txt.data_ptr(), e, p, d, out.data_ptr(), _stream()))
+    return out
+
+
+def fuse_rank(emd, clip, pooled_count, sum_vva, sum_vta, union_count, inter, alpha, static_threshold,
+              dynamic_threshold, nms_iou_threshold=None, out=None):
+    """Returns dict(scores [E,P] f64, order [E,P] i32, flags [E,P] u8, summary [E,4] i32)."""
+    e, p = clip.shape
+    dev = clip.device
+    emd = _cuda(emd, torch.float64, "emd").reshape(e, p)
+    if out is None:
+        out = dict(scores=torch.empty((e, p), device=dev, dtype=torch.float64),
+                   order=torch.empty((e, p), device=dev, dtype=torch.int32),
+                   flags=torch.empty((e, p), device=dev, dtype=torch.uint8),
+                   summary=torch.empty((e, 4), device=dev, dtype=torch.int32))
+    use_nms = inter is not None and nms_iou_threshold is not None and nms_iou_threshold >= 0
+    check(lib.marsb200_fuse_rank(emd.data_ptr(), clip.data_ptr(), pooled_count.data_ptr(), sum_vva.data_ptr(),
+                                 sum_vta.data_ptr(), union_count.data_ptr(), _ptr(inter) if use_nms else None, e, p,
+                                 float(alpha), float(static_threshold), float(dynamic_threshold),
+                                 float(nms_iou_threshold) if use_nms else -1.0, out["scores"].data_ptr(),
+                                 out["order"].data_ptr(), out["flags"].data_ptr(), out["summary"].data_ptr(), _stream()))
+    return out
+
+
+def merge_masks(bits: torch.Tensor, flags: torch.Tensor, hw: int, want_bits=False, want_f32=True, out=None):
+    """OR of the rows whose flag has bit 1 set.  Returns (merged_bits [E,wpm] | None, merged_f32 [E,HW] | None)."""
+    e, p, wpm = bits.shape
+    out = out or {}
+    mb = out.get("bits")
+    mf = out.get("f32")
+    if want_bits and mb is None:
+        mb = torch.empty((e, wpm), device=bits.device, dtype=torch.int32)
+    if want_f32 and mf is None:
+        mf = torch.empty((e, hw), device=bits.device, dtype=torch.float32)
+    check(lib.marsb200_merge_masks(bits.data_ptr(), flags.data_ptr(), e, p, hw, _ptr(mb) if want_bits else None,
+                                   _ptr(mf) if want_f32 else None, _stream()))
+    return (mb if want_bits else None), (mf if want_f32 else None)
+
+
+# ----------------------------------------------------------------------------- A12 / 8f-3
+def points_in_masks(bits: torch.Tensor, h: int, w: int, points: torch.Tensor) -> torch.Tensor:
+    n = bits.numel() // bits.shape[-1]
+    points = _cuda(points, torch.int32, "points").reshape(-1, 2)
+    out = torch.empty((n,), device=bits.device, dtype=torch.int32)
+    check(lib.marsb200_points_in_masks(bits.data_ptr(), n, h, w, points.data_ptr(), points.shape[0], out.data_ptr(), _stream()))
+    return out
+
+
+def matcher_scores(points_in, pooled_count, emd, k: int, alpha: float, beta: float, exp: float):
+    n = points_in.numel()
+    emd = _cuda(emd, torch.float32, "emd")
+    purity = torch.empty((n,), device=emd.device, dtype=torch.float32)
+    coverage = torch.empty_like(purity)
+    scores = torch.empty_like(purity)
+    check(lib.marsb200_matcher_scores(points_in.data_ptr(), pooled_count.data_ptr(), emd.data_ptr(), n, k, alpha, beta,
+                                      exp, purity.data_ptr(), coverage.data_ptr(), scores.data_ptr(), _stream()))
+    return purity, coverage, scores
+
+
+def eval_areas(pred: torch.Tensor, gt: torch.Tensor, ignore: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pred, gt, ignore [n, H, W] -> int32 [n, 4] = {inter_bg, inter_fg, union_bg, union_fg}."""
+    pred = _cuda(pred, torch.float32, "pred")
+    gt = _cuda(gt, torch.float32, "gt")
+    n = pred.shape[0]
+    hw = pred.numel() // n
+    ig = None if ignore is None else _cuda(ignore, torch.float32, "ignore")
+    out = torch.empty((n, 4), device=pred.device, dtype=torch.int32)
+    check(lib.marsb200_eval_areas(pred.data_ptr(), gt.data_ptr(), _ptr(ig), n, hw, out.data_ptr(), _stream()))
+    return out

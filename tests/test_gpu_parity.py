@@ -1,0 +1,450 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
+
+Bars (BASELINE.json north_star): integer work (packed bits, pooled bitmaps, areas, intersections,
+NMS keep-sets, merged masks) bit-exact; float scores within 1e-4 relative; ranking order identical
+except for ties inside that tolerance.
+"""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import mars_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-4  # the north-star tolerance for floating-point scores
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import marsb200
+
+    return marsb200
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def np_pack(masks: np.ndarray, wpm: int) -> np.ndarray:
+    """Reference packing: bit k of word w = pixel 32*w + k, zero padded to wpm words."""
+    n = masks.shape[0]
+    flat = (masks.reshape(n, -1) > 0)
+    padded = np.zeros((n, wpm * 32), dtype=bool)
+    padded[:, : flat.shape[1]] = flat
+    return np.packbits(padded.reshape(n, wpm, 32), axis=-1, bitorder="little").view(np.uint32).reshape(n, wpm)
+
+
+def unpack_pooled(pooled: torch.Tensor, n: int) -> np.ndarray:
+    p = pooled.cpu().numpy().view(np.uint32)
+    bits = np.unpackbits(p.view(np.uint8).reshape(p.shape[0], -1), axis=-1, bitorder="little")
+    return bits[:, :n].astype(bool)
+
+
+def assert_order_matches(order_gpu, scores_gpu, order_ref, scores_ref, rtol=RTOL):
+    """Identical order except where the swapped proposals' reference scores tie within the tolerance."""
+    order_gpu, order_ref = np.asarray(order_gpu), np.asarray(order_ref)
+    np.testing.assert_allclose(scores_gpu, scores_ref, rtol=rtol, atol=1e-6)
+    for r in np.nonzero(order_gpu != order_ref)[0]:
+        a, b = scores_ref[order_gpu[r]], scores_ref[order_ref[r]]
+        assert abs(a - b) <= rtol * max(abs(a), abs(b)) + 1e-9, f"rank {r}: {order_gpu[r]} vs {order_ref[r]}"
+
+
+# ------------------------------------------------------------------------------------------ ingest
+@pytest.mark.parametrize("shape,dtype", [
+    ((6, 518, 518), torch.float32),   # vector path (HW % 4 == 0)
+    ((6, 518, 518), torch.uint8),     # scalar path (HW % 16 != 0)
+    ((3, 1024, 1024), torch.float32),
+    ((3, 1024, 1024), torch.uint8),   # vector path
+    ((3, 1024, 1024), torch.bool),
+    ((5, 37, 41), torch.float32),     # odd size -> scalar path
+    ((1, 1, 1), torch.float32),
+])
+def test_pack_masks_bit_exact(mb, shape, dtype):
+    n, h, w = shape
+    g = torch.Generator().manual_seed(5)
+    m = (torch.rand(shape, generator=g) < 0.3)
+    m[0] = False            # empty mask
+    if n > 1:
+        m[1] = True         # full mask
+    bits = mb.ops.pack_masks(m.to(dtype).to(dev()))
+    wpm = mb.ops.words_per_mask(h * w)
+    assert bits.shape == (n, wpm)
+    np.testing.assert_array_equal(bits.cpu().numpy().view(np.uint32), np_pack(m.numpy(), wpm))
+
+
+def test_pack_nonbinary_values(mb):
+    """Pixels are set iff value > 0 (the reference pools and thresholds with `> 0`)."""
+    m = torch.tensor([[[0.0, 0.5, -1.0, 2.0, 1e-30, -0.0, 255.0, 0.0]]])
+    bits = mb.ops.pack_masks(m.to(dev()))
+    assert int(bits[0, 0].item()) & 0xFF == 0b01011010
+
+
+@pytest.mark.parametrize("h,g", [(100, 7), (140, 10), (518, 37), (1024, 37), (64, 64)])
+def test_pooling_matches_adaptive_max_pool(mb, h, g):
+    masks = cases.blob_masks(7, h, h, seed=h + g, min_frac=0.0005, max_frac=0.2)
+    masks[0] = 0
+    masks[0, h - 1, h - 1] = 1  # single pixel in the last (possibly shared) bin
+    masks[1] = 0                # empty
+    ref = orc.pool_mask(masks, g).reshape(7, -1).numpy()
+    d = masks.to(dev())
+    np.testing.assert_array_equal(mb.ops.pool_mask(d, g).cpu().numpy() > 0, ref)
+    bits = mb.ops.pack_masks(d)
+    pooled, area, cnt = mb.ops.pool_packed(bits, h, h, g)
+    np.testing.assert_array_equal(unpack_pooled(pooled, g * g), ref)
+    np.testing.assert_array_equal(area.cpu().numpy(), (masks > 0).flatten(1).sum(1).numpy())
+    np.testing.assert_array_equal(cnt.cpu().numpy(), ref.sum(1))
+
+
+@pytest.mark.parametrize("p,h", [(9, 100), (64, 140), (130, 200), (257, 64)])
+def test_pairwise_intersections_bit_exact(mb, p, h):
+    masks = cases.blob_masks(p, h, h, seed=p, min_frac=0.01, max_frac=0.3, dup_every=7)
+    inter_ref, area_ref = orc.pairwise_intersections(masks)
+    bits = mb.ops.pack_masks(masks.to(dev()))[None]
+    inter = mb.ops.pairwise_inter(bits, backend=mb.ops.PAIR_POPC)[0].cpu()
+    assert torch.equal(inter, inter_ref)
+    assert torch.equal(torch.diagonal(inter), area_ref)
+
+
+def test_pairwise_batched_episodes(mb):
+    masks = cases.blob_masks(3 * 20, 96, 96, seed=77).reshape(3, 20, 96, 96)
+    bits = mb.ops.pack_masks(masks.to(dev()))
+    inter = mb.ops.pairwise_inter(bits).cpu()
+    for e in range(3):
+        assert torch.equal(inter[e], orc.pairwise_intersections(masks[e])[0])
+
+
+# ------------------------------------------------------------------------------------------ VVA
+def _backends(mb):
+    return [mb.ops.GEMM_SIMT, mb.ops.GEMM_TCGEN05]
+
+
+@pytest.mark.parametrize("name", list(cases.VVA_CASES))
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
+def test_similarity_and_prior(mb, name, backend):
+    z = np.load(os.path.join(GOLD, f"vva_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.vva_inputs(spec)
+    g, ns = spec["g"], spec["ns"]
+    n, m, k = g * g, ns * g * g, spec["C"]
+    fs = mb.ops.normalize_split(c["feat_s"].reshape(1, m, k).to(dev()))
+    fq = mb.ops.normalize_split(c["feat_q"][None].to(dev()))
+    # A1: hi + lo is the normalised row
+    fs_ref = orc.normalize_rows(c["feat_s"])
+    np.testing.assert_allclose((fs[0] + fs[1])[0, :m, :k].cpu().numpy(), fs_ref.numpy(), rtol=0, atol=3e-7)
+    assert float((fs[0] + fs[1])[0, m:].abs().max() if fs[0].shape[1] > m else 0.0) == 0.0
+    row_fg = mb.ops.pool_mask(c["support_mask"].to(dev()), g).reshape(1, m)
+    res = mb.ops.sim_contract(fs, fq, m, n, k, want_sim=True, want_cost=True, row_fg=row_fg, backend=backend)
+    st = int(z["stride"])
+    np.testing.assert_allclose(res["sim"][0].cpu().numpy()[::st, ::st], z["sim"], rtol=0, atol=3e-6)
+    np.testing.assert_allclose(res["cost"][0].cpu().numpy()[::st, ::st], z["cost"], rtol=0, atol=3e-6)
+    prior = mb.ops.vva_finalize(res["colstats"], row_fg, m, n)[0].cpu()
+    fq_ref = orc.normalize_rows(c["feat_q"])
+    prior_ref = orc.vva_prior(fs_ref, fq_ref, orc.pool_mask(c["support_mask"], g).reshape(-1), g).reshape(-1)
+    np.testing.assert_allclose(prior.numpy(), prior_ref.numpy(), rtol=RTOL, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", list(cases.VVA_CASES))
+def test_vva_module_matches_reference(mb, name):
+    """The drop-in class with a fake backbone against the reference module's golden output."""
+    z = np.load(os.path.join(GOLD, f"vva_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.vva_inputs(spec)
+    regs, cdim, ns, h = spec["regs"], spec["C"], spec["ns"], spec["H"]
+
+    class FakeDino(torch.nn.Module):
+        embed_dim = cdim
+
+        def __init__(self):
+            super().__init__()
+            pad = lambda f: torch.cat([torch.full((f.shape[0], 1 + regs, cdim), 7.0), f], dim=1).to(dev())
+            self.feats = [pad(c["feat_s"]), pad(c["feat_q"][None])]
+
+        def forward_features(self, imgs):
+            return {"x_prenorm": self.feats.pop(0)}
+
+        def get_last_self_attention(self, img):
+            return tuple(a.to(dev()) for a in c["attn_maps"])
+
+    mod = mb.VisualVisualAlignmentModule(
+        model=FakeDino(), model_transforms=lambda x: x, model_patch_size=14,
+        model_embedding_spatial_dimensions=spec["g"], model_num_regs=regs,
+        vva_refinement_box_threshold=spec["thr"], last_n_attention_maps_for_refinement=spec["last_n"], device=dev())
+    out = mod.compute(torch.zeros(1, ns, 3, h, h), c["support_mask"][None], torch.zeros(1, 3, h, h))
+    np.testing.assert_allclose(out.cpu().numpy(), z["vva_refined"], rtol=RTOL, atol=2e-5)
+    st = int(z["stride"])
+    np.testing.assert_allclose(mod.cost_matrix.cpu().numpy()[::st, ::st], z["cost"], rtol=0, atol=3e-6)
+    mod.clear()
+    assert mod.cost_matrix is None and mod.similarity_matrix is None
+
+
+def test_vva_empty_support_raises(mb):
+    spec = cases.VVA_CASES["g10_allfg"]
+    c = cases.vva_inputs(spec)
+
+    class Fake(torch.nn.Module):
+        embed_dim = spec["C"]
+
+        def forward_features(self, imgs):
+            return {"x_prenorm": torch.randn(imgs.shape[0], 1 + 100, spec["C"], device=dev())}
+
+        def get_last_self_attention(self, img):
+            return tuple(a.to(dev()) for a in c["attn_maps"])
+
+    mod = mb.VisualVisualAlignmentModule(Fake(), lambda x: x, 14, 10, 0, 0.5, 1, dev())
+    with pytest.raises(RuntimeError):
+        mod.compute(torch.zeros(1, 1, 3, 140, 140), torch.zeros(1, 1, 140, 140), torch.zeros(1, 3, 140, 140))
+
+
+# ------------------------------------------------------------------------------------------ PIR
+@pytest.mark.parametrize("name", list(cases.PIR_CASES))
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
+def test_pir_matches_reference(mb, name, backend):
+    z = np.load(os.path.join(GOLD, f"pir_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.pir_inputs(spec)
+    g = spec["g"]
+    maps = [a.to(dev()) for a in c["attn_maps"]][-spec["last_n"]:]
+    attn = mb.ops.attn_mean(maps, skip=1 + spec["regs"])
+    a_ref = orc.attention_mean(c["attn_maps"], spec["last_n"], spec["regs"])
+    np.testing.assert_allclose(attn.cpu().numpy(), a_ref.numpy(), rtol=2e-6, atol=1e-9)
+    out, box = mb.ops.pir_refine(c["prior"].reshape(1, -1).to(dev()), attn[None], g, spec["thr"], want_box=True,
+                                 backend=backend)
+    b_ref = np.zeros((g, g), dtype=np.uint8)
+    for x0, y0, x1, y1 in z["boxes"][: int(z["cnt"])]:
+        b_ref[y0:y1, x0:x1] = 1
+    np.testing.assert_array_equal(box.reshape(g, g).cpu().numpy(), b_ref)
+    np.testing.assert_allclose(out.reshape(g, g).cpu().numpy(), z["refined"], rtol=RTOL, atol=1e-7)
+
+
+def test_pir_module_fp16_and_3d_maps(mb):
+    spec = cases.PIR_CASES["g33_border"]
+    c = cases.pir_inputs(spec)
+    maps16 = [a.half() for a in c["attn_maps"]]
+    ref = orc.pir_refine(c["prior"], orc.attention_mean(maps16, spec["last_n"], 0), spec["thr"])
+    mod = mb.PriorInformationRefinementModule(spec["thr"], spec["last_n"], dev(), num_regs=0)
+    out = mod.compute(c["prior"], [a.to(dev()) for a in maps16])
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=RTOL, atol=1e-7)
+
+
+def test_resize_minmax(mb):
+    x = torch.rand(3, 33, 33, generator=torch.Generator().manual_seed(3))
+    out = mb.ops.resize_minmax(x.to(dev()), 37).reshape(3, 37, 37).cpu()
+    for e in range(3):
+        ref = orc.minmax(orc.nearest_resize(x[e], (37, 37)))
+        np.testing.assert_allclose(out[e].numpy(), ref.numpy(), rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------ fuse / rank / merge
+@pytest.mark.parametrize("name", list(cases.FM_CASES))
+def test_filtering_merging_module_matches_reference(mb, name):
+    z = np.load(os.path.join(GOLD, f"fm_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.fm_inputs(spec)
+    h = spec["H"]
+    mod = mb.FilteringMergingModule(None, None, None, alpha=spec["alpha"], static_threshold=spec["static"],
+                                    dynamic_threshold=spec["dynamic"], device=dev())
+    kw = dict(query_img=torch.zeros(1, 3, h, h), mask_proposals=c["masks"], support_mask=c["support_mask"][None],
+              cost_matrix=c["cost"].to(dev()), patch_features_spatial_dimension=spec["g"], vva=c["vva"], vta=c["vta"],
+              text=["a thing."], emd_scores=z["emd"], alphaclip_feats=(c["clip_img"], c["clip_txt"]))
+    ranked = mod._score_proposals(**kw)
+    order = [[i for i in range(spec["P"]) if m.data_ptr() == c["masks"][i].data_ptr()][0] for m, _ in ranked]
+    scores_by_index_ref = np.empty(spec["P"])
+    scores_by_index_ref[z["order"]] = z["scores"]
+    scores_by_index = np.empty(spec["P"])
+    scores_by_index[order] = [s for _, s in ranked]
+    assert_order_matches(order, scores_by_index, z["order"], scores_by_index_ref)
+    merged_ref = np.unpackbits(z["merged_bits"])[: h * h].reshape(h, h) > 0
+    merged = mod.compute(**kw)
+    np.testing.assert_array_equal(merged.cpu().numpy() > 0, merged_ref)
+    assert merged.dtype == torch.float32 and tuple(merged.shape) == (h, h)
+    np.testing.assert_array_equal(mod._merge_masks(ranked).cpu().numpy() > 0, merged_ref)
+
+
+def test_filtering_merging_host_emd_path(mb):
+    """Without precomputed EMD the module gathers the cost sub-matrix and calls the host solver, like the reference."""
+    z = np.load(os.path.join(GOLD, "fm_g7_overlap.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.fm_inputs(spec)
+    mod = mb.FilteringMergingModule(None, None, None, spec["alpha"], spec["static"], spec["dynamic"], dev(),
+                                    emd_fn=orc.emd_exact)
+    ranked = mod._score_proposals(torch.zeros(1, 3, 100, 100), c["masks"], c["support_mask"][None], c["cost"].to(dev()),
+                                  spec["g"], c["vva"], c["vta"], ["x"], alphaclip_feats=(c["clip_img"], c["clip_txt"]))
+    np.testing.assert_allclose([s for _, s in ranked], z["scores"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("p,thr", [(12, 0.5), (64, 0.7), (200, 0.3), (1, 0.7)])
+def test_nms_keep_set_bit_exact(mb, p, thr):
+    h = 96
+    masks = cases.blob_masks(p, h, h, seed=100 + p, min_frac=0.02, max_frac=0.3, dup_every=3)
+    rs = np.random.RandomState(p)
+    scores = rs.rand(p)
+    if p > 4:
+        scores[3] = scores[1]  # exact tie: the stable rule keeps index order
+    inter_ref, area_ref = orc.pairwise_intersections(masks)
+    order_ref = orc.stable_rank(scores)
+    keep_ref = orc.mask_nms(order_ref, inter_ref, area_ref, thr)
+    # drive fuse_rank so that its fused score equals `scores`: emd/clip constant, pvv = pvt = 2*score
+    d = dev()
+    bits = mb.ops.pack_masks(masks.to(d))[None]
+    inter = mb.ops.pairwise_inter(bits)
+    cnt = torch.ones((1, p), dtype=torch.int32, device=d)
+    sv = torch.as_tensor(2 * scores, dtype=torch.float32, device=d).reshape(1, p)
+    uc = torch.ones((1,), dtype=torch.int32, device=d)
+    zero = torch.zeros((1, p), device=d)
+    res = mb.ops.fuse_rank(zero.double(), zero, cnt, sv, sv, uc, inter, alpha=1.0, static_threshold=0.0,
+                           dynamic_threshold=0.0, nms_iou_threshold=thr)
+    order = res["order"][0].cpu().numpy()
+    s32 = (2 * scores).astype(np.float32).astype(np.float64) / (1e-7 + 1)
+    order_expected = orc.stable_rank((s32 + s32) / 4)
+    np.testing.assert_array_equal(order, order_expected)
+    keep_expected = orc.mask_nms(order_expected, inter_ref, area_ref, thr)
+    flags = res["flags"][0].cpu().numpy()
+    np.testing.assert_array_equal((flags & 1).astype(bool), keep_expected)
+    assert int(res["summary"][0, 0]) == int(keep_expected.sum())
+    if np.array_equal(order_expected, order_ref):
+        np.testing.assert_array_equal(keep_expected, keep_ref)
+
+
+# ------------------------------------------------------------------------------------------ whole episodes
+def _run_engine(mb, shape, n_ep, cfg, mask_dtype=torch.float32, seed0=0):
+    eps = [mb.make_episode(shape, seed0 + i, "cpu", mask_dtype) for i in range(n_ep)]
+    eng = mb.RankingEngine(shape, n_ep, cfg, dev(), mask_dtype)
+    out = eng.run(mb.to_device(mb.stack_episodes(eps), dev()))
+    torch.cuda.synchronize()
+    return eps, eng, {k: (v.cpu() if v is not None else None) for k, v in out.items()}
+
+
+def _check_episode(mb, shape, cfg, ep, out, e):
+    ocfg = dict(g=shape.g, vva_box_threshold=cfg.vva_box_threshold, vta_box_threshold=cfg.vta_box_threshold,
+                alpha=cfg.alpha, static_threshold=cfg.static_threshold, dynamic_threshold=cfg.dynamic_threshold,
+                nms_iou_threshold=cfg.nms_iou_threshold)
+    ep = dict(ep)
+    ep["masks"] = ep["masks"].float()
+    ref = orc.run_episode(ep, ocfg)
+    n = shape.N
+    np.testing.assert_array_equal(out["row_fg"][e].reshape(-1).numpy() > 0, ref["support_bits"].numpy())
+    np.testing.assert_allclose(out["prior"][e].numpy(), ref["prior"].reshape(-1).numpy(), rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(out["vva"][e].numpy(), ref["vva"].reshape(-1).numpy(), rtol=RTOL, atol=5e-5)
+    np.testing.assert_allclose(out["vta"][e].numpy(), ref["vta"].reshape(-1).numpy(), rtol=RTOL, atol=5e-5)
+    np.testing.assert_array_equal(unpack_pooled(out["pooled"][e], n), ref["pooled"].reshape(shape.P, -1))
+    np.testing.assert_allclose(out["clip"][e].numpy(), ref["clip"], rtol=RTOL, atol=1e-6)
+    if cfg.nms_iou_threshold is not None:
+        assert torch.equal(out["inter"][e], ref["inter"])
+        assert torch.equal(out["area"][e], ref["area"])
+    assert_order_matches(out["order"][e].numpy(), out["scores"][e].numpy(), ref["order"], ref["scores"])
+    if np.array_equal(out["order"][e].numpy(), ref["order"]):
+        flags = out["flags"][e].numpy()
+        if cfg.nms_iou_threshold is not None:
+            np.testing.assert_array_equal((flags & 1).astype(bool), ref["keep"])
+        sel = np.zeros(shape.P, dtype=bool)
+        sel[ref["selected"]] = True
+        # selection compares scores against thresholds; allow a flip only for a score within tolerance of the bound
+        top = ref["scores"][ref["order"][0]]
+        bound = cfg.dynamic_threshold * top if top < cfg.static_threshold else cfg.static_threshold
+        diff = np.nonzero(((flags & 2) > 0) != sel)[0]
+        assert all(abs(ref["scores"][i] - bound) <= RTOL * bound for i in diff)
+        if len(diff) == 0:
+            np.testing.assert_array_equal(out["merged"][e].reshape(shape.H, shape.W).numpy() > 0,
+                                          ref["merged"].numpy() > 0)
+
+
+@pytest.mark.parametrize("nms", [None, 0.7])
+@pytest.mark.parametrize("mask_dtype", [torch.float32, torch.uint8])
+def test_engine_small_episodes(mb, nms, mask_dtype):
+    shape = mb.EpisodeShape(ns=2, g=10, C=64, P=24, H=140, W=140, gt=8, D=32)
+    cfg = mb.RankingConfig(nms_iou_threshold=nms, want_sim=True, want_cost=True)
+    eps, eng, out = _run_engine(mb, shape, 3, cfg, mask_dtype)
+    for e in range(3):
+        _check_episode(mb, shape, cfg, eps[e], out, e)
+
+
+def test_engine_c1_shape_against_oracle(mb):
+    """BASELINE config 1 (the reference's CPU-runnable case): N=1369, C=1024, P=128 at 518x518."""
+    shape = mb.CONFIGS["c1"]
+    cfg = mb.RankingConfig(nms_iou_threshold=0.7)
+    eps, eng, out = _run_engine(mb, shape, 1, cfg)
+    _check_episode(mb, shape, cfg, eps[0], out, 0)
+
+
+def test_engine_graph_replay_matches_eager(mb):
+    shape = mb.EpisodeShape(ns=1, g=10, C=64, P=16, H=140, W=140, gt=8, D=32)
+    cfg = mb.RankingConfig(nms_iou_threshold=0.7)
+    batch = mb.to_device(mb.stack_episodes([mb.make_episode(shape, i) for i in range(2)]), dev())
+    eng = mb.RankingEngine(shape, 2, cfg, dev())
+    eager = {k: v.clone() for k, v in eng.run(batch).items() if v is not None}
+    eng.capture(batch)
+    replay = eng.replay(batch)
+    torch.cuda.synchronize()
+    for k, v in eager.items():
+        assert torch.equal(v, replay[k]), k
+    rec = mb.decode_records(eng.records().cpu(), shape.P)
+    assert torch.equal(rec["order"], replay["order"].cpu())
+
+
+def test_full_size_properties_c2(mb):
+    """Size-independent properties at BASELINE config 2 (P=256 at 1024x1024), where the oracle is too slow to loop."""
+    shape = mb.CONFIGS["c2"]
+    d = dev()
+    gen = torch.Generator(device=d).manual_seed(9)
+    from marsb200.synthetic import random_masks
+
+    masks = random_masks(shape.P, shape.H, shape.W, gen, d)
+    bits = mb.ops.pack_masks(masks)
+    # round trip: merging a single packed row and expanding it gives the mask back
+    for i in (0, 17, 255):
+        flags = torch.zeros((1, shape.P), dtype=torch.uint8, device=d)
+        flags[0, i] = 3
+        _, back = mb.ops.merge_masks(bits[None], flags, shape.H * shape.W)
+        assert torch.equal(back.reshape(shape.H, shape.W), masks[i])
+    # u8 ingest packs to the same bits
+    assert torch.equal(mb.ops.pack_masks(masks.to(torch.uint8)), bits)
+    inter = mb.ops.pairwise_inter(bits[None])[0]
+    area = masks.flatten(1).sum(1).to(torch.int32)
+    assert torch.equal(torch.diagonal(inter), area)
+    assert torch.equal(inter, inter.T)
+    assert bool((inter <= torch.minimum(area[:, None], area[None, :])).all())
+    # spot rows against an exact torch contraction on the device
+    flat = masks.flatten(1)
+    for i in (3, 200):
+        assert torch.equal(inter[i], (flat * flat[i]).sum(1).to(torch.int32))
+    # duplicates injected by the generator have IoU 1 with their source
+    pooled, area2, cnt = mb.ops.pool_packed(bits, shape.H, shape.W, shape.g)
+    assert torch.equal(area2, area)
+    ref_pool = torch.nn.functional.adaptive_max_pool2d(masks[:8, None], (shape.g, shape.g)).flatten(1) > 0
+    np.testing.assert_array_equal(unpack_pooled(pooled[:8], shape.N), ref_pool.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------ Matcher / evaluator
+def test_matcher_scoring(mb):
+    h, g, n, k = 140, 10, 14, 60
+    masks = cases.blob_masks(n, h, h, seed=41, min_frac=0.01, max_frac=0.2)
+    rs = np.random.RandomState(4)
+    pts = np.stack([rs.randint(-3, h + 3, k), rs.randint(-3, h + 3, k)], axis=1)  # some outside: clipped
+    purity_ref, cov_ref = orc.matcher_mask_scores(masks.numpy() > 0, pts, g)
+    emd = torch.rand(n)
+    ref_scores = orc.matcher_fuse(emd, purity_ref, cov_ref, 1.0, 0.5, 2.0)
+    bits = mb.ops.pack_masks(masks.to(dev()))
+    pin = mb.ops.points_in_masks(bits, h, h, torch.as_tensor(pts, dtype=torch.int32, device=dev()))
+    _, _, cnt = mb.ops.pool_packed(bits, h, h, g)
+    purity, cov, scores = mb.ops.matcher_scores(pin, cnt, emd.to(dev()), k, 1.0, 0.5, 2.0)
+    np.testing.assert_allclose(purity.cpu().numpy(), purity_ref.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(cov.cpu().numpy(), cov_ref.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(scores.cpu().numpy(), ref_scores.numpy(), rtol=1e-5)
+
+
+def test_evaluator_areas(mb):
+    g = torch.Generator().manual_seed(8)
+    pred = (torch.rand(3, 90, 70, generator=g) < 0.4).float()
+    gt = (torch.rand(3, 90, 70, generator=g) < 0.5).float()
+    ignore = ((torch.rand(3, 90, 70, generator=g) < 0.1) & (gt == 0)).float()
+    for ig in (None, ignore):
+        inter_ref, union_ref = orc.evaluator_areas(pred, gt, ig)
+        out = mb.ops.eval_areas(pred.to(dev()), gt.to(dev()), None if ig is None else ig.to(dev())).cpu()
+        np.testing.assert_array_equal(out[:, :2].numpy(), inter_ref.t().numpy().astype(np.int32))
+        np.testing.assert_array_equal(out[:, 2:].numpy(), union_ref.t().numpy().astype(np.int32))
