@@ -101,20 +101,22 @@ def test_pooling_matches_adaptive_max_pool(mb, h, g):
     np.testing.assert_array_equal(cnt.cpu().numpy(), ref.sum(1))
 
 
-@pytest.mark.parametrize("p,h", [(9, 100), (64, 140), (130, 200), (257, 64)])
-def test_pairwise_intersections_bit_exact(mb, p, h):
+@pytest.mark.parametrize("p,h", [(9, 100), (64, 140), (130, 200), (257, 64), (300, 96), (600, 64)])
+@pytest.mark.parametrize("backend", [0, 1], ids=["popc", "mma"])
+def test_pairwise_intersections_bit_exact(mb, p, h, backend):
     masks = cases.blob_masks(p, h, h, seed=p, min_frac=0.01, max_frac=0.3, dup_every=7)
     inter_ref, area_ref = orc.pairwise_intersections(masks)
     bits = mb.ops.pack_masks(masks.to(dev()))[None]
-    inter = mb.ops.pairwise_inter(bits, backend=mb.ops.PAIR_POPC)[0].cpu()
+    inter = mb.ops.pairwise_inter(bits, backend=backend)[0].cpu()
     assert torch.equal(inter, inter_ref)
     assert torch.equal(torch.diagonal(inter), area_ref)
 
 
-def test_pairwise_batched_episodes(mb):
+@pytest.mark.parametrize("backend", [0, 1], ids=["popc", "mma"])
+def test_pairwise_batched_episodes(mb, backend):
     masks = cases.blob_masks(3 * 20, 96, 96, seed=77).reshape(3, 20, 96, 96)
     bits = mb.ops.pack_masks(masks.to(dev()))
-    inter = mb.ops.pairwise_inter(bits).cpu()
+    inter = mb.ops.pairwise_inter(bits, backend=backend).cpu()
     for e in range(3):
         assert torch.equal(inter[e], orc.pairwise_intersections(masks[e])[0])
 
