@@ -43,7 +43,7 @@ __device__ __forceinline__ bool ranks_before(double sa, int ia, double sb, int i
 __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
     const double* __restrict__ emd, const float* __restrict__ clip, const int32_t* __restrict__ pooled_count,
     const float* __restrict__ sum_vva, const float* __restrict__ sum_vta, const int32_t* __restrict__ union_count,
-    const int32_t* __restrict__ inter, int P, int n2, double alpha, double static_thr, double dynamic_thr,
+    const int32_t* __restrict__ inter, int P, int n2, int use_bitmask, double alpha, double static_thr, double dynamic_thr,
     float nms_thr, double* __restrict__ scores, int32_t* __restrict__ order, uint8_t* __restrict__ flags,
     int32_t* __restrict__ summary) {
     extern __shared__ unsigned char smem_raw[];
@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
     int* s_idx = reinterpret_cast<int*>(s_key + n2);                   // n2
     int* s_rank = s_idx + n2;                                          // P: proposal index -> rank
     int* s_area = s_rank + P;                                          // P
-    unsigned char* s_removed = reinterpret_cast<unsigned char*>(s_area + P);  // P
+    unsigned char* s_removed = reinterpret_cast<unsigned char*>(s_area + P);  // P (+ pad to 4)
+    uint32_t* s_sup = use_bitmask ? reinterpret_cast<uint32_t*>(s_removed + ((P + 3) & ~3)) : nullptr;  // P * ceil(P/32)
     __shared__ double s_scratch_d[FUSE_THREADS / 32];
     __shared__ float s_scratch_f[FUSE_THREADS / 32];
     __shared__ int s_counts[2];
@@ -141,20 +142,60 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
         const int32_t* im = inter + e * (int64_t)P * P;
         for (int p = tid; p < P; p += FUSE_THREADS) s_area[p] = im[(int64_t)p * P + p];
         __syncthreads();
-        for (int r = 0; r < P; ++r) {
-            const int i = s_idx[r];
-            if (s_removed[i]) continue;  // uniform: shared state is stable between barriers
-            const int ai = s_area[i];
-            const int32_t* row = im + (int64_t)i * P;
-            for (int j = tid; j < P; j += FUSE_THREADS) {
-                if (s_rank[j] > r && !s_removed[j]) {
-                    const int in = row[j];
-                    const int un = ai + s_area[j] - in;
-                    const float iou = un > 0 ? __fdiv_rn((float)in, (float)un) : 0.f;
-                    if (iou > nms_thr) s_removed[j] = 1;
+        if (s_sup != nullptr) {
+            // (a) all threads: suppression bits in rank space, sup[ri] bit rj = IoU(order[ri], order[rj]) > thr
+            const int nw = (P + 31) >> 5;
+            for (int idx = tid; idx < P * nw; idx += FUSE_THREADS) {
+                const int ri = idx / nw, w = idx - ri * nw;
+                uint32_t bitsw = 0;
+                if (w * 32 + 31 > ri) {  // only later ranks can be suppressed by ri
+                    const int i = s_idx[ri];
+                    const int ai = s_area[i];
+                    const int32_t* row = im + (int64_t)i * P;
+#pragma unroll 8
+                    for (int b = 0; b < 32; ++b) {
+                        const int rj = w * 32 + b;
+                        if (rj > ri && rj < P) {
+                            const int j = s_idx[rj];
+                            const int in = row[j];
+                            const int un = ai + s_area[j] - in;
+                            const float iou = un > 0 ? __fdiv_rn((float)in, (float)un) : 0.f;
+                            if (iou > nms_thr) bitsw |= 1u << b;
+                        }
+                    }
+                }
+                s_sup[idx] = bitsw;
+            }
+            __syncthreads();
+            // (b) one warp walks the ranks; lane w owns word w of the removed mask (P <= 1024)
+            if (tid < 32) {
+                uint32_t removed = 0;
+                for (int r = 0; r < P; ++r) {
+                    const uint32_t word = __shfl_sync(0xffffffffu, removed, r >> 5);
+                    if (!((word >> (r & 31)) & 1u) && tid < nw) removed |= s_sup[r * nw + tid];
+                }
+                for (int b = 0; b < 32; ++b) {
+                    const int r = tid * 32 + b;
+                    if (tid < nw && r < P) s_removed[s_idx[r]] = (removed >> b) & 1u;
                 }
             }
             __syncthreads();
+        } else {
+            for (int r = 0; r < P; ++r) {
+                const int i = s_idx[r];
+                if (s_removed[i]) continue;  // uniform: shared state is stable between barriers
+                const int ai = s_area[i];
+                const int32_t* row = im + (int64_t)i * P;
+                for (int j = tid; j < P; j += FUSE_THREADS) {
+                    if (s_rank[j] > r && !s_removed[j]) {
+                        const int in = row[j];
+                        const int un = ai + s_area[j] - in;
+                        const float iou = un > 0 ? __fdiv_rn((float)in, (float)un) : 0.f;
+                        if (iou > nms_thr) s_removed[j] = 1;
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
 
@@ -210,11 +251,16 @@ int marsb200_fuse_rank(const double* emd, const float* clip, const int32_t* pool
     MARS_REQUIRE(E > 0 && P > 0 && P <= 8192, "shape (P <= 8192)");
     int n2 = 1;
     while (n2 < P) n2 <<= 1;
-    const size_t smem = (size_t)n2 * (sizeof(double) + sizeof(int)) + (size_t)P * (2 * sizeof(int) + 1) + 16;
+    size_t smem = (size_t)n2 * (sizeof(double) + sizeof(int)) + (size_t)P * (2 * sizeof(int) + 1) + 16;
+    // rank-space suppression bitmask (P * ceil(P/32) words) when it fits in shared memory
+    const bool nms = inter != nullptr && nms_iou_threshold >= 0.f;
+    const size_t sup_bytes = (size_t)P * ((P + 31) / 32) * 4;
+    const int use_bitmask = nms && P <= 1024 && smem + sup_bytes <= 200 * 1024;
+    if (use_bitmask) smem += sup_bytes;
     if (smem > 48 * 1024)
         MARS_CUDA_OK(cudaFuncSetAttribute(fuse_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fuse_rank_kernel<<<E, FUSE_THREADS, smem, as_stream(stream)>>>(emd, clip, pooled_count, sum_vva, sum_vta,
-                                                                   union_count, inter, P, n2, alpha, static_threshold,
+                                                                   union_count, inter, P, n2, use_bitmask, alpha, static_threshold,
                                                                    dynamic_threshold, nms_iou_threshold, scores, order,
                                                                    flags, summary);
     MARS_LAUNCH_OK();

@@ -19,6 +19,8 @@ struct GemmEpilogue {
     int64_t M, N;
     int64_t ld_out, ld_max;
     int tiles_m;
+    int symmetric;          // C == C^T (A == B, M == N): only tiles with tile_n >= tile_m are computed and
+                            // every off-diagonal tile is also written mirrored (tcgen05 back end only)
 };
 
 // tile: BM x BN fp32 values in shared memory with row stride `lds` (floats).  All `nthreads` threads
@@ -32,17 +34,69 @@ __device__ __forceinline__ void tile_epilogue(const float* tile, int lds, unsign
     const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
 
     if (ep.out0 || ep.out1) {
-        for (int r = warp; r < GEMM_BM; r += nwarps) {
-            const int64_t m = m0 + r;
-            if (m >= ep.M) break;
+        // each warp owns a contiguous band of rows; 4 rows x BN/32 columns are loaded before any store so
+        // that the `maxwith` reads of a band overlap instead of serialising on global latency
+        constexpr int CH = BN / 32;
+        constexpr int RU = 4;
+        const int rows_per_warp = GEMM_BM / nwarps;
+        for (int rb = warp * rows_per_warp; rb < (warp + 1) * rows_per_warp; rb += RU) {
+            float v[RU][CH];
 #pragma unroll
-            for (int c = lane; c < BN; c += 32) {
-                const int64_t n = n0 + c;
-                if (n < ep.N) {
-                    float v = tile[r * lds + c];
-                    if (ep.maxwith) v = fmaxf(v, ep.maxwith[(e * ep.M + m) * ep.ld_max + n]);
-                    if (ep.out0) ep.out0[(e * ep.M + m) * ep.ld_out + n] = v;
-                    if (ep.out1) ep.out1[(e * ep.M + m) * ep.ld_out + n] = (1.0f - v) / 2.0f;
+            for (int i = 0; i < RU; ++i) {
+                const int64_t m = m0 + rb + i;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int64_t n = n0 + c * 32 + lane;
+                    float mw = -INFINITY;
+                    if (ep.maxwith && m < ep.M && n < ep.N) mw = ep.maxwith[(e * ep.M + m) * ep.ld_max + n];
+                    const float t = tile[(rb + i) * lds + c * 32 + lane];
+                    v[i][c] = ep.maxwith ? fmaxf(t, mw) : t;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RU; ++i) {
+                const int64_t m = m0 + rb + i;
+                if (m >= ep.M) continue;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int64_t n = n0 + c * 32 + lane;
+                    if (n < ep.N) {
+                        if (ep.out0) ep.out0[(e * ep.M + m) * ep.ld_out + n] = v[i][c];
+                        if (ep.out1) ep.out1[(e * ep.M + m) * ep.ld_out + n] = (1.0f - v[i][c]) / 2.0f;
+                    }
+                }
+            }
+        }
+        if (ep.symmetric && tile_m != tile_n) {
+            // mirrored block: output row = tile column, output columns = tile rows (BN == GEMM_BM here)
+            const int cols_per_warp = BN / nwarps;
+            constexpr int RH = GEMM_BM / 32;
+            for (int cb = warp * cols_per_warp; cb < (warp + 1) * cols_per_warp; cb += RU) {
+                float v[RU][RH];
+#pragma unroll
+                for (int i = 0; i < RU; ++i) {
+                    const int64_t orow = n0 + cb + i;
+#pragma unroll
+                    for (int c = 0; c < RH; ++c) {
+                        const int64_t ocol = m0 + c * 32 + lane;
+                        float mw = -INFINITY;
+                        if (ep.maxwith && orow < ep.M && ocol < ep.N) mw = ep.maxwith[(e * ep.M + orow) * ep.ld_max + ocol];
+                        const float t = tile[(c * 32 + lane) * lds + cb + i];
+                        v[i][c] = ep.maxwith ? fmaxf(t, mw) : t;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < RU; ++i) {
+                    const int64_t orow = n0 + cb + i;
+                    if (orow >= ep.M) continue;
+#pragma unroll
+                    for (int c = 0; c < RH; ++c) {
+                        const int64_t ocol = m0 + c * 32 + lane;
+                        if (ocol < ep.N) {
+                            if (ep.out0) ep.out0[(e * ep.M + orow) * ep.ld_out + ocol] = v[i][c];
+                            if (ep.out1) ep.out1[(e * ep.M + orow) * ep.ld_out + ocol] = (1.0f - v[i][c]) / 2.0f;
+                        }
+                    }
                 }
             }
         }

@@ -40,7 +40,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     unsigned char* flags = base_ptr + TC_STAGES * TC_STAGE_BYTES + 128;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile_n = blockIdx.x, tile_m = blockIdx.y, e = blockIdx.z;
+    int tile_n = blockIdx.x, tile_m = blockIdx.y;
+    const int e = blockIdx.z;
+    if (ep.symmetric) {  // blockIdx.x enumerates the upper-triangular tile pairs row by row
+        int t = blockIdx.x, tm = 0;
+        while (t >= ep.tiles_m - tm) {
+            t -= ep.tiles_m - tm;
+            ++tm;
+        }
+        tile_m = tm;
+        tile_n = tm + t;
+    }
 
     if (tid == 0) {
         tma_prefetch_desc(&map_a_hi);
@@ -156,6 +166,12 @@ int gemm_tcgen05(const float* a_hi, const float* a_lo, const float* b_hi, const 
         attr_set = true;
     }
     dim3 grid((unsigned)(n_pad / TC_BN), (unsigned)(m_pad / GEMM_BM), E);
+    if (ep.symmetric) {
+        if (M != N || a_hi != b_hi || a_lo != b_lo)
+            return fail(MARSB200_ERR_ARG, "%s: symmetric epilogue needs A == B", "gemm_tcgen05");
+        const unsigned t = (unsigned)(m_pad / GEMM_BM);
+        grid = dim3(t * (t + 1) / 2, 1, E);
+    }
     gemm_tcgen05_kernel<<<grid, 128, TC_SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], (int)(k_pad / TC_BK), ep);
     MARS_LAUNCH_OK();
     return MARSB200_OK;

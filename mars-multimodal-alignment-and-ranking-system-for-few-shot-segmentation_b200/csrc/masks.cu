@@ -134,60 +134,92 @@ __global__ void pool_mask_kernel(const T* __restrict__ masks, int64_t n, int H, 
 }
 
 // --------------------------------------------------------------------------------------------
-// pooled bitmap / area / pooled count of a packed mask: one block per mask, reads the row once.
+// pooled bitmap / area / pooled count of a packed mask: one block per mask, the packed row is read
+// once with 128-bit loads (4 in flight per thread).  Pass 1 ORs every non-zero word into a
+// row-aligned bit row per patch-row bin (shared memory, g x (W/32 + 1) words); pass 2 tests the
+// column window of every bin.  Bins follow the adaptive-pool rule and may overlap.
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pool_packed_kernel(const uint32_t* __restrict__ bits, int64_t n, int H, int W,
-                                                          int g, int64_t wpm, int npw, uint32_t* __restrict__ pooled,
-                                                          int32_t* __restrict__ area,
-                                                          int32_t* __restrict__ pooled_count) {
-    extern __shared__ uint32_t s_pool[];  // npw words + 2 counters
-    int* s_cnt = reinterpret_cast<int*>(s_pool + npw);
+constexpr int POOL_THREADS = 256;
+constexpr int POOL_UNROLL = 4;
+
+__device__ __forceinline__ void smem_or(uint32_t* p, uint32_t v) {
+    if ((*p & v) != v) atomicOr(p, v);
+}
+
+__global__ void __launch_bounds__(POOL_THREADS) pool_packed_kernel(const uint32_t* __restrict__ bits, int64_t n, int H,
+                                                                   int W, int g, int64_t wpm, int npw, int rw,
+                                                                   uint32_t* __restrict__ pooled,
+                                                                   int32_t* __restrict__ area,
+                                                                   int32_t* __restrict__ pooled_count) {
+    extern __shared__ uint32_t s_mem_pool[];
+    uint32_t* binrow = s_mem_pool;             // g * rw
+    uint32_t* s_pool = binrow + g * rw;        // npw
+    int* s_cnt = reinterpret_cast<int*>(s_pool + npw);  // 2
     const int64_t m = blockIdx.x;
-    for (int i = threadIdx.x; i < npw + 2; i += blockDim.x) s_pool[i] = 0;
+    for (int i = threadIdx.x; i < g * rw + npw + 2; i += POOL_THREADS) s_mem_pool[i] = 0;
     __syncthreads();
 
-    const int64_t HW = (int64_t)H * W;
-    const int64_t words = ceil_div64(HW, 32);
-    const uint32_t* row = bits + m * wpm;
+    const uint4* row = reinterpret_cast<const uint4*>(bits + m * wpm);
+    const int quads = (int)(wpm / 4);
     int my_area = 0;
-    for (int64_t w = threadIdx.x; w < words; w += blockDim.x) {
-        uint32_t word = row[w];
-        if (word == 0) continue;
-        my_area += __popc(word);
-        int64_t px = w * 32;
-        int y = (int)(px / W), x = (int)(px % W);
-        int consumed = 0;
-        while (consumed < 32 && word != 0 && y < H) {
-            const int len = min(32 - consumed, W - x);
-            const uint32_t seg = (len == 32) ? word : (word & ((1u << len) - 1u));
-            if (seg != 0) {
-                const int first = __ffs(seg) - 1, last = 31 - __clz(seg);
-                const int jy0 = bin_lo_of(y, H, g), jy1 = bin_hi_of(y, H, g);
-                const int jx0 = bin_lo_of(x + first, W, g), jx1 = bin_hi_of(x + last, W, g);
-                for (int jx = jx0; jx <= jx1; ++jx) {
-                    const int lo = max(bin_start(jx, W, g) - x, 0);
-                    const int hi = min(bin_end(jx, W, g) - x, len);  // exclusive
-                    if (hi <= lo) continue;
-                    const uint32_t window = ((hi - lo) == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-                    if ((seg & window) == 0) continue;
-                    for (int jy = jy0; jy <= jy1; ++jy) {
-                        const int b = jy * g + jx;
-                        const uint32_t bit = 1u << (b & 31);
-                        if ((s_pool[b >> 5] & bit) == 0) atomicOr(&s_pool[b >> 5], bit);
+    for (int q0 = threadIdx.x; q0 < quads; q0 += POOL_THREADS * POOL_UNROLL) {
+        uint4 v[POOL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < POOL_UNROLL; ++u) {
+            const int q = q0 + u * POOL_THREADS;
+            v[u] = (q < quads) ? __ldg(row + q) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < POOL_UNROLL; ++u) {
+            if ((v[u].x | v[u].y | v[u].z | v[u].w) == 0) continue;
+            const uint32_t words[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t word = words[k];
+                if (word == 0) continue;
+                my_area += __popc(word);
+                const uint32_t px = ((uint32_t)(q0 + u * POOL_THREADS) * 4u + k) * 32u;
+                int y = (int)(px / (uint32_t)W);
+                int x = (int)(px - (uint32_t)y * (uint32_t)W);
+                int left = 32;
+                while (word != 0 && y < H) {  // a word may straddle rows when W % 32 != 0
+                    const int len = min(left, W - x);
+                    const uint32_t seg = (len == 32) ? word : (word & ((1u << len) - 1u));
+                    if (seg != 0) {
+                        const int wi = x >> 5, sh = x & 31;
+                        const uint32_t lo = seg << sh;
+                        const uint32_t hi = sh ? (seg >> (32 - sh)) : 0u;
+                        const int jy0 = bin_lo_of(y, H, g), jy1 = bin_hi_of(y, H, g);
+                        for (int jy = jy0; jy <= jy1; ++jy) {
+                            if (lo) smem_or(&binrow[jy * rw + wi], lo);
+                            if (hi) smem_or(&binrow[jy * rw + wi + 1], hi);
+                        }
                     }
+                    word = (len == 32) ? 0u : (word >> len);
+                    left -= len;
+                    x = 0;
+                    ++y;
                 }
             }
-            word = (len == 32) ? 0u : (word >> len);
-            consumed += len;
-            x = 0;
-            ++y;
         }
     }
     my_area = warp_sum(my_area);
     if ((threadIdx.x & 31) == 0 && my_area) atomicAdd(&s_cnt[0], my_area);
     __syncthreads();
+    for (int b = threadIdx.x; b < g * g; b += POOL_THREADS) {
+        const int jy = b / g, jx = b - jy * g;
+        const int xs = bin_start(jx, W, g), xe = bin_end(jx, W, g);  // [xs, xe)
+        bool hit = false;
+        for (int wi = xs >> 5; wi <= (xe - 1) >> 5; ++wi) {
+            const int lo = max(xs - wi * 32, 0), hi = min(xe - wi * 32, 32);
+            const uint32_t window = ((hi - lo) == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+            hit |= (binrow[jy * rw + wi] & window) != 0;
+        }
+        if (hit) atomicOr(&s_pool[b >> 5], 1u << (b & 31));
+    }
+    __syncthreads();
     int pc = 0;
-    for (int i = threadIdx.x; i < npw; i += blockDim.x) {
+    for (int i = threadIdx.x; i < npw; i += POOL_THREADS) {
         const uint32_t v = s_pool[i];
         pooled[m * npw + i] = v;
         pc += __popc(v);
@@ -231,22 +263,27 @@ __global__ void region_sums_kernel(const uint32_t* __restrict__ pooled, int64_t 
     }
 }
 
-__global__ void union_count_kernel(const uint32_t* __restrict__ pooled, int P, int npw,
-                                   int32_t* __restrict__ union_count) {
-    __shared__ int s_total;
-    if (threadIdx.x == 0) s_total = 0;
+// 256 threads per episode: thread t ORs word (t % 64 ...) over a slice of the proposals, then a
+// shared-memory OR per word and a popcount.
+__global__ void __launch_bounds__(256) union_count_kernel(const uint32_t* __restrict__ pooled, int P, int npw,
+                                                          int32_t* __restrict__ union_count) {
+    extern __shared__ uint32_t s_union[];  // npw words + 1 counter
+    for (int i = threadIdx.x; i <= npw; i += blockDim.x) s_union[i] = 0;
     __syncthreads();
     const int64_t e = blockIdx.x;
-    int c = 0;
-    for (int w = threadIdx.x; w < npw; w += blockDim.x) {
-        uint32_t acc = 0;
-        for (int p = 0; p < P; ++p) acc |= pooled[(e * P + p) * npw + w];
-        c += __popc(acc);
+    const uint32_t* base = pooled + e * P * npw;
+    const int total = P * npw;
+    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x) {
+        const uint32_t v = base[i0];
+        if (v) smem_or(&s_union[i0 % npw], v);
     }
-    c = warp_sum(c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_total, c);
     __syncthreads();
-    if (threadIdx.x == 0) union_count[e] = s_total;
+    int c = 0;
+    for (int w = threadIdx.x; w < npw; w += blockDim.x) c += __popc(s_union[w]);
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(reinterpret_cast<int*>(&s_union[npw]), c);
+    __syncthreads();
+    if (threadIdx.x == 0) union_count[e] = (int)s_union[npw];
 }
 
 // --------------------------------------------------------------------------------------------
@@ -491,8 +528,12 @@ int marsb200_pool_packed(const uint32_t* bits, int64_t n, int H, int W, int g, u
     const int npw = ceil_div(g * g, 32);
     const int64_t wpm = marsb200_words_per_mask((int64_t)H * W);
     MARS_REQUIRE(n < (1ll << 31), "too many masks");
-    pool_packed_kernel<<<(unsigned)n, 256, (npw + 2) * sizeof(uint32_t), as_stream(stream)>>>(
-        bits, n, H, W, g, wpm, npw, pooled, area, pooled_count);
+    MARS_REQUIRE((int64_t)H * W < (1ll << 31), "mask too large");
+    const int rw = W / 32 + 2;  // row-aligned bit row: ceil(W/32) words + 1 spill word
+    const size_t smem = ((size_t)g * rw + npw + 2) * sizeof(uint32_t);
+    MARS_REQUIRE(smem <= 48 * 1024, "g * W too large for the pooling scratch");
+    pool_packed_kernel<<<(unsigned)n, POOL_THREADS, smem, as_stream(stream)>>>(bits, n, H, W, g, wpm, npw, rw, pooled,
+                                                                             area, pooled_count);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }
@@ -506,7 +547,7 @@ int marsb200_region_sums(const uint32_t* pooled, int E, int P, int N, const floa
     region_sums_kernel<<<(unsigned)ceil_div64(total, 8), 256, 0, as_stream(stream)>>>(pooled, total, P, N, npw, vva, vta,
                                                                                       sum_vva, sum_vta);
     MARS_LAUNCH_OK();
-    union_count_kernel<<<E, 64, 0, as_stream(stream)>>>(pooled, P, npw, union_count);
+    union_count_kernel<<<E, 256, (npw + 1) * sizeof(uint32_t), as_stream(stream)>>>(pooled, P, npw, union_count);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }

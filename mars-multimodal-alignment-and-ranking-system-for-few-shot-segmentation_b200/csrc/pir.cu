@@ -143,8 +143,18 @@ __global__ void __launch_bounds__(128) colsum_partial_kernel(const float* __rest
     partial[(e * COLSUM_SPLITS + split) * N + col] = acc;
 }
 
+__global__ void colsum_final_kernel(const double* __restrict__ partial, int N, float* __restrict__ colsum) {
+    const int64_t e = blockIdx.y;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= N) return;
+    double cs = 0.0;
+#pragma unroll
+    for (int s = 0; s < COLSUM_SPLITS; ++s) cs += partial[(e * COLSUM_SPLITS + s) * N + col];
+    colsum[e * N + col] = (float)cs;
+}
+
 __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restrict__ attn, int64_t ld, int N,
-                                                            const double* __restrict__ partial, int64_t n_pad,
+                                                            const float* __restrict__ colsum, int64_t n_pad,
                                                             int64_t k_pad, float* __restrict__ D,
                                                             float* __restrict__ hi, float* __restrict__ lo) {
     __shared__ double s_red[8];
@@ -163,10 +173,7 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restr
     float* d = D + (e * N + row) * k_pad;
     double acc = 0.0;
     for (int c = threadIdx.x; c < N; c += blockDim.x) {
-        double cs = 0.0;
-#pragma unroll
-        for (int s = 0; s < COLSUM_SPLITS; ++s) cs += partial[(e * COLSUM_SPLITS + s) * N + c];
-        const float v = __fdiv_rn(a[c], (float)cs);
+        const float v = __fdiv_rn(a[c], colsum[e * N + c]);
         d[c] = v;
         acc += (double)v;
     }
@@ -211,6 +218,7 @@ struct PirWorkspace {
     float* R;         // [E, N, N]
     float* v;         // [E, N]
     float* t;         // [E, N]
+    float* colsum;    // [E, N]
     int64_t bytes;
 };
 
@@ -233,6 +241,8 @@ static PirWorkspace carve(void* base, int E, int64_t N) {
     w.v = reinterpret_cast<float*>(p + off);
     off += align((int64_t)E * N * 4);
     w.t = reinterpret_cast<float*>(p + off);
+    off += align((int64_t)E * N * 4);
+    w.colsum = reinterpret_cast<float*>(p + off);
     off += align((int64_t)E * N * 4);
     w.bytes = off;
     return w;
@@ -291,7 +301,9 @@ int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, 
 
     colsum_partial_kernel<<<dim3(ceil_div(N, 128), COLSUM_SPLITS, E), 128, 0, s>>>(attn, ld_attn, N, w.partial);
     MARS_LAUNCH_OK();
-    row_normalize_kernel<<<dim3((unsigned)n_pad, E), 256, 0, s>>>(attn, ld_attn, N, w.partial, n_pad, k_pad, w.D, w.hi,
+    colsum_final_kernel<<<dim3(ceil_div(N, 128), E), 128, 0, s>>>(w.partial, N, w.colsum);
+    MARS_LAUNCH_OK();
+    row_normalize_kernel<<<dim3((unsigned)n_pad, E), 256, 0, s>>>(attn, ld_attn, N, w.colsum, n_pad, k_pad, w.D, w.hi,
                                                                     w.lo);
     MARS_LAUNCH_OK();
 
@@ -306,6 +318,7 @@ int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, 
     ep.ld_out = N;
     ep.ld_max = k_pad;
     ep.tiles_m = (int)(n_pad / GEMM_BM);
+    ep.symmetric = (backend == MARSB200_GEMM_TCGEN05) ? 1 : 0;  // D D^T: compute the upper triangle only
     int rc;
     if (backend == MARSB200_GEMM_SIMT)
         rc = gemm_simt(w.hi, w.lo, w.hi, w.lo, E, N, N, N, ep, s);

@@ -40,7 +40,7 @@ def kernel_launches_per_run(cfg: RankingConfig) -> int:
     n += 1                     # pool_mask
     n += 1                     # sim_contract
     n += 1                     # vva_finalize
-    n += 2 * (1 + 2 + 1 + 2)   # two PIR passes: box mask, colsum+rownorm, contraction, two mat-vecs
+    n += 2 * (1 + 3 + 1 + 2)   # two PIR passes: box mask, colsum x2 + rownorm, contraction, two mat-vecs
     n += 1                     # min-max of the refined vva
     n += 1                     # resize + min-max of the vta
     n += 1                     # pack
