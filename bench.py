@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--e2e-episodes-per-step", type=int, default=2)
     ap.add_argument("--mask-dtype", default="f32", choices=["f32", "u8"])
     ap.add_argument("--nms", type=float, default=0.7)
+    ap.add_argument("--fused-ingest", action="store_true", help="one-pass pack + pairwise kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-episodes", type=int, default=2)
@@ -165,7 +166,7 @@ def run_ours(args):
 
     shape = marsb200.CONFIGS[args.workload]
     md = torch.float32 if args.mask_dtype == "f32" else torch.uint8
-    cfg = marsb200.RankingConfig(nms_iou_threshold=args.nms)
+    cfg = marsb200.RankingConfig(nms_iou_threshold=args.nms, fused_ingest=args.fused_ingest)
     E = args.episodes_per_step
     eng = marsb200.RankingEngine(shape, E, cfg, dev, md)
 
@@ -223,6 +224,8 @@ def run_ours(args):
     iters = max(4, min(args.steps, 20))
     pack_ms = time_kernel(lambda i: ops.pack_masks(batches[i % n_batches]["masks"], out=eng.bits), iters)
     pair_ms = time_kernel(lambda i: ops.pairwise_inter(eng.bits, backend=cfg.pair_backend, out=eng.inter), iters)
+    fused_ms = time_kernel(lambda i: ops.pack_pairwise(batches[i % n_batches]["masks"], backend=cfg.pair_backend,
+                                                       out=(eng.bits, eng.inter)), iters)
     hw = shape.H * shape.W
     wpm = ops.words_per_mask(hw)
     pack_bytes = E * shape.P * (hw * (4 if md == torch.float32 else 1) + wpm * 4)
@@ -234,6 +237,9 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": pack_bytes, "ms_per_launch": pack_ms}
     pairwise = {"kernel": "pairwise_inter", "unordered_pairs_per_s": pairs / (pair_ms / 1e3), "ms_per_launch": pair_ms,
                 "word_ops_per_s": pairs * wpm / (pair_ms / 1e3)}
+    fused = {"kernel": "pack_pairwise (one pass: packed bits + intersections)", "ms_per_launch": fused_ms,
+             "achieved_gbs": pack_bytes / (fused_ms / 1e3) / 1e9, "frac_of_hbm_peak": pack_bytes / (fused_ms / 1e3) / 1e9 / peak,
+             "unordered_pairs_per_s": pairs / (fused_ms / 1e3)}
 
     # ---- end to end: pinned host inputs -> H2D -> ranking -> D2H of the result records, every step
     e2e = None
@@ -289,10 +295,11 @@ def run_ours(args):
                        "input_bytes_per_step_per_gpu": bytes_per_step,
                        "l2": "two resident batches alternate; each step's inputs exceed the 126 MB L2",
                        "gemm_backend": "tcgen05" if ops.DEFAULT_GEMM == ops.GEMM_TCGEN05 else "simt",
-                       "pair_backend": "popc" if ops.DEFAULT_PAIR == ops.PAIR_POPC else "mma"},
+                       "pair_backend": "popc" if ops.DEFAULT_PAIR == ops.PAIR_POPC else "mma",
+                       "fused_ingest": bool(args.fused_ingest)},
             "clocks": clocks, "e2e": e2e,
             "gpu_launches": marsb200.kernel_launches_per_run(cfg) * args.steps * world,
-            "roofline": roofline, "pairwise": pairwise, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "pairwise": pairwise, "fused_ingest": fused, "cpu_baseline": cpu_baseline,
         }))
     if world > 1:
         dist.destroy_process_group()

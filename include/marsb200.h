@@ -127,6 +127,14 @@ int marsb200_region_sums(const uint32_t* pooled, int E, int P, int N, const floa
 int marsb200_pairwise_inter(const uint32_t* bits, int E, int P, int64_t words_per_mask, int32_t* inter,
                             int backend, void* stream);
 
+/* Fused ingest: bits = pack(masks) AND inter = pairwise intersections in ONE pass over the masks
+ * (float32 masks, P <= 256, tensor-core back end: the masks are read once at HBM rate and the int8 MMAs run
+ * underneath the stream).  Other shapes / dtypes / back ends run marsb200_pack_masks followed by
+ * marsb200_pairwise_inter internally, so the call is always valid.  masks [E, P, HW]; bits [E, P, wpm];
+ * inter [E, P, P]. */
+int marsb200_pack_pairwise(const void* masks, int mask_dtype, int E, int P, int64_t HW, uint32_t* bits,
+                           int32_t* inter, int pair_backend, void* stream);
+
 /* ---- A8: AlphaCLIP cosine scores -----------------------------------------------------------
  * clip[e,p] = img[e,p,:] . txt[e,:].  Replaces img_feats @ text_feats.T, FilteringMergingModule.py:97. */
 int marsb200_clip_scores(const float* img, const float* txt, int E, int P, int D, float* out, void* stream);

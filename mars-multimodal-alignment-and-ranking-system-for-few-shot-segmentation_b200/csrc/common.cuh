@@ -43,6 +43,12 @@ __host__ __device__ static inline int bin_end(int i, int L, int g) { return (int
 __host__ __device__ static inline int bin_lo_of(int x, int L, int g) { return (int)(((int64_t)x * g) / L); }
 __host__ __device__ static inline int bin_hi_of(int x, int L, int g) { return (int)((((int64_t)x + 1) * g + L - 1) / L) - 1; }
 
+// 32-bit variants for device hot loops (valid while L <= 32768 and g <= 4096: products stay below 2^31)
+__device__ __forceinline__ int bin_start32(int i, int L, int g) { return (int)((uint32_t)(i * L) / (uint32_t)g); }
+__device__ __forceinline__ int bin_end32(int i, int L, int g) { return (int)((uint32_t)((i + 1) * L + g - 1) / (uint32_t)g); }
+__device__ __forceinline__ int bin_lo_of32(int x, int L, int g) { return (int)((uint32_t)(x * g) / (uint32_t)L); }
+__device__ __forceinline__ int bin_hi_of32(int x, int L, int g) { return (int)((uint32_t)((x + 1) * g + L - 1) / (uint32_t)L) - 1; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -19,7 +19,7 @@ __global__ void clip_scores_kernel(const float* __restrict__ img, const float* _
 }
 
 // block-wide reductions through shared memory (blockDim.x == FUSE_THREADS)
-constexpr int FUSE_THREADS = 256;
+constexpr int FUSE_THREADS = 1024;
 
 template <typename T, typename Op>
 __device__ T block_reduce(T v, Op op, T* scratch) {

@@ -155,12 +155,16 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_packed_kernel(const uint32_
     uint32_t* binrow = s_mem_pool;             // g * rw
     uint32_t* s_pool = binrow + g * rw;        // npw
     int* s_cnt = reinterpret_cast<int*>(s_pool + npw);  // 2
+    uint16_t* s_rowbins = reinterpret_cast<uint16_t*>(s_cnt + 2);  // H: first | last << 8 patch-row bin of row y
     const int64_t m = blockIdx.x;
     for (int i = threadIdx.x; i < g * rw + npw + 2; i += POOL_THREADS) s_mem_pool[i] = 0;
+    for (int y = threadIdx.x; y < H; y += POOL_THREADS)
+        s_rowbins[y] = (uint16_t)(bin_lo_of32(y, H, g) | (bin_hi_of32(y, H, g) << 8));
     __syncthreads();
 
     const uint4* row = reinterpret_cast<const uint4*>(bits + m * wpm);
     const int quads = (int)(wpm / 4);
+    const int quads_per_row = (W % 128 == 0) ? W / 128 : 0;  // > 0 selects the word-aligned fast path
     int my_area = 0;
     for (int q0 = threadIdx.x; q0 < quads; q0 += POOL_THREADS * POOL_UNROLL) {
         uint4 v[POOL_UNROLL];
@@ -173,12 +177,28 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_packed_kernel(const uint32_
         for (int u = 0; u < POOL_UNROLL; ++u) {
             if ((v[u].x | v[u].y | v[u].z | v[u].w) == 0) continue;
             const uint32_t words[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            const uint32_t quad = (uint32_t)(q0 + u * POOL_THREADS);
+            if (quads_per_row > 0) {
+                // W % 128 == 0: the four words sit in one image row, word-aligned with the bit rows
+                const uint32_t y = quad / (uint32_t)quads_per_row;
+                if ((int)y < H) {
+                    const int wi0 = (int)(quad - y * (uint32_t)quads_per_row) * 4;
+                    const int rb = s_rowbins[y];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (words[k] == 0) continue;
+                        my_area += __popc(words[k]);
+                        for (int jy = rb & 0xff; jy <= (rb >> 8); ++jy) smem_or(&binrow[jy * rw + wi0 + k], words[k]);
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 uint32_t word = words[k];
                 if (word == 0) continue;
                 my_area += __popc(word);
-                const uint32_t px = ((uint32_t)(q0 + u * POOL_THREADS) * 4u + k) * 32u;
+                const uint32_t px = (quad * 4u + k) * 32u;
                 int y = (int)(px / (uint32_t)W);
                 int x = (int)(px - (uint32_t)y * (uint32_t)W);
                 int left = 32;
@@ -189,7 +209,8 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_packed_kernel(const uint32_
                         const int wi = x >> 5, sh = x & 31;
                         const uint32_t lo = seg << sh;
                         const uint32_t hi = sh ? (seg >> (32 - sh)) : 0u;
-                        const int jy0 = bin_lo_of(y, H, g), jy1 = bin_hi_of(y, H, g);
+                        const int rb = s_rowbins[y];
+                        const int jy0 = rb & 0xff, jy1 = rb >> 8;
                         for (int jy = jy0; jy <= jy1; ++jy) {
                             if (lo) smem_or(&binrow[jy * rw + wi], lo);
                             if (hi) smem_or(&binrow[jy * rw + wi + 1], hi);
@@ -208,7 +229,7 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_packed_kernel(const uint32_
     __syncthreads();
     for (int b = threadIdx.x; b < g * g; b += POOL_THREADS) {
         const int jy = b / g, jx = b - jy * g;
-        const int xs = bin_start(jx, W, g), xe = bin_end(jx, W, g);  // [xs, xe)
+        const int xs = bin_start32(jx, W, g), xe = bin_end32(jx, W, g);  // [xs, xe)
         bool hit = false;
         for (int wi = xs >> 5; wi <= (xe - 1) >> 5; ++wi) {
             const int lo = max(xs - wi * 32, 0), hi = min(xe - wi * 32, 32);
@@ -530,7 +551,8 @@ int marsb200_pool_packed(const uint32_t* bits, int64_t n, int H, int W, int g, u
     MARS_REQUIRE(n < (1ll << 31), "too many masks");
     MARS_REQUIRE((int64_t)H * W < (1ll << 31), "mask too large");
     const int rw = W / 32 + 2;  // row-aligned bit row: ceil(W/32) words + 1 spill word
-    const size_t smem = ((size_t)g * rw + npw + 2) * sizeof(uint32_t);
+    MARS_REQUIRE(g <= 255 && H <= 32768 && W <= 32768, "g <= 255, H, W <= 32768");
+    const size_t smem = ((size_t)g * rw + npw + 2) * sizeof(uint32_t) + (size_t)H * sizeof(uint16_t);
     MARS_REQUIRE(smem <= 48 * 1024, "g * W too large for the pooling scratch");
     pool_packed_kernel<<<(unsigned)n, POOL_THREADS, smem, as_stream(stream)>>>(bits, n, H, W, g, wpm, npw, rw, pooled,
                                                                              area, pooled_count);

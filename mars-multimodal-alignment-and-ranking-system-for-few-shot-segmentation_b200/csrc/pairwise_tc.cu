@@ -122,6 +122,18 @@ pairwise_mma_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int b
                 const uint32_t a_base = diagonal ? st : st + PM_TILE_BYTES;
                 for (int mt = 0; mt < m_tiles; ++mt) {
                     const uint64_t a_desc = make_sw128_kmajor_desc(a_base + mt * 128 * 128);
+                    if (diagonal && mt == 1) {
+                        // symmetric block: rows 128..255 only need columns 128..255 (N = 128); the lower-left
+                        // quarter is the mirror of what m-tile 0 computed
+                        constexpr uint32_t idesc_half = make_idesc(2, 0, 0, 128, 128);
+                        const uint64_t b_half = make_sw128_kmajor_desc(st + 128 * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            mma_i8(tmem_acc + PM_ROWS + 128, a_desc + adv, b_half + adv, idesc_half, (i | k) != 0);
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {  // 32 bytes (= 32 u8 elements) per MMA
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);
@@ -145,6 +157,8 @@ pairwise_mma_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int b
             const int i = bi * PM_ROWS + mt * 128 + quad * 32 + lane;
             for (int c = 0; c < 4; ++c) {
                 const int col0 = half * 128 + c * 32;
+                if (diagonal && mt == 1 && col0 < 128) continue;  // not computed: mirrored from m-tile 0 below
+                const bool mirror = !diagonal || (mt == 0 && col0 >= 128);
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * PM_ROWS + col0), v);
                 tmem_ld_wait();
@@ -155,7 +169,7 @@ pairwise_mma_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int b
                         const int val = (int)v[q];
                         if (j < P && val != 0) {
                             atomicAdd(&out[(int64_t)i * P + j], val);
-                            if (!diagonal) atomicAdd(&out[(int64_t)j * P + i], val);
+                            if (mirror) atomicAdd(&out[(int64_t)j * P + i], val);
                         }
                     }
                 }

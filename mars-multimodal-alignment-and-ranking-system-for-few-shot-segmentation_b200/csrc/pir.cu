@@ -195,17 +195,21 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restr
     }
 }
 
-// y[e, i] = sum_j R[e, i, j] x[e, j]; one warp per row, double accumulation.
-__global__ void __launch_bounds__(256) matvec_kernel(const float* __restrict__ R, int64_t ld, int N,
-                                                     const float* __restrict__ x, float* __restrict__ y) {
+// y[e, i] = sum_j max(D[e, i, j], G[e, i, j]) x[e, j] = (R x)_i with R = max(D, D D^T) formed on the fly
+// (PriorInformationRefinementModule.py:74-75); one warp per row, double accumulation.  Keeping the max out of
+// the contraction's epilogue keeps that epilogue store-only: its loads would queue behind the operand feed.
+__global__ void __launch_bounds__(256) matvec_kernel(const float* __restrict__ G, int64_t ld, const float* __restrict__ D,
+                                                     int64_t ld_d, int N, const float* __restrict__ x,
+                                                     float* __restrict__ y) {
     const int lane = threadIdx.x & 31;
     const int64_t e = blockIdx.y;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= N) return;
-    const float* r = R + (e * N + row) * ld;
+    const float* r = G + (e * N + row) * ld;
+    const float* d = D + (e * N + row) * ld_d;
     const float* xv = x + e * N;
     double acc = 0.0;
-    for (int j = lane; j < N; j += 32) acc += (double)r[j] * (double)xv[j];
+    for (int j = lane; j < N; j += 32) acc += (double)fmaxf(d[j], r[j]) * (double)xv[j];
     acc = warp_sum(acc);
     if (lane == 0) y[e * N + row] = (float)acc;
 }
@@ -215,7 +219,7 @@ struct PirWorkspace {
     float* D;         // [E, N, k_pad]
     float* hi;        // [E, n_pad, k_pad]
     float* lo;        // [E, n_pad, k_pad]
-    float* R;         // [E, N, N]
+    float* R;         // [E, N, N]: G = D D^T (the max with D is taken in the mat-vecs)
     float* v;         // [E, N]
     float* t;         // [E, N]
     float* colsum;    // [E, N]
@@ -310,7 +314,7 @@ int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, 
     GemmEpilogue ep{};
     ep.out0 = w.R;
     ep.out1 = nullptr;
-    ep.maxwith = w.D;
+    ep.maxwith = nullptr;  // R = max(D, G) is applied inside the mat-vecs
     ep.row_fg = nullptr;
     ep.colstats = nullptr;
     ep.M = N;
@@ -329,9 +333,9 @@ int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, 
     if (rc != MARSB200_OK) return rc;
 
     dim3 mv_grid(ceil_div(N, 8), E);
-    matvec_kernel<<<mv_grid, 256, 0, s>>>(w.R, N, N, w.v, w.t);
+    matvec_kernel<<<mv_grid, 256, 0, s>>>(w.R, N, w.D, k_pad, N, w.v, w.t);
     MARS_LAUNCH_OK();
-    matvec_kernel<<<mv_grid, 256, 0, s>>>(w.R, N, N, w.t, out);
+    matvec_kernel<<<mv_grid, 256, 0, s>>>(w.R, N, w.D, k_pad, N, w.t, out);
     MARS_LAUNCH_OK();
     if (apply_minmax) return minmax_rows(out, E, N, s);
     return MARSB200_OK;

@@ -33,6 +33,33 @@ __global__ void __launch_bounds__(256) normalize_split_kernel(const float* __res
         return;
     }
     const float* src = x + (e * rows + r) * ld_x;
+    // fast path: 16-byte aligned rows of at most 1024 floats stay in registers (one read of x)
+    if (k <= 1024 && (k & 3) == 0 && (ld_x & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        constexpr int MAXV = 1024 / 128;  // float4 per lane
+        float4 v[MAXV];
+        const int nvec = (int)(k >> 2);
+        double ss = 0.0;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = i * 32 + lane;
+            v[i] = (c < nvec) ? __ldg(reinterpret_cast<const float4*>(src) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ss += (double)v[i].x * v[i].x + (double)v[i].y * v[i].y + (double)v[i].z * v[i].z + (double)v[i].w * v[i].w;
+        }
+        float denom = 1.f;
+        if (normalize) denom = fmaxf((float)sqrt(warp_sum(ss)), 1e-12f);
+        const int nvec_pad = (int)(k_pad >> 2);
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = i * 32 + lane;
+            if (c >= nvec_pad) continue;
+            float4 a = v[i];
+            if (normalize) a = make_float4(__fdiv_rn(a.x, denom), __fdiv_rn(a.y, denom), __fdiv_rn(a.z, denom), __fdiv_rn(a.w, denom));
+            const float4 hh = make_float4(round_tf32(a.x), round_tf32(a.y), round_tf32(a.z), round_tf32(a.w));
+            reinterpret_cast<float4*>(h)[c] = hh;
+            reinterpret_cast<float4*>(l)[c] = make_float4(a.x - hh.x, a.y - hh.y, a.z - hh.z, a.w - hh.w);
+        }
+        return;
+    }
     float denom = 1.f;
     if (normalize) {
         double ss = 0.0;

@@ -30,6 +30,8 @@ class RankingConfig:
     want_sim: bool = False             # export S like VisualVisualAlignmentModule.similarity_matrix
     want_cost: bool = False            # export (1 - S) / 2 (the EMD cost)
     want_merged_f32: bool = True       # the float32 [H, W] map the reference returns
+    overlap_streams: bool = True       # mask chain (HBM-bound) on a second stream beside the contractions
+    fused_ingest: bool = False         # one-pass pack + pairwise kernel (owns all TMEM: cannot overlap the contractions)
     gemm_backend: Optional[int] = None
     pair_backend: Optional[int] = None
 
@@ -43,11 +45,11 @@ def kernel_launches_per_run(cfg: RankingConfig) -> int:
     n += 2 * (1 + 3 + 1 + 2)   # two PIR passes: box mask, colsum x2 + rownorm, contraction, two mat-vecs
     n += 1                     # min-max of the refined vva
     n += 1                     # resize + min-max of the vta
-    n += 1                     # pack
+    n += 1                     # pack (memset not counted)
+    if cfg.nms_iou_threshold is not None and not cfg.fused_ingest:
+        n += 1                 # pairwise intersections (part of the pack kernel with fused_ingest)
     n += 1                     # pool_packed
     n += 2                     # region sums + union count
-    if cfg.nms_iou_threshold is not None:
-        n += 1                 # pairwise intersections (memset not counted)
     n += 1                     # clip scores
     n += 1                     # fuse / rank / nms / select
     n += 1                     # merge
@@ -93,11 +95,50 @@ class RankingEngine:
             self.merge_out["f32"] = new((e, s.H * s.W), f32)
         self._graph = None
         self._static = None
+        self._side = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
+        self._side2 = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
+        self._ev_fork = torch.cuda.Event()
+        self._ev_join = torch.cuda.Event()
+        self._ev_pack = torch.cuda.Event()
+        self._ev_pool = torch.cuda.Event()
 
     # ------------------------------------------------------------------ the kernel sequence
+    def _mask_chain(self, batch: dict):
+        """Ingest side: pack -> pooled bitmaps / areas -> pairwise intersections (depends on the masks only)."""
+        s, cfg = self.shape, self.cfg
+        if self.inter is not None and cfg.fused_ingest:
+            # one pass over the masks: packed bits + intersections (falls back to two kernels when not fusable)
+            ops.pack_pairwise(batch["masks"], backend=cfg.pair_backend, out=(self.bits, self.inter))
+            ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
+            return
+        ops.pack_masks(batch["masks"], out=self.bits)
+        if self.inter is None:
+            ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
+        elif self._side2 is None:
+            ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
+            ops.pairwise_inter(self.bits, backend=cfg.pair_backend, out=self.inter)
+        else:
+            # pooling (re-reads the bits, HBM/issue-bound) runs beside the tensor-core pairwise kernel
+            cur = torch.cuda.current_stream()
+            self._ev_pack.record(cur)
+            self._side2.wait_event(self._ev_pack)
+            with torch.cuda.stream(self._side2):
+                ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
+                self._ev_pool.record(self._side2)
+            ops.pairwise_inter(self.bits, backend=cfg.pair_backend, out=self.inter)
+            cur.wait_event(self._ev_pool)
+
     def run(self, batch: dict) -> dict:
         s, e, cfg = self.shape, self.E, self.cfg
         n, m = s.N, s.ns * s.N
+        main = torch.cuda.current_stream()
+        if self._side is not None:
+            # the mask chain is HBM-bound and the alignment chain tensor/L2-bound: let them share the SMs
+            self._ev_fork.record(main)
+            self._side.wait_event(self._ev_fork)
+            with torch.cuda.stream(self._side):
+                self._mask_chain(batch)
+                self._ev_join.record(self._side)
         ops.normalize_split(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
         ops.normalize_split(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
         ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
@@ -109,12 +150,12 @@ class RankingEngine:
         ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
                        backend=cfg.gemm_backend, workspace=self.pir_ws, out=self.vta_ref)
         ops.resize_minmax(self.vta_ref.reshape(e, s.gt, s.gt), s.g, True, out=self.vta)
-        ops.pack_masks(batch["masks"], out=self.bits)
-        ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
-        ops.region_sums(self.pool_out[0], self.vva, self.vta, out=self.region_out)
-        if self.inter is not None:
-            ops.pairwise_inter(self.bits, backend=cfg.pair_backend, out=self.inter)
         ops.clip_scores(batch["clip_img"], batch["clip_txt"], out=self.clip)
+        if self._side is not None:
+            main.wait_event(self._ev_join)
+        else:
+            self._mask_chain(batch)
+        ops.region_sums(self.pool_out[0], self.vva, self.vta, out=self.region_out)
         ops.fuse_rank(batch["emd"], self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
                       self.region_out[2], self.inter, cfg.alpha, cfg.static_threshold, cfg.dynamic_threshold,
                       cfg.nms_iou_threshold, out=self.rank_out)

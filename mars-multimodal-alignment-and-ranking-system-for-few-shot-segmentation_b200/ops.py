@@ -17,7 +17,7 @@ from ._lib import GEMM_SIMT, GEMM_TCGEN05, MASK_F32, MASK_U8, PAIR_MMA, PAIR_POP
 
 __all__ = [
     "words_per_mask", "pad_rows", "pad_k", "normalize_split", "pool_mask", "sim_contract", "vva_finalize",
-    "attn_mean", "pir_refine", "resize_minmax", "pack_masks", "pool_packed", "region_sums", "pairwise_inter",
+    "attn_mean", "pir_refine", "resize_minmax", "pack_masks", "pack_pairwise", "pool_packed", "region_sums", "pairwise_inter",
     "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas",
     "GEMM_TCGEN05", "GEMM_SIMT", "PAIR_POPC", "PAIR_MMA",
 ]
@@ -25,7 +25,7 @@ __all__ = [
 # default back ends (module-level so tests can pin either one)
 # (MARSB200_GEMM=simt / MARSB200_PAIR=popc|mma select the validation kernels, for debugging only)
 DEFAULT_GEMM = GEMM_SIMT if os.environ.get("MARSB200_GEMM", "") == "simt" else GEMM_TCGEN05
-DEFAULT_PAIR = PAIR_MMA if os.environ.get("MARSB200_PAIR", "") == "mma" else PAIR_POPC
+DEFAULT_PAIR = PAIR_POPC if os.environ.get("MARSB200_PAIR", "") == "popc" else PAIR_MMA
 
 
 def _stream() -> int:
@@ -242,6 +242,23 @@ def pairwise_inter(bits: torch.Tensor, backend=None, out=None) -> torch.Tensor:
     check(lib.marsb200_pairwise_inter(bits.data_ptr(), e, p, wpm, out.data_ptr(),
                                       DEFAULT_PAIR if backend is None else backend, _stream()))
     return out
+
+
+def pack_pairwise(masks: torch.Tensor, backend=None, out=None):
+    """masks [E, P, H, W] -> (bits [E, P, wpm], inter [E, P, P]) in one pass over the masks when possible."""
+    m, dt = _mask_tensor(masks)
+    if m.dim() == 3:
+        m = m[None]
+    e, p, h, w = m.shape
+    wpm = words_per_mask(h * w)
+    if out is None:
+        bits = torch.empty((e, p, wpm), device=m.device, dtype=torch.int32)
+        inter = torch.empty((e, p, p), device=m.device, dtype=torch.int32)
+    else:
+        bits, inter = out
+    check(lib.marsb200_pack_pairwise(m.data_ptr(), dt, e, p, h * w, bits.data_ptr(), inter.data_ptr(),
+                                     DEFAULT_PAIR if backend is None else backend, _stream()))
+    return bits, inter
 
 
 # ----------------------------------------------------------------------------- A8 / A10 / A11

@@ -121,6 +121,20 @@ def test_pairwise_batched_episodes(mb, backend):
         assert torch.equal(inter[e], orc.pairwise_intersections(masks[e])[0])
 
 
+@pytest.mark.parametrize("e,p,h,dtype", [(1, 9, 100, torch.float32), (2, 200, 96, torch.float32),
+                                           (3, 256, 64, torch.float32), (1, 130, 518, torch.float32),
+                                           (1, 300, 64, torch.float32),   # P > 256 -> two-kernel path
+                                           (2, 64, 96, torch.uint8)])     # u8 -> two-kernel path
+def test_fused_pack_pairwise(mb, e, p, h, dtype):
+    masks = cases.blob_masks(e * p, h, h, seed=3 * p + e, min_frac=0.01, max_frac=0.3, dup_every=5).reshape(e, p, h, h)
+    bits, inter = mb.ops.pack_pairwise(masks.to(dtype).to(dev()), backend=mb.ops.PAIR_MMA)
+    wpm = mb.ops.words_per_mask(h * h)
+    np.testing.assert_array_equal(bits.cpu().numpy().view(np.uint32).reshape(e * p, wpm),
+                                  np_pack(masks.reshape(e * p, h, h).numpy(), wpm))
+    for i in range(e):
+        assert torch.equal(inter[i].cpu(), orc.pairwise_intersections(masks[i])[0])
+
+
 # ------------------------------------------------------------------------------------------ VVA
 def _backends(mb):
     return [mb.ops.GEMM_SIMT, mb.ops.GEMM_TCGEN05]
