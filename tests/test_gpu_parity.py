@@ -464,3 +464,108 @@ def test_evaluator_areas(mb):
         out = mb.ops.eval_areas(pred.to(dev()), gt.to(dev()), None if ig is None else ig.to(dev())).cpu()
         np.testing.assert_array_equal(out[:, :2].numpy(), inter_ref.t().numpy().astype(np.int32))
         np.testing.assert_array_equal(out[:, 2:].numpy(), union_ref.t().numpy().astype(np.int32))
+
+
+# ------------------------------------------------------------------------------------------ other BASELINE configs
+def test_engine_5shot_c3_like(mb):
+    """5-shot episodes (BASELINE config 3 geometry at a reduced size): shot-major support rows, T > N possible."""
+    shape = mb.EpisodeShape(ns=5, g=12, C=96, P=40, H=168, W=168, gt=9, D=48)
+    cfg = mb.RankingConfig(nms_iou_threshold=0.6)
+    eps, eng, out = _run_engine(mb, shape, 2, cfg)
+    for e in range(2):
+        _check_episode(mb, shape, cfg, eps[e], out, e)
+
+
+def test_high_proposal_c4_like(mb):
+    """P = 1000 (BASELINE config 4) at a reduced resolution: multi-block tensor-core pairwise + bitmask NMS."""
+    p, h = 1000, 128
+    masks = cases.blob_masks(p, h, h, seed=4242, min_frac=0.01, max_frac=0.25, dup_every=9)
+    inter_ref, area_ref = orc.pairwise_intersections(masks)
+    d = dev()
+    bits = mb.ops.pack_masks(masks.to(d))[None]
+    for backend in (mb.ops.PAIR_MMA, mb.ops.PAIR_POPC):
+        assert torch.equal(mb.ops.pairwise_inter(bits, backend=backend)[0].cpu(), inter_ref)
+    inter = mb.ops.pairwise_inter(bits)
+    rs = np.random.RandomState(7)
+    scores = rs.rand(p)
+    cnt = torch.ones((1, p), dtype=torch.int32, device=d)
+    sv = torch.as_tensor(2 * scores, dtype=torch.float32, device=d).reshape(1, p)
+    uc = torch.ones((1,), dtype=torch.int32, device=d)
+    zero = torch.zeros((1, p), device=d)
+    res = mb.ops.fuse_rank(zero.double(), zero, cnt, sv, sv, uc, inter, alpha=1.0, static_threshold=0.9,
+                           dynamic_threshold=0.5, nms_iou_threshold=0.7)
+    s32 = (2 * scores).astype(np.float32).astype(np.float64) / (1e-7 + 1)
+    fused = (s32 + s32) / 4
+    order_expected = orc.stable_rank(fused)
+    np.testing.assert_array_equal(res["order"][0].cpu().numpy(), order_expected)
+    keep_expected = orc.mask_nms(order_expected, inter_ref, area_ref, 0.7)
+    flags = res["flags"][0].cpu().numpy()
+    np.testing.assert_array_equal((flags & 1).astype(bool), keep_expected)
+    sel_expected = np.zeros(p, dtype=bool)
+    sel_ranked = orc.merge_select(fused[order_expected], 0.9, 0.5) & keep_expected[order_expected]
+    sel_expected[order_expected[sel_ranked]] = True
+    np.testing.assert_array_equal((flags & 2) > 0, sel_expected)
+    _, merged = mb.ops.merge_masks(bits, res["flags"], h * h)
+    ref = orc.merge_masks(masks, np.nonzero(sel_expected)[0])
+    np.testing.assert_array_equal(merged.reshape(h, h).cpu().numpy() > 0, ref.numpy() > 0)
+
+
+def test_mars_predict_dropin(mb):
+    """MARS.predict with fake PyTorch producers: same composition as mars/MARS.py:33-104, checked against the oracle."""
+    spec = cases.VVA_CASES["g10_2shot"]
+    c = cases.vva_inputs(spec)
+    g, h, ns, cdim, regs = spec["g"], spec["H"], spec["ns"], spec["C"], spec["regs"]
+    p = 14
+    masks = cases.blob_masks(p, h, h, seed=91, min_frac=0.02, max_frac=0.3)
+    gen = torch.Generator().manual_seed(17)
+    vta_raw = torch.rand(8, 8, generator=gen)
+    img = torch.nn.functional.normalize(torch.randn(p, 24, generator=gen), dim=1)
+    txt = torch.nn.functional.normalize(torch.randn(24, generator=gen), dim=0)
+    emd = torch.rand(p, generator=gen, dtype=torch.float64)
+
+    class FakeDino(torch.nn.Module):
+        embed_dim = cdim
+
+        def __init__(self):
+            super().__init__()
+            pad = lambda f: torch.cat([torch.zeros(f.shape[0], 1 + regs, cdim), f], dim=1).to(dev())
+            self.feats = [pad(c["feat_s"]), pad(c["feat_q"][None])]
+
+        def forward_features(self, imgs):
+            return {"x_prenorm": self.feats.pop(0)}
+
+        def get_last_self_attention(self, img):
+            return tuple(a.to(dev()) for a in c["attn_maps"])
+
+    class FakeText:
+        def get_conceptual_information(self, support_images, support_masks):
+            return "thing", ""
+
+    class FakeVTA:
+        def compute(self, query_image, fg_label, bg_labels):
+            return vta_raw
+
+    vva_mod = mb.VisualVisualAlignmentModule(FakeDino(), lambda x: x, 14, g, regs, spec["thr"], spec["last_n"], dev())
+    fm = mb.FilteringMergingModule(None, None, None, alpha=0.85, static_threshold=0.55, dynamic_threshold=0.95,
+                                   device=dev())
+    orig = fm.compute
+    fm.compute = lambda **kw: orig(emd_scores=emd.numpy(), alphaclip_feats=(img, txt), **kw)
+    mars = mb.MARS(FakeText(), FakeVTA(), vva_mod, fm)
+    pred = mars.predict(torch.zeros(1, ns, 3, h, h), c["support_mask"][None], torch.zeros(1, 3, h, h), masks)
+    assert mars.time_start_ranking <= mars.time_start_ranking_after_text_extraction <= mars.time_end_ranking
+    # oracle composition of the same stage
+    fs, fq = orc.normalize_rows(c["feat_s"]), orc.normalize_rows(c["feat_q"])
+    bits = orc.pool_mask(c["support_mask"], g).reshape(-1)
+    prior = orc.vva_prior(fs, fq, bits, g)
+    a = orc.attention_mean(c["attn_maps"], spec["last_n"], regs)
+    vva = orc.minmax(orc.pir_refine(prior, a, spec["thr"]))
+    vta = orc.minmax(orc.nearest_resize(vta_raw, (g, g)))
+    pooled, cov, avv, avt = orc.region_scores(masks, vva.numpy(), vta.numpy(), g)
+    scores = orc.fuse_scores(emd.numpy(), orc.clip_scores(img, txt), cov, avv, avt, 0.85)
+    order = orc.stable_rank(scores)
+    sel = orc.merge_select(scores[order], 0.55, 0.95)
+    ref = orc.merge_masks(masks, order[sel])
+    assert_order_matches(fm.last["order"][0].cpu().numpy(), fm.last["scores"][0].cpu().numpy(), order, scores)
+    np.testing.assert_array_equal(pred.cpu().numpy() > 0, ref.numpy() > 0)
+    mars.clear()
+    assert vva_mod.cost_matrix is None
