@@ -45,6 +45,19 @@ def parse_args():
     return ap.parse_args()
 
 
+def ncu_traffic_bytes(kernel, workload, episodes, mask_dtype):
+    """dram read+write bytes per launch of `kernel` from the committed `ncu --set full` capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            for row in json.load(f):
+                if (row["kernel"], row["workload"], row["episodes_per_launch"], row["mask_dtype"]) == \
+                        (kernel, workload, episodes, mask_dtype):
+                    return row["dram_read_bytes"] + row["dram_write_bytes"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -54,30 +67,77 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML in a thread; nvidia-smi as fallback)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self.windows = []  # [t0, t1] perf_counter intervals of the timed regions
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _nvml_loop(self):
+        nv, h = self._nvml
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                t = time.perf_counter()
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.sm.append((t, mhz, [name for name, bit in bits.items() if r & bit]))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map through the UUID torch reports
+            props = torch.cuda.get_device_properties(self.index)
+            uuid = "GPU-" + str(props.uuid) if not str(props.uuid).startswith("GPU-") else str(props.uuid)
+            try:
+                h = nv.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._nvml = (nv, h)
+            self._thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
-            self.thread.start()
+            self._thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self._thread.start()
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self._nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            inside = [x for x in self.sm if any(a <= x[0] <= b for a, b in self.windows)] or self.sm
+            reasons = sorted({r for x in inside for r in x[2]})
+            return {"sm_mhz": statistics.median(x[1] for x in inside) if inside else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(inside), "samples_total": len(self.sm), "reasons": reasons, "source": "nvml",
+                    "note": "samples taken inside the timed regions (device-resident loop and e2e loop)"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source available"]}
         time.sleep(0.15)
         self.proc.terminate()
-        self.thread.join(timeout=2)
+        self._thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -93,7 +153,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def workload_description(shape, args):
@@ -198,12 +258,13 @@ def run_ours(args):
     sampler.start()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.perf_counter()
     start.record()
     for i in range(args.steps):
         step(i)
     stop.record()
     barrier()
-    clocks = sampler.stop()
+    sampler.windows.append((w0, time.perf_counter()))
     elapsed_ms = start.elapsed_time(stop)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev)
@@ -233,7 +294,9 @@ def run_ours(args):
     achieved = pack_bytes / (pack_ms / 1e3) / 1e9
     pairs = E * shape.P * (shape.P + 1) // 2
     roofline = {"kernel": "pack_masks (mask ingest -> packed bits)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic_bytes("pack_f32_vec_kernel" if md == torch.float32 else "pack_u8_vec_kernel",
+                                             args.workload, E, args.mask_dtype),
                 "algorithmic_bytes_per_launch": pack_bytes, "ms_per_launch": pack_ms}
     pairwise = {"kernel": "pairwise_inter", "unordered_pairs_per_s": pairs / (pair_ms / 1e3), "ms_per_launch": pair_ms,
                 "word_ops_per_s": pairs * wpm / (pair_ms / 1e3)}
@@ -242,11 +305,12 @@ def run_ours(args):
              "unordered_pairs_per_s": pairs / (fused_ms / 1e3)}
 
     # ---- end to end: pinned host inputs -> H2D -> ranking -> D2H of the result records, every step
-    e2e = None
-    if not args.no_e2e:
+    def run_e2e(e2e_dtype):
         Ee = args.e2e_episodes_per_step
-        eng2 = marsb200.RankingEngine(shape, Ee, cfg, dev, md)
-        host = {k: v[:Ee].cpu().pin_memory() for k, v in batches[0].items()}
+        eng2 = marsb200.RankingEngine(shape, Ee, cfg, dev, e2e_dtype)
+        host = {k: v[:Ee].cpu() for k, v in batches[0].items()}
+        host["masks"] = host["masks"].to(e2e_dtype)
+        host = {k: v.pin_memory() for k, v in host.items()}
         dev_in = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
         rec_host = torch.empty((Ee, eng2.record_bytes()), dtype=torch.uint8).pin_memory()
         h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -263,20 +327,29 @@ def run_ours(args):
             e2e_step()
         barrier()
         s2, t2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
         s2.record()
         for _ in range(args.steps):
             e2e_step()
         t2.record()
         barrier()
+        sampler.windows.append((w0, time.perf_counter()))
         ms2 = s2.elapsed_time(t2)
         if world > 1:
             t = torch.tensor([ms2], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms2 = float(t.item())
-        e2e = {"value": world * Ee * args.steps / (ms2 / 1e3), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "episodes_per_step": Ee, "ms_per_step": ms2 / args.steps}
-        del eng2, host, dev_in
+        return {"value": world * Ee * args.steps / (ms2 / 1e3), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "episodes_per_step": Ee, "ms_per_step": ms2 / args.steps,
+                "host_mask_dtype": "f32" if e2e_dtype == torch.float32 else "u8"}
 
+    e2e, e2e_variants = None, None
+    if not args.no_e2e:
+        e2e = run_e2e(md)
+        if md == torch.float32:  # the same call with 1-byte host masks (PCIe carries 4x fewer bytes)
+            e2e_variants = {"u8_host_masks": run_e2e(torch.uint8)}
+
+    clocks = sampler.stop()
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         times = cpu_reference_episodes(shape, args, args.cpu_sample_episodes, dev)
@@ -297,7 +370,7 @@ def run_ours(args):
                        "gemm_backend": "tcgen05" if ops.DEFAULT_GEMM == ops.GEMM_TCGEN05 else "simt",
                        "pair_backend": "popc" if ops.DEFAULT_PAIR == ops.PAIR_POPC else "mma",
                        "fused_ingest": bool(args.fused_ingest)},
-            "clocks": clocks, "e2e": e2e,
+            "clocks": clocks, "e2e": e2e, "e2e_variants": e2e_variants,
             "gpu_launches": marsb200.kernel_launches_per_run(cfg) * args.steps * world,
             "roofline": roofline, "pairwise": pairwise, "fused_ingest": fused, "cpu_baseline": cpu_baseline,
         }))

@@ -1,0 +1,87 @@
+"""Matcher-derived scoring and merging on packed masks.
+
+Mirrors the arithmetic of `RobustPromptSampler.get_mask_scores` (matcher/Matcher.py:1152-1210), the score
+fusion (:719-720), the metric filters (:732-746) and the two merge rules (:749-787 score filter, :788-832
+top-k) for ALL masks of a target at once: the masks are bit-packed once, purity / coverage come from point
+lookups and the pooled bitmap counts, and the selected masks are OR-merged from the packed rows.
+LSAP matching, prompt sampling and the SAM calls of Matcher stay outside.
+The selection rules act on a few hundred scores and use torch sort / topk on the device, exactly the calls
+the reference makes (its tie order is unspecified there too).
+"""
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+class MatcherScorer:
+    def __init__(self, encoder_feat_size: int, alpha: float = 1.0, beta: float = 0.0, exp: float = 0.0,
+                 num_merging_mask: int = 10, score_filter_cfg: Optional[Dict] = None, device="cuda"):
+        self.encoder_feat_size = encoder_feat_size
+        self.alpha, self.beta, self.exp = alpha, beta, exp
+        self.num_merging_mask = num_merging_mask
+        self.score_filter_cfg = dict(emd=0.0, purity=0.0, coverage=0.0, score_filter=False, score=0.33,
+                                     score_norm=0.1, topk_scores_threshold=0.0)
+        if score_filter_cfg:
+            self.score_filter_cfg.update(score_filter_cfg)
+        self.device = torch.device(device)
+
+    # ------------------------------------------------------------------ get_mask_scores for all masks
+    def mask_scores(self, masks: torch.Tensor, all_points, emd: torch.Tensor):
+        """masks [n,H,W] (bool / uint8 / float), all_points [K,2] (x, y), emd [n] (= 1 - emd2, host solver).
+
+        Returns dict(bits, purity, coverage, scores) with the reference's `+ 1e-6` offsets (Matcher.py:1206-1207).
+        """
+        masks = masks.to(self.device)
+        n, h, w = masks.shape
+        bits = ops.pack_masks(masks)
+        _, _, pooled_count = ops.pool_packed(bits, h, w, self.encoder_feat_size)
+        pts = torch.as_tensor(all_points, dtype=torch.int32, device=self.device).reshape(-1, 2)
+        inside = ops.points_in_masks(bits, h, w, pts)
+        purity, coverage, scores = ops.matcher_scores(inside, pooled_count, emd.to(self.device).float(), pts.shape[0],
+                                                      self.alpha, self.beta, self.exp)
+        return dict(bits=bits, purity=purity, coverage=coverage, emd=emd.to(self.device).float(), scores=scores,
+                    shape=(h, w))
+
+    # ------------------------------------------------------------------ metric filters (Matcher.py:732-746)
+    def metric_filter(self, res: dict) -> torch.Tensor:
+        idx = torch.arange(res["scores"].numel(), device=self.device)
+        metrics = {k: res[k] for k in ("purity", "coverage", "emd")}
+        for metric in ("coverage", "emd", "purity"):
+            thr = self.score_filter_cfg[metric]
+            if thr > 0:
+                t = min(thr, float(metrics[metric].max()))
+                keep = torch.where(metrics[metric] >= t)[0]
+                idx = idx[keep]
+                metrics = {k: v[keep] for k, v in metrics.items()}
+        return idx
+
+    # ------------------------------------------------------------------ merge rules
+    def merge(self, res: dict) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Returns (merged mask float32 [1,H,W], mean score) like Matcher.mask_generation (:834)."""
+        idx = self.metric_filter(res)
+        scores = res["scores"][idx]
+        cfg = self.score_filter_cfg
+        if cfg["score_filter"]:
+            distances, rank = torch.sort(1 - scores, descending=False)
+            norm = (distances - distances.min()) / (distances.max() + 1e-6)
+            keep = distances < cfg["score"]
+            keep[..., 0] = True
+            keep = keep & (norm < cfg["score_norm"])
+            chosen = rank[keep][: self.num_merging_mask]
+            final = scores[chosen].mean()
+        else:
+            topk = min(self.num_merging_mask, scores.numel())
+            top_idx = scores.topk(topk)[1]
+            top_scores = scores[top_idx]
+            if cfg["topk_scores_threshold"] > 0:
+                top_scores = top_scores / top_scores.max()
+            sel = top_scores > cfg["topk_scores_threshold"]
+            chosen = top_idx[sel]
+            final = top_scores[sel].mean()
+        h, w = res["shape"]
+        flags = torch.zeros((1, res["bits"].shape[0]), dtype=torch.uint8, device=self.device)
+        flags[0, idx[chosen]] = 3
+        _, merged = ops.merge_masks(res["bits"][None], flags, h * w)
+        return merged.reshape(1, h, w), final

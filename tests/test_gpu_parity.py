@@ -569,3 +569,44 @@ def test_mars_predict_dropin(mb):
     np.testing.assert_array_equal(pred.cpu().numpy() > 0, ref.numpy() > 0)
     mars.clear()
     assert vva_mod.cost_matrix is None
+
+
+@pytest.mark.parametrize("mode", ["topk", "score_filter", "metric_filter"])
+def test_matcher_scorer_merge(mb, mode):
+    """MatcherScorer against the oracle restatement of matcher/Matcher.py:719-834."""
+    h, g, n, k = 140, 10, 18, 80
+    masks = cases.blob_masks(n, h, h, seed=55, min_frac=0.01, max_frac=0.15)
+    rs = np.random.RandomState(5)
+    pts = np.stack([rs.randint(0, h, k), rs.randint(0, h, k)], axis=1)
+    emd = torch.rand(n, generator=torch.Generator().manual_seed(6))
+    cfg = dict(topk=dict(topk_scores_threshold=0.6), score_filter=dict(score_filter=True, score=0.6, score_norm=0.5),
+               metric_filter=dict(coverage=0.05, emd=0.3, purity=0.01))[mode]
+    scorer = mb.MatcherScorer(g, alpha=1.0, beta=0.5, exp=1.0, num_merging_mask=6, score_filter_cfg=cfg, device=dev())
+    res = scorer.mask_scores(masks, pts, emd)
+    merged, score = scorer.merge(res)
+    purity, coverage = orc.matcher_mask_scores(masks.numpy() > 0, pts, g)
+    scores = orc.matcher_fuse(emd, purity, coverage, 1.0, 0.5, 1.0)
+    np.testing.assert_allclose(res["scores"].cpu().numpy(), scores.numpy(), rtol=1e-5)
+    full = dict(emd=0.0, purity=0.0, coverage=0.0)
+    full.update({k_: v for k_, v in cfg.items() if k_ in full})
+    fscores, idx = orc.matcher_metric_filter(scores, dict(purity=purity, coverage=coverage, emd=emd), full)
+    if cfg.get("score_filter"):
+        chosen, ref_score = orc.matcher_merge_score_filter(fscores, 6, cfg["score"], cfg["score_norm"])
+    else:
+        chosen, ref_score = orc.matcher_merge_topk(fscores, 6, cfg.get("topk_scores_threshold", 0.0))
+    ref = orc.merge_masks(masks, idx.numpy()[chosen])
+    np.testing.assert_array_equal(merged[0].cpu().numpy() > 0, ref.numpy() > 0)
+    np.testing.assert_allclose(float(score), float(ref_score), rtol=1e-5)
+    assert merged.shape == (1, h, h) and merged.dtype == torch.float32
+
+
+def test_evaluator_dropin(mb):
+    g = torch.Generator().manual_seed(18)
+    pred = (torch.rand(2, 64, 80, generator=g) < 0.4).float()
+    gt = (torch.rand(2, 64, 80, generator=g) < 0.5).float()
+    ignore = ((torch.rand(2, 64, 80, generator=g) < 0.1) & (gt == 0)).float()
+    mb.Evaluator.initialize()
+    inter, union = mb.Evaluator.classify_prediction(pred.to(dev()), dict(query_mask=gt, query_ignore_idx=ignore))
+    inter_ref, union_ref = orc.evaluator_areas(pred, gt, ignore)
+    np.testing.assert_array_equal(inter.cpu().numpy(), inter_ref.numpy())
+    np.testing.assert_array_equal(union.cpu().numpy(), union_ref.numpy())
