@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
-    ap.add_argument("--episodes-per-step", type=int, default=8)
+    ap.add_argument("--episodes-per-step", type=int, default=16)
     ap.add_argument("--e2e-episodes-per-step", type=int, default=2)
     ap.add_argument("--mask-dtype", default="f32", choices=["f32", "u8"])
     ap.add_argument("--nms", type=float, default=0.7)

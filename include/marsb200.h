@@ -135,6 +135,18 @@ int marsb200_pairwise_inter(const uint32_t* bits, int E, int P, int64_t words_pe
 int marsb200_pack_pairwise(const void* masks, int mask_dtype, int E, int P, int64_t HW, uint32_t* bits,
                            int32_t* inter, int pair_backend, void* stream);
 
+/* ---- A7: exact EMD scores on the device ---------------------------------------------
+ * score[e,p] = 1 - EMD(uniform 1/T over the fg support rows, uniform 1/M_p over the proposal's pooled patches,
+ * cost = C[fg rows][patches] in float64): the transportation LP of ot.emd2 at FilteringMergingModule.py:160-167 and
+ * matcher/Matcher.py:1187-1194, solved exactly (successive shortest paths on integer flows), one CTA per proposal.
+ * cost [E, m_rows, N] fp32 ((1 - S) / 2 from marsb200_sim_contract); row_fg [E, m_rows] uint8; pooled [E, P, ceil(N/32)].
+ * t_cap bounds the number of fg rows the workspace is sized for; *status receives 0, or the needed t_cap if an
+ * episode exceeded it (its scores are NaN).  An empty proposal or empty support scores 1.0 (zero transport). */
+int64_t marsb200_emd_workspace_bytes(int E, int P, int N, int t_cap);
+int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t* pooled, int E, int P, int64_t m_rows,
+                        int N, int t_cap, void* workspace, int64_t workspace_bytes, double* out, int32_t* status,
+                        void* stream);
+
 /* ---- A8: AlphaCLIP cosine scores -----------------------------------------------------------
  * clip[e,p] = img[e,p,:] . txt[e,:].  Replaces img_feats @ text_feats.T, FilteringMergingModule.py:97. */
 int marsb200_clip_scores(const float* img, const float* txt, int E, int P, int D, float* out, void* stream);

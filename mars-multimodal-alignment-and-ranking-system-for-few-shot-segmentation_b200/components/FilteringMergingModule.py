@@ -7,10 +7,12 @@ AlphaCLIP scores, ranked (stable, like Python's sorted) and OR-merged.
 The Python loop over proposals of the reference (FilteringMergingModule.py:103-123)
 and its 3*P device->host copies disappear.
 
-EMD (`ot.emd2`, an exact LP per proposal) is not one of this stage's kernels
-(SURVEY.md D3): `_compute_emd` calls POT on the host exactly like the reference
-when POT is importable, or a user-supplied `emd_fn`; `emd_scores` can also be
-passed in precomputed.
+EMD (`ot.emd2`, an exact transport LP per proposal, FilteringMergingModule.py:142-169)
+is solved exactly on the device for all proposals at once (`ops.emd_scores`,
+successive shortest paths on integer flows).  `emd_fn=` (a host solver taking the
+cost sub-matrix, e.g. a POT wrapper) or precomputed `emd_scores=` override it;
+`_compute_emd` keeps the reference's per-proposal host signature for callers that
+use it directly.
 """
 from typing import Callable, Optional
 
@@ -121,9 +123,13 @@ class FilteringMergingModule:
         clip = ops.clip_scores(img.to(dev).float()[None], txt.to(dev).float().reshape(1, -1))
         if emd_scores is None:
             sup = ops.pool_mask(support_mask.to(dev).permute(1, 0, 2, 3), g).reshape(-1)
-            pooled_np = self._unpack_pooled(pooled[0], n)
-            emd_scores = [self._compute_emd(sup, pooled_np[i], cost_matrix) for i in range(p)]
-        emd = torch.as_tensor(np.asarray(emd_scores, dtype=np.float64), device=dev).reshape(1, p)
+            if self.emd_fn is None:
+                emd = ops.emd_scores(cost_matrix.to(dev).float()[None], sup[None], pooled)
+            else:
+                pooled_np = self._unpack_pooled(pooled[0], n)
+                emd_scores = [self._compute_emd(sup, pooled_np[i], cost_matrix) for i in range(p)]
+        if emd_scores is not None:
+            emd = torch.as_tensor(np.asarray(emd_scores, dtype=np.float64), device=dev).reshape(1, p)
         inter = ops.pairwise_inter(bits) if self.nms_iou_threshold is not None else None
         res = ops.fuse_rank(emd, clip, cnt, sv, st, uc, inter, self.alpha, self.static_threshold,
                             self.dynamic_threshold, self.nms_iou_threshold)

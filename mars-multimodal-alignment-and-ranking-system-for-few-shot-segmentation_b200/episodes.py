@@ -32,6 +32,8 @@ class RankingConfig:
     want_merged_f32: bool = True       # the float32 [H, W] map the reference returns
     overlap_streams: bool = True       # mask chain (HBM-bound) on a second stream beside the contractions
     fused_ingest: bool = False         # one-pass pack + pairwise kernel (owns all TMEM: cannot overlap the contractions)
+    emd_on_device: bool = False        # solve the P transport LPs per episode on the device instead of taking batch["emd"]
+    emd_t_cap: Optional[int] = None    # max fg support rows the EMD workspace is sized for (default min(ns*N, 2048))
     gemm_backend: Optional[int] = None
     pair_backend: Optional[int] = None
 
@@ -50,6 +52,8 @@ def kernel_launches_per_run(cfg: RankingConfig) -> int:
         n += 1                 # pairwise intersections (part of the pack kernel with fused_ingest)
     n += 1                     # pool_packed
     n += 2                     # region sums + union count
+    if cfg.emd_on_device:
+        n += 1                 # exact EMD, one CTA per proposal
     n += 1                     # clip scores
     n += 1                     # fuse / rank / nms / select
     n += 1                     # merge
@@ -74,8 +78,14 @@ class RankingEngine:
         self.gemm_out = dict(colstats=new((e, ops.pad_rows(m) // 128, 4, n), f32))
         if cfg.want_sim:
             self.gemm_out["sim"] = new((e, m, n), f32)
-        if cfg.want_cost:
+        if cfg.want_cost or cfg.emd_on_device:
             self.gemm_out["cost"] = new((e, m, n), f32)
+        self.emd_ws = None
+        if cfg.emd_on_device:
+            self.emd_t_cap = cfg.emd_t_cap or min(m, 2048)
+            nbytes = int(ops.lib.marsb200_emd_workspace_bytes(e, s.P, n, self.emd_t_cap))
+            self.emd_ws = new((nbytes,), u8)
+            self.emd_out = new((e, s.P), torch.float64)
         self.prior = new((e, n), f32)
         self.vva = new((e, n), f32)
         self.vta_ref = new((e, nt), f32)
@@ -142,7 +152,7 @@ class RankingEngine:
         ops.normalize_split(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
         ops.normalize_split(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
         ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
-        ops.sim_contract(self.fs, self.fq, m, n, s.C, want_sim=cfg.want_sim, want_cost=cfg.want_cost,
+        ops.sim_contract(self.fs, self.fq, m, n, s.C, want_sim=cfg.want_sim, want_cost=cfg.want_cost or cfg.emd_on_device,
                          row_fg=self.row_fg, backend=cfg.gemm_backend, out=self.gemm_out)
         ops.vva_finalize(self.gemm_out["colstats"], self.row_fg, m, n, out=self.prior)
         ops.pir_refine(self.prior, batch["attn_vva"], s.g, cfg.vva_box_threshold, apply_minmax=True,
@@ -156,7 +166,11 @@ class RankingEngine:
         else:
             self._mask_chain(batch)
         ops.region_sums(self.pool_out[0], self.vva, self.vta, out=self.region_out)
-        ops.fuse_rank(batch["emd"], self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
+        emd = batch.get("emd")
+        if cfg.emd_on_device:
+            emd = ops.emd_scores(self.gemm_out["cost"], self.row_fg.reshape(e, m), self.pool_out[0], t_cap=self.emd_t_cap,
+                                 workspace=self.emd_ws, out=self.emd_out, check=False)
+        ops.fuse_rank(emd, self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
                       self.region_out[2], self.inter, cfg.alpha, cfg.static_threshold, cfg.dynamic_threshold,
                       cfg.nms_iou_threshold, out=self.rank_out)
         ops.merge_masks(self.bits, self.rank_out["flags"], s.H * s.W, want_bits=True,
@@ -168,7 +182,8 @@ class RankingEngine:
                    pooled=self.pool_out[0], area=self.pool_out[1], pooled_count=self.pool_out[2],
                    sum_vva=self.region_out[0], sum_vta=self.region_out[1], union_count=self.region_out[2],
                    inter=self.inter, clip=self.clip, merged_bits=self.merge_out["bits"],
-                   merged=self.merge_out.get("f32"), sim=self.gemm_out.get("sim"), cost=self.gemm_out.get("cost"))
+                   merged=self.merge_out.get("f32"), sim=self.gemm_out.get("sim"), cost=self.gemm_out.get("cost"),
+                   emd=self.emd_out if self.cfg.emd_on_device else None)
         out.update(self.rank_out)
         return out
 

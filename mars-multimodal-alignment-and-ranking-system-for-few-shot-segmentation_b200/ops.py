@@ -18,7 +18,7 @@ from ._lib import GEMM_SIMT, GEMM_TCGEN05, MASK_F32, MASK_U8, PAIR_MMA, PAIR_POP
 __all__ = [
     "words_per_mask", "pad_rows", "pad_k", "normalize_split", "pool_mask", "sim_contract", "vva_finalize",
     "attn_mean", "pir_refine", "resize_minmax", "pack_masks", "pack_pairwise", "pool_packed", "region_sums", "pairwise_inter",
-    "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas",
+    "emd_scores", "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas",
     "GEMM_TCGEN05", "GEMM_SIMT", "PAIR_POPC", "PAIR_MMA",
 ]
 
@@ -259,6 +259,41 @@ def pack_pairwise(masks: torch.Tensor, backend=None, out=None):
     check(lib.marsb200_pack_pairwise(m.data_ptr(), dt, e, p, h * w, bits.data_ptr(), inter.data_ptr(),
                                      DEFAULT_PAIR if backend is None else backend, _stream()))
     return bits, inter
+
+
+# ----------------------------------------------------------------------------- A7
+def emd_scores(cost: torch.Tensor, row_fg: torch.Tensor, pooled: torch.Tensor, t_cap: Optional[int] = None,
+               workspace=None, out=None, check=True) -> torch.Tensor:
+    """Exact `1 - emd2` of every proposal: cost [E, m_rows, N] fp32, row_fg [E, m_rows] u8, pooled [E, P, npw].
+
+    `t_cap` (max fg support rows the workspace is sized for) is read from `row_fg` when omitted - one small
+    device->host sync, like the reference's own host EMD.  With `check` the status word is read back and an
+    exception raised if an episode exceeded `t_cap`.
+    """
+    cost = _cuda(cost, torch.float32, "cost")
+    if cost.dim() == 2:
+        cost = cost[None]
+    e, m_rows, n = cost.shape
+    row_fg = _cuda(row_fg, torch.uint8, "row_fg").reshape(e, m_rows)
+    pooled = pooled.reshape(e, -1, pooled.shape[-1])
+    p = pooled.shape[1]
+    if t_cap is None:
+        t_cap = max(1, int((row_fg != 0).sum(dim=1).max().item()))
+    nbytes = int(lib.marsb200_emd_workspace_bytes(e, p, n, t_cap))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, device=cost.device, dtype=torch.uint8)
+    if out is None:
+        out = torch.empty((e, p), device=cost.device, dtype=torch.float64)
+    status = torch.zeros(1, device=cost.device, dtype=torch.int32)
+    check_rc = lib.marsb200_emd_scores(cost.data_ptr(), row_fg.data_ptr(), pooled.data_ptr(), e, p, m_rows, n, t_cap,
+                                       workspace.data_ptr(), workspace.numel(), out.data_ptr(), status.data_ptr(),
+                                       _stream())
+    _lib.check(check_rc)
+    if check:
+        need = int(status.item())
+        if need:
+            raise _lib.MarsB200Error(f"emd_scores: an episode has {need} foreground support rows > t_cap={t_cap}")
+    return out
 
 
 # ----------------------------------------------------------------------------- A8 / A10 / A11

@@ -610,3 +610,99 @@ def test_evaluator_dropin(mb):
     inter_ref, union_ref = orc.evaluator_areas(pred, gt, ignore)
     np.testing.assert_array_equal(inter.cpu().numpy(), inter_ref.numpy())
     np.testing.assert_array_equal(union.cpu().numpy(), union_ref.numpy())
+
+
+# ------------------------------------------------------------------------------------------ exact EMD on the device
+def _emd_inputs(ns, g, p, h, seed):
+    n = g * g
+    fs = torch.nn.functional.normalize(cases.proto_features(ns * n, 24, seed), dim=1)
+    fq = torch.nn.functional.normalize(cases.proto_features(n, 24, seed + 1), dim=1)
+    cost = ((1 - fs @ fq.T) / 2).contiguous()
+    support = cases.blob_masks(ns, h, h, seed + 2, 0.03, 0.2)
+    masks = cases.blob_masks(p, h, h, seed + 3, 0.01, 0.25)
+    return cost, support, masks
+
+
+@pytest.mark.parametrize("ns,g,p,h", [(1, 7, 9, 100), (2, 10, 12, 140), (1, 12, 6, 168)])
+def test_emd_scores_match_exact_lp(mb, ns, g, p, h):
+    """Device EMD against the oracle's exact LP (HiGHS) on the same cost sub-matrices."""
+    cost, support, masks = _emd_inputs(ns, g, p, h, seed=300 + g)
+    masks[p - 1] = 0  # empty proposal: defined as zero transport cost
+    d = dev()
+    row_fg = mb.ops.pool_mask(support.to(d), g).reshape(1, -1)
+    bits = mb.ops.pack_masks(masks.to(d))
+    pooled, _, _ = mb.ops.pool_packed(bits, h, h, g)
+    got = mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None])[0].cpu().numpy()
+    sup = orc.pool_mask(support, g).reshape(-1)
+    pm = orc.pool_mask(masks, g).reshape(p, -1)
+    want = np.asarray([orc.emd_score(sup, pm[i], cost) for i in range(p)])
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
+    assert got[p - 1] == 1.0
+
+
+def test_emd_square_case_equals_assignment(mb):
+    """T == M: the transport LP is an assignment problem; compare with scipy's exact LSAP at a larger size."""
+    from scipy.optimize import linear_sum_assignment
+
+    g, n_sel = 20, 180
+    n = g * g
+    gen = torch.Generator().manual_seed(77)
+    cost = torch.rand(n, n, generator=gen)
+    rows = torch.randperm(n, generator=gen)[:n_sel].sort().values
+    cols = torch.randperm(n, generator=gen)[:n_sel].sort().values
+    row_fg = torch.zeros(1, n, dtype=torch.uint8)
+    row_fg[0, rows] = 1
+    pooled_bits = np.zeros((1, (n + 31) // 32 * 32), dtype=bool)
+    pooled_bits[0, cols.numpy()] = True
+    pooled = torch.from_numpy(np.packbits(pooled_bits.reshape(1, -1, 32), axis=-1, bitorder="little").view(np.int32).reshape(1, 1, -1))
+    got = float(mb.ops.emd_scores(cost.to(dev())[None], row_fg.to(dev()), pooled.to(dev()))[0, 0])
+    sub = cost[rows][:, cols].double().numpy()
+    r, c = linear_sum_assignment(sub)
+    want = 1.0 - sub[r, c].sum() / n_sel
+    assert abs(got - want) < 1e-9
+
+
+def test_emd_feeds_the_fused_ranking(mb):
+    """Full FilteringMerging drop-in with the device EMD against the reference's golden scores (host LP there)."""
+    z = np.load(os.path.join(GOLD, "fm_g10_dynamic.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.fm_inputs(spec)
+    d = dev()
+    g, h = spec["g"], spec["H"]
+    row_fg = mb.ops.pool_mask(c["support_mask"].to(d), g).reshape(1, -1)
+    bits = mb.ops.pack_masks(c["masks"].to(d))
+    pooled, _, _ = mb.ops.pool_packed(bits, h, h, g)
+    emd = mb.ops.emd_scores(c["cost"].to(d)[None], row_fg, pooled[None])[0]
+    np.testing.assert_allclose(emd.cpu().numpy(), z["emd"], rtol=0, atol=1e-9)
+    mod = mb.FilteringMergingModule(None, None, None, spec["alpha"], spec["static"], spec["dynamic"], d)
+    ranked = mod._score_proposals(torch.zeros(1, 3, h, h), c["masks"], c["support_mask"][None], c["cost"].to(d), g,
+                                  c["vva"], c["vta"], ["x"], emd_scores=emd.cpu().numpy(),
+                                  alphaclip_feats=(c["clip_img"], c["clip_txt"]))
+    np.testing.assert_allclose([s for _, s in ranked], z["scores"], rtol=RTOL)
+
+
+def test_engine_with_device_emd(mb):
+    """Whole episode with the EMD solved on the device, against the oracle running its exact LP per proposal."""
+    shape = mb.EpisodeShape(ns=1, g=8, C=48, P=10, H=112, W=112, gt=6, D=24)
+    cfg = mb.RankingConfig(nms_iou_threshold=0.7, emd_on_device=True)
+    eps = [mb.make_episode(shape, 70 + i, "cpu", with_emd=False) for i in range(2)]
+    eng = mb.RankingEngine(shape, 2, cfg, dev())
+    out = eng.run(mb.to_device(mb.stack_episodes(eps), dev()))
+    torch.cuda.synchronize()
+    ocfg = dict(g=shape.g, vva_box_threshold=cfg.vva_box_threshold, vta_box_threshold=cfg.vta_box_threshold,
+                alpha=cfg.alpha, static_threshold=cfg.static_threshold, dynamic_threshold=cfg.dynamic_threshold,
+                nms_iou_threshold=cfg.nms_iou_threshold)
+    for e, ep in enumerate(eps):
+        ref = orc.run_episode(ep, ocfg, emd_fn=orc.emd_score)
+        assert_order_matches(out["order"][e].cpu().numpy(), out["scores"][e].cpu().numpy(), ref["order"], ref["scores"])
+
+
+def test_filtering_merging_default_device_emd(mb):
+    """The drop-in's default EMD path (no POT, no emd_fn) reproduces the reference's golden ranking."""
+    z = np.load(os.path.join(GOLD, "fm_g7_overlap.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.fm_inputs(spec)
+    mod = mb.FilteringMergingModule(None, None, None, spec["alpha"], spec["static"], spec["dynamic"], dev())
+    ranked = mod._score_proposals(torch.zeros(1, 3, 100, 100), c["masks"], c["support_mask"][None], c["cost"].to(dev()),
+                                  spec["g"], c["vva"], c["vta"], ["x"], alphaclip_feats=(c["clip_img"], c["clip_txt"]))
+    np.testing.assert_allclose([s for _, s in ranked], z["scores"], rtol=RTOL)
