@@ -75,6 +75,15 @@ int marsb200_sim_contract(const float* a_hi, const float* a_lo, const float* b_h
                           int64_t M, int64_t N, int64_t K, float* sim_out, float* cost_out,
                           const uint8_t* row_fg, float* colstats, int backend, void* stream);
 
+/* Row top-k (k <= 8, per support patch over the query patches) and column arg-max (per query patch over the
+ * support rows selected by row_mask, or all rows when NULL) of S with warp-shuffle reductions: the
+ * mutual-nearest-neighbour candidates of bidirectional matching (north-star kernel 1).  The reference's Matcher
+ * matches with two exact assignments (matcher/Matcher.py:443-477); these are its GPU-side candidates, SURVEY.md D1.
+ * sim [E, M, N]; row_vals/row_idx [E, M, k]; col_vals/col_idx [E, N]; either output pair may be NULL.
+ * Ties resolve to the lowest index. */
+int marsb200_match_argmax(const float* sim, const uint8_t* row_mask, int E, int M, int N, int k, float* row_vals,
+                          int32_t* row_idx, float* col_vals, int32_t* col_idx, void* stream);
+
 /* vva = mean_fg*max_fg - mean_bg*max_bg (bg skipped when there is no bg row), then min-max with eps 1e-7.
  * Replaces VisualVisualAlignmentModule.py:82-102.  out [E, N].  Returns an error when an episode has no fg row
  * only at the Python level (the kernel writes NaN for such an episode). */

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import GEMM_SIMT, GEMM_TCGEN05, MASK_F32, MASK_U8, PAIR_MMA, PAIR_POPC, check, lib
 
 __all__ = [
-    "words_per_mask", "pad_rows", "pad_k", "normalize_split", "pool_mask", "sim_contract", "vva_finalize",
+    "words_per_mask", "pad_rows", "pad_k", "normalize_split", "pool_mask", "sim_contract", "match_argmax", "mutual_matches", "vva_finalize",
     "attn_mean", "pir_refine", "resize_minmax", "pack_masks", "pack_pairwise", "pool_packed", "region_sums", "pairwise_inter",
     "emd_scores", "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas",
     "GEMM_TCGEN05", "GEMM_SIMT", "PAIR_POPC", "PAIR_MMA",
@@ -121,6 +121,40 @@ def sim_contract(a, b, m: int, n: int, k: int, want_sim=True, want_cost=False, r
                                     _ptr(sim), _ptr(cost), _ptr(row_fg), _ptr(colstats),
                                     DEFAULT_GEMM if backend is None else backend, _stream()))
     return dict(sim=sim, cost=cost, colstats=colstats)
+
+
+def match_argmax(sim: torch.Tensor, k: int = 1, row_mask: Optional[torch.Tensor] = None, rows=True, cols=True):
+    """sim [E, M, N] -> dict(row_vals/row_idx [E, M, k], col_vals/col_idx [E, N]); ties -> lowest index."""
+    sim = _cuda(sim, torch.float32, "sim")
+    if sim.dim() == 2:
+        sim = sim[None]
+    e, m, n = sim.shape
+    dev = sim.device
+    rv = torch.empty((e, m, k), device=dev, dtype=torch.float32) if rows else None
+    ri = torch.empty((e, m, k), device=dev, dtype=torch.int32) if rows else None
+    cv = torch.empty((e, n), device=dev, dtype=torch.float32) if cols else None
+    ci = torch.empty((e, n), device=dev, dtype=torch.int32) if cols else None
+    mk = None if row_mask is None else _cuda(row_mask, torch.uint8, "row_mask").reshape(e, m)
+    check(lib.marsb200_match_argmax(sim.data_ptr(), _ptr(mk), e, m, n, k, _ptr(rv), _ptr(ri), _ptr(cv), _ptr(ci), _stream()))
+    return dict(row_vals=rv, row_idx=ri, col_vals=cv, col_idx=ci)
+
+
+def mutual_matches(sim: torch.Tensor, row_fg: torch.Tensor):
+    """Bidirectional arg-max matching for one episode: fg support rows whose best query patch points back into the mask.
+
+    Forward: every fg support row takes its best query patch.  Reverse: that query patch takes its best support row
+    over ALL rows; the pair is kept when the reverse match is a fg row (the arg-max analogue of the retain rule at
+    matcher/Matcher.py:468-477).  Returns (support_rows, query_patches, similarity) of the kept pairs.
+    """
+    sim = sim.reshape(1, *sim.shape[-2:])
+    fg = _cuda(row_fg, torch.uint8, "row_fg").reshape(1, -1)
+    fwd = match_argmax(sim, k=1, cols=False)
+    rev = match_argmax(sim, rows=False)
+    rows = torch.nonzero(fg[0]).flatten()
+    q = fwd["row_idx"][0, rows, 0].long()
+    back = rev["col_idx"][0, q].long()
+    keep = fg[0, back] != 0
+    return rows[keep], q[keep], fwd["row_vals"][0, rows, 0][keep]
 
 
 def vva_finalize(colstats: torch.Tensor, row_fg: torch.Tensor, m: int, n: int, out=None) -> torch.Tensor:

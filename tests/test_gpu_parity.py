@@ -706,3 +706,29 @@ def test_filtering_merging_default_device_emd(mb):
     ranked = mod._score_proposals(torch.zeros(1, 3, 100, 100), c["masks"], c["support_mask"][None], c["cost"].to(dev()),
                                   spec["g"], c["vva"], c["vta"], ["x"], alphaclip_feats=(c["clip_img"], c["clip_txt"]))
     np.testing.assert_allclose([s for _, s in ranked], z["scores"], rtol=RTOL)
+
+
+def test_match_argmax_topk_and_mutual(mb):
+    """Warp-shuffle row top-k / column arg-max against torch, and the mutual-NN retain rule."""
+    gen = torch.Generator().manual_seed(21)
+    e, m, n, k = 2, 150, 137, 5
+    sim = torch.rand(e, m, n, generator=gen)
+    sim[0, 3, 10] = sim[0, 3, 50] = 2.0       # tie in a row -> lowest column first
+    sim[1, 7, 20] = sim[1, 90, 20] = 3.0      # tie in a column -> lowest row
+    mask = (torch.rand(e, m, generator=gen) < 0.4).to(torch.uint8)
+    res = mb.ops.match_argmax(sim.to(dev()), k=k, row_mask=mask.to(dev()))
+    tv, ti = torch.sort(sim, dim=2, descending=True, stable=True)
+    np.testing.assert_array_equal(res["row_idx"].cpu().numpy(), ti[:, :, :k].numpy())
+    np.testing.assert_array_equal(res["row_vals"].cpu().numpy(), tv[:, :, :k].numpy())
+    masked = sim.masked_fill(mask[:, :, None] == 0, float("-inf"))
+    cv = masked.max(dim=1).values
+    ci = (masked == cv[:, None, :]).float().argmax(dim=1)  # first row attaining the max
+    np.testing.assert_array_equal(res["col_vals"].cpu().numpy(), cv.numpy())
+    np.testing.assert_array_equal(res["col_idx"].cpu().numpy(), ci.numpy())
+    rows, q, val = mb.ops.mutual_matches(sim[0].to(dev()), mask[0].to(dev()))
+    fg = torch.nonzero(mask[0]).flatten()
+    fwd = sim[0].argmax(dim=1)
+    back = sim[0].argmax(dim=0)
+    keep = mask[0][back[fwd[fg]]] != 0
+    np.testing.assert_array_equal(rows.cpu().numpy(), fg[keep].numpy())
+    np.testing.assert_array_equal(q.cpu().numpy(), fwd[fg][keep].numpy())
