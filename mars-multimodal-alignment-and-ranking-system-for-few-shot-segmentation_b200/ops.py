@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import GEMM_SIMT, GEMM_TCGEN05, MASK_F32, MASK_U8, PAIR_MMA, PAIR_POPC, check, lib
 
 __all__ = [
-    "words_per_mask", "pad_rows", "pad_k", "normalize_split", "pool_mask", "sim_contract", "match_argmax", "mutual_matches", "vva_finalize",
+    "words_per_mask", "pad_rows", "pad_k", "normalize_split", "pool_mask", "sim_contract", "match_argmax", "mutual_matches", "lsap", "vva_finalize",
     "attn_mean", "pir_refine", "resize_minmax", "pack_masks", "pack_pairwise", "pool_packed", "region_sums", "pairwise_inter",
     "emd_scores", "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas",
     "GEMM_TCGEN05", "GEMM_SIMT", "PAIR_POPC", "PAIR_MMA",
@@ -155,6 +155,28 @@ def mutual_matches(sim: torch.Tensor, row_fg: torch.Tensor):
     back = rev["col_idx"][0, q].long()
     keep = fg[0, back] != 0
     return rows[keep], q[keep], fwd["row_vals"][0, rows, 0][keep]
+
+
+def lsap(sim: torch.Tensor, row_sel: Optional[torch.Tensor] = None, col_sel: Optional[torch.Tensor] = None,
+         maximize: bool = True, check_status: bool = True):
+    """Exact assignment on sim [E, R, C] restricted to the selected rows / columns.
+
+    Returns (row_to_col [E, R] int32 with -1 for unassigned rows, objective [E] float64).
+    """
+    sim = _cuda(sim, torch.float32, "sim")
+    if sim.dim() == 2:
+        sim = sim[None]
+    e, r, c = sim.shape
+    rs = None if row_sel is None else _cuda(row_sel, torch.uint8, "row_sel").reshape(e, r)
+    cs = None if col_sel is None else _cuda(col_sel, torch.uint8, "col_sel").reshape(e, c)
+    r2c = torch.empty((e, r), device=sim.device, dtype=torch.int32)
+    obj = torch.empty((e,), device=sim.device, dtype=torch.float64)
+    status = torch.zeros(1, device=sim.device, dtype=torch.int32)
+    check(lib.marsb200_lsap(sim.data_ptr(), _ptr(rs), _ptr(cs), e, r, c, int(maximize), r2c.data_ptr(), obj.data_ptr(),
+                            status.data_ptr(), _stream()))
+    if check_status and int(status.item()):
+        raise _lib.MarsB200Error(f"lsap: a problem of size {int(status.item())} exceeds the shared-memory state")
+    return r2c, obj
 
 
 def vva_finalize(colstats: torch.Tensor, row_fg: torch.Tensor, m: int, n: int, out=None) -> torch.Tensor:

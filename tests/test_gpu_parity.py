@@ -732,3 +732,62 @@ def test_match_argmax_topk_and_mutual(mb):
     keep = mask[0][back[fwd[fg]]] != 0
     np.testing.assert_array_equal(rows.cpu().numpy(), fg[keep].numpy())
     np.testing.assert_array_equal(q.cpu().numpy(), fwd[fg][keep].numpy())
+
+
+@pytest.mark.parametrize("r,c,maximize", [(40, 90, True), (90, 40, True), (64, 64, False), (300, 1369, True), (1, 5, True)])
+def test_lsap_matches_scipy(mb, r, c, maximize):
+    """Exact assignment against scipy.optimize.linear_sum_assignment (the solver Matcher calls, Matcher.py:449,471)."""
+    from scipy.optimize import linear_sum_assignment
+
+    gen = torch.Generator().manual_seed(r * 7 + c)
+    sim = torch.rand(2, r, c, generator=gen)
+    row_sel = (torch.rand(2, r, generator=gen) < 0.7).to(torch.uint8)
+    row_sel[:, 0] = 1
+    r2c, obj = mb.ops.lsap(sim.to(dev()), row_sel=row_sel.to(dev()), maximize=maximize)
+    r2c, obj = r2c.cpu().numpy(), obj.cpu().numpy()
+    for e in range(2):
+        rows = np.nonzero(row_sel[e].numpy())[0]
+        sub = sim[e][rows].double().numpy()
+        ri, ci = linear_sum_assignment(sub, maximize=maximize)
+        assert abs(obj[e] - sub[ri, ci].sum()) < 1e-9
+        got = r2c[e]
+        assigned = got[got >= 0]
+        assert len(set(assigned.tolist())) == len(assigned) == min(len(rows), c)
+        assert (got[np.setdiff1d(np.arange(r), rows)] == -1).all()
+        expect = np.full(r, -1)
+        expect[rows[ri]] = ci
+        np.testing.assert_array_equal(got, expect)  # random costs: the optimum is unique
+
+
+def test_bidirectional_lsap_matching(mb):
+    """Forward + reverse assignment and the retain rule of Matcher.patch_level_matching (Matcher.py:443-477)."""
+    from scipy.optimize import linear_sum_assignment
+
+    spec = cases.VVA_CASES["g10_2shot"]
+    c = cases.vva_inputs(spec)
+    g = spec["g"]
+    fs, fq = orc.normalize_rows(c["feat_s"]), orc.normalize_rows(c["feat_q"])
+    sim = fs @ fq.T                                   # [ns*N, N]
+    mask = orc.pool_mask(c["support_mask"], g).reshape(-1)
+    # reference restatement with scipy
+    s_fwd = sim[mask]
+    fr, fc = linear_sum_assignment(s_fwd.numpy(), maximize=True)
+    s_rev = sim.t()[fc]
+    rr, rc = linear_sum_assignment(s_rev.numpy(), maximize=True)
+    mask_idx = torch.nonzero(mask).flatten().numpy()
+    retain_ref = np.isin(rc, mask_idx)
+    # device
+    d = dev()
+    sim_d = sim.to(d)
+    r2c, _ = mb.ops.lsap(sim_d, row_sel=mask.to(torch.uint8).to(d))
+    fwd_cols = r2c[0][torch.nonzero(mask.to(d)).flatten()].long()
+    np.testing.assert_array_equal(fwd_cols.cpu().numpy(), fc)
+    sel = torch.zeros(sim.shape[1], dtype=torch.uint8, device=d)
+    sel[fwd_cols] = 1
+    q2s, _ = mb.ops.lsap(sim_d.t().contiguous(), row_sel=sel)
+    # scipy's reverse problem has rows in forward-match order; map by query patch
+    ref_by_patch = {int(fc[k]): int(rc[k]) for k in range(len(fc))}
+    got_by_patch = {int(p): int(q2s[0][p]) for p in fc}
+    assert ref_by_patch == got_by_patch
+    retain = np.isin(np.asarray([got_by_patch[int(p)] for p in fc]), mask_idx)
+    np.testing.assert_array_equal(retain, retain_ref)
