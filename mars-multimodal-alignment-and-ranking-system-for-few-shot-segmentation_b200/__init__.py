@@ -13,7 +13,7 @@ from .synthetic import CONFIGS, EpisodeShape, make_episode, stack_episodes, to_d
 from .components import (FilteringMergingModule, PriorInformationRefinementModule,  # noqa: F401
                          VisualVisualAlignmentModule)
 from .MARS import MARS, build_MARS_fss  # noqa: F401
-from .matcher_scoring import MatcherScorer  # noqa: F401
+from .matcher_scoring import MatcherScorer, PatchMatcher  # noqa: F401
 from .evaluation import Evaluator  # noqa: F401
 
 __version__ = "0.1.0"

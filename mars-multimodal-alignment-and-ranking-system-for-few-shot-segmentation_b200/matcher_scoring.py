@@ -85,3 +85,65 @@ class MatcherScorer:
         flags[0, idx[chosen]] = 3
         _, merged = ops.merge_masks(res["bits"][None], flags, h * w)
         return merged.reshape(1, h, w), final
+
+
+class PatchMatcher:
+    """Bidirectional patch matching of Matcher on the device.
+
+    Follows `Matcher.patch_level_matching` (matcher/Matcher.py:436-547): S = ref @ tar^T and C = (1 - S) / 2 from the
+    tcgen05 contraction, forward assignment of the masked support patches to query patches, reverse assignment of
+    the matched query patches to support patches (both exact LSAP, `ops.lsap`), retain the pairs whose reverse match
+    lies in the mask, keep the better half when more than 40 survive, de-duplicate and convert to patch-centre pixel
+    coordinates.  Prompt sampling / negative priors / SAM stay outside.
+    """
+
+    def __init__(self, encoder_feat_size: int, patch_size: int, input_size, device="cuda"):
+        self.encoder_feat_size = encoder_feat_size
+        self.patch_size = patch_size
+        self.input_size = tuple(input_size)  # (H, W)
+        self.device = torch.device(device)
+
+    def match(self, ref_feats: torch.Tensor, tar_feat: torch.Tensor, ref_masks_pool: torch.Tensor):
+        """ref_feats [ns*N, C] and tar_feat [N, C] (raw or normalised rows), ref_masks_pool [ns*N] (0/1).
+
+        Returns dict(points [K,2] (x, y) int64, points_discarded [K',2], S, C, reduced_points_num, sim_matched,
+        indices_forward (support rows, query patches), retain).
+        """
+        dev = self.device
+        ref = ops.normalize_split(ref_feats.to(dev).float())
+        tar = ops.normalize_split(tar_feat.to(dev).float())
+        m, c = ref_feats.shape
+        n = tar_feat.shape[0]
+        res = ops.sim_contract(ref, tar, m, n, c, want_sim=True, want_cost=True)
+        S, C = res["sim"][0], res["cost"][0]
+        mask = ref_masks_pool.to(dev).flatten() != 0
+        idx_mask = torch.nonzero(mask).flatten()
+        # forward: masked support rows -> query patches
+        r2c, _ = ops.lsap(S, row_sel=mask.to(torch.uint8))
+        fwd_rows = idx_mask[r2c[0][idx_mask] >= 0]
+        fwd_cols = r2c[0][fwd_rows].long()
+        sim_f = S[fwd_rows, fwd_cols]
+        # reverse: matched query patches -> all support rows
+        sel = torch.zeros(n, dtype=torch.uint8, device=dev)
+        sel[fwd_cols] = 1
+        q2s, _ = ops.lsap(S.t().contiguous(), row_sel=sel)
+        rev_rows = q2s[0][fwd_cols].long()
+        retain = mask[rev_rows.clamp(min=0)] & (rev_rows >= 0)
+        if bool(retain.any()):
+            pos_cols, neg_cols, sim_pos = fwd_cols[retain], fwd_cols[~retain], sim_f[retain]
+        else:  # the reference keeps everything when nothing survives (Matcher.py:483-497)
+            pos_cols, neg_cols, sim_pos = fwd_cols, fwd_cols, sim_f
+        reduced = len(sim_pos) // 2 if len(sim_pos) > 40 else len(sim_pos)
+        order = torch.sort(sim_pos, descending=True)[1][:reduced]
+        matched = torch.unique(pos_cols[order])
+        unmatched = torch.unique(neg_cols)
+        return dict(points=self._centres(matched), points_discarded=self._centres(unmatched), S=S, C=C,
+                    reduced_points_num=reduced, sim_matched=sim_pos, indices_forward=(fwd_rows, fwd_cols),
+                    retain=retain)
+
+    def _centres(self, patch_idx: torch.Tensor) -> torch.Tensor:
+        g, ps = self.encoder_feat_size, self.patch_size
+        x = (patch_idx % g) * ps + ps // 2
+        y = (patch_idx // g) * ps + ps // 2
+        ok = (x < self.input_size[1]) & (y < self.input_size[0])
+        return torch.stack([x[ok], y[ok]], dim=1)

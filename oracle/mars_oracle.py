@@ -351,6 +351,43 @@ def mask_nms(order: np.ndarray, inter: torch.Tensor, area: torch.Tensor, iou_thr
 # --------------------------------------------------------------------------
 # A12: Matcher-derived scoring and merging
 # --------------------------------------------------------------------------
+def matcher_patch_matching(ref_feats: torch.Tensor, tar_feat: torch.Tensor, ref_masks_pool: torch.Tensor, g: int,
+                           patch_size: int, input_size):
+    """Forward / reverse LSAP matching, retain rule, half selection, de-duplication and patch-centre coordinates.
+
+    Follows matcher/Matcher.py:436-547 with scipy's linear_sum_assignment (the reference's solver).  Returns the
+    matched and discarded points as sorted lists of (x, y) and the number of points kept by the half rule.
+    """
+    from scipy.optimize import linear_sum_assignment
+
+    sim = ref_feats @ tar_feat.t()
+    mask = ref_masks_pool.flatten().bool()
+    s_fwd = sim[mask]
+    fr, fc = linear_sum_assignment(s_fwd.numpy(), maximize=True)
+    sim_f = s_fwd[fr, fc]
+    idx_mask = mask.nonzero()[:, 0]
+    s_rev = sim.t()[fc]
+    rr, rc = linear_sum_assignment(s_rev.numpy(), maximize=True)
+    retain = torch.isin(torch.as_tensor(rc), idx_mask)
+    fc_t = torch.as_tensor(fc)
+    if not (retain == False).all().item():  # noqa: E712  (mirrors the reference's test)
+        pos, neg, sim_pos = fc_t[retain], fc_t[~retain], sim_f[retain]
+    else:
+        pos, neg, sim_pos = fc_t, fc_t, sim_f
+    reduced = len(sim_pos) // 2 if len(sim_pos) > 40 else len(sim_pos)
+    order = torch.sort(sim_pos, descending=True)[1][:reduced]
+
+    def centres(idx):
+        out = set()
+        for p in set(idx.tolist()):
+            x, y = (p % g) * patch_size + patch_size // 2, (p // g) * patch_size + patch_size // 2
+            if x < input_size[1] and y < input_size[0]:
+                out.add((int(x), int(y)))
+        return sorted(out)
+
+    return centres(pos[order]), centres(neg), reduced
+
+
 def matcher_mask_scores(masks: np.ndarray, all_points: np.ndarray, g: int):
     """Purity and coverage of every mask from the matched points.
 

@@ -791,3 +791,22 @@ def test_bidirectional_lsap_matching(mb):
     assert ref_by_patch == got_by_patch
     retain = np.isin(np.asarray([got_by_patch[int(p)] for p in fc]), mask_idx)
     np.testing.assert_array_equal(retain, retain_ref)
+
+
+@pytest.mark.parametrize("name", ["g10_2shot", "g37_1shot"])
+def test_patch_matcher_against_scipy_restatement(mb, name):
+    """PatchMatcher (device LSAP) against the oracle restatement of Matcher.patch_level_matching."""
+    spec = cases.VVA_CASES[name]
+    c = cases.vva_inputs(spec)
+    g, h = spec["g"], spec["H"]
+    fs, fq = orc.normalize_rows(c["feat_s"]), orc.normalize_rows(c["feat_q"])
+    pool = orc.pool_mask(c["support_mask"], g).reshape(-1).float()
+    pts_ref, neg_ref, reduced_ref = orc.matcher_patch_matching(fs, fq, pool, g, 14, (h, h))
+    pm = mb.PatchMatcher(g, 14, (h, h), dev())
+    res = pm.match(fs, fq, pool)
+    assert res["reduced_points_num"] == reduced_ref
+    got = sorted(map(tuple, res["points"].cpu().tolist()))
+    got_neg = sorted(map(tuple, res["points_discarded"].cpu().tolist()))
+    assert got == pts_ref
+    assert got_neg == neg_ref
+    np.testing.assert_allclose(res["C"].cpu().numpy(), ((1 - fs @ fq.T) / 2).numpy(), atol=3e-6)
