@@ -14,8 +14,21 @@
 
 namespace marsb200 {
 
+#ifdef MARSB200_EMD_PROFILE
+__device__ long long g_emd_prof[16];
+#define EMD_TIC(t) long long t = clock64()
+#define EMD_TOC(slot, t) do { if (threadIdx.x == 0) atomicAdd((unsigned long long*)&g_emd_prof[slot], (unsigned long long)(clock64() - (t))); } while (0)
+#define EMD_COUNT(slot) do { if (threadIdx.x == 0) atomicAdd((unsigned long long*)&g_emd_prof[slot], 1ull); } while (0)
+#else
+#define EMD_TIC(t)
+#define EMD_TOC(slot, t)
+#define EMD_COUNT(slot)
+#endif
+
 constexpr int EMD_THREADS = 512;  // the relaxation gathers cost entries from L2: latency hidden by many threads
 constexpr double EMD_INF = 1e300;
+constexpr int EMD_INLINE = 6;        // a sink of a (near-)basic solution is fed by ~ (T + M) / M sources
+constexpr int EMD_OVERFLOW = 255;
 
 struct EmdSmem {
     double* u;       // [t_cap]  source duals
@@ -32,10 +45,12 @@ struct EmdSmem {
     int* pred_src;   // [n_cap]  source that gave sink j its distance
     int* demand;     // [n_cap]
     unsigned char* reached;  // [t_cap]
+    short* feeders;          // [n_cap][EMD_INLINE] sources with positive flow into sink j (when they fit)
+    unsigned char* nfeed;    // [n_cap] how many, or EMD_OVERFLOW: scan the flow row in global memory instead
 };
 
 __host__ __device__ inline size_t emd_smem_bytes(int t_cap, int n_cap) {
-    return (size_t)t_cap * (2 * 8 + 5 * 4 + 1) + (size_t)n_cap * (3 * 8 + 3 * 4) + 64;
+    return (size_t)t_cap * (2 * 8 + 5 * 4 + 1) + (size_t)n_cap * (3 * 8 + 3 * 4 + 2 * EMD_INLINE + 1) + 64;
 }
 
 __device__ inline EmdSmem emd_carve(unsigned char* base, int t_cap, int n_cap) {
@@ -55,7 +70,9 @@ __device__ inline EmdSmem emd_carve(unsigned char* base, int t_cap, int n_cap) {
     s.cols = s.newlist + t_cap;
     s.pred_src = s.cols + n_cap;
     s.demand = s.pred_src + n_cap;
-    s.reached = reinterpret_cast<unsigned char*>(s.demand + n_cap);
+    s.feeders = reinterpret_cast<short*>(s.demand + n_cap);
+    s.reached = reinterpret_cast<unsigned char*>(s.feeders + (size_t)n_cap * EMD_INLINE);
+    s.nfeed = s.reached + t_cap;
     return s;
 }
 
@@ -157,11 +174,14 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_kernel(const float* __restric
         for (int i = 0; i < T; ++i) mn = fmin(mn, c(i, j));
         s.v[j] = mn;
         s.demand[j] = T;
+        s.nfeed[j] = 0;
     }
     __syncthreads();
 
     for (int r = 0; r < T; ++r) {
         while (s.supply[r] > 0) {  // uniform: shared state only changes between barriers
+            EMD_COUNT(0);
+            EMD_TIC(t_init);
             // ---- Dijkstra from source r over the sinks
             const double ur = s.u[r];
             for (int j = tid; j < M; j += EMD_THREADS) {
@@ -183,27 +203,51 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_kernel(const float* __restric
             int jstar;
             if (tid == 0) s_nnew[0] = s_nnew[1] = 0;
             __syncthreads();
+            EMD_TOC(8, t_init);
             for (int step = 0;; ++step) {
                 const int pp = step & 1;  // ping-pong scratch / counters: one barrier fewer per step
+                EMD_COUNT(1);
+                EMD_TIC(t_arg);
                 block_argmin(s.key, M, D, jstar, s_val[pp], s_idx[pp]);
+                EMD_TOC(9, t_arg);
                 if (s.demand[jstar] > 0) break;  // demands only change in the augmentation below: uniform
                 if (tid == 0) {
                     s.key[jstar] = EMD_INF;  // scanned
                     s_nnew[pp ^ 1] = 0;      // the other counter is idle during this step
                 }
+                EMD_TIC(t_col);
                 // saturated sink: every source feeding it becomes reachable at distance D (tight backward arcs)
-                const int16_t* frow = fT + (int64_t)jstar * T;
-                for (int i = tid; i < T; i += EMD_THREADS) {
-                    if (!s.reached[i] && frow[i] > 0) {
-                        s.reached[i] = 1;
-                        s.dsrc[i] = D;
-                        s.pred_sink[i] = jstar;
-                        s.newlist[atomicAdd(&s_nnew[pp], 1)] = i;
-                        s.list[atomicAdd(&s_nreached, 1)] = i;
+                const int nf = s.nfeed[jstar];
+                if (nf != EMD_OVERFLOW) {  // the usual case: the feeders are listed in shared memory
+                    if (tid < nf) {
+                        const int i = s.feeders[jstar * EMD_INLINE + tid];
+                        if (!s.reached[i]) {
+                            s.reached[i] = 1;
+                            s.dsrc[i] = D;
+                            s.pred_sink[i] = jstar;
+                            s.newlist[atomicAdd(&s_nnew[pp], 1)] = i;
+                            s.list[atomicAdd(&s_nreached, 1)] = i;
+                        }
+                    }
+                } else {
+                    const int16_t* frow = fT + (int64_t)jstar * T;
+                    for (int i = tid; i < T; i += EMD_THREADS) {
+                        if (!s.reached[i] && frow[i] > 0) {
+                            s.reached[i] = 1;
+                            s.dsrc[i] = D;
+                            s.pred_sink[i] = jstar;
+                            s.newlist[atomicAdd(&s_nnew[pp], 1)] = i;
+                            s.list[atomicAdd(&s_nreached, 1)] = i;
+                        }
                     }
                 }
                 __syncthreads();
+                EMD_TOC(10, t_col);
+                EMD_TIC(t_rel);
                 const int nnew = s_nnew[pp];
+#ifdef MARSB200_EMD_PROFILE
+                if (tid == 0) atomicAdd((unsigned long long*)&g_emd_prof[2], (unsigned long long)nnew);
+#endif
                 // relax every unscanned sink against the newly reached sources (usually 0-2 per step)
                 for (int j = tid; j < M; j += EMD_THREADS) {
                     if (s.key[j] >= EMD_INF) continue;
@@ -237,7 +281,9 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_kernel(const float* __restric
                     }
                 }
                 __syncthreads();
+                EMD_TOC(11, t_rel);
             }
+            EMD_TIC(t_dual);
             if (tid == 0) s.key[jstar] = EMD_INF;  // the terminal sink counts as scanned for the dual update
             __syncthreads();
             // ---- dual update: keeps every flow arc tight and all reduced costs non-negative
@@ -249,6 +295,8 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_kernel(const float* __restric
             for (int j = tid; j < M; j += EMD_THREADS)
                 if (s.key[j] >= EMD_INF) s.v[j] -= D - s.dist[j];
             __syncthreads();
+            EMD_TOC(12, t_dual);
+            EMD_TIC(t_aug);
             // ---- augment along the alternating path jstar <- pred_src <- pred_sink <- ... <- r
             if (tid == 0) {
                 int delta = min(s.supply[r], s.demand[jstar]);
@@ -263,16 +311,37 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_kernel(const float* __restric
                 j = jstar;
                 while (true) {
                     const int i = s.pred_src[j];
-                    fT[(int64_t)j * T + i] += (int16_t)delta;
+                    const int16_t before = fT[(int64_t)j * T + i];
+                    fT[(int64_t)j * T + i] = (int16_t)(before + delta);
+                    if (before == 0) {  // new feeder of sink j
+                        const int nf = s.nfeed[j];
+                        if (nf < EMD_INLINE) {
+                            s.feeders[j * EMD_INLINE + nf] = (short)i;
+                            s.nfeed[j] = (unsigned char)(nf + 1);
+                        } else {
+                            s.nfeed[j] = EMD_OVERFLOW;
+                        }
+                    }
                     if (i == r) break;
                     const int jp = s.pred_sink[i];
-                    fT[(int64_t)jp * T + i] -= (int16_t)delta;
+                    const int16_t left = (int16_t)(fT[(int64_t)jp * T + i] - delta);
+                    fT[(int64_t)jp * T + i] = left;
+                    if (left == 0 && s.nfeed[jp] != EMD_OVERFLOW) {  // i no longer feeds sink jp: swap-remove
+                        const int nf = s.nfeed[jp];
+                        for (int q = 0; q < nf; ++q)
+                            if (s.feeders[jp * EMD_INLINE + q] == (short)i) {
+                                s.feeders[jp * EMD_INLINE + q] = s.feeders[jp * EMD_INLINE + nf - 1];
+                                s.nfeed[jp] = (unsigned char)(nf - 1);
+                                break;
+                            }
+                    }
                     j = jp;
                 }
                 s.supply[r] -= delta;
                 s.demand[jstar] -= delta;
             }
             __syncthreads();
+            EMD_TOC(13, t_aug);
         }
     }
 
@@ -299,6 +368,18 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_kernel(const float* __restric
 }  // namespace marsb200
 
 using namespace marsb200;
+
+#ifdef MARSB200_EMD_PROFILE
+extern "C" int marsb200_debug_emd_profile(long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_emd_prof, sizeof(long long) * 16);
+    if (reset) {
+        long long z[16] = {0};
+        cudaMemcpyToSymbol(g_emd_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 extern "C" {
 

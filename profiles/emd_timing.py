@@ -28,3 +28,12 @@ pm = ((pooled[0][:, :, None] >> torch.arange(32, device=dev, dtype=torch.int32))
 idx = [0, 1, 2]
 t0 = time.perf_counter(); ref = [orc.emd_score(sup, pm[i], cm) for i in idx]; t1 = time.perf_counter()
 print("host exact LP:", (t1 - t0) / len(idx) * 1e3, "ms per LP; max |diff|", max(abs(out[0, i].item() - ref[k]) for k, i in enumerate(idx)))
+# per-LP latency by size: the launch is bounded by its largest problem
+order = torch.argsort(cnt[0], descending=True)
+for rank in (0, 64, 128, 255):
+    p = int(order[rank])
+    one = pooled[0:1, p:p + 1].contiguous()
+    ops.emd_scores(cost[0:1], row_fg[0:1], one)
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); ops.emd_scores(cost[0:1], row_fg[0:1], one, t_cap=T[0]); c.record(); torch.cuda.synchronize()
+    print(f"single LP T={T[0]} M={int(cnt[0, p])}: {a.elapsed_time(c):.2f} ms")
