@@ -50,13 +50,14 @@ int64_t marsb200_words_per_mask(int64_t hw);
 int64_t marsb200_pad_rows(int64_t rows);  /* -> multiple of 128 */
 int64_t marsb200_pad_k(int64_t k);        /* -> multiple of 32  */
 
-/* ---- A1: row L2-normalise + TF32 hi/lo split -------------------------------------------
+/* ---- A1: row L2-normalise into the contraction's operand layout ---------------------------
  * Replaces F.normalize(feats, p=2, dim=1): VisualVisualAlignmentModule.py:124-125,
- * matcher/Matcher.py:297-298.  x [E, rows, k] fp32 -> xn [E, rows_pad, k_pad] fp32 normalised,
- * hi/lo [E, rows_pad, k_pad] with hi = tf32(xn), lo = xn - hi; padding is zero-filled.
- * If `normalize` is 0 the rows are only split (used for the PIR matrix D). */
-int marsb200_normalize_split(const float* x, int64_t ld_x, int E, int64_t rows, int64_t k, int normalize,
-                             float* hi, float* lo, void* stream);
+ * matcher/Matcher.py:297-298.  x [E, rows, k] fp32 -> out [E, pad_rows(rows), pad_k(k)] fp32, rows divided by
+ * max(||row||, 1e-12), and out_lo of the same shape = out - (out with its low 13 mantissa bits cleared): the
+ * residual the error-compensated tensor-core product needs (kind::tf32 reads only the top 19 bits of `out`).
+ * Padding is zero-filled.  If `normalize` is 0 the rows are only copied into the layout. */
+int marsb200_normalize_rows(const float* x, int64_t ld_x, int E, int64_t rows, int64_t k, int normalize, float* out,
+                            float* out_lo, void* stream);
 
 /* ---- A3/A6: adaptive max pool of masks to the patch grid ---------------------------------
  * Replaces F.adaptive_max_pool2d(mask, (g, g)) > 0: VisualVisualAlignmentModule.py:72-76,
@@ -66,14 +67,16 @@ int marsb200_pool_mask(const void* masks, int mask_dtype, int64_t n, int H, int 
 /* ---- A2 + A3: S = Fs Fq^T with fused masked column statistics -----------------------------
  * Replaces torch.matmul at VisualVisualAlignmentModule.py:69 and the two recomputed products
  * + max/mean reductions at :78-102, and matcher/Matcher.py:437-440.
- * a_hi/a_lo [E, pad_rows(M), pad_k(K)], b_hi/b_lo [E, pad_rows(N), pad_k(K)] from normalize_split.
+ * a, a_lo [E, pad_rows(M), pad_k(K)], b, b_lo [E, pad_rows(N), pad_k(K)] fp32 from marsb200_normalize_rows.
  * sim_out / cost_out [E, M, N] are optional (NULL to skip); cost = (1 - S) / 2.
  * row_fg [E, M] uint8 (pooled support mask, shot-major) and colstats [E, tiles_m, 4, N] are optional
  * (both or neither): per 128-row tile, the per-column {max over fg rows, sum over fg rows,
- * max over bg rows, sum over bg rows}; -inf / 0 when a tile has no such row. tiles_m = pad_rows(M)/128. */
-int marsb200_sim_contract(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int E,
-                          int64_t M, int64_t N, int64_t K, float* sim_out, float* cost_out,
-                          const uint8_t* row_fg, float* colstats, int backend, void* stream);
+ * max over bg rows, sum over bg rows}; -inf / 0 when a tile has no such row. tiles_m = pad_rows(M)/128.
+ * The tcgen05 back end is an error-compensated 3xTF32 product (fp32-grade accuracy, fp32 accumulate in TMEM):
+ * a*b ~ a*b_ + a_lo*b + a*b_lo with the tensor core truncating a, b to tf32; the SIMT back end ignores *_lo. */
+int marsb200_sim_contract(const float* a, const float* a_lo, const float* b, const float* b_lo, int E, int64_t M,
+                          int64_t N, int64_t K, float* sim_out, float* cost_out, const uint8_t* row_fg,
+                          float* colstats, int backend, void* stream);
 
 /* Row top-k (k <= 8, per support patch over the query patches) and column arg-max (per query patch over the
  * support rows selected by row_mask, or all rows when NULL) of S with warp-shuffle reductions: the

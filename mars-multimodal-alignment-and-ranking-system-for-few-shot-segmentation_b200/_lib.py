@@ -38,7 +38,7 @@ SIGNATURES = {
     "marsb200_words_per_mask": (_l, [_l]),
     "marsb200_pad_rows": (_l, [_l]),
     "marsb200_pad_k": (_l, [_l]),
-    "marsb200_normalize_split": (_i, [_p, _l, _i, _l, _l, _i, _p, _p, _p]),
+    "marsb200_normalize_rows": (_i, [_p, _l, _i, _l, _l, _i, _p, _p, _p]),
     "marsb200_pool_mask": (_i, [_p, _i, _l, _i, _i, _i, _p, _p]),
     "marsb200_sim_contract": (_i, [_p, _p, _p, _p, _i, _l, _l, _l, _p, _p, _p, _p, _i, _p]),
     "marsb200_match_argmax": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),

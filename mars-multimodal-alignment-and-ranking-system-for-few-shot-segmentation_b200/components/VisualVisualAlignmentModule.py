@@ -44,8 +44,8 @@ class VisualVisualAlignmentModule:
         attn_maps = list(self.model.get_last_self_attention(
             self.model_transforms(query_img[0]).unsqueeze(0).to(self.device)))
         m, c = fs_raw.shape
-        fs = ops.normalize_split(fs_raw)
-        fq = ops.normalize_split(fq_raw)
+        fs = ops.normalize_rows(fs_raw)
+        fq = ops.normalize_rows(fq_raw)
         row_fg = ops.pool_mask(support_masks.permute(1, 0, 2, 3), g).reshape(1, m)
         if not bool(row_fg.any()):
             # the reference fails here too: max over an empty foreground (VisualVisualAlignmentModule.py:82)
@@ -68,9 +68,9 @@ class VisualVisualAlignmentModule:
 
     def _extract_patch_features(self, imgs) -> torch.Tensor:
         """L2-normalised patch features, as the reference method returns them (:113-127)."""
-        hi, lo = ops.normalize_split(self._backbone_patch_tokens(imgs))
-        raw_rows = hi.shape[1]
-        feats = (hi + lo)[0]
+        padded, _ = ops.normalize_rows(self._backbone_patch_tokens(imgs))
+        raw_rows = padded.shape[1]
+        feats = padded[0]
         rows = sum(1 for _ in imgs) * self.model_embedding_spatial_dimensions ** 2
         return feats[:min(rows, raw_rows), :self.model.embed_dim]
 

@@ -1,7 +1,7 @@
 // Shared pieces of the NT contraction C[m,n] = sum_k A[m,k] B[n,k] used for S = Fs Fq^T (A2/A3)
 // and D D^T (A4): operand layout, the epilogue parameter block and the tile epilogue that both the
-// tcgen05 kernel and the SIMT validation kernel run once their 128 x BN fp32 tile sits in shared
-// memory.
+// SIMT validation kernel runs once its 128 x BN fp32 tile sits in shared memory (the tcgen05 kernel has its
+// own warp-specialised version of the same arithmetic).
 #pragma once
 #include "common.cuh"
 
@@ -132,10 +132,27 @@ __device__ __forceinline__ void tile_epilogue(const float* tile, int lds, unsign
     }
 }
 
-// back ends (gemm_simt in vva.cu, gemm_tcgen05 in gemm_tc.cu).  Operands hi/lo: [E, rows_pad, k_pad].
-int gemm_simt(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int E, int64_t M, int64_t N,
-              int64_t K, const GemmEpilogue& ep, cudaStream_t s);
-int gemm_tcgen05(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int E, int64_t M,
-                 int64_t N, int64_t K, const GemmEpilogue& ep, cudaStream_t s);
+// lo = x - (x with the low 13 mantissa bits cleared): exact in fp32.  kind::tf32 reads only the top 19 bits of an
+// fp32 word, so (x, lo) is the hi/lo pair of the error-compensated product without storing hi separately.
+__device__ __forceinline__ float tf32_residual(float x) {
+    return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+}
+
+// One fp32 operand of the contraction: [E][rows][ld] with k contiguous, plus its tf32 residual array of the same
+// layout (only the tensor-core back end reads it).  Rows >= `rows` and columns >= K read as zero (TMA
+// out-of-bounds fill in the tensor-core kernel, explicit checks in the SIMT kernel).
+struct GemmOperand {
+    const float* p;
+    const float* lo;    // tf32_residual(p), same layout
+    int64_t rows;       // rows present per episode
+    int64_t ld;         // row stride in floats (multiple of 4, >= K)
+    int64_t ep_stride;  // floats between episodes
+};
+
+// back ends (gemm_simt in vva.cu, gemm_tcgen05 in gemm_tc.cu)
+int gemm_simt(const GemmOperand& a, const GemmOperand& b, int E, int64_t M, int64_t N, int64_t K, const GemmEpilogue& ep,
+              cudaStream_t s);
+int gemm_tcgen05(const GemmOperand& a, const GemmOperand& b, int E, int64_t M, int64_t N, int64_t K,
+                 const GemmEpilogue& ep, cudaStream_t s);
 
 }  // namespace marsb200

@@ -1,14 +1,21 @@
-// tcgen05 contraction C[m,n] = sum_k A[m,k] B[n,k] for fp32 operands with fp32-grade accuracy:
-// each operand is pre-split into hi = tf32(x) and lo = x - hi, and every 128x128x32 k-block issues
-// hi*hi + hi*lo + lo*hi as kind::tf32 MMAs (3xTF32 error compensation) accumulating in fp32 in TMEM.
-// Operand tiles arrive by TMA (128-byte swizzle) through a 3-stage mbarrier ring; one thread issues the
-// MMAs; the epilogue moves the accumulator TMEM -> registers -> shared memory and runs tile_epilogue
-// (coalesced S / cost / max(D, .) stores, fused fg/bg column statistics).
+// tcgen05 contraction C[m,n] = sum_k A[m,k] B[n,k] for fp32 operands with fp32-grade accuracy (3xTF32):
+// x = hi + lo with hi = the top 19 bits of x (what kind::tf32 reads of an fp32 word: the tensor core ignores
+// the low 13 mantissa bits, so the fp32 array itself is the `hi` operand) and lo = x - hi (exact, produced by the
+// kernels that write the operands).  Per k-step of 8 the products hi*hi, hi*lo and lo*hi accumulate in fp32 in
+// TMEM as TWO instructions: a_hi x [b_hi; b_lo] (N = 256: the b_lo tile sits right behind the b_hi tile in shared
+// memory, so one descriptor covers both and the two products land in two 128-column halves of the accumulator)
+// and a_lo x b_hi (N = 128).  That reads 20 KB of shared memory per k-step instead of 24 KB; the epilogue adds
+// the two halves.
 //
-// Roles (128 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (warp 1 owns the TMEM
-// allocation), all four warps = epilogue (warp w reads TMEM lanes 32w..32w+31).
+// TMA (128-byte swizzle) feeds a 3-stage ring of {A_hi, A_lo, B_hi, B_lo} 16 KB tiles.  Persistent: one CTA per
+// SM loops over output tiles; the accumulator (256 columns) is double buffered in TMEM (all 512 columns), so the
+// epilogue warps drain tile i while the MMA thread works on tile i+1 and the TMA thread prefetches operands
+// across tile boundaries.  The issue of a tcgen05.mma blocks until the tensor pipe accepts it, so the MMA thread
+// does nothing else per k-block than one barrier wait and one commit.
+// Roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (+ TMEM alloc),
+// warps 2..5 = epilogue (warp w drains TMEM lanes 32*(w%4).., one 32x32 chunk at a time through a private
+// padded staging tile: coalesced stores, mirrored stores, per-warp column partials).
 #include <algorithm>
-#include <cstdlib>
 
 #include "gemm_common.cuh"
 #include "tc_common.cuh"
@@ -19,132 +26,12 @@ using namespace tc;
 
 constexpr int TC_BN = 128;
 constexpr int TC_BK = 32;                            // fp32 elements = one 128 B swizzle row
-constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = GEMM_BM * TC_BK * 4;   // 16 KB per operand tile
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;    // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_EPI_LDS = TC_BN + 1;                // padded fp32 row of the epilogue tile
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers, flags*/;
-static_assert(GEMM_BM * TC_EPI_LDS * 4 <= TC_STAGES * TC_STAGE_BYTES, "epilogue tile must fit in the stage ring");
+constexpr int TC_PAIR_BYTES = 2 * TC_TILE_BYTES;     // A tile then B tile
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo (B_lo directly behind B_hi)
+constexpr int TC_STAGES = 3;
+constexpr int TC_ACC_COLS = 2 * TC_BN;             // [hi*hi + lo*hi | hi*lo]
 
-__global__ void __launch_bounds__(128, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                    int num_kb, GemmEpilogue ep) {
-    extern __shared__ unsigned char smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
-    unsigned char* base_ptr = smem_raw + (base - raw);
-    const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
-    // barrier block: full[STAGES], empty[STAGES], tmem_full, then the TMEM address and the row flags
-    auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (TC_STAGES + s); };
-    const uint32_t tmem_full_bar = bars + 8u * (2 * TC_STAGES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + TC_STAGES * TC_STAGE_BYTES + 8 * (2 * TC_STAGES + 1));
-    unsigned char* flags = base_ptr + TC_STAGES * TC_STAGE_BYTES + 128;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int tile_n = blockIdx.x, tile_m = blockIdx.y;
-    const int e = blockIdx.z;
-    if (ep.symmetric) {  // blockIdx.x enumerates the upper-triangular tile pairs row by row
-        int t = blockIdx.x, tm = 0;
-        while (t >= ep.tiles_m - tm) {
-            t -= ep.tiles_m - tm;
-            ++tm;
-        }
-        tile_m = tm;
-        tile_n = tm + t;
-    }
-
-    if (tid == 0) {
-        tma_prefetch_desc(&map_a_hi);
-        tma_prefetch_desc(&map_a_lo);
-        tma_prefetch_desc(&map_b_hi);
-        tma_prefetch_desc(&map_b_lo);
-        for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
-        }
-        mbar_init(tmem_full_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TC_BN);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_acc = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ---- TMA producer
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % TC_STAGES;
-                const uint32_t phase = (kb / TC_STAGES) & 1;
-                mbar_wait(empty_bar(s), phase ^ 1);
-                mbar_expect_tx(full_bar(s), TC_STAGE_BYTES);
-                const uint32_t st = base + s * TC_STAGE_BYTES;
-                const int k0 = kb * TC_BK, m0 = tile_m * GEMM_BM, n0 = tile_n * TC_BN;
-                tma_load_3d(st, &map_a_hi, full_bar(s), k0, m0, e);
-                tma_load_3d(st + TC_TILE_BYTES, &map_a_lo, full_bar(s), k0, m0, e);
-                tma_load_3d(st + 2 * TC_TILE_BYTES, &map_b_hi, full_bar(s), k0, n0, e);
-                tma_load_3d(st + 3 * TC_TILE_BYTES, &map_b_lo, full_bar(s), k0, n0, e);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ---- MMA issuer: 4 k-steps of 8 per block, 3 products per k-step
-            constexpr uint32_t idesc = make_idesc(/*C=F32*/ 1, /*A=TF32*/ 2, /*B=TF32*/ 2, GEMM_BM, TC_BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % TC_STAGES;
-                const uint32_t phase = (kb / TC_STAGES) & 1;
-                mbar_wait(full_bar(s), phase);
-                tc_fence_after();
-                const uint32_t st = base + s * TC_STAGE_BYTES;
-                const uint64_t a_hi = make_sw128_kmajor_desc(st);
-                const uint64_t a_lo = make_sw128_kmajor_desc(st + TC_TILE_BYTES);
-                const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * TC_TILE_BYTES);
-                const uint64_t b_lo = make_sw128_kmajor_desc(st + 3 * TC_TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {
-                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 B per k-step, in 16 B units
-                    mma_tf32(tmem_acc, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-                    mma_tf32(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1);
-                    mma_tf32(tmem_acc, a_hi + adv, b_hi + adv, idesc, 1);
-                }
-                tc_commit(empty_bar(s));  // frees the stage once these MMAs have read it
-            }
-            tc_commit(tmem_full_bar);  // accumulator complete
-        }
-        __syncwarp();
-    }
-
-    // ---- epilogue: TMEM -> registers -> shared memory tile (reuses the stage ring)
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    float* tile = reinterpret_cast<float*>(base_ptr);
-    const int row = warp * 32 + lane;
-#pragma unroll
-    for (int c = 0; c < TC_BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tile[row * TC_EPI_LDS + c * 32 + j] = __uint_as_float(v[j]);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_acc, TC_BN);
-    tile_epilogue<TC_BN>(tile, TC_EPI_LDS, flags, ep, e, tile_m, tile_n, tid, 128);
-}
-
-// ================================================================================================
-// Persistent variant: one CTA per SM loops over tiles; the accumulator is double buffered in TMEM
-// (2 x 128 columns) so that four dedicated epilogue warps drain tile i while the MMA thread already
-// works on tile i+1 and the TMA thread prefetches operands across tile boundaries.
-// Roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (+ TMEM alloc),
-// warps 2..5 = epilogue (warp w drains TMEM lanes 32*(w%4).., one 32x32 chunk at a time through a
-// private padded staging tile: coalesced stores, mirrored stores, per-warp column partials).
-// ================================================================================================
 constexpr int PG_THREADS = 192;
 constexpr int PG_EPI_WARPS = 4;
 constexpr int PG_STAGING_FLOATS = 32 * 33;                         // per epilogue warp
@@ -153,6 +40,18 @@ constexpr int PG_OFF_PARTIAL = PG_OFF_STAGING + PG_EPI_WARPS * PG_STAGING_FLOATS
 constexpr int PG_OFF_FLAGS = PG_OFF_PARTIAL + PG_EPI_WARPS * 4 * TC_BN * 4;   // [warp][stat][col] floats
 constexpr int PG_OFF_BARS = PG_OFF_FLAGS + 128;
 constexpr int PG_SMEM_BYTES = PG_OFF_BARS + 256 + 1024;
+static_assert(PG_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+#ifdef MARSB200_GEMM_PROFILE
+__device__ long long g_gemm_prof[128];
+#define GP_STAMP(slot) do { if (blockIdx.x == 0) g_gemm_prof[slot] = clock64(); } while (0)
+#define GP_CLOCK() clock64()
+#define GP_PUT(slot, v) do { if (blockIdx.x == 0) g_gemm_prof[slot] = (v); } while (0)
+#else
+#define GP_STAMP(slot) do { } while (0)
+#define GP_CLOCK() 0ll
+#define GP_PUT(slot, v) do { } while (0)
+#endif
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -162,13 +61,13 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, con
                                int num_kb, int tiles_n, int tiles_per_ep, int total_tiles, GemmEpilogue ep) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
     unsigned char* base_ptr = smem_raw + (base - raw);
     const uint32_t bars = base + PG_OFF_BARS;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (TC_STAGES + s); };
-    auto acc_full_bar = [&](int a) { return bars + 8u * (2 * TC_STAGES + a); };
-    auto acc_empty_bar = [&](int a) { return bars + 8u * (2 * TC_STAGES + 2 + a); };
+    auto acc_full = [&](int a) { return bars + 8u * (2 * TC_STAGES + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (2 * TC_STAGES + 2 + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + PG_OFF_BARS + 8 * (2 * TC_STAGES + 4));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -200,12 +99,12 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, con
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(acc_full_bar(a), 1);
-            mbar_init(acc_empty_bar(a), PG_EPI_WARPS);
+            mbar_init(acc_full(a), 1);
+            mbar_init(acc_empty(a), PG_EPI_WARPS);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * TC_BN);
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * TC_ACC_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -213,54 +112,56 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, con
 
     if (warp == 0) {
         if (lane == 0) {
+            // ---- TMA producer
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int e, tile_m, tile_n;
                 decode(tile, e, tile_m, tile_n);
+                const int m0 = tile_m * GEMM_BM, n0 = tile_n * TC_BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % TC_STAGES;
-                    const uint32_t phase = (it / TC_STAGES) & 1;
-                    mbar_wait(empty_bar(s), phase ^ 1);
+                    mbar_wait(empty_bar(s), ((it / TC_STAGES) & 1) ^ 1);
                     mbar_expect_tx(full_bar(s), TC_STAGE_BYTES);
                     const uint32_t st = base + s * TC_STAGE_BYTES;
-                    const int k0 = kb * TC_BK, m0 = tile_m * GEMM_BM, n0 = tile_n * TC_BN;
-                    tma_load_3d(st, &map_a_hi, full_bar(s), k0, m0, e);
-                    tma_load_3d(st + TC_TILE_BYTES, &map_a_lo, full_bar(s), k0, m0, e);
-                    tma_load_3d(st + 2 * TC_TILE_BYTES, &map_b_hi, full_bar(s), k0, n0, e);
-                    tma_load_3d(st + 3 * TC_TILE_BYTES, &map_b_lo, full_bar(s), k0, n0, e);
+                    tma_load_3d(st, &map_a_hi, full_bar(s), kb * TC_BK, m0, e);
+                    tma_load_3d(st + 2 * TC_TILE_BYTES, &map_b_hi, full_bar(s), kb * TC_BK, n0, e);
+                    tma_load_3d(st + TC_TILE_BYTES, &map_a_lo, full_bar(s), kb * TC_BK, m0, e);
+                    tma_load_3d(st + 3 * TC_TILE_BYTES, &map_b_lo, full_bar(s), kb * TC_BK, n0, e);
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(/*C=F32*/ 1, /*A=TF32*/ 2, /*B=TF32*/ 2, GEMM_BM, TC_BN);
+            // ---- MMA issuer: 4 k-steps of 8 per block, two instructions per k-step
+            constexpr uint32_t idesc_n256 = make_idesc(/*C=F32*/ 1, /*A=TF32*/ 2, /*B=TF32*/ 2, GEMM_BM, 2 * TC_BN);
+            constexpr uint32_t idesc_n128 = make_idesc(/*C=F32*/ 1, /*A=TF32*/ 2, /*B=TF32*/ 2, GEMM_BM, TC_BN);
             uint32_t it = 0, tl = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
                 const uint32_t a = tl & 1, aphase = (tl >> 1) & 1;
-                mbar_wait(acc_empty_bar(a), aphase ^ 1);  // the epilogue has drained this accumulator
+                GP_STAMP(tl * 8 + 0);
+                mbar_wait(acc_empty(a), aphase ^ 1);  // the epilogue has drained this accumulator
+                GP_STAMP(tl * 8 + 1);
                 tc_fence_after();
-                const uint32_t tmem_acc = tmem_base + a * TC_BN;
+                const uint32_t tmem_acc = tmem_base + a * TC_ACC_COLS;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % TC_STAGES;
-                    const uint32_t phase = (it / TC_STAGES) & 1;
-                    mbar_wait(full_bar(s), phase);
+                    mbar_wait(full_bar(s), (it / TC_STAGES) & 1);
                     tc_fence_after();
                     const uint32_t st = base + s * TC_STAGE_BYTES;
                     const uint64_t a_hi = make_sw128_kmajor_desc(st);
                     const uint64_t a_lo = make_sw128_kmajor_desc(st + TC_TILE_BYTES);
-                    const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * TC_TILE_BYTES);
-                    const uint64_t b_lo = make_sw128_kmajor_desc(st + 3 * TC_TILE_BYTES);
+                    const uint64_t b_hl = make_sw128_kmajor_desc(st + 2 * TC_TILE_BYTES);  // 256 rows: b_hi then b_lo
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
-                        mma_tf32(tmem_acc, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-                        mma_tf32(tmem_acc, a_hi + adv, b_lo + adv, idesc, 1);
-                        mma_tf32(tmem_acc, a_hi + adv, b_hi + adv, idesc, 1);
+                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 B per k-step, in 16 B units
+                        mma_tf32(tmem_acc, a_hi + adv, b_hl + adv, idesc_n256, (kb | k) != 0);
+                        mma_tf32(tmem_acc, a_lo + adv, b_hl + adv, idesc_n128, 1);
                     }
-                    tc_commit(empty_bar(s));
+                    tc_commit(empty_bar(s));  // the stage is free once these MMAs have read it
                 }
-                tc_commit(acc_full_bar(a));
+                tc_commit(acc_full(a));
+                GP_STAMP(tl * 8 + 2);
             }
         }
         __syncwarp();
@@ -282,96 +183,91 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, con
                 const int64_t m = m0 + lane;
                 flags[lane] = (m < ep.M) ? (ep.row_fg[(int64_t)e * ep.M + m] ? 1 : 2) : 0;
             }
-            mbar_wait(acc_full_bar(a), aphase);
+            if (ew == 0 && lane == 0) GP_STAMP(tl * 8 + 3);
+            mbar_wait(acc_full(a), aphase);
+            if (ew == 0 && lane == 0) GP_STAMP(tl * 8 + 4);
             tc_fence_after();
             const bool mirror = ep.symmetric && tile_m != tile_n;
+            float* o0 = ep.out0 ? ep.out0 + (int64_t)e * ep.M * ep.ld_out : nullptr;
+            float* o1 = ep.out1 ? ep.out1 + (int64_t)e * ep.M * ep.ld_out : nullptr;
 #pragma unroll 1
             for (int c = 0; c < TC_BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + a * TC_BN + (uint32_t)(c * 32), v);
+                uint32_t v[32], w[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * TC_ACC_COLS + (uint32_t)(c * 32);
+                tmem_ld_32x32(taddr, v);
+                tmem_ld_32x32(taddr + TC_BN, w);
                 tmem_ld_wait();
                 if (c == TC_BN / 32 - 1) {  // accumulator fully read: hand it back to the MMA thread
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty_bar(a));
+                    if (lane == 0) mbar_arrive(acc_empty(a));
+                    if (ew == 0 && lane == 0) GP_STAMP(tl * 8 + 5);
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) staging[lane * 33 + j] = __uint_as_float(v[j]);
+                for (int j = 0; j < 32; ++j) staging[lane * 33 + j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
                 __syncwarp();
                 const int64_t nc = n0 + c * 32;
-                if (ep.out0 || ep.out1) {
-                    // direct block: lane = column; all 32 rows of `maxwith` loads in flight at once
-#pragma unroll 1
-                    for (int r0 = 0; r0 < 32; r0 += 32) {
-                        float val[32];
-#pragma unroll
+                if (o0 || o1) {
+                    // direct block: lane = column, 32 coalesced row segments
+                    const int64_t n = nc + lane;
+                    if (n < ep.N) {
+#pragma unroll 8
                         for (int i = 0; i < 32; ++i) {
-                            const int64_t m = m0 + r0 + i, n = nc + lane;
-                            float t = staging[(r0 + i) * 33 + lane];
-                            if (ep.maxwith && m < ep.M && n < ep.N)
-                                t = fmaxf(t, ep.maxwith[((int64_t)e * ep.M + m) * ep.ld_max + n]);
-                            val[i] = t;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int64_t m = m0 + r0 + i, n = nc + lane;
-                            if (m < ep.M && n < ep.N) {
-                                if (ep.out0) ep.out0[((int64_t)e * ep.M + m) * ep.ld_out + n] = val[i];
-                                if (ep.out1) ep.out1[((int64_t)e * ep.M + m) * ep.ld_out + n] = (1.0f - val[i]) / 2.0f;
+                            const int64_t m = m0 + i;
+                            if (m < ep.M) {
+                                const float t = staging[i * 33 + lane];
+                                if (o0) o0[m * ep.ld_out + n] = t;
+                                if (o1) o1[m * ep.ld_out + n] = (1.0f - t) / 2.0f;
                             }
                         }
                     }
                     if (mirror) {
-                        // mirrored block: output row = tile column nc + cc, lane = tile row (contiguous in the output)
-#pragma unroll 1
-                        for (int c0 = 0; c0 < 32; c0 += 32) {
-                            float val[32];
-#pragma unroll
+                        // mirrored block: output row = tile column nc + i, lane = tile row (contiguous in the output)
+                        const int64_t ocol = m0 + lane;
+                        if (ocol < ep.N) {
+#pragma unroll 8
                             for (int i = 0; i < 32; ++i) {
-                                const int64_t orow = nc + c0 + i, ocol = m0 + lane;
-                                float t = staging[lane * 33 + c0 + i];
-                                if (ep.maxwith && orow < ep.M && ocol < ep.N)
-                                    t = fmaxf(t, ep.maxwith[((int64_t)e * ep.M + orow) * ep.ld_max + ocol]);
-                                val[i] = t;
-                            }
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int64_t orow = nc + c0 + i, ocol = m0 + lane;
-                                if (orow < ep.M && ocol < ep.N) {
-                                    if (ep.out0) ep.out0[((int64_t)e * ep.M + orow) * ep.ld_out + ocol] = val[i];
-                                    if (ep.out1) ep.out1[((int64_t)e * ep.M + orow) * ep.ld_out + ocol] = (1.0f - val[i]) / 2.0f;
+                                const int64_t orow = nc + i;
+                                if (orow < ep.M) {
+                                    const float t = staging[lane * 33 + i];
+                                    if (o0) o0[orow * ep.ld_out + ocol] = t;
+                                    if (o1) o1[orow * ep.ld_out + ocol] = (1.0f - t) / 2.0f;
                                 }
                             }
                         }
                     }
                 }
                 if (ep.colstats) {
-                    // this warp's 32 rows of column nc + lane
+                    // this warp's 32 rows of column nc + lane; fp32 sums over 32 values (four interleaved chains),
+                    // everything above the band is combined in double.  (fp64 arithmetic here ran ~6x slower
+                    // whenever the MMA thread was issuing.)
                     float fg_max = -INFINITY, bg_max = -INFINITY;
-                    double fg_sum = 0.0, bg_sum = 0.0;
-#pragma unroll 8
+                    float fs[4] = {0.f, 0.f, 0.f, 0.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
                     for (int r = 0; r < 32; ++r) {
                         const float t = staging[r * 33 + lane];
                         const unsigned char f = flags[r];
-                        if (f == 1) {
-                            fg_max = fmaxf(fg_max, t);
-                            fg_sum += (double)t;
-                        } else if (f == 2) {
-                            bg_max = fmaxf(bg_max, t);
-                            bg_sum += (double)t;
-                        }
+                        const bool is_fg = (f == 1), is_bg = (f == 2);
+                        fg_max = is_fg ? fmaxf(fg_max, t) : fg_max;
+                        bg_max = is_bg ? fmaxf(bg_max, t) : bg_max;
+                        fs[r & 3] += is_fg ? t : 0.f;
+                        bs[r & 3] += is_bg ? t : 0.f;
                     }
+                    const float fg_sum = (fs[0] + fs[1]) + (fs[2] + fs[3]);
+                    const float bg_sum = (bs[0] + bs[1]) + (bs[2] + bs[3]);
                     float* pw = partial + (ew * 4) * TC_BN + c * 32 + lane;
                     pw[0] = fg_max;
-                    pw[TC_BN] = (float)fg_sum;
+                    pw[TC_BN] = fg_sum;
                     pw[2 * TC_BN] = bg_max;
-                    pw[3 * TC_BN] = (float)bg_sum;
+                    pw[3 * TC_BN] = bg_sum;
                 }
                 __syncwarp();  // staging is reused by the next chunk
             }
+            if (ew == 0 && lane == 0) GP_STAMP(tl * 8 + 7);
             if (ep.colstats) {
                 epi_bar_sync();  // all four bands have written their partials
-                const int col = (warp - 2) * 32 + lane;
+                if (ew == 0 && lane == 0) GP_STAMP(64 + tl * 2);
+                const int col = ew * 32 + lane;
                 const int64_t n = n0 + col;
                 if (n < ep.N) {
                     // combine the four 32-row bands in row order (TMEM quadrant order), deterministically
@@ -392,21 +288,24 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, con
                     cs[2 * ep.N] = bg_max;
                     cs[3 * ep.N] = (float)bg_sum;
                 }
+                if (ew == 0 && lane == 0) GP_STAMP(64 + tl * 2 + 1);
                 epi_bar_sync();  // partials may be overwritten by the next tile
             }
+            if (ew == 0 && lane == 0) GP_STAMP(tl * 8 + 6);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * TC_BN);
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * TC_ACC_COLS);
 }
 
-static int make_operand_map(CUtensorMap* map, const float* ptr, int E, int64_t rows_pad, int64_t k_pad, int box_rows) {
+// 3-D tensor map [K, rows, E] of an fp32 array; elements outside (rows, K) arrive as zeros
+static int make_operand_map(CUtensorMap* map, const float* ptr, const GemmOperand& op, int E, int64_t K) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail(MARSB200_ERR_CUDA, "%s: cuTensorMapEncodeTiled entry point unavailable", "gemm_tcgen05");
-    cuuint64_t dims[3] = {(cuuint64_t)k_pad, (cuuint64_t)rows_pad, (cuuint64_t)E};
-    cuuint64_t strides[2] = {(cuuint64_t)k_pad * 4, (cuuint64_t)rows_pad * k_pad * 4};
-    cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_rows, 1};
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)op.rows, (cuuint64_t)E};
+    cuuint64_t strides[2] = {(cuuint64_t)op.ld * 4, (cuuint64_t)op.ep_stride * 4};
+    cuuint32_t box[3] = {TC_BK, GEMM_BM, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -415,47 +314,51 @@ static int make_operand_map(CUtensorMap* map, const float* ptr, int E, int64_t r
     return MARSB200_OK;
 }
 
-int gemm_tcgen05(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int E, int64_t M,
-                 int64_t N, int64_t K, const GemmEpilogue& ep, cudaStream_t s) {
-    const int64_t m_pad = marsb200_pad_rows(M), n_pad = marsb200_pad_rows(N), k_pad = marsb200_pad_k(K);
-    for (const float* p : {a_hi, a_lo, b_hi, b_lo})
-        if (reinterpret_cast<uintptr_t>(p) & 15)
-            return fail(MARSB200_ERR_ARG, "%s: operands must be 16-byte aligned", "gemm_tcgen05");
+#ifdef MARSB200_GEMM_PROFILE
+}  // namespace marsb200
+extern "C" int marsb200_debug_gemm_profile(long long* out128, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out128, marsb200::g_gemm_prof, sizeof(long long) * 128);
+    if (reset) {
+        long long z[128] = {0};
+        cudaMemcpyToSymbol(marsb200::g_gemm_prof, z, sizeof(z));
+    }
+    return 0;
+}
+namespace marsb200 {
+#endif
+
+int gemm_tcgen05(const GemmOperand& a, const GemmOperand& b, int E, int64_t M, int64_t N, int64_t K,
+                 const GemmEpilogue& ep, cudaStream_t s) {
+    for (const GemmOperand* o : {&a, &b})
+        if (!o->lo || ((reinterpret_cast<uintptr_t>(o->p) | reinterpret_cast<uintptr_t>(o->lo)) & 15) || (o->ld & 3) ||
+            (o->ep_stride & 3) || o->ld < K)
+            return fail(MARSB200_ERR_ARG,
+                        "%s: operands need their residual array, 16-byte alignment and strides that are multiples of 4 floats",
+                        "gemm_tcgen05");
     CUtensorMap maps[4];
     int rc;
-    if ((rc = make_operand_map(&maps[0], a_hi, E, m_pad, k_pad, GEMM_BM))) return rc;
-    if ((rc = make_operand_map(&maps[1], a_lo, E, m_pad, k_pad, GEMM_BM))) return rc;
-    if ((rc = make_operand_map(&maps[2], b_hi, E, n_pad, k_pad, TC_BN))) return rc;
-    if ((rc = make_operand_map(&maps[3], b_lo, E, n_pad, k_pad, TC_BN))) return rc;
-    static bool attr_set = false;
-    static int num_sms = 148;
-    static bool one_tile_per_cta = false;
-    if (!attr_set) {
-        MARS_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    if ((rc = make_operand_map(&maps[0], a.p, a, E, K))) return rc;
+    if ((rc = make_operand_map(&maps[1], a.lo, a, E, K))) return rc;
+    if ((rc = make_operand_map(&maps[2], b.p, b, E, K))) return rc;
+    if ((rc = make_operand_map(&maps[3], b.lo, b, E, K))) return rc;
+    static int num_sms = 0;
+    if (!num_sms) {
         MARS_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM_BYTES));
         int dev = 0;
         MARS_CUDA_OK(cudaGetDevice(&dev));
         MARS_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        const char* env = getenv("MARSB200_GEMM_ONE_TILE");  // debugging: the non-persistent kernel
-        one_tile_per_cta = env && env[0] == '1';
-        attr_set = true;
     }
-    const int tiles_m = (int)(m_pad / GEMM_BM), tiles_n = (int)(n_pad / TC_BN);
+    const int tiles_m = (int)ceil_div64(M, GEMM_BM), tiles_n = (int)ceil_div64(N, TC_BN);
     int tiles_per_ep = tiles_m * tiles_n;
     if (ep.symmetric) {
-        if (M != N || a_hi != b_hi || a_lo != b_lo)
-            return fail(MARSB200_ERR_ARG, "%s: symmetric epilogue needs A == B", "gemm_tcgen05");
+        if (M != N || a.p != b.p) return fail(MARSB200_ERR_ARG, "%s: symmetric epilogue needs A == B", "gemm_tcgen05");
         tiles_per_ep = tiles_m * (tiles_m + 1) / 2;
     }
-    if (one_tile_per_cta) {
-        dim3 grid(ep.symmetric ? tiles_per_ep : tiles_n, ep.symmetric ? 1 : tiles_m, E);
-        gemm_tcgen05_kernel<<<grid, 128, TC_SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], (int)(k_pad / TC_BK), ep);
-    } else {
-        const int total = tiles_per_ep * E;
-        const int grid = std::min(total, num_sms);
-        gemm_tcgen05_persistent_kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, s>>>(
-            maps[0], maps[1], maps[2], maps[3], (int)(k_pad / TC_BK), tiles_n, tiles_per_ep, total, ep);
-    }
+    const int total = tiles_per_ep * E;
+    const int grid = std::min(total, num_sms);
+    gemm_tcgen05_persistent_kernel<<<grid, PG_THREADS, PG_SMEM_BYTES, s>>>(
+        maps[0], maps[1], maps[2], maps[3], (int)ceil_div64(K, TC_BK), tiles_n, tiles_per_ep, total, ep);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }

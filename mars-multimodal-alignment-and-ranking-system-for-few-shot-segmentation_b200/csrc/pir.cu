@@ -154,23 +154,14 @@ __global__ void colsum_final_kernel(const double* __restrict__ partial, int N, f
 }
 
 __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restrict__ attn, int64_t ld, int N,
-                                                            const float* __restrict__ colsum, int64_t n_pad,
-                                                            int64_t k_pad, float* __restrict__ D,
-                                                            float* __restrict__ hi, float* __restrict__ lo) {
+                                                            const float* __restrict__ colsum, int64_t k_pad,
+                                                            float* __restrict__ D, float* __restrict__ D_lo) {
     __shared__ double s_red[8];
     const int64_t e = blockIdx.y;
     const int row = blockIdx.x;
-    float* h = hi + (e * n_pad + row) * k_pad;
-    float* l = lo + (e * n_pad + row) * k_pad;
-    if (row >= N) {  // zero the padding rows of the operands
-        for (int64_t c = threadIdx.x; c < k_pad; c += blockDim.x) {
-            h[c] = 0.f;
-            l[c] = 0.f;
-        }
-        return;
-    }
     const float* a = attn + (e * N + row) * ld;
     float* d = D + (e * N + row) * k_pad;
+    float* dl = D_lo + (e * N + row) * k_pad;
     double acc = 0.0;
     for (int c = threadIdx.x; c < N; c += blockDim.x) {
         const float v = __fdiv_rn(a[c], colsum[e * N + c]);
@@ -187,11 +178,7 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restr
         float v = 0.f;
         if (c < N) v = __fdiv_rn(d[c], rs);
         d[c] = v;
-        uint32_t r;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-        const float vh = __uint_as_float(r);
-        h[c] = vh;
-        l[c] = v - vh;
+        dl[c] = tf32_residual(v);
     }
 }
 
@@ -216,9 +203,8 @@ __global__ void __launch_bounds__(256) matvec_kernel(const float* __restrict__ G
 
 struct PirWorkspace {
     double* partial;  // [E, 16, N]
-    float* D;         // [E, N, k_pad]
-    float* hi;        // [E, n_pad, k_pad]
-    float* lo;        // [E, n_pad, k_pad]
+    float* D;         // [E, N, k_pad]: the doubly normalised attention, also the contraction operand
+    float* D_lo;      // [E, N, k_pad]: its tf32 residual
     float* R;         // [E, N, N]: G = D D^T (the max with D is taken in the mat-vecs)
     float* v;         // [E, N]
     float* t;         // [E, N]
@@ -227,7 +213,7 @@ struct PirWorkspace {
 };
 
 static PirWorkspace carve(void* base, int E, int64_t N) {
-    const int64_t n_pad = marsb200_pad_rows(N), k_pad = marsb200_pad_k(N);
+    const int64_t k_pad = marsb200_pad_k(N);
     auto align = [](int64_t b) { return (b + 255) / 256 * 256; };
     char* p = reinterpret_cast<char*>(base);
     int64_t off = 0;
@@ -236,10 +222,8 @@ static PirWorkspace carve(void* base, int E, int64_t N) {
     off += align((int64_t)E * COLSUM_SPLITS * N * 8);
     w.D = reinterpret_cast<float*>(p + off);
     off += align((int64_t)E * N * k_pad * 4);
-    w.hi = reinterpret_cast<float*>(p + off);
-    off += align((int64_t)E * n_pad * k_pad * 4);
-    w.lo = reinterpret_cast<float*>(p + off);
-    off += align((int64_t)E * n_pad * k_pad * 4);
+    w.D_lo = reinterpret_cast<float*>(p + off);
+    off += align((int64_t)E * N * k_pad * 4);
     w.R = reinterpret_cast<float*>(p + off);
     off += align((int64_t)E * N * N * 4);
     w.v = reinterpret_cast<float*>(p + off);
@@ -307,8 +291,7 @@ int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, 
     MARS_LAUNCH_OK();
     colsum_final_kernel<<<dim3(ceil_div(N, 128), E), 128, 0, s>>>(w.partial, N, w.colsum);
     MARS_LAUNCH_OK();
-    row_normalize_kernel<<<dim3((unsigned)n_pad, E), 256, 0, s>>>(attn, ld_attn, N, w.colsum, n_pad, k_pad, w.D, w.hi,
-                                                                    w.lo);
+    row_normalize_kernel<<<dim3((unsigned)N, E), 256, 0, s>>>(attn, ld_attn, N, w.colsum, k_pad, w.D, w.D_lo);
     MARS_LAUNCH_OK();
 
     GemmEpilogue ep{};
@@ -324,10 +307,11 @@ int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, 
     ep.tiles_m = (int)(n_pad / GEMM_BM);
     ep.symmetric = (backend == MARSB200_GEMM_TCGEN05) ? 1 : 0;  // D D^T: compute the upper triangle only
     int rc;
+    const GemmOperand od{w.D, w.D_lo, N, k_pad, (int64_t)N * k_pad};  // rows beyond N are zero-filled by the loader
     if (backend == MARSB200_GEMM_SIMT)
-        rc = gemm_simt(w.hi, w.lo, w.hi, w.lo, E, N, N, N, ep, s);
+        rc = gemm_simt(od, od, E, N, N, N, ep, s);
     else if (backend == MARSB200_GEMM_TCGEN05)
-        rc = gemm_tcgen05(w.hi, w.lo, w.hi, w.lo, E, N, N, N, ep, s);
+        rc = gemm_tcgen05(od, od, E, N, N, N, ep, s);
     else
         return fail(MARSB200_ERR_ARG, "%s: unknown backend %lld", "marsb200_pir_refine", backend);
     if (rc != MARSB200_OK) return rc;

@@ -1,4 +1,4 @@
-// Visual-visual alignment: row normalise + TF32 split (A1), the SIMT validation contraction,
+// Visual-visual alignment: row normalise (A1), the SIMT validation contraction,
 // the similarity entry point (A2/A3), the vva finalisation (A3) and the nearest-resize + min-max
 // of the vta map (A5).
 #include "gemm_common.cuh"
@@ -6,25 +6,20 @@
 namespace marsb200 {
 
 // --------------------------------------------------------------------------------------------
-// A1: one warp per row: x / max(||x||, 1e-12), then hi = tf32(xn) (round to nearest), lo = xn - hi.
+// A1: one warp per row: x / max(||x||, 1e-12) into the zero-padded operand layout [E, rows_pad, k_pad], plus the
+// tf32 residual of every element (the `lo` operand of the 3xTF32 product).
 // Rows >= `rows` and columns >= k of the padded outputs are written as zero.
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ float round_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-__global__ void __launch_bounds__(256) normalize_split_kernel(const float* __restrict__ x, int64_t ld_x, int64_t rows,
-                                                              int64_t k, int64_t rows_pad, int64_t k_pad,
-                                                              int normalize, int64_t total_rows,
-                                                              float* __restrict__ hi, float* __restrict__ lo) {
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ x, int64_t ld_x, int64_t rows,
+                                                             int64_t k, int64_t rows_pad, int64_t k_pad, int normalize,
+                                                             int64_t total_rows, float* __restrict__ out,
+                                                             float* __restrict__ out_lo) {
     const int lane = threadIdx.x & 31;
     const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wg >= total_rows) return;
     const int64_t e = wg / rows_pad, r = wg % rows_pad;
-    float* h = hi + wg * k_pad;
-    float* l = lo + wg * k_pad;
+    float* h = out + wg * k_pad;
+    float* l = out_lo + wg * k_pad;
     if (r >= rows) {
         for (int64_t c = lane; c < k_pad; c += 32) {
             h[c] = 0.f;
@@ -54,9 +49,9 @@ __global__ void __launch_bounds__(256) normalize_split_kernel(const float* __res
             if (c >= nvec_pad) continue;
             float4 a = v[i];
             if (normalize) a = make_float4(__fdiv_rn(a.x, denom), __fdiv_rn(a.y, denom), __fdiv_rn(a.z, denom), __fdiv_rn(a.w, denom));
-            const float4 hh = make_float4(round_tf32(a.x), round_tf32(a.y), round_tf32(a.z), round_tf32(a.w));
-            reinterpret_cast<float4*>(h)[c] = hh;
-            reinterpret_cast<float4*>(l)[c] = make_float4(a.x - hh.x, a.y - hh.y, a.z - hh.z, a.w - hh.w);
+            reinterpret_cast<float4*>(h)[c] = a;
+            reinterpret_cast<float4*>(l)[c] =
+                make_float4(tf32_residual(a.x), tf32_residual(a.y), tf32_residual(a.z), tf32_residual(a.w));
         }
         return;
     }
@@ -73,22 +68,19 @@ __global__ void __launch_bounds__(256) normalize_split_kernel(const float* __res
     for (int64_t c = lane; c < k_pad; c += 32) {
         float v = 0.f;
         if (c < k) v = normalize ? __fdiv_rn(src[c], denom) : src[c];
-        const float vh = round_tf32(v);
-        h[c] = vh;
-        l[c] = v - vh;
+        h[c] = v;
+        l[c] = tf32_residual(v);
     }
 }
 
 // --------------------------------------------------------------------------------------------
-// SIMT validation contraction: fp32 FFMA on the exact operands hi + lo.  128 x 64 tile, 256 threads,
-// 8 x 4 outputs per thread.  Not the product path for throughput; it pins the tensor-core kernel.
+// SIMT validation contraction: plain fp32 FFMA.  128 x 64 tile, 256 threads, 8 x 4 outputs per thread.
+// Not the product path for throughput; it pins the tensor-core kernel.
 // --------------------------------------------------------------------------------------------
 constexpr int SIMT_BN = 64;
 constexpr int SIMT_BK = 16;
 
-__global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict__ a_hi, const float* __restrict__ a_lo,
-                                                        const float* __restrict__ b_hi, const float* __restrict__ b_lo,
-                                                        int64_t m_pad, int64_t n_pad, int64_t k_pad, GemmEpilogue ep) {
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmOperand A, GemmOperand B, int64_t K, GemmEpilogue ep) {
     __shared__ float sA[SIMT_BK][GEMM_BM + 4];
     __shared__ float sB[SIMT_BK][SIMT_BN + 4];
     __shared__ float sTile[GEMM_BM][SIMT_BN + 1];
@@ -97,25 +89,24 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
     const int64_t e = blockIdx.z;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads: rows ty + 16*i (i<8), cols tx + 16*j (j<4)
-    const float* Ah = a_hi + (e * m_pad + (int64_t)tile_m * GEMM_BM) * k_pad;
-    const float* Al = a_lo + (e * m_pad + (int64_t)tile_m * GEMM_BM) * k_pad;
-    const float* Bh = b_hi + (e * n_pad + (int64_t)tile_n * SIMT_BN) * k_pad;
-    const float* Bl = b_lo + (e * n_pad + (int64_t)tile_n * SIMT_BN) * k_pad;
+    const int64_t ra0 = (int64_t)tile_m * GEMM_BM, rb0 = (int64_t)tile_n * SIMT_BN;
+    const float* Ap = A.p + e * A.ep_stride;
+    const float* Bp = B.p + e * B.ep_stride;
     float acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int64_t k0 = 0; k0 < k_pad; k0 += SIMT_BK) {
+    for (int64_t k0 = 0; k0 < K; k0 += SIMT_BK) {
         // A: 128 rows x 16 k = 2048 values, 8 per thread; B: 64 x 16 = 1024, 4 per thread
         for (int i = tid; i < GEMM_BM * SIMT_BK; i += 256) {
             const int r = i / SIMT_BK, c = i % SIMT_BK;
-            sA[c][r] = Ah[(int64_t)r * k_pad + k0 + c] + Al[(int64_t)r * k_pad + k0 + c];
+            sA[c][r] = (ra0 + r < A.rows && k0 + c < K) ? Ap[(ra0 + r) * A.ld + k0 + c] : 0.f;
         }
         for (int i = tid; i < SIMT_BN * SIMT_BK; i += 256) {
             const int r = i / SIMT_BK, c = i % SIMT_BK;
-            sB[c][r] = Bh[(int64_t)r * k_pad + k0 + c] + Bl[(int64_t)r * k_pad + k0 + c];
+            sB[c][r] = (rb0 + r < B.rows && k0 + c < K) ? Bp[(rb0 + r) * B.ld + k0 + c] : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -140,11 +131,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
     tile_epilogue<SIMT_BN>(&sTile[0][0], SIMT_BN + 1, sFlags, ep, e, tile_m, tile_n, tid, 256);
 }
 
-int gemm_simt(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int E, int64_t M, int64_t N,
-              int64_t K, const GemmEpilogue& ep, cudaStream_t s) {
-    const int64_t m_pad = marsb200_pad_rows(M), n_pad = marsb200_pad_rows(N), k_pad = marsb200_pad_k(K);
-    dim3 grid((unsigned)(n_pad / SIMT_BN), (unsigned)(m_pad / GEMM_BM), E);
-    gemm_simt_kernel<<<grid, 256, 0, s>>>(a_hi, a_lo, b_hi, b_lo, m_pad, n_pad, k_pad, ep);
+int gemm_simt(const GemmOperand& a, const GemmOperand& b, int E, int64_t M, int64_t N, int64_t K, const GemmEpilogue& ep,
+              cudaStream_t s) {
+    dim3 grid((unsigned)ceil_div64(N, SIMT_BN), (unsigned)ceil_div64(M, GEMM_BM), E);
+    gemm_simt_kernel<<<grid, 256, 0, s>>>(a, b, K, ep);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }
@@ -252,22 +242,22 @@ const char* marsb200_last_error(void) { return last_error_buffer(); }
 int64_t marsb200_pad_rows(int64_t rows) { return ceil_div64(rows, GEMM_BM) * GEMM_BM; }
 int64_t marsb200_pad_k(int64_t k) { return ceil_div64(k, GEMM_PAD_K) * GEMM_PAD_K; }
 
-int marsb200_normalize_split(const float* x, int64_t ld_x, int E, int64_t rows, int64_t k, int normalize, float* hi,
-                             float* lo, void* stream) {
-    MARS_REQUIRE(x && hi && lo, "null pointer");
+int marsb200_normalize_rows(const float* x, int64_t ld_x, int E, int64_t rows, int64_t k, int normalize, float* out,
+                            float* out_lo, void* stream) {
+    MARS_REQUIRE(x && out && out_lo, "null pointer");
     MARS_REQUIRE(E > 0 && rows > 0 && k > 0 && ld_x >= k, "shape");
     const int64_t rows_pad = marsb200_pad_rows(rows), k_pad = marsb200_pad_k(k);
     const int64_t total = (int64_t)E * rows_pad;
-    normalize_split_kernel<<<(unsigned)ceil_div64(total, 8), 256, 0, as_stream(stream)>>>(
-        x, ld_x, rows, k, rows_pad, k_pad, normalize, total, hi, lo);
+    normalize_rows_kernel<<<(unsigned)ceil_div64(total, 8), 256, 0, as_stream(stream)>>>(
+        x, ld_x, rows, k, rows_pad, k_pad, normalize, total, out, out_lo);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }
 
-int marsb200_sim_contract(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int E, int64_t M,
+int marsb200_sim_contract(const float* a, const float* a_lo, const float* b, const float* b_lo, int E, int64_t M,
                           int64_t N, int64_t K, float* sim_out, float* cost_out, const uint8_t* row_fg,
                           float* colstats, int backend, void* stream) {
-    MARS_REQUIRE(a_hi && a_lo && b_hi && b_lo, "null operand");
+    MARS_REQUIRE(a && a_lo && b && b_lo, "null operand");
     MARS_REQUIRE(E > 0 && E <= 65535 && M > 0 && N > 0 && K > 0, "shape");
     MARS_REQUIRE((row_fg == nullptr) == (colstats == nullptr), "row_fg and colstats go together");
     MARS_REQUIRE(sim_out || cost_out || colstats, "no output requested");
@@ -282,8 +272,10 @@ int marsb200_sim_contract(const float* a_hi, const float* a_lo, const float* b_h
     ep.ld_out = N;
     ep.ld_max = 0;
     ep.tiles_m = (int)(marsb200_pad_rows(M) / GEMM_BM);
-    if (backend == MARSB200_GEMM_SIMT) return gemm_simt(a_hi, a_lo, b_hi, b_lo, E, M, N, K, ep, as_stream(stream));
-    if (backend == MARSB200_GEMM_TCGEN05) return gemm_tcgen05(a_hi, a_lo, b_hi, b_lo, E, M, N, K, ep, as_stream(stream));
+    const int64_t m_pad = marsb200_pad_rows(M), n_pad = marsb200_pad_rows(N), k_pad = marsb200_pad_k(K);
+    const GemmOperand oa{a, a_lo, m_pad, k_pad, m_pad * k_pad}, ob{b, b_lo, n_pad, k_pad, n_pad * k_pad};
+    if (backend == MARSB200_GEMM_SIMT) return gemm_simt(oa, ob, E, M, N, K, ep, as_stream(stream));
+    if (backend == MARSB200_GEMM_TCGEN05) return gemm_tcgen05(oa, ob, E, M, N, K, ep, as_stream(stream));
     return fail(MARSB200_ERR_ARG, "%s: unknown backend %lld", "marsb200_sim_contract", backend);
 }
 

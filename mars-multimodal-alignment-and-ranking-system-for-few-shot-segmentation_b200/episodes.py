@@ -40,7 +40,7 @@ class RankingConfig:
 
 def kernel_launches_per_run(cfg: RankingConfig) -> int:
     """How many of our kernels one `RankingEngine.run` launches (counted from the sequence below)."""
-    n = 2                      # normalize_split x2
+    n = 2                      # normalize_rows x2
     n += 1                     # pool_mask
     n += 1                     # sim_contract
     n += 1                     # vva_finalize
@@ -149,8 +149,8 @@ class RankingEngine:
             with torch.cuda.stream(self._side):
                 self._mask_chain(batch)
                 self._ev_join.record(self._side)
-        ops.normalize_split(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
-        ops.normalize_split(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
+        ops.normalize_rows(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
+        ops.normalize_rows(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
         ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
         ops.sim_contract(self.fs, self.fq, m, n, s.C, want_sim=cfg.want_sim, want_cost=cfg.want_cost or cfg.emd_on_device,
                          row_fg=self.row_fg, backend=cfg.gemm_backend, out=self.gemm_out)

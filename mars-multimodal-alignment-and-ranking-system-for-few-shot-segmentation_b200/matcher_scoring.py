@@ -110,8 +110,8 @@ class PatchMatcher:
         indices_forward (support rows, query patches), retain).
         """
         dev = self.device
-        ref = ops.normalize_split(ref_feats.to(dev).float())
-        tar = ops.normalize_split(tar_feat.to(dev).float())
+        ref = ops.normalize_rows(ref_feats.to(dev).float())
+        tar = ops.normalize_rows(tar_feat.to(dev).float())
         m, c = ref_feats.shape
         n = tar_feat.shape[0]
         res = ops.sim_contract(ref, tar, m, n, c, want_sim=True, want_cost=True)

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import GEMM_SIMT, GEMM_TCGEN05, MASK_F32, MASK_U8, PAIR_MMA, PAIR_POPC, check, lib
 
 __all__ = [
-    "words_per_mask", "pad_rows", "pad_k", "normalize_split", "pool_mask", "sim_contract", "match_argmax", "mutual_matches", "lsap", "vva_finalize",
+    "words_per_mask", "pad_rows", "pad_k", "normalize_rows", "pool_mask", "sim_contract", "match_argmax", "mutual_matches", "lsap", "vva_finalize",
     "attn_mean", "pir_refine", "resize_minmax", "pack_masks", "pack_pairwise", "pool_packed", "region_sums", "pairwise_inter",
     "emd_scores", "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas",
     "GEMM_TCGEN05", "GEMM_SIMT", "PAIR_POPC", "PAIR_MMA",
@@ -70,19 +70,20 @@ def pad_k(k: int) -> int:
 
 
 # ----------------------------------------------------------------------------- A1
-def normalize_split(x: torch.Tensor, normalize: bool = True, out=None):
-    """x [E, rows, k] -> (hi, lo) [E, pad_rows, pad_k]; hi + lo is the (normalised) fp32 row."""
+def normalize_rows(x: torch.Tensor, normalize: bool = True, out=None):
+    """x [E, rows, k] -> (xn, lo), both [E, pad_rows, pad_k] fp32: the (normalised) rows in the contraction's
+    zero-padded layout and their tf32 residuals (xn minus its top 19 bits), the operand pair of `sim_contract`."""
     x = _cuda(x, torch.float32, "x")
     if x.dim() == 2:
         x = x[None]
     e, rows, k = x.shape
     if out is None:
-        hi = torch.empty((e, pad_rows(rows), pad_k(k)), device=x.device, dtype=torch.float32)
-        lo = torch.empty_like(hi)
+        xn = torch.empty((e, pad_rows(rows), pad_k(k)), device=x.device, dtype=torch.float32)
+        lo = torch.empty_like(xn)
     else:
-        hi, lo = out
-    check(lib.marsb200_normalize_split(x.data_ptr(), k, e, rows, k, int(normalize), hi.data_ptr(), lo.data_ptr(), _stream()))
-    return hi, lo
+        xn, lo = out
+    check(lib.marsb200_normalize_rows(x.data_ptr(), k, e, rows, k, int(normalize), xn.data_ptr(), lo.data_ptr(), _stream()))
+    return xn, lo
 
 
 # ----------------------------------------------------------------------------- A3 / A6
@@ -99,11 +100,10 @@ def pool_mask(masks: torch.Tensor, g: int, out=None) -> torch.Tensor:
 
 # ----------------------------------------------------------------------------- A2 + A3
 def sim_contract(a, b, m: int, n: int, k: int, want_sim=True, want_cost=False, row_fg=None, backend=None, out=None):
-    """S = A B^T on operands from normalize_split.  Returns dict(sim, cost, colstats)."""
-    a_hi, a_lo = a
-    b_hi, b_lo = b
-    e = a_hi.shape[0]
-    dev = a_hi.device
+    """S = A B^T on operands from normalize_rows.  Returns dict(sim, cost, colstats)."""
+    (a, a_lo), (b, b_lo) = a, b
+    e = a.shape[0]
+    dev = a.device
     out = out or {}
     sim = out.get("sim") if want_sim else None
     cost = out.get("cost") if want_cost else None
@@ -117,7 +117,7 @@ def sim_contract(a, b, m: int, n: int, k: int, want_sim=True, want_cost=False, r
         colstats = out.get("colstats")
         if colstats is None:
             colstats = torch.empty((e, pad_rows(m) // 128, 4, n), device=dev, dtype=torch.float32)
-    check(lib.marsb200_sim_contract(a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), e, m, n, k,
+    check(lib.marsb200_sim_contract(a.data_ptr(), a_lo.data_ptr(), b.data_ptr(), b_lo.data_ptr(), e, m, n, k,
                                     _ptr(sim), _ptr(cost), _ptr(row_fg), _ptr(colstats),
                                     DEFAULT_GEMM if backend is None else backend, _stream()))
     return dict(sim=sim, cost=cost, colstats=colstats)

@@ -9,7 +9,7 @@ E = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 eps = [marsb200.make_episode(shape, 40 + i, dev) for i in range(E)]
 b = marsb200.stack_episodes(eps)
 n, g = shape.N, shape.g
-fs = ops.normalize_split(b["feat_s"].reshape(E, n, shape.C)); fq = ops.normalize_split(b["feat_q"])
+fs = ops.normalize_rows(b["feat_s"].reshape(E, n, shape.C)); fq = ops.normalize_rows(b["feat_q"])
 row_fg = ops.pool_mask(b["support_mask"], g).reshape(E, n)
 cost = ops.sim_contract(fs, fq, n, n, shape.C, want_sim=False, want_cost=True)["cost"]
 bits = ops.pack_masks(b["masks"]); pooled, area, cnt = ops.pool_packed(bits, shape.H, shape.W, g)

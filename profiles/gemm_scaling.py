@@ -10,7 +10,7 @@ E, M, N = 8, 1369, 1369
 for K in (256, 1024, 2048, 4096):
     a = torch.randn(E, M, K, device=dev)
     b = torch.randn(E, N, K, device=dev)
-    fa, fb = ops.normalize_split(a), ops.normalize_split(b)
+    fa, fb = ops.normalize_rows(a), ops.normalize_rows(b)
     row_fg = (torch.rand(E, M, device=dev) < 0.3).to(torch.uint8)
     out = {}
     for mode, kw in (("colstats", dict(want_sim=False, row_fg=row_fg)), ("store S", dict(want_sim=True))):

@@ -28,7 +28,7 @@ def t(name, fn, iters=10):
     return ms
 
 tot = 0
-tot += t("normalize_split x2", lambda b: (ops.normalize_split(b["feat_s"].reshape(e, m, s.C), True, out=eng.fs), ops.normalize_split(b["feat_q"].reshape(e, n, s.C), True, out=eng.fq)))
+tot += t("normalize_rows x2", lambda b: (ops.normalize_rows(b["feat_s"].reshape(e, m, s.C), True, out=eng.fs), ops.normalize_rows(b["feat_q"].reshape(e, n, s.C), True, out=eng.fq)))
 tot += t("pool_mask", lambda b: ops.pool_mask(b["support_mask"], s.g, out=eng.row_fg))
 tot += t("sim_contract", lambda b: ops.sim_contract(eng.fs, eng.fq, m, n, s.C, want_sim=False, row_fg=eng.row_fg, out=eng.gemm_out))
 tot += t("vva_finalize", lambda b: ops.vva_finalize(eng.gemm_out["colstats"], eng.row_fg, m, n, out=eng.prior))

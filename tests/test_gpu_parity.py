@@ -148,12 +148,17 @@ def test_similarity_and_prior(mb, name, backend):
     c = cases.vva_inputs(spec)
     g, ns = spec["g"], spec["ns"]
     n, m, k = g * g, ns * g * g, spec["C"]
-    fs = mb.ops.normalize_split(c["feat_s"].reshape(1, m, k).to(dev()))
-    fq = mb.ops.normalize_split(c["feat_q"][None].to(dev()))
-    # A1: hi + lo is the normalised row
+    fs = mb.ops.normalize_rows(c["feat_s"].reshape(1, m, k).to(dev()))
+    fq = mb.ops.normalize_rows(c["feat_q"][None].to(dev()))
+    # A1: the normalised rows in the zero-padded operand layout
     fs_ref = orc.normalize_rows(c["feat_s"])
-    np.testing.assert_allclose((fs[0] + fs[1])[0, :m, :k].cpu().numpy(), fs_ref.numpy(), rtol=0, atol=3e-7)
-    assert float((fs[0] + fs[1])[0, m:].abs().max() if fs[0].shape[1] > m else 0.0) == 0.0
+    xn, lo = fs
+    np.testing.assert_allclose(xn[0, :m, :k].cpu().numpy(), fs_ref.numpy(), rtol=0, atol=3e-7)
+    assert float(xn[0, m:].abs().max() if xn.shape[1] > m else 0.0) == 0.0
+    assert float(xn[0, :, k:].abs().max() if xn.shape[2] > k else 0.0) == 0.0
+    # the residual is exactly what the top 19 bits of the fp32 word leave out
+    hi = (xn.view(torch.int32) & ~0x1fff).view(torch.float32)
+    assert torch.equal(hi + lo, xn) and float(lo.abs().max()) < 2.0 ** -10
     row_fg = mb.ops.pool_mask(c["support_mask"].to(dev()), g).reshape(1, m)
     res = mb.ops.sim_contract(fs, fq, m, n, k, want_sim=True, want_cost=True, row_fg=row_fg, backend=backend)
     st = int(z["stride"])
