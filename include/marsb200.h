@@ -158,14 +158,17 @@ int marsb200_pack_pairwise(const void* masks, int mask_dtype, int E, int P, int6
 /* ---- A7: exact EMD scores on the device ---------------------------------------------
  * score[e,p] = 1 - EMD(uniform 1/T over the fg support rows, uniform 1/M_p over the proposal's pooled patches,
  * cost = C[fg rows][patches] in float64): the transportation LP of ot.emd2 at FilteringMergingModule.py:160-167 and
- * matcher/Matcher.py:1187-1194, solved exactly (successive shortest paths on integer flows), one CTA per proposal.
+ * matcher/Matcher.py:1187-1194, solved exactly on integer flows (primal-dual method: multi-source shortest-path
+ * phases, all sinks at the minimum distance settled per step), one CTA per proposal, largest problems first.
  * cost [E, m_rows, N] fp32 ((1 - S) / 2 from marsb200_sim_contract); row_fg [E, m_rows] uint8; pooled [E, P, ceil(N/32)].
- * t_cap bounds the number of fg rows the workspace is sized for; *status receives 0, or the needed t_cap if an
- * episode exceeded it (its scores are NaN).  An empty proposal or empty support scores 1.0 (zero transport). */
-int64_t marsb200_emd_workspace_bytes(int E, int P, int N, int t_cap);
+ * t_cap / m_cap bound the number of fg rows / of pooled patches per proposal the shared-memory state and the
+ * workspace are sized for (m_cap <= 0 means N; a smaller m_cap lets more problems share an SM).  *status receives 0,
+ * the needed t_cap, or (1 << 24) + needed m_cap if a problem exceeded the caps (its score is NaN), -1 on an internal
+ * capacity fault.  An empty proposal or empty support scores 1.0 (zero transport).  workspace: 256-byte aligned. */
+int64_t marsb200_emd_workspace_bytes(int E, int P, int N, int t_cap, int m_cap);
 int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t* pooled, int E, int P, int64_t m_rows,
-                        int N, int t_cap, void* workspace, int64_t workspace_bytes, double* out, int32_t* status,
-                        void* stream);
+                        int N, int t_cap, int m_cap, void* workspace, int64_t workspace_bytes, double* out,
+                        int32_t* status, void* stream);
 
 /* ---- A8: AlphaCLIP cosine scores -----------------------------------------------------------
  * clip[e,p] = img[e,p,:] . txt[e,:].  Replaces img_feats @ text_feats.T, FilteringMergingModule.py:97. */

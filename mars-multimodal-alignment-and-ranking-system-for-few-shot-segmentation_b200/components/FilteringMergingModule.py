@@ -124,7 +124,7 @@ class FilteringMergingModule:
         if emd_scores is None:
             sup = ops.pool_mask(support_mask.to(dev).permute(1, 0, 2, 3), g).reshape(-1)
             if self.emd_fn is None:
-                emd = ops.emd_scores(cost_matrix.to(dev).float()[None], sup[None], pooled)
+                emd = ops.emd_scores(cost_matrix.to(dev).float()[None], sup[None], pooled, pooled_count=cnt)
             else:
                 pooled_np = self._unpack_pooled(pooled[0], n)
                 emd_scores = [self._compute_emd(sup, pooled_np[i], cost_matrix) for i in range(p)]

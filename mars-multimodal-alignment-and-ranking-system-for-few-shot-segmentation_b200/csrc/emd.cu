@@ -3,365 +3,520 @@
 // (FilteringMergingModule.py:142-169, matcher/Matcher.py:1187-1194), uniform marginals 1/T and 1/M,
 // cost = C[fg support rows][proposal patches] in float64.
 //
-// One CTA per (episode, proposal).  Flows are kept in integer units of 1/(T*M) (supplies M, demands T),
-// so the primal solution is exact; the solver is the successive-shortest-path (Hungarian-type)
-// algorithm for the transportation problem on dense reduced costs: for each source with supply left,
-// a Dijkstra over the sinks (block-wide argmin, parallel relaxation), dual update, augmentation along
-// the alternating path.  The cost matrix is never gathered: c(i, j) = C[rows[i]][cols[j]] is read
-// from the episode's [M_rows, N] cost matrix (L2 resident).  Optimal value is unique, so the result
-// matches any exact LP solver up to float64 rounding.
+// One CTA per (episode, proposal), LPs handed out largest first from a device-side queue.  Flows are kept in
+// integer units of 1/(T*M) (supplies M, demands T), so the primal solution is exact.  The solver is the
+// primal-dual (Hungarian-type) method for the transportation problem on dense reduced costs, organised for a
+// CTA instead of a scalar core:
+//   * a PHASE grows a shortest-path forest from ALL sources that still have supply (multi-source Dijkstra over
+//     the sinks) and augments along the tree path of every sink with open demand it settles - a few hundred
+//     phases instead of a Dijkstra per augmentation;
+//   * a WAVE settles every unscanned sink whose tentative distance EQUALS the current minimum at once.  Tree
+//     arcs of earlier phases have reduced cost exactly 0, so ties are the rule: 5-8x fewer sequential steps than
+//     one sink per step, with no tolerance involved (only exactly equal keys are merged);
+//   * the flow is a set of per-sink linked lists in shared memory (a basic solution has at most T + M - 1
+//     positive arcs), so settling a saturated sink, the capacity walk and the augmentation never touch global
+//     memory; the only global traffic is the gather of cost entries c(i, j) = C[rows[i]][cols[j]] from the
+//     episode's L2-resident cost matrix when new sources relax the unscanned sinks.
+// The optimal value is unique, so the result matches any exact LP solver up to float64 rounding.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace marsb200 {
 
 #ifdef MARSB200_EMD_PROFILE
 __device__ long long g_emd_prof[16];
-#define EMD_TIC(t) long long t = clock64()
-#define EMD_TOC(slot, t) do { if (threadIdx.x == 0) atomicAdd((unsigned long long*)&g_emd_prof[slot], (unsigned long long)(clock64() - (t))); } while (0)
-#define EMD_COUNT(slot) do { if (threadIdx.x == 0) atomicAdd((unsigned long long*)&g_emd_prof[slot], 1ull); } while (0)
+#define EP_TIC() const long long ep_t0 = clock64()
+#define EP_LAP(slot) do { const long long ep_t1 = clock64(); ep_acc[slot] += ep_t1 - ep_last; ep_last = ep_t1; } while (0)
+#define EP_COUNT(slot) do { ep_acc[slot] += 1; } while (0)
 #else
-#define EMD_TIC(t)
-#define EMD_TOC(slot, t)
-#define EMD_COUNT(slot)
+#define EP_LAP(slot) do { } while (0)
+#define EP_COUNT(slot) do { } while (0)
 #endif
 
-constexpr int EMD_THREADS = 512;  // the relaxation gathers cost entries from L2: latency hidden by many threads
+constexpr int EMD_THREADS = 256;
+constexpr int EMD_WARPS = EMD_THREADS / 32;
 constexpr double EMD_INF = 1e300;
-constexpr int EMD_INLINE = 6;        // a sink of a (near-)basic solution is fed by ~ (T + M) / M sources
-constexpr int EMD_OVERFLOW = 255;
+
+__host__ __device__ inline int emd_pool_nodes(int t_cap, int n_cap) { return 2 * (t_cap + n_cap) + 64; }
 
 struct EmdSmem {
-    double* u;       // [t_cap]  source duals
-    double* dsrc;    // [t_cap]  distance at which a source was reached
-    double* v;       // [n_cap]  sink duals
-    double* dist;    // [n_cap]  tentative / final sink distances
-    double* key;     // [n_cap]  dist for unscanned sinks, INF once scanned
-    int* rows;       // [t_cap]  support row of source i
-    int* pred_sink;  // [t_cap]  sink through which source i was reached (backward arc)
-    int* supply;     // [t_cap]
-    int* list;       // [t_cap]  reached sources (all) ...
-    int* newlist;    // [t_cap]  ... and the ones reached in the current step
-    int* cols;       // [n_cap]  patch index of sink j
-    int* pred_src;   // [n_cap]  source that gave sink j its distance
-    int* demand;     // [n_cap]
-    unsigned char* reached;  // [t_cap]
-    short* feeders;          // [n_cap][EMD_INLINE] sources with positive flow into sink j (when they fit)
-    unsigned char* nfeed;    // [n_cap] how many, or EMD_OVERFLOW: scan the flow row in global memory instead
+    double* u;       // [t_cap] source duals
+    double* dsrc;    // [t_cap] distance at which a source was reached in this phase
+    double* v;       // [n_cap] sink duals
+    double* dist;    // [n_cap] tentative / final sink distances
+    int* reached;    // [t_cap] 0/1 (int: claimed with atomicExch)
+    short* rows;     // [t_cap] support row of source i
+    short* supply;   // [t_cap]
+    short* capflow;  // [t_cap] flow on the tree arc (pred_sink[i] -> i) = what a path through i can take back
+    short* pred_sink;  // [t_cap] sink through which source i was reached, -1 for a root
+    short* newlist;  // [t_cap] sources reached in the current wave (also the root list while a phase starts)
+    short* cols;     // [n_cap] patch index of sink j
+    short* demand;   // [n_cap]
+    short* pred_src;  // [n_cap] source that gave sink j its distance
+    short* batch;    // [n_cap] sinks settled in the current wave
+    short* head;     // [n_cap] first flow node of sink j, -1 = none
+    short* node_src;   // [pool] flow nodes: source, flow, next node of the same sink (or next free node)
+    short* node_flow;  // [pool]
+    short* node_next;  // [pool]
+    unsigned char* scanned;  // [n_cap]
 };
 
 __host__ __device__ inline size_t emd_smem_bytes(int t_cap, int n_cap) {
-    return (size_t)t_cap * (2 * 8 + 5 * 4 + 1) + (size_t)n_cap * (3 * 8 + 3 * 4 + 2 * EMD_INLINE + 1) + 64;
+    return (size_t)t_cap * (2 * 8 + 4 + 5 * 2) + (size_t)n_cap * (2 * 8 + 5 * 2 + 1) + (size_t)emd_pool_nodes(t_cap, n_cap) * 6 + 64;
 }
 
 __device__ inline EmdSmem emd_carve(unsigned char* base, int t_cap, int n_cap) {
     EmdSmem s;
+    const int pool = emd_pool_nodes(t_cap, n_cap);
     double* d = reinterpret_cast<double*>(base);
     s.u = d;
     s.dsrc = s.u + t_cap;
     s.v = s.dsrc + t_cap;
     s.dist = s.v + n_cap;
-    s.key = s.dist + n_cap;
-    int* i = reinterpret_cast<int*>(s.key + n_cap);
-    s.rows = i;
-    s.pred_sink = s.rows + t_cap;
-    s.supply = s.pred_sink + t_cap;
-    s.list = s.supply + t_cap;
-    s.newlist = s.list + t_cap;
+    s.reached = reinterpret_cast<int*>(s.dist + n_cap);
+    short* h = reinterpret_cast<short*>(s.reached + t_cap);
+    s.rows = h;
+    s.supply = s.rows + t_cap;
+    s.capflow = s.supply + t_cap;
+    s.pred_sink = s.capflow + t_cap;
+    s.newlist = s.pred_sink + t_cap;
     s.cols = s.newlist + t_cap;
-    s.pred_src = s.cols + n_cap;
-    s.demand = s.pred_src + n_cap;
-    s.feeders = reinterpret_cast<short*>(s.demand + n_cap);
-    s.reached = reinterpret_cast<unsigned char*>(s.feeders + (size_t)n_cap * EMD_INLINE);
-    s.nfeed = s.reached + t_cap;
+    s.demand = s.cols + n_cap;
+    s.pred_src = s.demand + n_cap;
+    s.batch = s.pred_src + n_cap;
+    s.head = s.batch + n_cap;
+    s.node_src = s.head + n_cap;
+    s.node_flow = s.node_src + pool;
+    s.node_next = s.node_flow + pool;
+    s.scanned = reinterpret_cast<unsigned char*>(s.node_next + pool);
     return s;
 }
 
-// block-wide argmin of key[0..M) (ties -> smaller index); every thread gets the result
-__device__ inline void block_argmin(const double* key, int M, double& best, int& best_j, double* s_val, int* s_idx) {
-    // s_val / s_idx: [2 * (warps + 1)] scratch; callers alternate the half they pass, so no trailing barrier is needed
+// ordered compaction of the indices k in [0, n) with pred(k) into out[0..cap); returns the total count
+template <typename Pred>
+__device__ inline int block_compact(int n, int cap, short* out, Pred pred, int* s_warp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int base = 0;
+    for (int k0 = 0; k0 < n; k0 += EMD_THREADS) {
+        const int k = k0 + tid;
+        const bool p = k < n && pred(k);
+        const unsigned bal = __ballot_sync(0xffffffffu, p);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int off = base, total = base;
+        for (int w = 0; w < EMD_WARPS; ++w) {
+            if (w < warp) off += s_warp[w];
+            total += s_warp[w];
+        }
+        if (p) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            if (pos < cap) out[pos] = (short)k;
+        }
+        base = total;
+        __syncthreads();
+    }
+    return base;
+}
+
+// order-preserving map double -> uint64 (handles the odd -1e-17 a rounded reduced cost can produce)
+__device__ __forceinline__ unsigned long long dkey(double d) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// block-wide minimum of dist over the unscanned sinks; every thread gets the result
+__device__ inline double block_min_key(const EmdSmem& s, int M, unsigned long long* s_val) {
     double v = EMD_INF;
-    int j = 0x7fffffff;
-    for (int t = threadIdx.x; t < M; t += EMD_THREADS) {
-        const double k = key[t];
-        if (k < v) {
-            v = k;
-            j = t;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, j, o);
-        if (ov < v || (ov == v && oj < j)) {
-            v = ov;
-            j = oj;
-        }
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        s_val[warp] = v;
-        s_idx[warp] = j;
-    }
+    for (int j = threadIdx.x; j < M; j += EMD_THREADS)
+        if (!s.scanned[j]) v = fmin(v, s.dist[j]);
+    // warp minimum with two integer reductions (high word, then low word among the lanes that hold the minimum high word)
+    const unsigned long long k = dkey(v);
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    if ((threadIdx.x & 31) == 0) s_val[threadIdx.x >> 5] = ((unsigned long long)mhi << 32) | mlo;
     __syncthreads();
-    // every thread combines the few warp results itself (same order everywhere -> same answer)
-    best = s_val[0];
-    best_j = s_idx[0];
+    unsigned long long best = s_val[0];
 #pragma unroll
-    for (int w = 1; w < EMD_THREADS / 32; ++w) {
-        const double ov = s_val[w];
-        const int oj = s_idx[w];
-        if (ov < best || (ov == best && oj < best_j)) {
-            best = ov;
-            best_j = oj;
+    for (int w = 1; w < EMD_WARPS; ++w) best = min(best, s_val[w]);
+    return dkey_inv(best);
+}
+
+// ---- sizes of every LP and their processing order (largest T*M first: the launch ends with the small ones)
+__global__ void __launch_bounds__(256) emd_sizes_kernel(const uint8_t* __restrict__ row_fg, const uint32_t* __restrict__ pooled,
+                                                         int P, int64_t m_rows, int npw, int64_t total,
+                                                         int64_t* __restrict__ key) {
+    const int lane = threadIdx.x & 31;
+    const int64_t lp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (lp >= total) return;
+    const int64_t e = lp / P;
+    int t = 0, m = 0;
+    for (int64_t r = lane; r < m_rows; r += 32) t += row_fg[e * m_rows + r] ? 1 : 0;
+    for (int w = lane; w < npw; w += 32) m += __popc(pooled[lp * npw + w]);
+    t = warp_sum(t);
+    m = warp_sum(m);
+    if (lane == 0) key[lp] = (int64_t)t * m;
+}
+
+__global__ void __launch_bounds__(256) emd_rank_kernel(const int64_t* __restrict__ key, int64_t total,
+                                                        int32_t* __restrict__ order, int32_t* __restrict__ counter) {
+    __shared__ int64_t s_key[256];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *counter = 0;
+    const int64_t mine = i < total ? key[i] : 0;
+    int64_t rank = 0;
+    for (int64_t k0 = 0; k0 < total; k0 += 256) {
+        __syncthreads();
+        s_key[threadIdx.x] = (k0 + threadIdx.x < total) ? key[k0 + threadIdx.x] : -1;
+        __syncthreads();
+        const int lim = (int)min((int64_t)256, total - k0);
+        for (int k = 0; k < lim; ++k) {
+            const int64_t other = s_key[k];
+            rank += (other > mine || (other == mine && k0 + k < i)) ? 1 : 0;
+        }
+    }
+    if (i < total) order[rank] = (int32_t)i;
+}
+
+// For every sink j (all of them when INIT, the unscanned ones otherwise): best = min over the listed sources i of
+// c(i, j) - u[i], c(i, j) = cmat[rows[i] * stride + cols[j]].  INIT starts a phase (dist = best - v, or v = best and dist = 0 in the very first phase);
+// otherwise the sink is relaxed with dbase + best - v.  `lanes` (a power of two <= 32) threads share a sink and
+// split the source list, so small problems still use the whole CTA.  A thread owns up to EMD_SPT sinks and walks
+// the source list four at a time: up to 4 * EMD_SPT independent gathers are in flight per thread.
+constexpr int EMD_SPT = 3;
+constexpr int EMD_CHUNK = 4;
+
+template <bool INIT>
+__device__ inline void scan_sources(const EmdSmem& s, const float* __restrict__ cmat, int stride, int M, const short* list,
+                                    int n, int lanes, double dbase, bool first_phase) {
+    const int tid = threadIdx.x;
+    const int sub = tid & (lanes - 1);
+    const int groups = EMD_THREADS / lanes;
+    // all threads of a group run the same trip count (shuffles below): iterate over the padded sink range
+    const int m_pad = (M + groups * EMD_SPT - 1) / (groups * EMD_SPT) * (groups * EMD_SPT);
+    for (int j0 = tid / lanes; j0 < m_pad; j0 += groups * EMD_SPT) {
+        bool live[EMD_SPT];
+        const float* col[EMD_SPT];
+        double best[EMD_SPT];
+        int best_i[EMD_SPT];
+#pragma unroll
+        for (int t = 0; t < EMD_SPT; ++t) {
+            const int j = j0 + t * groups;
+            live[t] = j < M && (INIT || !s.scanned[j]);
+            best[t] = EMD_INF;
+            best_i[t] = -1;
+            col[t] = cmat + (live[t] ? (int)s.cols[j] : 0);
+        }
+        bool any = false;
+#pragma unroll
+        for (int t = 0; t < EMD_SPT; ++t) any |= live[t];
+        if (any) {
+            // full chunks: EMD_CHUNK sources x EMD_SPT sinks of independent gathers in flight
+            int k = sub;
+            for (; k + (EMD_CHUNK - 1) * lanes < n; k += EMD_CHUNK * lanes) {
+                int idx[EMD_CHUNK];
+                int64_t off[EMD_CHUNK];
+                double ui[EMD_CHUNK];
+#pragma unroll
+                for (int q = 0; q < EMD_CHUNK; ++q) {
+                    idx[q] = list[k + q * lanes];
+                    off[q] = (int64_t)s.rows[idx[q]] * stride;
+                    ui[q] = s.u[idx[q]];
+                }
+                float cv[EMD_SPT][EMD_CHUNK];
+#pragma unroll
+                for (int t = 0; t < EMD_SPT; ++t)
+#pragma unroll
+                    for (int q = 0; q < EMD_CHUNK; ++q) cv[t][q] = live[t] ? col[t][off[q]] : 0.f;
+#pragma unroll
+                for (int t = 0; t < EMD_SPT; ++t)
+#pragma unroll
+                    for (int q = 0; q < EMD_CHUNK; ++q) {
+                        const double d = (double)cv[t][q] - ui[q];
+                        if (d < best[t]) {
+                            best[t] = d;
+                            best_i[t] = idx[q];
+                        }
+                    }
+            }
+            // remainder: one source at a time, still EMD_SPT gathers in flight
+            for (; k < n; k += lanes) {
+                const int i = list[k];
+                const int64_t off = (int64_t)s.rows[i] * stride;
+                const double ui = s.u[i];
+                float cv[EMD_SPT];
+#pragma unroll
+                for (int t = 0; t < EMD_SPT; ++t) cv[t] = live[t] ? col[t][off] : 0.f;
+#pragma unroll
+                for (int t = 0; t < EMD_SPT; ++t) {
+                    const double d = (double)cv[t] - ui;
+                    if (d < best[t]) {
+                        best[t] = d;
+                        best_i[t] = i;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < EMD_SPT; ++t) {
+            for (int o = lanes >> 1; o > 0; o >>= 1) {  // groups are aligned sub-warps
+                const double ob = __shfl_xor_sync(0xffffffffu, best[t], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, best_i[t], o);
+                if (ob < best[t] || (ob == best[t] && oi >= 0 && (best_i[t] < 0 || oi < best_i[t]))) {
+                    best[t] = ob;
+                    best_i[t] = oi;
+                }
+            }
+            const int j = j0 + t * groups;
+            if (live[t] && sub == 0 && best_i[t] >= 0) {
+                if (INIT) {
+                    if (first_phase) {  // v_j = min_i c_ij: every sink starts with a tight arc
+                        s.v[j] = best[t];
+                        s.dist[j] = 0.0;
+                    } else {
+                        s.dist[j] = best[t] - s.v[j];
+                    }
+                    s.pred_src[j] = (short)best_i[t];
+                } else {
+                    const double nd = (dbase + best[t]) - s.v[j];
+                    if (nd < s.dist[j]) {
+                        s.dist[j] = nd;
+                        s.pred_src[j] = (short)best_i[t];
+                    }
+                }
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(EMD_THREADS) emd_kernel(const float* __restrict__ cost, const uint8_t* __restrict__ row_fg,
+// every source feeding sink j becomes reachable at distance d (tight backward arcs)
+__device__ inline void expand_feeders(const EmdSmem& s, int j, double d, int* nnew) {
+    for (int n = s.head[j]; n >= 0; n = s.node_next[n]) {
+        const int i = s.node_src[n];
+        if (atomicExch(&s.reached[i], 1) == 0) {
+            s.dsrc[i] = d;
+            s.pred_sink[i] = (short)j;
+            s.capflow[i] = s.node_flow[n];
+            s.newlist[atomicAdd(nnew, 1)] = (short)i;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __restrict__ cost, const uint8_t* __restrict__ row_fg,
                                                            const uint32_t* __restrict__ pooled, int P, int64_t m_rows,
-                                                           int N, int npw, int t_cap, int16_t* __restrict__ flow_ws,
+                                                           int N, int npw, int t_cap, int m_cap, int total_lps,
+                                                           const int32_t* __restrict__ order, int32_t* __restrict__ counter,
                                                            double* __restrict__ out, int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char emd_smem_raw[];
-    EmdSmem s = emd_carve(emd_smem_raw, t_cap, N);
-    __shared__ double s_val[2][EMD_THREADS / 32];
-    __shared__ int s_idx[2][EMD_THREADS / 32];
-    __shared__ int s_T, s_M, s_nreached, s_nnew[2];
+    EmdSmem s = emd_carve(emd_smem_raw, t_cap, m_cap);
+    __shared__ unsigned long long s_val[EMD_WARPS];
+    __shared__ double s_acc[EMD_WARPS];
+    __shared__ int s_warp[EMD_WARPS];
+    __shared__ int s_lp, s_ndef, s_nnew, s_left, s_free, s_fault;
     const int tid = threadIdx.x;
-    const int64_t lp = blockIdx.x;  // e * P + p
-    const int64_t e = lp / P;
-    const float* C = cost + e * m_rows * N;
-    const uint8_t* fg = row_fg + e * m_rows;
-    const uint32_t* pw = pooled + lp * npw;
-    int16_t* fT = flow_ws + lp * (int64_t)t_cap * N;  // [M][T] flows (sink-major: a sink's sources are contiguous)
+    const int pool = emd_pool_nodes(t_cap, m_cap);
 
-    // ---- index lists (ascending order, like boolean indexing in the reference)
-    if (tid == 0) {
-        int t = 0;
-        for (int64_t r = 0; r < m_rows; ++r)
-            if (fg[r]) {
-                if (t < t_cap) s.rows[t] = (int)r;
-                ++t;
-            }
-        s_T = t;
-        int m = 0;
-        for (int b = 0; b < N; ++b)
-            if ((pw[b >> 5] >> (b & 31)) & 1u) s.cols[m++] = b;
-        s_M = m;
-    }
-    __syncthreads();
-    const int T = s_T, M = s_M;
-    if (T == 0 || M == 0) {  // empty marginal: defined as zero transport cost
-        if (tid == 0) out[lp] = 1.0;
-        return;
-    }
-    if (T > t_cap) {
+    while (true) {
+        __syncthreads();
         if (tid == 0) {
-            out[lp] = nan("");
-            atomicMax(status, T);  // tells the host the capacity it needs
+            const int q = atomicAdd(counter, 1);
+            s_lp = q < total_lps ? order[q] : -1;
         }
-        return;
-    }
-    auto c = [&](int i, int j) -> double { return (double)C[(int64_t)s.rows[i] * N + s.cols[j]]; };
-
-    // ---- initial state: zero flow, u = 0, v_j = min_i c_ij (reduced costs stay >= 0)
-    for (int64_t k = tid; k < (int64_t)T * M; k += EMD_THREADS) fT[k] = 0;
-    for (int i = tid; i < T; i += EMD_THREADS) {
-        s.u[i] = 0.0;
-        s.supply[i] = M;
-    }
-    for (int j = tid; j < M; j += EMD_THREADS) {
-        double mn = EMD_INF;
-        for (int i = 0; i < T; ++i) mn = fmin(mn, c(i, j));
-        s.v[j] = mn;
-        s.demand[j] = T;
-        s.nfeed[j] = 0;
-    }
-    __syncthreads();
-
-    for (int r = 0; r < T; ++r) {
-        while (s.supply[r] > 0) {  // uniform: shared state only changes between barriers
-            EMD_COUNT(0);
-            EMD_TIC(t_init);
-            // ---- Dijkstra from source r over the sinks
-            const double ur = s.u[r];
-            for (int j = tid; j < M; j += EMD_THREADS) {
-                const double d = c(r, j) - ur - s.v[j];
-                s.dist[j] = d;
-                s.key[j] = d;
-                s.pred_src[j] = r;
-            }
-            for (int i = tid; i < T; i += EMD_THREADS) s.reached[i] = 0;
-            __syncthreads();
-            if (tid == 0) {
-                s.reached[r] = 1;
-                s.dsrc[r] = 0.0;
-                s.list[0] = r;
-                s_nreached = 1;
-            }
-            __syncthreads();
-            double D;
-            int jstar;
-            if (tid == 0) s_nnew[0] = s_nnew[1] = 0;
-            __syncthreads();
-            EMD_TOC(8, t_init);
-            for (int step = 0;; ++step) {
-                const int pp = step & 1;  // ping-pong scratch / counters: one barrier fewer per step
-                EMD_COUNT(1);
-                EMD_TIC(t_arg);
-                block_argmin(s.key, M, D, jstar, s_val[pp], s_idx[pp]);
-                EMD_TOC(9, t_arg);
-                if (s.demand[jstar] > 0) break;  // demands only change in the augmentation below: uniform
-                if (tid == 0) {
-                    s.key[jstar] = EMD_INF;  // scanned
-                    s_nnew[pp ^ 1] = 0;      // the other counter is idle during this step
-                }
-                EMD_TIC(t_col);
-                // saturated sink: every source feeding it becomes reachable at distance D (tight backward arcs)
-                const int nf = s.nfeed[jstar];
-                if (nf != EMD_OVERFLOW) {  // the usual case: the feeders are listed in shared memory
-                    if (tid < nf) {
-                        const int i = s.feeders[jstar * EMD_INLINE + tid];
-                        if (!s.reached[i]) {
-                            s.reached[i] = 1;
-                            s.dsrc[i] = D;
-                            s.pred_sink[i] = jstar;
-                            s.newlist[atomicAdd(&s_nnew[pp], 1)] = i;
-                            s.list[atomicAdd(&s_nreached, 1)] = i;
-                        }
-                    }
-                } else {
-                    const int16_t* frow = fT + (int64_t)jstar * T;
-                    for (int i = tid; i < T; i += EMD_THREADS) {
-                        if (!s.reached[i] && frow[i] > 0) {
-                            s.reached[i] = 1;
-                            s.dsrc[i] = D;
-                            s.pred_sink[i] = jstar;
-                            s.newlist[atomicAdd(&s_nnew[pp], 1)] = i;
-                            s.list[atomicAdd(&s_nreached, 1)] = i;
-                        }
-                    }
-                }
-                __syncthreads();
-                EMD_TOC(10, t_col);
-                EMD_TIC(t_rel);
-                const int nnew = s_nnew[pp];
+        __syncthreads();
+        const int64_t lp = s_lp;
+        if (lp < 0) return;
 #ifdef MARSB200_EMD_PROFILE
-                if (tid == 0) atomicAdd((unsigned long long*)&g_emd_prof[2], (unsigned long long)nnew);
+        long long ep_acc[16] = {0};
+        long long ep_last = clock64();
 #endif
-                // relax every unscanned sink against the newly reached sources (usually 0-2 per step)
-                for (int j = tid; j < M; j += EMD_THREADS) {
-                    if (s.key[j] >= EMD_INF) continue;
-                    const float* ccol = C + s.cols[j];
-                    double best = EMD_INF;
-                    int best_i = -1;
-                    int k = 0;
-                    for (; k + 4 <= nnew; k += 4) {  // four independent gathers in flight
-                        const int i0 = s.newlist[k], i1 = s.newlist[k + 1], i2 = s.newlist[k + 2], i3 = s.newlist[k + 3];
-                        const float c0 = ccol[(int64_t)s.rows[i0] * N], c1 = ccol[(int64_t)s.rows[i1] * N];
-                        const float c2 = ccol[(int64_t)s.rows[i2] * N], c3 = ccol[(int64_t)s.rows[i3] * N];
-                        const double d0 = (double)c0 - s.u[i0], d1 = (double)c1 - s.u[i1];
-                        const double d2 = (double)c2 - s.u[i2], d3 = (double)c3 - s.u[i3];
-                        if (d0 < best) { best = d0; best_i = i0; }
-                        if (d1 < best) { best = d1; best_i = i1; }
-                        if (d2 < best) { best = d2; best_i = i2; }
-                        if (d3 < best) { best = d3; best_i = i3; }
-                    }
-                    for (; k < nnew; ++k) {
-                        const int i = s.newlist[k];
-                        const double d = (double)ccol[(int64_t)s.rows[i] * N] - s.u[i];
-                        if (d < best) { best = d; best_i = i; }
-                    }
-                    if (best_i >= 0) {
-                        const double nd = (D + best) - s.v[j];
-                        if (nd < s.dist[j]) {
-                            s.dist[j] = nd;
-                            s.key[j] = nd;
-                            s.pred_src[j] = best_i;
-                        }
-                    }
-                }
-                __syncthreads();
-                EMD_TOC(11, t_rel);
-            }
-            EMD_TIC(t_dual);
-            if (tid == 0) s.key[jstar] = EMD_INF;  // the terminal sink counts as scanned for the dual update
-            __syncthreads();
-            // ---- dual update: keeps every flow arc tight and all reduced costs non-negative
-            const int nreached = s_nreached;
-            for (int k = tid; k < nreached; k += EMD_THREADS) {
-                const int i = s.list[k];
-                s.u[i] += D - s.dsrc[i];
-            }
-            for (int j = tid; j < M; j += EMD_THREADS)
-                if (s.key[j] >= EMD_INF) s.v[j] -= D - s.dist[j];
-            __syncthreads();
-            EMD_TOC(12, t_dual);
-            EMD_TIC(t_aug);
-            // ---- augment along the alternating path jstar <- pred_src <- pred_sink <- ... <- r
-            if (tid == 0) {
-                int delta = min(s.supply[r], s.demand[jstar]);
-                int j = jstar;
-                while (true) {
-                    const int i = s.pred_src[j];
-                    if (i == r) break;
-                    const int jp = s.pred_sink[i];
-                    delta = min(delta, (int)fT[(int64_t)jp * T + i]);
-                    j = jp;
-                }
-                j = jstar;
-                while (true) {
-                    const int i = s.pred_src[j];
-                    const int16_t before = fT[(int64_t)j * T + i];
-                    fT[(int64_t)j * T + i] = (int16_t)(before + delta);
-                    if (before == 0) {  // new feeder of sink j
-                        const int nf = s.nfeed[j];
-                        if (nf < EMD_INLINE) {
-                            s.feeders[j * EMD_INLINE + nf] = (short)i;
-                            s.nfeed[j] = (unsigned char)(nf + 1);
-                        } else {
-                            s.nfeed[j] = EMD_OVERFLOW;
-                        }
-                    }
-                    if (i == r) break;
-                    const int jp = s.pred_sink[i];
-                    const int16_t left = (int16_t)(fT[(int64_t)jp * T + i] - delta);
-                    fT[(int64_t)jp * T + i] = left;
-                    if (left == 0 && s.nfeed[jp] != EMD_OVERFLOW) {  // i no longer feeds sink jp: swap-remove
-                        const int nf = s.nfeed[jp];
-                        for (int q = 0; q < nf; ++q)
-                            if (s.feeders[jp * EMD_INLINE + q] == (short)i) {
-                                s.feeders[jp * EMD_INLINE + q] = s.feeders[jp * EMD_INLINE + nf - 1];
-                                s.nfeed[jp] = (unsigned char)(nf - 1);
-                                break;
-                            }
-                    }
-                    j = jp;
-                }
-                s.supply[r] -= delta;
-                s.demand[jstar] -= delta;
-            }
-            __syncthreads();
-            EMD_TOC(13, t_aug);
-        }
-    }
+        const int64_t e = lp / P;
+        const float* C = cost + e * m_rows * N;
+        const uint8_t* fg = row_fg + e * m_rows;
+        const uint32_t* pw = pooled + lp * npw;
 
-    // ---- objective: sum f_ij c_ij / (T M), float64
-    double acc = 0.0;
-    for (int64_t k = tid; k < (int64_t)T * M; k += EMD_THREADS) {
-        const int f = fT[k];
-        if (f) {
-            const int j = (int)(k / T), i = (int)(k - (int64_t)j * T);
-            acc += (double)f * c(i, j);
+        // ---- index lists (ascending order, like boolean indexing in the reference)
+        const int T = block_compact((int)m_rows, t_cap, s.rows, [&](int r) { return fg[r] != 0; }, s_warp);
+        const int M = block_compact(N, m_cap, s.cols, [&](int b) { return ((pw[b >> 5] >> (b & 31)) & 1u) != 0; }, s_warp);
+        if (T == 0 || M == 0) {  // empty marginal: defined as zero transport cost
+            if (tid == 0) out[lp] = 1.0;
+            continue;
         }
-    }
-    acc = warp_sum(acc);
-    __syncthreads();
-    if ((tid & 31) == 0) s_val[0][tid >> 5] = acc;
-    __syncthreads();
-    if (tid == 0) {
-        double total = 0.0;
-        for (int w = 0; w < EMD_THREADS / 32; ++w) total += s_val[0][w];
-        out[lp] = 1.0 - total / ((double)T * (double)M);  // the reference's emd_score = 1 - emd
+        if (T > t_cap || M > m_cap) {
+            if (tid == 0) {
+                out[lp] = nan("");
+                atomicMax(status, T > t_cap ? T : (1 << 24) + M);  // tells the host the capacity it needs
+            }
+            continue;
+        }
+
+        const float* cmat = C;  // c(i, j) = C[rows[i]][cols[j]] gathered from the episode's L2-resident cost matrix
+        const int cstride = N;
+        // ---- initial state: zero flow, u = 0, v_j = min_i c_ij (reduced costs stay >= 0)
+        for (int i = tid; i < T; i += EMD_THREADS) {
+            s.u[i] = 0.0;
+            s.supply[i] = (short)M;
+        }
+        for (int j = tid; j < M; j += EMD_THREADS) {
+            s.v[j] = 0.0;
+            s.demand[j] = (short)T;
+            s.head[j] = -1;
+        }
+        for (int k = tid; k < pool; k += EMD_THREADS) s.node_next[k] = (short)(k + 1 < pool ? k + 1 : -1);
+        if (tid == 0) {
+            s_left = T * M;
+            s_free = 0;
+            s_fault = 0;
+            s_ndef = 0;
+            s_nnew = 0;
+        }
+        int lanes = 1;  // threads per sink in the source scans
+        while (lanes < 32 && 2 * lanes * M <= EMD_THREADS) lanes *= 2;
+        __syncthreads();
+
+        bool first_phase = true;
+        EP_LAP(0);  // setup
+        while (s_left > 0 && !s_fault) {  // uniform: shared state only changes between barriers
+            EP_COUNT(8);
+            // ---- phase start: every source with supply left is a root at distance 0
+            const int nroots = block_compact(T, T, s.newlist, [&](int i) { return s.supply[i] > 0; }, s_warp);
+            for (int i = tid; i < T; i += EMD_THREADS) {
+                s.reached[i] = s.supply[i] > 0 ? 1 : 0;
+                s.dsrc[i] = 0.0;
+                s.pred_sink[i] = -1;
+            }
+            for (int j = tid; j < M; j += EMD_THREADS) s.scanned[j] = 0;
+            scan_sources<true>(s, cmat, cstride, M, s.newlist, nroots, lanes, 0.0, first_phase);
+            first_phase = false;
+            __syncthreads();
+            EP_LAP(1);  // phase init
+
+            double D = 0.0;
+            while (true) {
+                EP_COUNT(9);
+                // ---- wave: settle every unscanned sink at the minimum distance
+                const double dmin = block_min_key(s, M, s_val);
+                EP_LAP(2);  // argmin
+                if (dmin >= EMD_INF) break;  // every sink is scanned
+                D = dmin;
+                for (int j = tid; j < M; j += EMD_THREADS)
+                    if (!s.scanned[j] && s.dist[j] == dmin) {
+                        s.scanned[j] = 1;
+                        if (s.demand[j] > 0) s.batch[atomicAdd(&s_ndef, 1)] = (short)j;  // open demand: augment first
+                        else expand_feeders(s, j, dmin, &s_nnew);  // its flow arcs cannot change in this wave
+                    }
+                __syncthreads();
+                EP_LAP(3);  // settle
+                const int ndef = s_ndef;
+                if (ndef > 0) {
+                    // ---- augment along the tree path of every settled sink with open demand (sequential: paths share arcs)
+                    if (tid == 0) {
+                        for (int b = 0; b < ndef; ++b) {
+                            const int j = s.batch[b];
+                            int delta = s.demand[j];
+                            int i = s.pred_src[j];
+                            while (s.pred_sink[i] >= 0) {
+                                delta = min(delta, (int)s.capflow[i]);
+                                i = s.pred_src[s.pred_sink[i]];
+                            }
+                            delta = min(delta, (int)s.supply[i]);
+                            if (delta <= 0) continue;  // the root is spent or a tree arc was emptied earlier in this phase
+                            s.supply[i] = (short)(s.supply[i] - delta);
+                            s.demand[j] = (short)(s.demand[j] - delta);
+                            s_left -= delta;
+                            int jj = j;
+                            while (true) {
+                                const int src = s.pred_src[jj];
+                                // forward arc src -> jj gains delta
+                                int n = s.head[jj];
+                                while (n >= 0 && s.node_src[n] != src) n = s.node_next[n];
+                                if (n >= 0) {
+                                    s.node_flow[n] = (short)(s.node_flow[n] + delta);
+                                } else {
+                                    n = s_free;
+                                    if (n < 0) {
+                                        s_fault = 1;  // flow-node pool exhausted (never seen: a basic solution has < T + M arcs)
+                                        break;
+                                    }
+                                    s_free = s.node_next[n];
+                                    s.node_src[n] = (short)src;
+                                    s.node_flow[n] = (short)delta;
+                                    s.node_next[n] = s.head[jj];
+                                    s.head[jj] = (short)n;
+                                }
+                                const int jp = s.pred_sink[src];
+                                if (jp < 0) break;
+                                // backward arc jp -> src loses delta
+                                s.capflow[src] = (short)(s.capflow[src] - delta);
+                                int prev = -1;
+                                n = s.head[jp];
+                                while (s.node_src[n] != src) {
+                                    prev = n;
+                                    n = s.node_next[n];
+                                }
+                                const int left = s.node_flow[n] - delta;
+                                if (left > 0) {
+                                    s.node_flow[n] = (short)left;
+                                } else {  // unlink the emptied arc
+                                    if (prev < 0) s.head[jp] = s.node_next[n];
+                                    else s.node_next[prev] = s.node_next[n];
+                                    s.node_next[n] = (short)s_free;
+                                    s_free = n;
+                                }
+                                jj = jp;
+                            }
+                            if (s_fault) break;
+                        }
+                    }
+                    __syncthreads();
+                    if (s_left <= 0 || s_fault) break;
+                    for (int b = tid; b < ndef; b += EMD_THREADS) expand_feeders(s, s.batch[b], dmin, &s_nnew);
+                    __syncthreads();
+                }
+                EP_LAP(4);  // augment
+                const int nnew = s_nnew;
+                // ---- relax every unscanned sink against the newly reached sources
+                if (nnew > 0) scan_sources<false>(s, cmat, cstride, M, s.newlist, nnew, lanes, dmin, false);
+                __syncthreads();  // everyone has read the counters; the next wave's settle pass starts after another barrier
+                if (tid == 0) {
+                    s_ndef = 0;
+                    s_nnew = 0;
+                }
+                EP_LAP(6);  // relax
+            }
+            // ---- dual update: keeps every flow arc tight and all reduced costs non-negative
+            for (int i = tid; i < T; i += EMD_THREADS)
+                if (s.reached[i]) s.u[i] += D - s.dsrc[i];
+            for (int j = tid; j < M; j += EMD_THREADS)
+                if (s.scanned[j]) s.v[j] -= D - s.dist[j];
+            if (tid == 0) {
+                s_ndef = 0;
+                s_nnew = 0;
+            }
+            __syncthreads();
+        }
+
+        // ---- objective: sum f_ij c_ij / (T M), float64
+        double acc = 0.0;
+        for (int j = tid; j < M; j += EMD_THREADS)
+            for (int n = s.head[j]; n >= 0; n = s.node_next[n]) acc += (double)s.node_flow[n] * (double)C[(int64_t)s.rows[s.node_src[n]] * N + s.cols[j]];
+        acc = warp_sum(acc);
+        if ((tid & 31) == 0) s_acc[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double total = 0.0;
+            for (int w = 0; w < EMD_WARPS; ++w) total += s_acc[w];
+            out[lp] = s_fault ? nan("") : 1.0 - total / ((double)T * (double)M);  // the reference's emd_score = 1 - emd
+            if (s_fault) atomicMin(status, -1);
+#ifdef MARSB200_EMD_PROFILE
+            EP_LAP(7);  // dual updates + objective (and everything not lapped)
+            for (int k = 0; k < 16; ++k) atomicAdd((unsigned long long*)&g_emd_prof[k], (unsigned long long)ep_acc[k]);
+#endif
+        }
     }
 }
 
@@ -383,26 +538,53 @@ extern "C" int marsb200_debug_emd_profile(long long* out16, int reset) {
 
 extern "C" {
 
-int64_t marsb200_emd_workspace_bytes(int E, int P, int N, int t_cap) {
+static int emd_ctas_per_sm(int t_cap, int m_cap) {  // 64 registers x 256 threads: at most 4 by the register file
+    const size_t smem = emd_smem_bytes(t_cap, m_cap);
+    return (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
+}
+
+// Workspace: size keys, processing order, queue head (the flows and duals live in shared memory).
+int64_t marsb200_emd_workspace_bytes(int E, int P, int N, int t_cap, int m_cap) {
     if (E <= 0 || P <= 0 || N <= 0 || t_cap <= 0) return 0;
-    return (int64_t)E * P * t_cap * N * (int64_t)sizeof(int16_t);
+    (void)m_cap;
+    const int64_t lps = (int64_t)E * P;
+    return (lps * 8 + lps * 4 + 256 + 255) / 256 * 256;
 }
 
 int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t* pooled, int E, int P, int64_t m_rows,
-                        int N, int t_cap, void* workspace, int64_t workspace_bytes, double* out, int32_t* status,
-                        void* stream) {
+                        int N, int t_cap, int m_cap, void* workspace, int64_t workspace_bytes, double* out,
+                        int32_t* status, void* stream) {
     MARS_REQUIRE(cost && row_fg && pooled && workspace && out && status, "null pointer");
-    MARS_REQUIRE(E > 0 && P > 0 && m_rows > 0 && N > 0 && t_cap > 0 && t_cap <= 32767 && N <= 32767, "shape");
+    MARS_REQUIRE(E > 0 && P > 0 && m_rows > 0 && N > 0 && t_cap > 0 && t_cap <= 32767 && N <= 32767 && m_rows <= 32767,
+                 "shape");
     MARS_REQUIRE((int64_t)E * P < (1ll << 31), "too many problems");
-    MARS_REQUIRE(workspace_bytes >= marsb200_emd_workspace_bytes(E, P, N, t_cap), "workspace too small");
-    const size_t smem = emd_smem_bytes(t_cap, N);
+    if (m_cap <= 0 || m_cap > N) m_cap = N;
+    MARS_REQUIRE(workspace_bytes >= marsb200_emd_workspace_bytes(E, P, N, t_cap, m_cap), "workspace too small");
+    MARS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    MARS_REQUIRE(emd_pool_nodes(t_cap, m_cap) <= 32767, "t_cap + N too large for 16-bit flow-node indices");
+    const size_t smem = emd_smem_bytes(t_cap, m_cap);
     MARS_REQUIRE(smem <= 200 * 1024, "t_cap + N too large for the shared-memory state");
     cudaStream_t s = as_stream(stream);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        MARS_CUDA_OK(cudaGetDevice(&dev));
+        MARS_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
     MARS_CUDA_OK(cudaFuncSetAttribute(emd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MARS_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+    const int64_t lps = (int64_t)E * P;
     const int npw = ceil_div(N, 32);
-    emd_kernel<<<(unsigned)((int64_t)E * P), EMD_THREADS, smem, s>>>(cost, row_fg, pooled, P, m_rows, N, npw, t_cap,
-                                                                    (int16_t*)workspace, out, status);
+    int64_t* key = reinterpret_cast<int64_t*>(workspace);
+    int32_t* order = reinterpret_cast<int32_t*>(key + lps);
+    int32_t* counter = order + lps;
+    emd_sizes_kernel<<<(unsigned)ceil_div64(lps * 32, 256), 256, 0, s>>>(row_fg, pooled, P, m_rows, npw, lps, key);
+    MARS_LAUNCH_OK();
+    emd_rank_kernel<<<(unsigned)ceil_div64(lps, 256), 256, 0, s>>>(key, lps, order, counter);
+    MARS_LAUNCH_OK();
+    const unsigned grid = (unsigned)std::min<int64_t>(lps, (int64_t)num_sms * emd_ctas_per_sm(t_cap, m_cap));
+    emd_kernel<<<grid, EMD_THREADS, smem, s>>>(cost, row_fg, pooled, P, m_rows, N, npw, t_cap, m_cap, (int)lps, order,
+                                               counter, out, status);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }

@@ -34,6 +34,7 @@ class RankingConfig:
     fused_ingest: bool = False         # one-pass pack + pairwise kernel (owns all TMEM: cannot overlap the contractions)
     emd_on_device: bool = False        # solve the P transport LPs per episode on the device instead of taking batch["emd"]
     emd_t_cap: Optional[int] = None    # max fg support rows the EMD workspace is sized for (default min(ns*N, 2048))
+    emd_m_cap: Optional[int] = None    # max pooled patches of a proposal (default N); smaller -> more LPs per SM
     gemm_backend: Optional[int] = None
     pair_backend: Optional[int] = None
 
@@ -53,7 +54,7 @@ def kernel_launches_per_run(cfg: RankingConfig) -> int:
     n += 1                     # pool_packed
     n += 2                     # region sums + union count
     if cfg.emd_on_device:
-        n += 1                 # exact EMD, one CTA per proposal
+        n += 3                 # exact EMD: problem sizes, processing order, the solver (one CTA per proposal)
     n += 1                     # clip scores
     n += 1                     # fuse / rank / nms / select
     n += 1                     # merge
@@ -83,7 +84,8 @@ class RankingEngine:
         self.emd_ws = None
         if cfg.emd_on_device:
             self.emd_t_cap = cfg.emd_t_cap or min(m, 2048)
-            nbytes = int(ops.lib.marsb200_emd_workspace_bytes(e, s.P, n, self.emd_t_cap))
+            self.emd_m_cap = min(cfg.emd_m_cap or n, n)
+            nbytes = int(ops.lib.marsb200_emd_workspace_bytes(e, s.P, n, self.emd_t_cap, self.emd_m_cap))
             self.emd_ws = new((nbytes,), u8)
             self.emd_out = new((e, s.P), torch.float64)
         self.prior = new((e, n), f32)
@@ -169,7 +171,7 @@ class RankingEngine:
         emd = batch.get("emd")
         if cfg.emd_on_device:
             emd = ops.emd_scores(self.gemm_out["cost"], self.row_fg.reshape(e, m), self.pool_out[0], t_cap=self.emd_t_cap,
-                                 workspace=self.emd_ws, out=self.emd_out, check=False)
+                                 m_cap=self.emd_m_cap, workspace=self.emd_ws, out=self.emd_out, check=False)
         ops.fuse_rank(emd, self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
                       self.region_out[2], self.inter, cfg.alpha, cfg.static_threshold, cfg.dynamic_threshold,
                       cfg.nms_iou_threshold, out=self.rank_out)

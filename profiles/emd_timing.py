@@ -14,11 +14,11 @@ row_fg = ops.pool_mask(b["support_mask"], g).reshape(E, n)
 cost = ops.sim_contract(fs, fq, n, n, shape.C, want_sim=False, want_cost=True)["cost"]
 bits = ops.pack_masks(b["masks"]); pooled, area, cnt = ops.pool_packed(bits, shape.H, shape.W, g)
 T = row_fg.sum(1).cpu().tolist(); print("T per episode", T, "M_p mean/max", float(cnt.float().mean()), int(cnt.max()))
-out = ops.emd_scores(cost, row_fg, pooled)
+out = ops.emd_scores(cost, row_fg, pooled, pooled_count=cnt)
 ts = []
 for _ in range(3):
     a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); out = ops.emd_scores(cost, row_fg, pooled, t_cap=max(T)); c.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(c))
+    a.record(); out = ops.emd_scores(cost, row_fg, pooled, t_cap=max(T), m_cap=int(cnt.max())); c.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(c))
 ms = statistics.median(ts)
 print(f"E={E}: {ms:.1f} ms for {E * shape.P} LPs -> {ms / E:.1f} ms/episode, {E * shape.P / ms * 1e3:.0f} LP/s")
 # host reference for a few LPs (HiGHS exact LP; POT is not installed)

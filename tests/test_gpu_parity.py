@@ -645,6 +645,29 @@ def test_emd_scores_match_exact_lp(mb, ns, g, p, h):
     assert got[p - 1] == 1.0
 
 
+def test_emd_caps_and_larger_problems(mb):
+    """m_cap / t_cap: a tight cap gives the same scores, a cap that is too small is reported; medium-size LPs
+    (hundreds of phases, many tied waves) against the oracle's exact LP."""
+    ns, g, p, h = 1, 24, 10, 336
+    cost, support, masks = _emd_inputs(ns, g, p, h, seed=911)
+    d = dev()
+    row_fg = mb.ops.pool_mask(support.to(d), g).reshape(1, -1)
+    bits = mb.ops.pack_masks(masks.to(d))
+    pooled, _, cnt = mb.ops.pool_packed(bits, h, h, g)
+    full = mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None])[0]
+    tight = mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], pooled_count=cnt)[0]
+    assert torch.equal(full, tight)
+    sup = orc.pool_mask(support, g).reshape(-1)
+    pm = orc.pool_mask(masks, g).reshape(p, -1)
+    big = sorted(range(p), key=lambda i: -int(cnt[i]))[:3]
+    want = np.asarray([orc.emd_score(sup, pm[i], cost) for i in big])
+    np.testing.assert_allclose(full.cpu().numpy()[big], want, rtol=0, atol=1e-9)
+    with pytest.raises(mb.MarsB200Error, match="m_cap"):
+        mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], m_cap=int(cnt.max()) - 1)
+    with pytest.raises(mb.MarsB200Error, match="t_cap"):
+        mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], t_cap=int(row_fg.sum()) - 1)
+
+
 def test_emd_square_case_equals_assignment(mb):
     """T == M: the transport LP is an assignment problem; compare with scipy's exact LSAP at a larger size."""
     from scipy.optimize import linear_sum_assignment
