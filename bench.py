@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--fused-ingest", action="store_true", help="one-pass pack + pairwise kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-emd", action="store_true", help="skip the full-scoring (device EMD) variant")
+    ap.add_argument("--cpu-emd-lps", type=int, default=4, help="transport LPs timed on the host for the EMD baseline")
     ap.add_argument("--cpu-sample-episodes", type=int, default=2)
     return ap.parse_args()
 
@@ -181,6 +183,23 @@ def cpu_reference_episodes(shape, args, n_episodes, device_for_generation):
         orc.run_episode(ep, cfg)
         times.append(time.perf_counter() - t0)
     return times
+
+
+def cpu_emd_sample(shape, batch, n_lps):
+    """Host time of the oracle's exact transport LP (HiGHS; POT is not installed) on a few proposals of episode 0."""
+    from oracle import mars_oracle as orc
+
+    ep = {k: v[0].cpu() for k, v in batch.items()}
+    fs, fq = orc.normalize_rows(ep["feat_s"].reshape(-1, shape.C)), orc.normalize_rows(ep["feat_q"])
+    _, cost = orc.similarity_and_cost(fs, fq)
+    sup = orc.pool_mask(ep["support_mask"].float(), shape.g).reshape(-1)
+    pm = orc.pool_mask(ep["masks"][:n_lps].float(), shape.g).reshape(n_lps, -1)
+    t0 = time.perf_counter()
+    for i in range(n_lps):
+        orc.emd_score(sup, pm[i], cost)
+    dt = time.perf_counter() - t0
+    return {"lps_per_s": n_lps / dt, "cores": 1, "kind": "port (HiGHS exact LP; POT 0.9.4 is not installed)",
+            "sample": f"{n_lps} LPs of episode 0 (T={int(sup.sum())} support patches)"}
 
 
 def run_reference(args):
@@ -349,6 +368,34 @@ def run_ours(args):
         if md == torch.float32:  # the same call with 1-byte host masks (PCIe carries 4x fewer bytes)
             e2e_variants = {"u8_host_masks": run_e2e(torch.uint8)}
 
+    # ---- full scoring: the P transport LPs per episode solved on the device as well
+    full = None
+    if not args.no_emd:
+        Ef = min(E, 8)
+        cfg_f = marsb200.RankingConfig(nms_iou_threshold=args.nms, emd_on_device=True)
+        eng_f = marsb200.RankingEngine(shape, Ef, cfg_f, dev, md)
+        sub = [{k: v[:Ef] for k, v in b.items()} for b in batches]
+        for i in range(2):
+            eng_f.run(sub[i % n_batches])
+        barrier()
+        s3, t3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_full = max(2, min(args.steps, 4))
+        w0 = time.perf_counter()
+        s3.record()
+        for i in range(n_full):
+            eng_f.run(sub[i % n_batches])
+        t3.record()
+        barrier()
+        sampler.windows.append((w0, time.perf_counter()))
+        ms3 = s3.elapsed_time(t3) / n_full
+        emd_ms = time_kernel(lambda i: ops.emd_scores(eng_f.gemm_out["cost"], eng_f.row_fg.reshape(Ef, -1), eng_f.pool_out[0],
+                                                      t_cap=eng_f.emd_t_cap, m_cap=eng_f.emd_m_cap, workspace=eng_f.emd_ws,
+                                                      out=eng_f.emd_out, check=False), 3)
+        full = {"what": "the same step with the P transport LPs per episode (ot.emd2) solved exactly on the device",
+                "episodes_per_step": Ef, "ms_per_step": ms3, "value": world * Ef / (ms3 / 1e3), "unit": "episodes/s",
+                "emd_kernel_ms": emd_ms, "emd_lps_per_s": Ef * shape.P / (emd_ms / 1e3)}
+        del eng_f
+
     clocks = sampler.stop()
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -357,6 +404,8 @@ def run_ours(args):
         cpu_baseline = {"value": len(times) / sum(times), "unit": "episodes/s", "cores": cores, "kind": "port",
                         "sample": f"{len(times)} episodes of {args.workload} through oracle.run_episode "
                                   f"(torch CPU, {cores} threads, EMD excluded)"}
+        if full is not None:
+            full["cpu_emd"] = cpu_emd_sample(shape, batches[0], args.cpu_emd_lps)
 
     if rank == 0:
         print(json.dumps({
@@ -372,7 +421,8 @@ def run_ours(args):
                        "fused_ingest": bool(args.fused_ingest)},
             "clocks": clocks, "e2e": e2e, "e2e_variants": e2e_variants,
             "gpu_launches": marsb200.kernel_launches_per_run(cfg) * args.steps * world,
-            "roofline": roofline, "pairwise": pairwise, "fused_ingest": fused, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "pairwise": pairwise, "fused_ingest": fused, "full_scoring": full,
+            "cpu_baseline": cpu_baseline,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -215,6 +215,45 @@ int marsb200_matcher_scores(const int32_t* points_in, const int32_t* pooled_coun
 int marsb200_eval_areas(const float* pred, const float* gt, const float* ignore, int64_t n, int64_t HW, int32_t* out,
                         void* stream);
 
+/* Per-class accumulation of those areas: AverageMeter.update, mars/utils/logger.py:61-66
+ * (intersection_buf / union_buf .index_add_(1, class_id, ...)).  areas [n, 4] int32 from marsb200_eval_areas;
+ * class_id [n] int64; inter_buf, union_buf [2, nclass] int64 pixel counts (exact; the reference keeps float32
+ * buffers).  *status is set to 1 if a class id lies outside [0, nclass).  Ranks combine their buffers with one
+ * all-reduce (sum). */
+int marsb200_eval_accumulate(const int32_t* areas, const int64_t* class_id, int64_t n, int nclass, int64_t* inter_buf,
+                             int64_t* union_buf, int32_t* status, void* stream);
+
+/* AverageMeter.compute_iou, mars/utils/logger.py:69-78: interest [k] int64 class ids;
+ * out [2 + k] float64 = {mIoU, FB-IoU, fg IoU of every class of interest}; IoU = inter / max(union, 1). */
+int marsb200_eval_iou(const int64_t* inter_buf, const int64_t* union_buf, int nclass, const int64_t* interest, int k,
+                      double* out, void* stream);
+
+/* ---- 8f-4: proposal wire format and SAM-AMG post-processing ------------------------------------------
+ * Uncompressed COCO RLE (column-major runs; counts of mask m are counts[offsets[m] .. offsets[m+1]), starting
+ * with a run of zeros - the output of mask_to_rle_pytorch, segment_anything/utils/amg.py:107-135) decoded into
+ * the packed row-major bits of marsb200_pack_masks: the inverse of rle_to_mask (amg.py:138-149) without ever
+ * materialising a byte or float mask.  H and W must be multiples of 32 (MARSB200_ERR_UNSUPPORTED otherwise).
+ * bits [n, words_per_mask(H*W)]; *status = 1 if some mask's counts do not sum to H*W. */
+int64_t marsb200_rle_workspace_bytes(int64_t n, int H, int W);
+int marsb200_rle_decode(const int32_t* counts, const int64_t* offsets, int64_t n, int H, int W, uint32_t* bits,
+                        void* workspace, int64_t workspace_bytes, int32_t* status, void* stream);
+
+/* XYXY boxes of packed masks, [0,0,0,0] for an empty mask: batched_mask_to_box, amg.py:310-353.  boxes [n, 4] int32. */
+int marsb200_mask_boxes(const uint32_t* bits, int64_t n, int H, int W, int32_t* boxes, void* stream);
+
+/* Stability score |logits > t + o| / |logits > t - o|: calculate_stability_score, amg.py:156-176.
+ * logits [n, HW] fp32; out [n] fp32; counts [n, 2] int32 receives the two pixel counts. */
+int marsb200_stability_score(const float* logits, int64_t n, int64_t HW, float mask_threshold, float threshold_offset,
+                             float* out, int32_t* counts, void* stream);
+
+/* Greedy box NMS with torchvision.ops.nms semantics (batched_nms with a single category at
+ * segment_anything/automatic_mask_generator.py:284-289, 370-375): boxes [n, 4] fp32 XYXY, scores [n];
+ * order [n] int32 = box indices by descending score (ties: lower index first); keep [n] uint8 by box index;
+ * *n_keep = number kept.  n <= 16384. */
+int64_t marsb200_box_nms_workspace_bytes(int n);
+int marsb200_box_nms(const float* boxes, const float* scores, int n, float iou_threshold, int32_t* order, uint8_t* keep,
+                     int32_t* n_keep, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

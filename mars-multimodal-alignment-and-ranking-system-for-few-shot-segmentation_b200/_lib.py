@@ -61,6 +61,14 @@ SIGNATURES = {
     "marsb200_points_in_masks": (_i, [_p, _l, _i, _i, _p, _i, _p, _p]),
     "marsb200_matcher_scores": (_i, [_p, _p, _p, _l, _i, _f, _f, _f, _p, _p, _p, _p]),
     "marsb200_eval_areas": (_i, [_p, _p, _p, _l, _l, _p, _p]),
+    "marsb200_eval_accumulate": (_i, [_p, _p, _l, _i, _p, _p, _p, _p]),
+    "marsb200_eval_iou": (_i, [_p, _p, _i, _p, _i, _p, _p]),
+    "marsb200_rle_workspace_bytes": (_l, [_l, _i, _i]),
+    "marsb200_rle_decode": (_i, [_p, _p, _l, _i, _i, _p, _p, _l, _p, _p]),
+    "marsb200_mask_boxes": (_i, [_p, _l, _i, _i, _p, _p]),
+    "marsb200_stability_score": (_i, [_p, _l, _l, _f, _f, _p, _p, _p]),
+    "marsb200_box_nms_workspace_bytes": (_l, [_i]),
+    "marsb200_box_nms": (_i, [_p, _p, _i, _f, _p, _p, _p, _p, _l, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -18,7 +18,7 @@ from ._lib import GEMM_SIMT, GEMM_TCGEN05, MASK_F32, MASK_U8, PAIR_MMA, PAIR_POP
 __all__ = [
     "words_per_mask", "pad_rows", "pad_k", "normalize_rows", "pool_mask", "sim_contract", "match_argmax", "mutual_matches", "lsap", "vva_finalize",
     "attn_mean", "pir_refine", "resize_minmax", "pack_masks", "pack_pairwise", "pool_packed", "region_sums", "pairwise_inter",
-    "emd_scores", "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas",
+    "emd_scores", "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas", "eval_accumulate", "eval_iou", "rle_decode", "mask_boxes", "stability_score", "box_nms",
     "GEMM_TCGEN05", "GEMM_SIMT", "PAIR_POPC", "PAIR_MMA",
 ]
 
@@ -439,3 +439,81 @@ def eval_areas(pred: torch.Tensor, gt: torch.Tensor, ignore: Optional[torch.Tens
     out = torch.empty((n, 4), device=pred.device, dtype=torch.int32)
     check(lib.marsb200_eval_areas(pred.data_ptr(), gt.data_ptr(), _ptr(ig), n, hw, out.data_ptr(), _stream()))
     return out
+
+
+def eval_accumulate(areas: torch.Tensor, class_id: torch.Tensor, inter_buf: torch.Tensor, union_buf: torch.Tensor,
+                    check_status: bool = False) -> None:
+    """inter_buf / union_buf [2, nclass] int64 += the areas [n, 4] of the samples' classes (AverageMeter.update)."""
+    areas = _cuda(areas, torch.int32, "areas")
+    class_id = _cuda(class_id.reshape(-1), torch.int64, "class_id")
+    n = areas.shape[0]
+    assert class_id.numel() == n and inter_buf.dtype == torch.int64 and union_buf.dtype == torch.int64
+    status = torch.zeros(1, device=areas.device, dtype=torch.int32)
+    check(lib.marsb200_eval_accumulate(areas.data_ptr(), class_id.data_ptr(), n, inter_buf.shape[1], inter_buf.data_ptr(),
+                                       union_buf.data_ptr(), status.data_ptr(), _stream()))
+    if check_status and int(status.item()):
+        raise _lib.MarsB200Error("eval_accumulate: class id outside [0, nclass)")
+
+
+def eval_iou(inter_buf: torch.Tensor, union_buf: torch.Tensor, interest: torch.Tensor) -> torch.Tensor:
+    """-> float64 [2 + k] = {mIoU, FB-IoU, fg IoU per class of interest} (AverageMeter.compute_iou)."""
+    interest = _cuda(interest.reshape(-1), torch.int64, "interest")
+    out = torch.empty(2 + interest.numel(), device=inter_buf.device, dtype=torch.float64)
+    check(lib.marsb200_eval_iou(inter_buf.data_ptr(), union_buf.data_ptr(), inter_buf.shape[1], interest.data_ptr(),
+                                interest.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- 8f-4: wire format / AMG post-processing
+def rle_decode(counts: torch.Tensor, offsets: torch.Tensor, h: int, w: int, out=None, check_status: bool = True):
+    """Uncompressed COCO RLE -> packed bits [n, words_per_mask(h*w)].
+
+    counts int32 [total] (all masks concatenated, each starting with a run of zeros), offsets int64 [n + 1].
+    """
+    counts = _cuda(counts, torch.int32, "counts")
+    offsets = _cuda(offsets, torch.int64, "offsets")
+    n = offsets.numel() - 1
+    if out is None:
+        out = torch.empty((n, words_per_mask(h * w)), device=counts.device, dtype=torch.int32)
+    ws = torch.empty(int(lib.marsb200_rle_workspace_bytes(n, h, w)), device=counts.device, dtype=torch.uint8)
+    status = torch.zeros(1, device=counts.device, dtype=torch.int32)
+    check(lib.marsb200_rle_decode(counts.data_ptr(), offsets.data_ptr(), n, h, w, out.data_ptr(), ws.data_ptr(),
+                                  ws.numel(), status.data_ptr(), _stream()))
+    if check_status and int(status.item()):
+        raise _lib.MarsB200Error("rle_decode: malformed RLE (counts of a mask do not sum to H*W)")
+    return out
+
+
+def mask_boxes(bits: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """packed bits [..., wpm] -> XYXY boxes int32 [..., 4] ([0,0,0,0] for empty masks)."""
+    lead = tuple(bits.shape[:-1])
+    n = bits.numel() // bits.shape[-1]
+    out = torch.empty(lead + (4,), device=bits.device, dtype=torch.int32)
+    check(lib.marsb200_mask_boxes(bits.data_ptr(), n, h, w, out.data_ptr(), _stream()))
+    return out
+
+
+def stability_score(logits: torch.Tensor, mask_threshold: float, threshold_offset: float):
+    """logits [n, H, W] fp32 -> (score fp32 [n], counts int32 [n, 2] = pixels above t + o / above t - o)."""
+    logits = _cuda(logits, torch.float32, "logits")
+    n = logits.shape[0]
+    out = torch.empty(n, device=logits.device, dtype=torch.float32)
+    counts = torch.empty((n, 2), device=logits.device, dtype=torch.int32)
+    check(lib.marsb200_stability_score(logits.data_ptr(), n, logits.numel() // n, float(mask_threshold),
+                                       float(threshold_offset), out.data_ptr(), counts.data_ptr(), _stream()))
+    return out, counts
+
+
+def box_nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float):
+    """torchvision.ops.nms semantics.  Returns (keep_idx int64 sorted by decreasing score, order, keep mask)."""
+    boxes = _cuda(boxes, torch.float32, "boxes")
+    scores = _cuda(scores, torch.float32, "scores")
+    n = boxes.shape[0]
+    order = torch.empty(n, device=boxes.device, dtype=torch.int32)
+    keep = torch.empty(n, device=boxes.device, dtype=torch.uint8)
+    n_keep = torch.zeros(1, device=boxes.device, dtype=torch.int32)
+    ws = torch.empty(int(lib.marsb200_box_nms_workspace_bytes(n)), device=boxes.device, dtype=torch.uint8)
+    check(lib.marsb200_box_nms(boxes.data_ptr(), scores.data_ptr(), n, float(iou_threshold), order.data_ptr(),
+                               keep.data_ptr(), n_keep.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    o = order.long()
+    return o[keep[o] != 0], order, keep

@@ -476,6 +476,85 @@ def evaluator_areas(pred_mask: torch.Tensor, gt_mask: torch.Tensor, ignore: Opti
     return inter, union
 
 
+def average_meter(area_inter, area_union, class_id, nclass: int, class_ids_interest):
+    """AverageMeter.update over all samples then compute_iou (mars/utils/logger.py:61-78), float32 like the reference.
+
+    area_inter / area_union ``[2, n]``; returns ``(intersection_buf, union_buf, miou, fb_iou, iou_fg)``.
+    """
+    inter_buf = torch.zeros(2, nclass)
+    union_buf = torch.zeros(2, nclass)
+    for i in range(area_inter.shape[1]):  # one episode per update, like main_MARS.py:72-73
+        inter_buf.index_add_(1, class_id[i:i + 1], area_inter[:, i:i + 1].float())
+        union_buf.index_add_(1, class_id[i:i + 1], area_union[:, i:i + 1].float())
+    interest = torch.as_tensor(class_ids_interest)
+    iou = inter_buf / torch.max(torch.stack([union_buf, torch.ones_like(union_buf)]), dim=0)[0]
+    iou = iou.index_select(1, interest)
+    miou = iou[1].mean() * 100
+    fb_iou = (inter_buf.index_select(1, interest).sum(dim=1) / union_buf.index_select(1, interest).sum(dim=1)).mean() * 100
+    return inter_buf, union_buf, float(miou), float(fb_iou), iou[1]
+
+
+# --------------------------------------------------------------------------
+# SAM automatic-mask-generator post-processing (SURVEY 8f-4)
+# --------------------------------------------------------------------------
+def mask_to_rle(mask: np.ndarray):
+    """Uncompressed COCO RLE counts of one ``[H, W]`` boolean mask (segment_anything/utils/amg.py:107-135)."""
+    flat = np.asarray(mask, dtype=bool).T.reshape(-1)  # Fortran order
+    change = np.nonzero(flat[1:] ^ flat[:-1])[0] + 1
+    idx = np.concatenate([[0], change, [flat.size]])
+    counts = (idx[1:] - idx[:-1]).tolist()
+    return counts if not flat[0] else [0] + counts
+
+
+def rle_to_mask(counts, h: int, w: int) -> np.ndarray:
+    """Inverse (amg.py:138-149)."""
+    mask = np.empty(h * w, dtype=bool)
+    idx, parity = 0, False
+    for c in counts:
+        mask[idx:idx + c] = parity
+        idx += c
+        parity ^= True
+    return mask.reshape(w, h).transpose()
+
+
+def mask_boxes(masks: torch.Tensor) -> torch.Tensor:
+    """XYXY boxes, ``[0,0,0,0]`` for empty masks (batched_mask_to_box, amg.py:310-353)."""
+    masks = masks > 0
+    out = torch.zeros((masks.shape[0], 4), dtype=torch.int64)
+    for i, m in enumerate(masks):
+        ys, xs = torch.nonzero(m.any(1)).flatten(), torch.nonzero(m.any(0)).flatten()
+        if ys.numel():
+            out[i] = torch.tensor([xs.min(), ys.min(), xs.max(), ys.max()])
+    return out
+
+
+def stability_score(logits: torch.Tensor, mask_threshold: float, offset: float) -> torch.Tensor:
+    """calculate_stability_score (amg.py:156-176)."""
+    inter = (logits > (mask_threshold + offset)).sum(-1, dtype=torch.int16).sum(-1, dtype=torch.int32)
+    union = (logits > (mask_threshold - offset)).sum(-1, dtype=torch.int16).sum(-1, dtype=torch.int32)
+    return inter / union
+
+
+def box_nms(boxes: torch.Tensor, scores: torch.Tensor, thr: float) -> torch.Tensor:
+    """Greedy NMS with torchvision semantics (automatic_mask_generator.py:370-375); ties: lower index first."""
+    order = sorted(range(len(scores)), key=lambda i: (-float(scores[i]), i))
+    b = boxes.float()
+    area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    keep = []
+    for i in order:
+        ok = True
+        for k in keep:
+            iw = torch.minimum(b[i, 2], b[k, 2]) - torch.maximum(b[i, 0], b[k, 0])
+            ih = torch.minimum(b[i, 3], b[k, 3]) - torch.maximum(b[i, 1], b[k, 1])
+            inter = iw.clamp(min=0) * ih.clamp(min=0)
+            if inter / (area[i] + area[k] - inter) > thr:
+                ok = False
+                break
+        if ok:
+            keep.append(i)
+    return torch.tensor(keep, dtype=torch.int64)
+
+
 # --------------------------------------------------------------------------
 # Whole-episode restatement (what bench.py times as the CPU baseline)
 # --------------------------------------------------------------------------

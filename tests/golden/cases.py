@@ -163,3 +163,56 @@ def fm_inputs(spec):
     vva = torch.rand(g, g, generator=gen)
     vta = torch.rand(g, g, generator=gen)
     return dict(masks=masks, support_mask=support, cost=cost.contiguous(), clip_img=img, clip_txt=txt, vva=vva, vta=vta)
+
+
+# ---- evaluator / AverageMeter: episodes of (prediction, ground truth, ignore band, class id)
+EVAL_CASES = {
+    "coco_like": dict(benchmark="coco", class_ids=list(range(0, 80, 4)), n=24, H=96, W=128, seed=801, ignore=False),
+    "pascal_ignore": dict(benchmark="pascal5i", class_ids=[1, 2, 3, 4, 5], n=15, H=80, W=80, seed=802, ignore=True),
+}
+
+
+def eval_inputs(spec):
+    """pred / gt [n,H,W] float32 0/1, ignore [n,H,W] (disjoint from gt) or None, class_id [n] int64 (0-based)."""
+    n, h, w = spec["n"], spec["H"], spec["W"]
+    gt = blob_masks(n, h, w, spec["seed"], 0.02, 0.4)
+    noise = blob_masks(n, h, w, spec["seed"] + 1, 0.01, 0.2)
+    pred = ((gt + torch.roll(noise, 3, dims=2)) > 0).float() * (torch.roll(gt, 5, dims=1) + noise > 0).float()
+    pred[0] = 0  # an empty prediction
+    pred[1] = gt[1]  # a perfect one
+    ignore = None
+    if spec["ignore"]:
+        band = blob_masks(n, h, w, spec["seed"] + 2, 0.01, 0.1)
+        ignore = band * (1 - gt)
+    rs = np.random.RandomState(spec["seed"] + 3)
+    ids = spec["class_ids"]
+    zero_based = [i - 1 for i in ids] if spec["benchmark"] == "pascal5i" else ids
+    class_id = torch.from_numpy(rs.choice(zero_based, size=n)).long()
+    return dict(pred=pred, gt=gt, ignore=ignore, class_id=class_id)
+
+
+# ---- SAM-AMG post-processing (SURVEY 8f-4)
+AMG_CASES = {
+    "blobs_64x96": dict(n=10, H=64, W=96, seed=901),
+    "blobs_128": dict(n=6, H=128, W=128, seed=902),
+}
+
+
+def amg_inputs(spec):
+    """masks [n,H,W] bool (one empty, one full, one single pixel), logits [n,H,W] fp32, boxes [k,4] fp32 + scores."""
+    n, h, w = spec["n"], spec["H"], spec["W"]
+    masks = blob_masks(n, h, w, spec["seed"], 0.02, 0.4) > 0
+    masks[0] = False
+    masks[1] = True
+    masks[2] = False
+    masks[2, h - 1, w - 1] = True
+    rs = np.random.RandomState(spec["seed"] + 1)
+    logits = torch.from_numpy(rs.randn(n, h, w).astype(np.float32)) * 2 + (masks.float() * 4 - 2)
+    k = 40
+    xy = rs.rand(k, 2) * np.array([w * 0.6, h * 0.6])
+    wh = rs.rand(k, 2) * np.array([w * 0.4, h * 0.4]) + 2
+    boxes = np.concatenate([xy, xy + wh], axis=1).astype(np.float32)
+    boxes[k // 2:] = boxes[:k - k // 2] + rs.randn(k - k // 2, 4).astype(np.float32)  # near duplicates
+    scores = rs.rand(k).astype(np.float32)
+    scores[5] = scores[7]  # a tie
+    return dict(masks=masks, logits=logits, boxes=torch.from_numpy(boxes), scores=torch.from_numpy(scores))

@@ -13,7 +13,7 @@ is replaced by the exact transport LP of ``oracle/mars_oracle.emd_exact``
 return seeded tensors, so the vectors pin everything the reference computes
 *after* the backbones.
 
-Outputs (small, committed): ``vva_*.npz``, ``pir_*.npz``, ``fm_*.npz``.
+Outputs (small, committed): ``vva_*.npz``, ``pir_*.npz``, ``fm_*.npz``, ``eval_*.npz``, ``amg_*.npz``.
 Inputs that would be large are regenerated from the recorded seed by
 ``tests/golden/cases.py`` and guarded by a checksum stored in the fixture.
 """
@@ -146,6 +146,62 @@ def gen_fm(name, spec):
     print("fm", name, order[:8], scores[:4])
 
 
+def gen_eval(name, spec):
+    """Evaluator.classify_prediction + AverageMeter.update / compute_iou of the reference, one episode per update
+    like main_MARS.py:72-73.  mars/utils/logger.py imports comet_ml and tensorboardX (not installed): shimmed."""
+    cm = types.ModuleType("comet_ml")
+    cm.Experiment = object
+    tb = types.ModuleType("tensorboardX")
+    tb.SummaryWriter = object
+    sys.modules.update({"comet_ml": cm, "tensorboardX": tb})
+    from mars.utils.evaluation import Evaluator
+    from mars.utils.logger import AverageMeter
+
+    c = cases.eval_inputs(spec)
+    Evaluator.initialize()
+    ds = types.SimpleNamespace(benchmark=spec["benchmark"], class_ids=spec["class_ids"])
+    meter = AverageMeter(ds, device="cpu")
+    inters, unions = [], []
+    for i in range(spec["n"]):
+        batch = dict(query_mask=c["gt"][i:i + 1].clone())
+        if c["ignore"] is not None:
+            batch["query_ignore_idx"] = c["ignore"][i:i + 1].clone()
+        ai, au = Evaluator.classify_prediction(c["pred"][i:i + 1].clone(), batch)
+        meter.update(ai, au, c["class_id"][i:i + 1], loss=None)
+        inters.append(ai[:, 0].numpy())
+        unions.append(au[:, 0].numpy())
+    miou, fb_iou, cats = meter.compute_iou()
+    np.savez_compressed(os.path.join(HERE, f"eval_{name}.npz"), spec=np.asarray(repr(spec)),
+                        area_inter=np.stack(inters), area_union=np.stack(unions),
+                        intersection_buf=meter.intersection_buf.numpy(), union_buf=meter.union_buf.numpy(),
+                        miou=np.float64(miou), fb_iou=np.float64(fb_iou), cats_iou=cats.numpy())
+
+
+def gen_amg(name, spec, ref_root):
+    """mask_to_rle_pytorch / rle_to_mask / batched_mask_to_box / calculate_stability_score of the reference's
+    segment_anything/utils/amg.py (loaded by path: the package __init__ needs matplotlib) and torchvision's nms,
+    which is what batched_nms with a single category reduces to (automatic_mask_generator.py:370-375)."""
+    import importlib.util
+
+    import torchvision
+
+    sp = importlib.util.spec_from_file_location("ref_amg", os.path.join(ref_root, "segment_anything", "utils", "amg.py"))
+    amg = importlib.util.module_from_spec(sp)
+    sp.loader.exec_module(amg)
+    c = cases.amg_inputs(spec)
+    rles = amg.mask_to_rle_pytorch(c["masks"])
+    for r, m in zip(rles, c["masks"]):
+        assert np.array_equal(amg.rle_to_mask(r), m.numpy())
+    counts = np.concatenate([np.asarray(r["counts"], dtype=np.int32) for r in rles])
+    offsets = np.cumsum([0] + [len(r["counts"]) for r in rles]).astype(np.int64)
+    boxes = amg.batched_mask_to_box(c["masks"]).numpy()
+    stab = amg.calculate_stability_score(c["logits"], 0.0, 1.0).numpy()
+    keep = torchvision.ops.nms(c["boxes"], c["scores"], 0.5).numpy()
+    np.savez_compressed(os.path.join(HERE, f"amg_{name}.npz"), spec=np.asarray(repr(spec)), counts=counts,
+                        offsets=offsets, boxes=boxes, stability=stab, nms_keep=keep,
+                        areas=np.asarray([amg.area_from_rle(r) for r in rles]))
+
+
 def main():
     ref_root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     install_shims(ref_root)
@@ -156,6 +212,10 @@ def main():
         gen_pir(name, spec)
     for name, spec in cases.FM_CASES.items():
         gen_fm(name, spec)
+    for name, spec in cases.EVAL_CASES.items():
+        gen_eval(name, spec)
+    for name, spec in cases.AMG_CASES.items():
+        gen_amg(name, spec, ref_root)
 
 
 if __name__ == "__main__":

@@ -617,6 +617,89 @@ def test_evaluator_dropin(mb):
     np.testing.assert_array_equal(union.cpu().numpy(), union_ref.numpy())
 
 
+@pytest.mark.parametrize("name", list(cases.EVAL_CASES))
+def test_average_meter_matches_reference(mb, name):
+    """Evaluator + AverageMeter drop-ins (device buffers, exact int64 counts) against the reference's golden run;
+    two meters fed with disjoint shards sum to the same buffers (what all_reduce does across ranks)."""
+    import types
+
+    z = np.load(os.path.join(GOLD, f"eval_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.eval_inputs(spec)
+    d = dev()
+    ds = types.SimpleNamespace(benchmark=spec["benchmark"], class_ids=spec["class_ids"])
+    mb.Evaluator.initialize()
+    meter = mb.AverageMeter(ds, device=d)
+    shard = [mb.AverageMeter(ds, device=d), mb.AverageMeter(ds, device=d)]
+    for i in range(spec["n"]):
+        batch = dict(query_mask=c["gt"][i:i + 1])
+        if c["ignore"] is not None:
+            batch["query_ignore_idx"] = c["ignore"][i:i + 1]
+        ai, au = mb.Evaluator.classify_prediction(c["pred"][i:i + 1].to(d), batch)
+        np.testing.assert_array_equal(ai[:, 0].cpu().numpy(), z["area_inter"][i])
+        np.testing.assert_array_equal(au[:, 0].cpu().numpy(), z["area_union"][i])
+        meter.update(ai, au, c["class_id"][i:i + 1], loss=None)
+        shard[i % 2].update(ai, au, c["class_id"][i:i + 1], loss=None)
+    np.testing.assert_array_equal(meter.intersection_buf.cpu().numpy(), z["intersection_buf"].astype(np.int64))
+    np.testing.assert_array_equal(meter.union_buf.cpu().numpy(), z["union_buf"].astype(np.int64))
+    assert torch.equal(shard[0].intersection_buf + shard[1].intersection_buf, meter.intersection_buf)
+    assert torch.equal(shard[0].union_buf + shard[1].union_buf, meter.union_buf)
+    miou, fb, cats = meter.compute_iou()
+    np.testing.assert_allclose(float(miou), float(z["miou"]), rtol=1e-5)   # the reference divides in float32
+    np.testing.assert_allclose(float(fb), float(z["fb_iou"]), rtol=1e-5)
+    np.testing.assert_allclose(cats.cpu().numpy(), z["cats_iou"], rtol=1e-5, atol=1e-7)
+    # batched path: all samples in one call
+    areas = mb.ops.eval_areas(c["pred"].to(d), c["gt"].to(d), None if c["ignore"] is None else c["ignore"].to(d))
+    m2 = mb.AverageMeter(ds, device=d)
+    m2.update_areas(areas, c["class_id"])
+    assert torch.equal(m2.intersection_buf, meter.intersection_buf) and torch.equal(m2.union_buf, meter.union_buf)
+    with pytest.raises(mb.MarsB200Error):
+        mb.ops.eval_accumulate(areas, torch.full((spec["n"],), 5000, device=d), m2.intersection_buf, m2.union_buf, check_status=True)
+
+
+# ------------------------------------------------------------------------------------------ wire format / AMG post-processing
+@pytest.mark.parametrize("name", list(cases.AMG_CASES))
+def test_amg_postprocessing(mb, name):
+    """RLE decode -> packed bits == pack(mask), boxes, stability score and box NMS against the reference's golden."""
+    z = np.load(os.path.join(GOLD, f"amg_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.amg_inputs(spec)
+    h, w, d = spec["H"], spec["W"], dev()
+    bits_ref = mb.ops.pack_masks(c["masks"].to(d))
+    bits = mb.ops.rle_decode(torch.from_numpy(z["counts"]).to(d), torch.from_numpy(z["offsets"]).to(d), h, w)
+    assert torch.equal(bits, bits_ref)
+    np.testing.assert_array_equal(mb.ops.mask_boxes(bits, h, w).cpu().numpy(), z["boxes"])
+    score, counts = mb.ops.stability_score(c["logits"].to(d), 0.0, 1.0)
+    np.testing.assert_array_equal(score.cpu().numpy(), z["stability"])
+    np.testing.assert_array_equal(counts[:, 0].cpu().numpy(), (c["logits"] > 1.0).flatten(1).sum(1).numpy())
+    keep, order, mask = mb.ops.box_nms(c["boxes"].to(d), c["scores"].to(d), 0.5)
+    np.testing.assert_array_equal(keep.cpu().numpy(), z["nms_keep"])
+    with pytest.raises(mb.MarsB200Error):  # counts that do not cover the image
+        bad = torch.from_numpy(z["counts"]).clone()
+        bad[0] += 1
+        mb.ops.rle_decode(bad.to(d), torch.from_numpy(z["offsets"]).to(d), h, w)
+
+
+def test_rle_ingest_full_size(mb):
+    """1024 x 1024 proposals: RLE -> bits equals the float32 ingest bit for bit; boxes from bits match torch."""
+    shape = mb.CONFIGS["c2"]
+    masks = mb.synthetic.random_masks(24, shape.H, shape.W, torch.Generator(device=dev()).manual_seed(5), dev())
+    mcpu = masks.cpu().numpy() > 0
+    rles = [orc.mask_to_rle(m) for m in mcpu]
+    counts = torch.from_numpy(np.concatenate([np.asarray(r, dtype=np.int32) for r in rles]))
+    offsets = torch.from_numpy(np.cumsum([0] + [len(r) for r in rles]).astype(np.int64))
+    bits = mb.ops.rle_decode(counts.to(dev()), offsets.to(dev()), shape.H, shape.W)
+    assert torch.equal(bits, mb.ops.pack_masks(masks))
+    np.testing.assert_array_equal(mb.ops.mask_boxes(bits, shape.H, shape.W).cpu().numpy(), orc.mask_boxes(masks.cpu()).numpy())
+    # a larger NMS problem against the oracle
+    gen = torch.Generator().manual_seed(9)
+    xy = torch.rand(300, 2, generator=gen) * 800
+    boxes = torch.cat([xy, xy + torch.rand(300, 2, generator=gen) * 200 + 4], dim=1)
+    scores = torch.rand(300, generator=gen)
+    keep, _, _ = mb.ops.box_nms(boxes.to(dev()), scores.to(dev()), 0.7)
+    np.testing.assert_array_equal(keep.cpu().numpy(), orc.box_nms(boxes, scores, 0.7).numpy())
+
+
 # ------------------------------------------------------------------------------------------ exact EMD on the device
 def _emd_inputs(ns, g, p, h, seed):
     n = g * g

@@ -94,3 +94,40 @@ def test_run_episode_consistency():
     mb = c["masks"].reshape(spec["P"], -1) > 0
     assert torch.equal(area, mb.sum(1).to(torch.int32))
     assert torch.equal(inter, (mb.float() @ mb.float().T).to(torch.int32))
+
+
+@pytest.mark.parametrize("name", list(cases.EVAL_CASES))
+def test_evaluator_and_average_meter_match_reference(name):
+    """Evaluator.classify_prediction + AverageMeter of the reference (golden) vs the oracle restatements."""
+    z = np.load(os.path.join(GOLD, f"eval_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.eval_inputs(spec)
+    inter, union = orc.evaluator_areas(c["pred"], c["gt"], c["ignore"])
+    np.testing.assert_array_equal(inter.t().numpy(), z["area_inter"])
+    np.testing.assert_array_equal(union.t().numpy(), z["area_union"])
+    nclass = z["intersection_buf"].shape[1]
+    ids = spec["class_ids"]
+    interest = [i - 1 for i in ids] if spec["benchmark"] == "pascal5i" else ids
+    ib, ub, miou, fb, cats = orc.average_meter(inter, union, c["class_id"], nclass, interest)
+    np.testing.assert_array_equal(ib.numpy(), z["intersection_buf"])
+    np.testing.assert_array_equal(ub.numpy(), z["union_buf"])
+    np.testing.assert_allclose(miou, float(z["miou"]), rtol=1e-6)
+    np.testing.assert_allclose(fb, float(z["fb_iou"]), rtol=1e-6)
+    np.testing.assert_allclose(cats.numpy()[:20], z["cats_iou"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(cases.AMG_CASES))
+def test_amg_postprocessing_matches_reference(name):
+    """RLE, boxes, stability score of the reference's amg.py and torchvision's nms (golden) vs the oracle."""
+    z = np.load(os.path.join(GOLD, f"amg_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.amg_inputs(spec)
+    h, w = spec["H"], spec["W"]
+    for i, m in enumerate(c["masks"]):
+        counts = orc.mask_to_rle(m.numpy())
+        np.testing.assert_array_equal(counts, z["counts"][z["offsets"][i]:z["offsets"][i + 1]])
+        np.testing.assert_array_equal(orc.rle_to_mask(counts, h, w), m.numpy())
+        assert sum(counts[1::2]) == int(z["areas"][i])
+    np.testing.assert_array_equal(orc.mask_boxes(c["masks"]).numpy(), z["boxes"])
+    np.testing.assert_array_equal(orc.stability_score(c["logits"], 0.0, 1.0).numpy(), z["stability"])
+    np.testing.assert_array_equal(orc.box_nms(c["boxes"], c["scores"], 0.5).numpy(), z["nms_keep"])
