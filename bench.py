@@ -324,11 +324,18 @@ def run_ours(args):
              "unordered_pairs_per_s": pairs / (fused_ms / 1e3)}
 
     # ---- end to end: pinned host inputs -> H2D -> ranking -> D2H of the result records, every step
-    def run_e2e(e2e_dtype):
+    def run_e2e(e2e_dtype, wire="dense"):
         Ee = args.e2e_episodes_per_step
         eng2 = marsb200.RankingEngine(shape, Ee, cfg, dev, e2e_dtype)
         host = {k: v[:Ee].cpu() for k, v in batches[0].items()}
-        host["masks"] = host["masks"].to(e2e_dtype)
+        if wire == "rle":  # SAM's own output format: uncompressed COCO RLE, decoded on the device
+            counts, offsets = marsb200.masks_to_rle(host.pop("masks").reshape(-1, shape.H, shape.W))
+            host["mask_rle_counts"], host["mask_rle_offsets"] = counts, offsets
+        elif wire == "bits":  # proposals kept bit-packed by the producer
+            host["mask_bits"] = ops.pack_masks(batches[0]["masks"][:Ee]).cpu()
+            host.pop("masks")
+        else:
+            host["masks"] = host["masks"].to(e2e_dtype)
         host = {k: v.pin_memory() for k, v in host.items()}
         dev_in = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
         rec_host = torch.empty((Ee, eng2.record_bytes()), dtype=torch.uint8).pin_memory()
@@ -360,21 +367,27 @@ def run_ours(args):
             ms2 = float(t.item())
         return {"value": world * Ee * args.steps / (ms2 / 1e3), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "episodes_per_step": Ee, "ms_per_step": ms2 / args.steps,
-                "host_mask_dtype": "f32" if e2e_dtype == torch.float32 else "u8"}
+                "host_mask_format": {"dense": "f32" if e2e_dtype == torch.float32 else "u8", "rle": "uncompressed COCO RLE",
+                                     "bits": "packed bits"}[wire]}
 
     e2e, e2e_variants = None, None
     if not args.no_e2e:
         e2e = run_e2e(md)
-        if md == torch.float32:  # the same call with 1-byte host masks (PCIe carries 4x fewer bytes)
-            e2e_variants = {"u8_host_masks": run_e2e(torch.uint8)}
+        if md == torch.float32:  # the same call with lighter proposal wire formats (PCIe carries far fewer bytes)
+            e2e_variants = {"u8_host_masks": run_e2e(torch.uint8), "rle_host_masks": run_e2e(md, "rle"),
+                            "packed_host_masks": run_e2e(md, "bits")}
 
     # ---- full scoring: the P transport LPs per episode solved on the device as well
     full = None
     if not args.no_emd:
         Ef = min(E, 8)
-        cfg_f = marsb200.RankingConfig(nms_iou_threshold=args.nms, emd_on_device=True)
-        eng_f = marsb200.RankingEngine(shape, Ef, cfg_f, dev, md)
         sub = [{k: v[:Ef] for k, v in b.items()} for b in batches]
+        # a deployment sizes the solver's state for the largest proposal it admits; here: the largest pooled
+        # proposal of the synthetic set, rounded up (read once, outside the timed region)
+        m_cap = max(int(ops.pool_packed(ops.pack_masks(b["masks"]), shape.H, shape.W, shape.g)[2].max()) for b in sub)
+        m_cap = min(shape.N, (m_cap + 63) // 64 * 64)
+        cfg_f = marsb200.RankingConfig(nms_iou_threshold=args.nms, emd_on_device=True, emd_m_cap=m_cap)
+        eng_f = marsb200.RankingEngine(shape, Ef, cfg_f, dev, md)
         for i in range(2):
             eng_f.run(sub[i % n_batches])
         barrier()
@@ -393,7 +406,7 @@ def run_ours(args):
                                                       out=eng_f.emd_out, check=False), 3)
         full = {"what": "the same step with the P transport LPs per episode (ot.emd2) solved exactly on the device",
                 "episodes_per_step": Ef, "ms_per_step": ms3, "value": world * Ef / (ms3 / 1e3), "unit": "episodes/s",
-                "emd_kernel_ms": emd_ms, "emd_lps_per_s": Ef * shape.P / (emd_ms / 1e3)}
+                "emd_kernel_ms": emd_ms, "emd_lps_per_s": Ef * shape.P / (emd_ms / 1e3), "emd_m_cap": m_cap}
         del eng_f
 
     clocks = sampler.stop()

@@ -5,11 +5,11 @@ libmarsb200.so (hand-written CUDA behind the C ABI of include/marsb200.h).
 Importing this package loads the shared library and fails if it is missing -
 there is no CPU fallback.
 """
-from . import _lib, ops  # noqa: F401  (loads libmarsb200.so)
+from . import _lib, ops, synthetic  # noqa: F401  (loads libmarsb200.so)
 from ._lib import MarsB200Error  # noqa: F401
 from .episodes import (RankingConfig, RankingEngine, decode_records, gather_records,  # noqa: F401
                        kernel_launches_per_run, shard_range)
-from .synthetic import CONFIGS, EpisodeShape, make_episode, stack_episodes, to_device  # noqa: F401
+from .synthetic import CONFIGS, EpisodeShape, make_episode, masks_to_rle, stack_episodes, to_device  # noqa: F401
 from .components import (FilteringMergingModule, PriorInformationRefinementModule,  # noqa: F401
                          VisualVisualAlignmentModule)
 from .MARS import MARS, build_MARS_fss  # noqa: F401

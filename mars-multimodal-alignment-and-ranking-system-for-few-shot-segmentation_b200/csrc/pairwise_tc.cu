@@ -187,15 +187,20 @@ int pairwise_mma(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter
     const int blocks = ceil_div(P, PM_ROWS);
     const int pairs = blocks * (blocks + 1) / 2;
     const int total_kb = (int)(wpm / 4);
-    // one CTA per SM: split the pixels so that about one wave of 148 CTAs covers the launch
-    int ksplit = std::max(1, std::min(total_kb, (148 + pairs * E - 1) / (pairs * E)));
+    static int num_sms = 0;
+    if (!num_sms) {
+        MARS_CUDA_OK(cudaFuncSetAttribute(pairwise_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PM_SMEM_BYTES));
+        int dev = 0;
+        MARS_CUDA_OK(cudaGetDevice(&dev));
+        MARS_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // one CTA per SM (all of TMEM, 193 KB of shared memory): split the pixels so that the launch fills whole waves
+    // from below - 160 CTAs on 148 SMs would run two waves with the second one 8 % full
+    const int units = pairs * E;
+    const int waves = ceil_div(units, num_sms);
+    int ksplit = std::max(1, std::min(total_kb, waves * num_sms / units));
     int kb_per_split = ceil_div(total_kb, ksplit);
     ksplit = ceil_div(total_kb, kb_per_split);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MARS_CUDA_OK(cudaFuncSetAttribute(pairwise_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PM_SMEM_BYTES));
-        attr_set = true;
-    }
     MARS_CUDA_OK(cudaMemsetAsync(inter, 0, sizeof(int32_t) * (size_t)E * P * P, s));
     dim3 grid(pairs, ksplit, E);
     pairwise_mma_kernel<<<grid, PM_THREADS, PM_SMEM_BYTES, s>>>(bits, P, wpm, blocks, kb_per_split, inter);

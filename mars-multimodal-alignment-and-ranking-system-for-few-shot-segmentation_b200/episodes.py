@@ -107,6 +107,7 @@ class RankingEngine:
             self.merge_out["f32"] = new((e, s.H * s.W), f32)
         self._graph = None
         self._static = None
+        self._rle_ws = None
         self._side = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
         self._side2 = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
         self._ev_fork = torch.cuda.Event()
@@ -115,15 +116,31 @@ class RankingEngine:
         self._ev_pool = torch.cuda.Event()
 
     # ------------------------------------------------------------------ the kernel sequence
+    def _ingest(self, batch: dict):
+        """Proposals -> packed bits.  Wire formats: `masks` [E,P,H,W] float32 / uint8 / bool (the reference's tensors),
+        `mask_rle_counts` + `mask_rle_offsets` (uncompressed COCO RLE of all E*P masks, SAM's output format), or
+        `mask_bits` [E,P,wpm] (already packed)."""
+        s = self.shape
+        if "mask_rle_counts" in batch:
+            if self._rle_ws is None:
+                self._rle_ws = torch.empty(int(ops.lib.marsb200_rle_workspace_bytes(self.E * s.P, s.H, s.W)),
+                                           device=self.device, dtype=torch.uint8)
+            ops.rle_decode(batch["mask_rle_counts"], batch["mask_rle_offsets"], s.H, s.W,
+                           out=self.bits.view(self.E * s.P, -1), check_status=False, workspace=self._rle_ws)
+        elif "mask_bits" in batch:
+            self.bits.copy_(batch["mask_bits"].view(self.bits.dtype).reshape(self.bits.shape))
+        else:
+            ops.pack_masks(batch["masks"], out=self.bits)
+
     def _mask_chain(self, batch: dict):
         """Ingest side: pack -> pooled bitmaps / areas -> pairwise intersections (depends on the masks only)."""
         s, cfg = self.shape, self.cfg
-        if self.inter is not None and cfg.fused_ingest:
+        if self.inter is not None and cfg.fused_ingest and "masks" in batch:
             # one pass over the masks: packed bits + intersections (falls back to two kernels when not fusable)
             ops.pack_pairwise(batch["masks"], backend=cfg.pair_backend, out=(self.bits, self.inter))
             ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
             return
-        ops.pack_masks(batch["masks"], out=self.bits)
+        self._ingest(batch)
         if self.inter is None:
             ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
         elif self._side2 is None:

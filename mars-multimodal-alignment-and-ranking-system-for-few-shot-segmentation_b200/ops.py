@@ -465,7 +465,8 @@ def eval_iou(inter_buf: torch.Tensor, union_buf: torch.Tensor, interest: torch.T
 
 
 # ----------------------------------------------------------------------------- 8f-4: wire format / AMG post-processing
-def rle_decode(counts: torch.Tensor, offsets: torch.Tensor, h: int, w: int, out=None, check_status: bool = True):
+def rle_decode(counts: torch.Tensor, offsets: torch.Tensor, h: int, w: int, out=None, check_status: bool = True,
+               workspace=None):
     """Uncompressed COCO RLE -> packed bits [n, words_per_mask(h*w)].
 
     counts int32 [total] (all masks concatenated, each starting with a run of zeros), offsets int64 [n + 1].
@@ -475,7 +476,9 @@ def rle_decode(counts: torch.Tensor, offsets: torch.Tensor, h: int, w: int, out=
     n = offsets.numel() - 1
     if out is None:
         out = torch.empty((n, words_per_mask(h * w)), device=counts.device, dtype=torch.int32)
-    ws = torch.empty(int(lib.marsb200_rle_workspace_bytes(n, h, w)), device=counts.device, dtype=torch.uint8)
+    nbytes = int(lib.marsb200_rle_workspace_bytes(n, h, w))
+    ws = workspace if workspace is not None and workspace.numel() >= nbytes else \
+        torch.empty(nbytes, device=counts.device, dtype=torch.uint8)
     status = torch.zeros(1, device=counts.device, dtype=torch.int32)
     check(lib.marsb200_rle_decode(counts.data_ptr(), offsets.data_ptr(), n, h, w, out.data_ptr(), ws.data_ptr(),
                                   ws.numel(), status.data_ptr(), _stream()))

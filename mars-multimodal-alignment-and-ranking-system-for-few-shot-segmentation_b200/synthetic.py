@@ -116,3 +116,23 @@ def stack_episodes(episodes) -> dict:
 
 def to_device(batch: dict, device, non_blocking=False) -> dict:
     return {k: v.to(device, non_blocking=non_blocking) for k, v in batch.items()}
+
+
+def masks_to_rle(masks: torch.Tensor):
+    """Uncompressed COCO RLE of [n, H, W] masks (column-major runs, first run = zeros) as (counts int32 [total],
+    offsets int64 [n + 1]) CPU tensors: SAM's wire format (segment_anything/utils/amg.py:107-135).  Host-side
+    input preparation for tests and benchmarks, not part of the ranking path."""
+    import numpy as np
+
+    m = (masks.detach().cpu().numpy() > 0)
+    counts, offsets = [], [0]
+    for one in m:
+        flat = one.T.reshape(-1)
+        change = np.nonzero(flat[1:] ^ flat[:-1])[0] + 1
+        idx = np.concatenate([[0], change, [flat.size]])
+        c = (idx[1:] - idx[:-1]).astype(np.int32)
+        if flat[0]:
+            c = np.concatenate([np.zeros(1, np.int32), c])
+        counts.append(c)
+        offsets.append(offsets[-1] + len(c))
+    return torch.from_numpy(np.concatenate(counts)), torch.tensor(offsets, dtype=torch.int64)

@@ -921,3 +921,22 @@ def test_patch_matcher_against_scipy_restatement(mb, name):
     assert got == pts_ref
     assert got_neg == neg_ref
     np.testing.assert_allclose(res["C"].cpu().numpy(), ((1 - fs @ fq.T) / 2).numpy(), atol=3e-6)
+
+
+def test_engine_wire_formats(mb):
+    """The engine ranks identically from float32 masks, uncompressed RLE and pre-packed bits."""
+    shape = mb.EpisodeShape(ns=1, g=12, C=64, P=16, H=160, W=160, gt=9, D=32)
+    cfg = mb.RankingConfig(nms_iou_threshold=0.7)
+    eps = [mb.make_episode(shape, 90 + i) for i in range(2)]
+    batch = mb.to_device(mb.stack_episodes(eps), dev())
+    eng = mb.RankingEngine(shape, 2, cfg, dev())
+    ref = {k: v.clone() for k, v in eng.run(batch).items() if k in ("order", "scores", "flags", "merged_bits", "inter")}
+    counts, offsets = mb.masks_to_rle(batch["masks"].reshape(-1, shape.H, shape.W))
+    rle = {k: v for k, v in batch.items() if k != "masks"}
+    rle["mask_rle_counts"], rle["mask_rle_offsets"] = counts.to(dev()), offsets.to(dev())
+    packed = {k: v for k, v in batch.items() if k != "masks"}
+    packed["mask_bits"] = mb.ops.pack_masks(batch["masks"])
+    for other in (rle, packed):
+        out = eng.run(other)
+        for k, v in ref.items():
+            assert torch.equal(out[k], v), k
