@@ -15,10 +15,14 @@ a builder-defined specification and says so.
 Pinning: ``tests/golden/make_golden.py`` runs the *reference's own modules*
 (imported from the reference checkout with three import shims) on seeded
 inputs and commits inputs+outputs under ``tests/golden/``; the CPU test-suite
-checks this oracle against those vectors.  The builder-defined pieces
-(`pairwise_intersections`, `mask_nms`) and the exact-EMD stand-in (POT is not
-installed anywhere we can run) have no reference output to pin against:
-**parity unpinned** for those three, pinned for everything else.
+checks this oracle against those vectors (alignment prior, prior refinement,
+proposal scoring / merging, evaluator + AverageMeter, SAM-AMG RLE / boxes /
+stability score, torchvision box NMS).  The builder-defined pieces
+(`pairwise_intersections`, `mask_nms`), the exact-EMD stand-in (POT is not
+installed anywhere we can run) and the Matcher assignment matching (scipy's
+LSAP tie-breaking is implementation-defined; compared by objective value) have
+no reference output to pin against: **parity unpinned** for those four, pinned
+for everything else.
 """
 from __future__ import annotations
 
