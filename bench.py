@@ -377,6 +377,23 @@ def run_ours(args):
             e2e_variants = {"u8_host_masks": run_e2e(torch.uint8), "rle_host_masks": run_e2e(md, "rle"),
                             "packed_host_masks": run_e2e(md, "bits")}
 
+    # ---- single-episode latency (the reference ranks one episode at a time, main_MARS.py:54-94): eager launches
+    # and one CUDA-graph replay of the same kernel sequence
+    def latency():
+        eng1 = marsb200.RankingEngine(shape, 1, cfg, dev, md)
+        one = [{k: v[i:i + 1].contiguous() for k, v in batches[0].items()} for i in range(2)]
+        for i in range(3):
+            eng1.run(one[i % 2])
+        eager = time_kernel(lambda i: eng1.run(one[i % 2]), 10)
+        eng1.capture(one[0])
+        for i in range(3):
+            eng1.replay()
+        graph = time_kernel(lambda i: eng1.replay(), 10)
+        return {"episodes": 1, "eager_ms": eager, "cuda_graph_ms": graph,
+                "note": "inputs resident in HBM; one episode = 1.07 GB of float32 masks (163 us at the HBM peak)"}
+
+    lat = latency() if not args.no_e2e else None
+
     # ---- full scoring: the P transport LPs per episode solved on the device as well
     full = None
     if not args.no_emd:
@@ -386,7 +403,9 @@ def run_ours(args):
         # proposal of the synthetic set, rounded up (read once, outside the timed region)
         m_cap = max(int(ops.pool_packed(ops.pack_masks(b["masks"]), shape.H, shape.W, shape.g)[2].max()) for b in sub)
         m_cap = min(shape.N, (m_cap + 63) // 64 * 64)
-        cfg_f = marsb200.RankingConfig(nms_iou_threshold=args.nms, emd_on_device=True, emd_m_cap=m_cap)
+        t_cap = max(int(ops.pool_mask(b["support_mask"], shape.g).reshape(Ef, -1).sum(1).max()) for b in sub)
+        t_cap = min(shape.ns * shape.N, (t_cap + 63) // 64 * 64)
+        cfg_f = marsb200.RankingConfig(nms_iou_threshold=args.nms, emd_on_device=True, emd_m_cap=m_cap, emd_t_cap=t_cap)
         eng_f = marsb200.RankingEngine(shape, Ef, cfg_f, dev, md)
         for i in range(2):
             eng_f.run(sub[i % n_batches])
@@ -406,7 +425,7 @@ def run_ours(args):
                                                       out=eng_f.emd_out, check=False), 3)
         full = {"what": "the same step with the P transport LPs per episode (ot.emd2) solved exactly on the device",
                 "episodes_per_step": Ef, "ms_per_step": ms3, "value": world * Ef / (ms3 / 1e3), "unit": "episodes/s",
-                "emd_kernel_ms": emd_ms, "emd_lps_per_s": Ef * shape.P / (emd_ms / 1e3), "emd_m_cap": m_cap}
+                "emd_kernel_ms": emd_ms, "emd_lps_per_s": Ef * shape.P / (emd_ms / 1e3), "emd_m_cap": m_cap, "emd_t_cap": t_cap}
         del eng_f
 
     clocks = sampler.stop()
@@ -435,7 +454,7 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "e2e_variants": e2e_variants,
             "gpu_launches": marsb200.kernel_launches_per_run(cfg) * args.steps * world,
             "roofline": roofline, "pairwise": pairwise, "fused_ingest": fused, "full_scoring": full,
-            "cpu_baseline": cpu_baseline,
+            "single_episode_latency": lat, "cpu_baseline": cpu_baseline,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -46,12 +46,12 @@ struct EmdSmem {
     double* v;       // [n_cap] sink duals
     double* dist;    // [n_cap] tentative / final sink distances
     int* reached;    // [t_cap] 0/1 (int: claimed with atomicExch)
-    short* rows;     // [t_cap] support row of source i
+    int* soff;       // [t_cap] offset of source i in the cost matrix (row * N, or the patch column when transposed)
+    int* koff;       // [n_cap] offset of sink j (patch column, or row * N when transposed): c(i, j) = C[soff[i] + koff[j]]
     short* supply;   // [t_cap]
     short* capflow;  // [t_cap] flow on the tree arc (pred_sink[i] -> i) = what a path through i can take back
     short* pred_sink;  // [t_cap] sink through which source i was reached, -1 for a root
     short* newlist;  // [t_cap] sources reached in the current wave (also the root list while a phase starts)
-    short* cols;     // [n_cap] patch index of sink j
     short* demand;   // [n_cap]
     short* pred_src;  // [n_cap] source that gave sink j its distance
     short* batch;    // [n_cap] sinks settled in the current wave
@@ -63,7 +63,7 @@ struct EmdSmem {
 };
 
 __host__ __device__ inline size_t emd_smem_bytes(int t_cap, int n_cap) {
-    return (size_t)t_cap * (2 * 8 + 4 + 5 * 2) + (size_t)n_cap * (2 * 8 + 5 * 2 + 1) + (size_t)emd_pool_nodes(t_cap, n_cap) * 6 + 64;
+    return (size_t)t_cap * (2 * 8 + 2 * 4 + 4 * 2) + (size_t)n_cap * (2 * 8 + 4 + 4 * 2 + 1) + (size_t)emd_pool_nodes(t_cap, n_cap) * 6 + 64;
 }
 
 __device__ inline EmdSmem emd_carve(unsigned char* base, int t_cap, int n_cap) {
@@ -75,14 +75,14 @@ __device__ inline EmdSmem emd_carve(unsigned char* base, int t_cap, int n_cap) {
     s.v = s.dsrc + t_cap;
     s.dist = s.v + n_cap;
     s.reached = reinterpret_cast<int*>(s.dist + n_cap);
-    short* h = reinterpret_cast<short*>(s.reached + t_cap);
-    s.rows = h;
-    s.supply = s.rows + t_cap;
+    s.soff = s.reached + t_cap;
+    s.koff = s.soff + t_cap;
+    short* h = reinterpret_cast<short*>(s.koff + n_cap);
+    s.supply = h;
     s.capflow = s.supply + t_cap;
     s.pred_sink = s.capflow + t_cap;
     s.newlist = s.pred_sink + t_cap;
-    s.cols = s.newlist + t_cap;
-    s.demand = s.cols + n_cap;
+    s.demand = s.newlist + t_cap;
     s.pred_src = s.demand + n_cap;
     s.batch = s.pred_src + n_cap;
     s.head = s.batch + n_cap;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) emd_rank_kernel(const int64_t* __restrict
 }
 
 // For every sink j (all of them when INIT, the unscanned ones otherwise): best = min over the listed sources i of
-// c(i, j) - u[i], c(i, j) = cmat[rows[i] * stride + cols[j]].  INIT starts a phase (dist = best - v, or v = best and dist = 0 in the very first phase);
+// c(i, j) - u[i], c(i, j) = cmat[soff[i] + koff[j]].  INIT starts a phase (dist = best - v, or v = best and dist = 0 in the very first phase);
 // otherwise the sink is relaxed with dbase + best - v.  `lanes` (a power of two <= 32) threads share a sink and
 // split the source list, so small problems still use the whole CTA.  A thread owns up to EMD_SPT sinks and walks
 // the source list four at a time: up to 4 * EMD_SPT independent gathers are in flight per thread.
@@ -192,7 +192,7 @@ constexpr int EMD_SPT = 3;
 constexpr int EMD_CHUNK = 4;
 
 template <bool INIT>
-__device__ inline void scan_sources(const EmdSmem& s, const float* __restrict__ cmat, int stride, int M, const short* list,
+__device__ inline void scan_sources(const EmdSmem& s, const float* __restrict__ cmat, int M, const short* list,
                                     int n, int lanes, double dbase, bool first_phase) {
     const int tid = threadIdx.x;
     const int sub = tid & (lanes - 1);
@@ -210,7 +210,7 @@ __device__ inline void scan_sources(const EmdSmem& s, const float* __restrict__ 
             live[t] = j < M && (INIT || !s.scanned[j]);
             best[t] = EMD_INF;
             best_i[t] = -1;
-            col[t] = cmat + (live[t] ? (int)s.cols[j] : 0);
+            col[t] = cmat + (live[t] ? s.koff[j] : 0);
         }
         bool any = false;
 #pragma unroll
@@ -220,12 +220,12 @@ __device__ inline void scan_sources(const EmdSmem& s, const float* __restrict__ 
             int k = sub;
             for (; k + (EMD_CHUNK - 1) * lanes < n; k += EMD_CHUNK * lanes) {
                 int idx[EMD_CHUNK];
-                int64_t off[EMD_CHUNK];
+                int off[EMD_CHUNK];
                 double ui[EMD_CHUNK];
 #pragma unroll
                 for (int q = 0; q < EMD_CHUNK; ++q) {
                     idx[q] = list[k + q * lanes];
-                    off[q] = (int64_t)s.rows[idx[q]] * stride;
+                    off[q] = s.soff[idx[q]];
                     ui[q] = s.u[idx[q]];
                 }
                 float cv[EMD_SPT][EMD_CHUNK];
@@ -247,7 +247,7 @@ __device__ inline void scan_sources(const EmdSmem& s, const float* __restrict__ 
             // remainder: one source at a time, still EMD_SPT gathers in flight
             for (; k < n; k += lanes) {
                 const int i = list[k];
-                const int64_t off = (int64_t)s.rows[i] * stride;
+                const int off = s.soff[i];
                 const double ui = s.u[i];
                 float cv[EMD_SPT];
 #pragma unroll
@@ -313,13 +313,13 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
                                                            const int32_t* __restrict__ order, int32_t* __restrict__ counter,
                                                            double* __restrict__ out, int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char emd_smem_raw[];
-    EmdSmem s = emd_carve(emd_smem_raw, t_cap, m_cap);
+    EmdSmem s = emd_carve(emd_smem_raw, min(t_cap, m_cap), max(t_cap, m_cap));  // (source cap, sink cap)
     __shared__ unsigned long long s_val[EMD_WARPS];
     __shared__ double s_acc[EMD_WARPS];
     __shared__ int s_warp[EMD_WARPS];
     __shared__ int s_lp, s_ndef, s_nnew, s_left, s_free, s_fault;
     const int tid = threadIdx.x;
-    const int pool = emd_pool_nodes(t_cap, m_cap);
+    const int pool = emd_pool_nodes(min(t_cap, m_cap), max(t_cap, m_cap));
 
     while (true) {
         __syncthreads();
@@ -339,23 +339,30 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
         const uint8_t* fg = row_fg + e * m_rows;
         const uint32_t* pw = pooled + lp * npw;
 
-        // ---- index lists (ascending order, like boolean indexing in the reference)
-        const int T = block_compact((int)m_rows, t_cap, s.rows, [&](int r) { return fg[r] != 0; }, s_warp);
-        const int M = block_compact(N, m_cap, s.cols, [&](int b) { return ((pw[b >> 5] >> (b & 31)) & 1u) != 0; }, s_warp);
-        if (T == 0 || M == 0) {  // empty marginal: defined as zero transport cost
+        // ---- index lists (ascending order, like boolean indexing in the reference), staged in two sink-sized arrays
+        const int k_cap = max(t_cap, m_cap);
+        const int T0 = block_compact((int)m_rows, k_cap, s.batch, [&](int r) { return fg[r] != 0; }, s_warp);
+        const int M0 = block_compact(N, k_cap, s.pred_src, [&](int b) { return ((pw[b >> 5] >> (b & 31)) & 1u) != 0; }, s_warp);
+        if (T0 == 0 || M0 == 0) {  // empty marginal: defined as zero transport cost
             if (tid == 0) out[lp] = 1.0;
             continue;
         }
-        if (T > t_cap || M > m_cap) {
+        if (T0 > t_cap || M0 > m_cap) {
             if (tid == 0) {
                 out[lp] = nan("");
-                atomicMax(status, T > t_cap ? T : (1 << 24) + M);  // tells the host the capacity it needs
+                atomicMax(status, T0 > t_cap ? T0 : (1 << 24) + M0);  // tells the host the capacity it needs
             }
             continue;
         }
+        // ---- orientation: the smaller side plays the sources.  The EMD is symmetric in its marginals; with few
+        // sources the per-sink flow lists stay short (a sink of a basic solution is fed by ~ (T + M) / #sinks
+        // sources) and every list walk - settling, augmenting - is sequential.
+        const bool swapped = 3 * M0 < T0;  // the transposed gathers walk cost rows: only worth it when the lists would be long
+        const int T = swapped ? M0 : T0, M = swapped ? T0 : M0;  // T sources, M sinks from here on
+        for (int i = tid; i < T; i += EMD_THREADS) s.soff[i] = swapped ? (int)s.pred_src[i] : (int)s.batch[i] * N;
+        for (int j = tid; j < M; j += EMD_THREADS) s.koff[j] = swapped ? (int)s.batch[j] * N : (int)s.pred_src[j];
+        __syncthreads();
 
-        const float* cmat = C;  // c(i, j) = C[rows[i]][cols[j]] gathered from the episode's L2-resident cost matrix
-        const int cstride = N;
         // ---- initial state: zero flow, u = 0, v_j = min_i c_ij (reduced costs stay >= 0)
         for (int i = tid; i < T; i += EMD_THREADS) {
             s.u[i] = 0.0;
@@ -390,7 +397,22 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
                 s.pred_sink[i] = -1;
             }
             for (int j = tid; j < M; j += EMD_THREADS) s.scanned[j] = 0;
-            scan_sources<true>(s, cmat, cstride, M, s.newlist, nroots, lanes, 0.0, first_phase);
+            scan_sources<true>(s, C, M, s.newlist, nroots, lanes, 0.0, first_phase);
+            if (first_phase) {
+                // row reduction: u_i = min_j (c_ij - v_j) >= 0 makes one more arc per source tight before the first
+                // forest is grown (about a fifth fewer waves on the larger problems); then the distances are redone
+                __syncthreads();
+                for (int i = tid >> 5; i < T; i += EMD_WARPS) {  // one warp per source, lanes stride over the sinks
+                    const float* row = C + s.soff[i];
+                    double best = EMD_INF;
+                    for (int j = tid & 31; j < M; j += 32) best = fmin(best, (double)row[s.koff[j]] - s.v[j]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
+                    if ((tid & 31) == 0) s.u[i] = best;
+                }
+                __syncthreads();
+                scan_sources<true>(s, C, M, s.newlist, nroots, lanes, 0.0, false);
+            }
             first_phase = false;
             __syncthreads();
             EP_LAP(1);  // phase init
@@ -480,7 +502,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
                 EP_LAP(4);  // augment
                 const int nnew = s_nnew;
                 // ---- relax every unscanned sink against the newly reached sources
-                if (nnew > 0) scan_sources<false>(s, cmat, cstride, M, s.newlist, nnew, lanes, dmin, false);
+                if (nnew > 0) scan_sources<false>(s, C, M, s.newlist, nnew, lanes, dmin, false);
                 __syncthreads();  // everyone has read the counters; the next wave's settle pass starts after another barrier
                 if (tid == 0) {
                     s_ndef = 0;
@@ -503,7 +525,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
         // ---- objective: sum f_ij c_ij / (T M), float64
         double acc = 0.0;
         for (int j = tid; j < M; j += EMD_THREADS)
-            for (int n = s.head[j]; n >= 0; n = s.node_next[n]) acc += (double)s.node_flow[n] * (double)C[(int64_t)s.rows[s.node_src[n]] * N + s.cols[j]];
+            for (int n = s.head[j]; n >= 0; n = s.node_next[n]) acc += (double)s.node_flow[n] * (double)C[s.soff[s.node_src[n]] + s.koff[j]];
         acc = warp_sum(acc);
         if ((tid & 31) == 0) s_acc[tid >> 5] = acc;
         __syncthreads();
@@ -539,7 +561,7 @@ extern "C" int marsb200_debug_emd_profile(long long* out16, int reset) {
 extern "C" {
 
 static int emd_ctas_per_sm(int t_cap, int m_cap) {  // 64 registers x 256 threads: at most 4 by the register file
-    const size_t smem = emd_smem_bytes(t_cap, m_cap);
+    const size_t smem = emd_smem_bytes(std::min(t_cap, m_cap), std::max(t_cap, m_cap));
     return (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
 }
 
@@ -562,7 +584,8 @@ int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t
     MARS_REQUIRE(workspace_bytes >= marsb200_emd_workspace_bytes(E, P, N, t_cap, m_cap), "workspace too small");
     MARS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
     MARS_REQUIRE(emd_pool_nodes(t_cap, m_cap) <= 32767, "t_cap + N too large for 16-bit flow-node indices");
-    const size_t smem = emd_smem_bytes(t_cap, m_cap);
+    MARS_REQUIRE(m_rows * (int64_t)N < (1ll << 31), "cost matrix too large for 32-bit offsets");
+    const size_t smem = emd_smem_bytes(std::min(t_cap, m_cap), std::max(t_cap, m_cap));
     MARS_REQUIRE(smem <= 200 * 1024, "t_cap + N too large for the shared-memory state");
     cudaStream_t s = as_stream(stream);
     static int num_sms = 0;
