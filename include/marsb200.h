@@ -207,6 +207,26 @@ int marsb200_matcher_scores(const int32_t* points_in, const int32_t* pooled_coun
                             float alpha, float beta, float exp, float* purity, float* coverage, float* scores,
                             void* stream);
 
+/* ---- A13: mask-pooled features and masked similarity statistics (diagnostics of the Matcher ancestry) -------
+ * Prototypes: out[e, p, :] = mean over the patches of pooled mask p of feats[e, patch, :] (unnormalised features),
+ * matcher/Matcher.py:1076-1079 (`feats[mask].mean(dim=0)`), computed for all masks at once as one
+ * masks-by-features contraction [P, N] x [N, C] on the tensor cores (0/1 is exact in tf32; the features use the
+ * error-compensated split).  pooled [E, P, ceil(N/32)]; feats [E, N, C]; out [E, P, C]; an empty mask gives NaN.
+ * workspace: 256-byte aligned, marsb200_masked_feature_means_workspace_bytes. */
+int64_t marsb200_masked_feature_means_workspace_bytes(int E, int P, int N, int C);
+int marsb200_masked_feature_means(const uint32_t* pooled, const float* feats, int E, int P, int N, int C, float* out,
+                                  void* workspace, int64_t workspace_bytes, int backend, void* stream);
+
+/* mean, max, unbiased std and element count of sim[e][row_mask][:, col_mask]: get_aposteriori_statistics,
+ * matcher/Matcher.py:1069-1085.  sim [E, M, N]; masks uint8; out [E, 4] float64 = {mean, max (0 if empty), std, n}. */
+int marsb200_masked_sim_stats(const float* sim, const uint8_t* row_mask, const uint8_t* col_mask, int E, int64_t M,
+                              int64_t N, double* out, void* stream);
+
+/* out[e, c] = mean over the selected rows of sim[e, :, c]: get_ref_to_target_similarity, matcher/Matcher.py:593-611
+ * (mean over the masked support patches of Fq Fs_masked^T).  out [E, N] fp32. */
+int marsb200_masked_row_mean(const float* sim, const uint8_t* row_mask, int E, int64_t M, int64_t N, float* out,
+                             void* stream);
+
 /* ---- 8f-3: evaluator -------------------------------------------------------------------------
  * Per-sample foreground/background intersection and union areas of a prediction against the
  * ground truth with an optional ignore mask.  Replaces Evaluator.classify_prediction,

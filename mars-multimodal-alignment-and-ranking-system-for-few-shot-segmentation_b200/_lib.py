@@ -60,6 +60,10 @@ SIGNATURES = {
     "marsb200_merge_masks": (_i, [_p, _p, _i, _i, _l, _p, _p, _p]),
     "marsb200_points_in_masks": (_i, [_p, _l, _i, _i, _p, _i, _p, _p]),
     "marsb200_matcher_scores": (_i, [_p, _p, _p, _l, _i, _f, _f, _f, _p, _p, _p, _p]),
+    "marsb200_masked_feature_means_workspace_bytes": (_l, [_i, _i, _i, _i]),
+    "marsb200_masked_feature_means": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _l, _i, _p]),
+    "marsb200_masked_sim_stats": (_i, [_p, _p, _p, _i, _l, _l, _p, _p]),
+    "marsb200_masked_row_mean": (_i, [_p, _p, _i, _l, _l, _p, _p]),
     "marsb200_eval_areas": (_i, [_p, _p, _p, _l, _l, _p, _p]),
     "marsb200_eval_accumulate": (_i, [_p, _p, _l, _i, _p, _p, _p, _p]),
     "marsb200_eval_iou": (_i, [_p, _p, _i, _p, _i, _p, _p]),

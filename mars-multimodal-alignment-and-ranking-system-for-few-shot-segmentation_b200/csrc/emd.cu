@@ -313,13 +313,14 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
                                                            const int32_t* __restrict__ order, int32_t* __restrict__ counter,
                                                            double* __restrict__ out, int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char emd_smem_raw[];
-    EmdSmem s = emd_carve(emd_smem_raw, min(t_cap, m_cap), max(t_cap, m_cap));  // (source cap, sink cap)
+    // sources: the support rows (<= t_cap) or, transposed, a proposal with fewer than t_cap / 3 patches; sinks: either side
+    EmdSmem s = emd_carve(emd_smem_raw, t_cap, max(t_cap, m_cap));
     __shared__ unsigned long long s_val[EMD_WARPS];
     __shared__ double s_acc[EMD_WARPS];
     __shared__ int s_warp[EMD_WARPS];
     __shared__ int s_lp, s_ndef, s_nnew, s_left, s_free, s_fault;
     const int tid = threadIdx.x;
-    const int pool = emd_pool_nodes(min(t_cap, m_cap), max(t_cap, m_cap));
+    const int pool = emd_pool_nodes(t_cap, max(t_cap, m_cap));
 
     while (true) {
         __syncthreads();
@@ -561,7 +562,7 @@ extern "C" int marsb200_debug_emd_profile(long long* out16, int reset) {
 extern "C" {
 
 static int emd_ctas_per_sm(int t_cap, int m_cap) {  // 64 registers x 256 threads: at most 4 by the register file
-    const size_t smem = emd_smem_bytes(std::min(t_cap, m_cap), std::max(t_cap, m_cap));
+    const size_t smem = emd_smem_bytes(t_cap, std::max(t_cap, m_cap));
     return (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
 }
 
@@ -583,9 +584,9 @@ int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t
     if (m_cap <= 0 || m_cap > N) m_cap = N;
     MARS_REQUIRE(workspace_bytes >= marsb200_emd_workspace_bytes(E, P, N, t_cap, m_cap), "workspace too small");
     MARS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
-    MARS_REQUIRE(emd_pool_nodes(t_cap, m_cap) <= 32767, "t_cap + N too large for 16-bit flow-node indices");
+    MARS_REQUIRE(emd_pool_nodes(t_cap, std::max(t_cap, m_cap)) <= 32767, "t_cap + N too large for 16-bit flow-node indices");
     MARS_REQUIRE(m_rows * (int64_t)N < (1ll << 31), "cost matrix too large for 32-bit offsets");
-    const size_t smem = emd_smem_bytes(std::min(t_cap, m_cap), std::max(t_cap, m_cap));
+    const size_t smem = emd_smem_bytes(t_cap, std::max(t_cap, m_cap));
     MARS_REQUIRE(smem <= 200 * 1024, "t_cap + N too large for the shared-memory state");
     cudaStream_t s = as_stream(stream);
     static int num_sms = 0;

@@ -141,6 +141,36 @@ class PatchMatcher:
                     reduced_points_num=reduced, sim_matched=sim_pos, indices_forward=(fwd_rows, fwd_cols),
                     retain=retain)
 
+    # ---- diagnostics of the Matcher ancestry
+    def get_ref_to_target_similarity(self, ref_feats, tar_feat, ref_masks_pool) -> torch.Tensor:
+        """Mean over the masked support patches of `Fq Fs_masked^T` -> [1, N] (matcher/Matcher.py:593-611)."""
+        dev = self.device
+        ref = ops.normalize_rows(ref_feats.to(dev).float(), normalize=False)
+        tar = ops.normalize_rows(tar_feat.to(dev).float(), normalize=False)
+        m, c = ref_feats.shape
+        n = tar_feat.shape[0]
+        S = ops.sim_contract(ref, tar, m, n, c, want_sim=True)["sim"]
+        return ops.masked_row_mean(S, ref_masks_pool.to(dev).reshape(1, m) != 0)
+
+    def get_aposteriori_statistics(self, S, ref_masks_pool, target_mask_pooled, unnormalized_ref_feats,
+                                   unnormalized_tar_feat) -> dict:
+        """Statistics of S[ref mask][:, target mask] and the distance between the two mask-pooled feature
+        prototypes (matcher/Matcher.py:1069-1089).  The prototypes are one masks-by-features contraction."""
+        dev = self.device
+        rm = (ref_masks_pool.to(dev).reshape(1, -1) != 0)
+        tm = (target_mask_pooled.to(dev).reshape(1, -1) != 0)
+        st = ops.masked_sim_stats(S.to(dev).float(), rm, tm)[0]
+
+        def proto(feats, mask):
+            n = feats.shape[0]
+            bits = ops.pack_masks(mask.reshape(1, 1, n).to(torch.uint8))  # one "mask" of n patches -> packed words
+            return ops.masked_feature_means(bits[:, :(n + 31) // 32].contiguous()[None], feats.to(dev).float()[None])[0, 0]
+
+        pr, pt = proto(unnormalized_ref_feats, rm), proto(unnormalized_tar_feat, tm)
+        return dict(aposteriori_similarity_mean=float(st[0]), aposteriori_similarity_max=float(st[1]),
+                    aposteriori_similarity_std=float(st[2]),
+                    embeddings_euclidean_distance=float(torch.norm(pr - pt, p=2)))
+
     def _centres(self, patch_idx: torch.Tensor) -> torch.Tensor:
         g, ps = self.encoder_feat_size, self.patch_size
         x = (patch_idx % g) * ps + ps // 2

@@ -18,7 +18,7 @@ from ._lib import GEMM_SIMT, GEMM_TCGEN05, MASK_F32, MASK_U8, PAIR_MMA, PAIR_POP
 __all__ = [
     "words_per_mask", "pad_rows", "pad_k", "normalize_rows", "pool_mask", "sim_contract", "match_argmax", "mutual_matches", "lsap", "vva_finalize",
     "attn_mean", "pir_refine", "resize_minmax", "pack_masks", "pack_pairwise", "pool_packed", "region_sums", "pairwise_inter",
-    "emd_scores", "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas", "eval_accumulate", "eval_iou", "rle_decode", "mask_boxes", "stability_score", "box_nms",
+    "emd_scores", "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas", "eval_accumulate", "eval_iou", "rle_decode", "mask_boxes", "stability_score", "box_nms", "masked_feature_means", "masked_sim_stats", "masked_row_mean",
     "GEMM_TCGEN05", "GEMM_SIMT", "PAIR_POPC", "PAIR_MMA",
 ]
 
@@ -520,3 +520,44 @@ def box_nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float):
                                keep.data_ptr(), n_keep.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
     o = order.long()
     return o[keep[o] != 0], order, keep
+
+
+# ----------------------------------------------------------------------------- A13: mask-pooled features / statistics
+def masked_feature_means(pooled: torch.Tensor, feats: torch.Tensor, backend=None) -> torch.Tensor:
+    """pooled bitmaps [E, P, npw] x feats [E, N, C] -> prototypes [E, P, C] (mean of the features under each mask)."""
+    feats = _cuda(feats, torch.float32, "feats")
+    if feats.dim() == 2:
+        feats = feats[None]
+    e, n, c = feats.shape
+    pooled = pooled.reshape(e, -1, pooled.shape[-1]).contiguous()
+    p = pooled.shape[1]
+    out = torch.empty((e, p, c), device=feats.device, dtype=torch.float32)
+    ws = torch.empty(int(lib.marsb200_masked_feature_means_workspace_bytes(e, p, n, c)), device=feats.device, dtype=torch.uint8)
+    check(lib.marsb200_masked_feature_means(pooled.data_ptr(), feats.data_ptr(), e, p, n, c, out.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), DEFAULT_GEMM if backend is None else backend, _stream()))
+    return out
+
+
+def masked_sim_stats(sim: torch.Tensor, row_mask: torch.Tensor, col_mask: torch.Tensor) -> torch.Tensor:
+    """sim [E, M, N] -> float64 [E, 4] = {mean, max, unbiased std, count} over sim[row_mask][:, col_mask]."""
+    sim = _cuda(sim, torch.float32, "sim")
+    if sim.dim() == 2:
+        sim = sim[None]
+    e, m, n = sim.shape
+    rm = _cuda(row_mask, torch.uint8, "row_mask").reshape(e, m)
+    cm = _cuda(col_mask, torch.uint8, "col_mask").reshape(e, n)
+    out = torch.empty((e, 4), device=sim.device, dtype=torch.float64)
+    check(lib.marsb200_masked_sim_stats(sim.data_ptr(), rm.data_ptr(), cm.data_ptr(), e, m, n, out.data_ptr(), _stream()))
+    return out
+
+
+def masked_row_mean(sim: torch.Tensor, row_mask: torch.Tensor) -> torch.Tensor:
+    """sim [E, M, N] -> [E, N]: mean over the selected rows."""
+    sim = _cuda(sim, torch.float32, "sim")
+    if sim.dim() == 2:
+        sim = sim[None]
+    e, m, n = sim.shape
+    rm = _cuda(row_mask, torch.uint8, "row_mask").reshape(e, m)
+    out = torch.empty((e, n), device=sim.device, dtype=torch.float32)
+    check(lib.marsb200_masked_row_mean(sim.data_ptr(), rm.data_ptr(), e, m, n, out.data_ptr(), _stream()))
+    return out

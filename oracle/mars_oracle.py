@@ -499,6 +499,28 @@ def average_meter(area_inter, area_union, class_id, nclass: int, class_ids_inter
 
 
 # --------------------------------------------------------------------------
+# A13: Matcher diagnostics
+# --------------------------------------------------------------------------
+def ref_to_target_similarity(ref_feats: torch.Tensor, tar_feat: torch.Tensor, ref_masks_pool: torch.Tensor) -> torch.Tensor:
+    """Mean over the masked support patches of ``Fq @ Fs_masked^T`` -> ``[N]`` (matcher/Matcher.py:593-611)."""
+    masked = ref_feats[ref_masks_pool.reshape(-1).bool()]
+    return (tar_feat @ masked.t()).mean(dim=-1)
+
+
+def aposteriori_statistics(S: torch.Tensor, ref_mask: torch.Tensor, tar_mask: torch.Tensor, unnorm_ref: torch.Tensor,
+                           unnorm_tar: torch.Tensor) -> dict:
+    """Similarity statistics of the masked sub-matrix and the prototype distance (matcher/Matcher.py:1069-1089)."""
+    ref_mask, tar_mask = ref_mask.reshape(-1).bool(), tar_mask.reshape(-1).bool()
+    sub = S[ref_mask, :][:, tar_mask]
+    ref_proto = unnorm_ref[ref_mask].mean(dim=0)
+    tar_proto = unnorm_tar[tar_mask].mean(dim=0)
+    return dict(aposteriori_similarity_mean=sub.mean().item(),
+                aposteriori_similarity_max=sub.max().item() if sub.numel() > 0 else 0,
+                aposteriori_similarity_std=sub.std().item(),
+                embeddings_euclidean_distance=torch.norm(ref_proto - tar_proto, p=2).item())
+
+
+# --------------------------------------------------------------------------
 # SAM automatic-mask-generator post-processing (SURVEY 8f-4)
 # --------------------------------------------------------------------------
 def mask_to_rle(mask: np.ndarray):

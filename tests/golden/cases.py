@@ -216,3 +216,17 @@ def amg_inputs(spec):
     scores = rs.rand(k).astype(np.float32)
     scores[5] = scores[7]  # a tie
     return dict(masks=masks, logits=logits, boxes=torch.from_numpy(boxes), scores=torch.from_numpy(scores))
+
+
+# ---- Matcher diagnostics
+DIAG_CASES = {"g12_2shot": dict(g=12, ns=2, C=48, seed=951), "g16_1shot": dict(g=16, ns=1, C=64, seed=952)}
+
+
+def diag_inputs(spec):
+    g, ns, c = spec["g"], spec["ns"], spec["C"]
+    n = g * g
+    ref_raw = proto_features(ns * n, c, spec["seed"]) * 3.0 + 0.5
+    tar_raw = proto_features(n, c, spec["seed"] + 1) * 3.0 + 0.5
+    ref_mask = blob_masks(ns, g, g, spec["seed"] + 2, 0.1, 0.4).reshape(ns, n)
+    tar_mask = blob_masks(1, g, g, spec["seed"] + 3, 0.1, 0.4).reshape(n)
+    return dict(ref_raw=ref_raw, tar_raw=tar_raw, ref_mask=ref_mask, tar_mask=tar_mask)

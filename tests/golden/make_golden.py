@@ -13,7 +13,7 @@ is replaced by the exact transport LP of ``oracle/mars_oracle.emd_exact``
 return seeded tensors, so the vectors pin everything the reference computes
 *after* the backbones.
 
-Outputs (small, committed): ``vva_*.npz``, ``pir_*.npz``, ``fm_*.npz``, ``eval_*.npz``, ``amg_*.npz``.
+Outputs (small, committed): ``vva_*.npz``, ``pir_*.npz``, ``fm_*.npz``, ``eval_*.npz``, ``amg_*.npz``, ``diag_*.npz``.
 Inputs that would be large are regenerated from the recorded seed by
 ``tests/golden/cases.py`` and guarded by a checksum stored in the fixture.
 """
@@ -202,6 +202,39 @@ def gen_amg(name, spec, ref_root):
                         areas=np.asarray([amg.area_from_rle(r) for r in rles]))
 
 
+def gen_diag(name, spec, ref_root):
+    """get_ref_to_target_similarity / get_aposteriori_statistics: matcher/Matcher.py cannot be imported here
+    (matplotlib, timm, POT), so the two method definitions are cut out of the file with `ast` and executed as
+    they are on a stand-in object that carries the attributes they read."""
+    import ast
+    import types as _t
+
+    import torch.nn.functional as F
+
+    src = open(os.path.join(ref_root, "matcher", "Matcher.py")).read()
+    tree = ast.parse(src)
+    wanted = {"get_ref_to_target_similarity", "get_aposteriori_statistics"}
+    funcs = [n for cls in tree.body if isinstance(cls, ast.ClassDef) for n in cls.body
+             if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {f.name for f in funcs} == wanted
+    ns_ = {"torch": torch, "F": F, "np": np}
+    exec(compile(ast.Module(body=funcs, type_ignores=[]), "Matcher.py[extract]", "exec"), ns_)
+    c = cases.diag_inputs(spec)
+    g, nshot = spec["g"], spec["ns"]
+    ref_n, tar_n = orc.normalize_rows(c["ref_raw"]), orc.normalize_rows(c["tar_raw"])
+    S = ref_n @ tar_n.t()
+    me = _t.SimpleNamespace(nshot=nshot, encoder=_t.SimpleNamespace(patch_size=1),
+                            generator=_t.SimpleNamespace(predictor=_t.SimpleNamespace(model=_t.SimpleNamespace(mask_threshold=0.0))),
+                            ref_masks_pool=c["ref_mask"].reshape(-1), S=S,
+                            unnormalized_ref_feats=c["ref_raw"], unnormalized_tar_feat=c["tar_raw"])
+    r2t = ns_["get_ref_to_target_similarity"](me, ref_n, tar_n, c["ref_mask"])
+    stats = ns_["get_aposteriori_statistics"](me, c["tar_mask"].reshape(1, 1, g, g).float())
+    np.savez_compressed(os.path.join(HERE, f"diag_{name}.npz"), spec=np.asarray(repr(spec)),
+                        ref_to_target=r2t.reshape(-1).numpy(),
+                        stats=np.asarray([stats["aposteriori_similarity_mean"], stats["aposteriori_similarity_max"],
+                                          stats["aposteriori_similarity_std"], stats["embeddings_euclidean_distance"]]))
+
+
 def main():
     ref_root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     install_shims(ref_root)
@@ -216,6 +249,8 @@ def main():
         gen_eval(name, spec)
     for name, spec in cases.AMG_CASES.items():
         gen_amg(name, spec, ref_root)
+    for name, spec in cases.DIAG_CASES.items():
+        gen_diag(name, spec, ref_root)
 
 
 if __name__ == "__main__":

@@ -657,6 +657,42 @@ def test_average_meter_matches_reference(mb, name):
         mb.ops.eval_accumulate(areas, torch.full((spec["n"],), 5000, device=d), m2.intersection_buf, m2.union_buf, check_status=True)
 
 
+# ------------------------------------------------------------------------------------------ Matcher diagnostics (A13)
+@pytest.mark.parametrize("name", list(cases.DIAG_CASES))
+def test_matcher_diagnostics(mb, name):
+    z = np.load(os.path.join(GOLD, f"diag_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.diag_inputs(spec)
+    g = spec["g"]
+    pm = mb.PatchMatcher(g, 14, (g * 14, g * 14), dev())
+    ref_n, tar_n = orc.normalize_rows(c["ref_raw"]), orc.normalize_rows(c["tar_raw"])
+    r2t = pm.get_ref_to_target_similarity(ref_n, tar_n, c["ref_mask"])
+    np.testing.assert_allclose(r2t[0].cpu().numpy(), z["ref_to_target"], rtol=RTOL, atol=1e-6)
+    S = (ref_n @ tar_n.t())
+    st = pm.get_aposteriori_statistics(S, c["ref_mask"], c["tar_mask"], c["ref_raw"], c["tar_raw"])
+    got = [st["aposteriori_similarity_mean"], st["aposteriori_similarity_max"], st["aposteriori_similarity_std"],
+           st["embeddings_euclidean_distance"]]
+    np.testing.assert_allclose(got, z["stats"], rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
+def test_masked_feature_means_all_proposals(mb, backend):
+    """Prototypes of every proposal at once ([P, N] x [N, C] on the tensor cores) vs feats[mask].mean(0)."""
+    g, p, cdim, h = 14, 20, 96, 196
+    masks = cases.blob_masks(p, h, h, 41, 0.01, 0.3)
+    masks[3] = 0
+    feats = cases.proto_features(g * g, cdim, 42) * 2.0 - 0.3
+    d = dev()
+    pooled, _, cnt = mb.ops.pool_packed(mb.ops.pack_masks(masks.to(d)), h, h, g)
+    got = mb.ops.masked_feature_means(pooled[None], feats.to(d)[None], backend=backend)[0].cpu()
+    pm = orc.pool_mask(masks, g).reshape(p, -1)
+    for i in range(p):
+        if i == 3:
+            assert bool(torch.isnan(got[i]).all())
+            continue
+        np.testing.assert_allclose(got[i].numpy(), feats[pm[i]].mean(dim=0).numpy(), rtol=1e-5, atol=1e-6)
+
+
 # ------------------------------------------------------------------------------------------ wire format / AMG post-processing
 @pytest.mark.parametrize("name", list(cases.AMG_CASES))
 def test_amg_postprocessing(mb, name):
@@ -749,6 +785,23 @@ def test_emd_caps_and_larger_problems(mb):
         mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], m_cap=int(cnt.max()) - 1)
     with pytest.raises(mb.MarsB200Error, match="t_cap"):
         mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], t_cap=int(row_fg.sum()) - 1)
+
+
+def test_emd_tight_caps_more_sources_than_sinks(mb):
+    """5-shot-like shape: more support rows than proposal patches, caps read from the data (t_cap > m_cap)."""
+    ns, g, p, h = 3, 12, 8, 168
+    cost, support, masks = _emd_inputs(ns, g, p, h, seed=77)
+    support = cases.blob_masks(ns, h, h, 78, 0.25, 0.45)   # large support masks: T around 200 of 432 rows
+    d = dev()
+    row_fg = mb.ops.pool_mask(support.to(d), g).reshape(1, -1)
+    bits = mb.ops.pack_masks(masks.to(d))
+    pooled, _, cnt = mb.ops.pool_packed(bits, h, h, g)
+    assert int(row_fg.sum()) > int(cnt.max())
+    got = mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], pooled_count=cnt)[0].cpu().numpy()
+    sup = orc.pool_mask(support, g).reshape(-1)
+    pm = orc.pool_mask(masks, g).reshape(p, -1)
+    want = np.asarray([orc.emd_score(sup, pm[i], cost) for i in range(p)])
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
 
 
 def test_emd_square_case_equals_assignment(mb):

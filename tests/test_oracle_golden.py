@@ -131,3 +131,18 @@ def test_amg_postprocessing_matches_reference(name):
     np.testing.assert_array_equal(orc.mask_boxes(c["masks"]).numpy(), z["boxes"])
     np.testing.assert_array_equal(orc.stability_score(c["logits"], 0.0, 1.0).numpy(), z["stability"])
     np.testing.assert_array_equal(orc.box_nms(c["boxes"], c["scores"], 0.5).numpy(), z["nms_keep"])
+
+
+@pytest.mark.parametrize("name", list(cases.DIAG_CASES))
+def test_matcher_diagnostics_match_reference(name):
+    """get_ref_to_target_similarity / get_aposteriori_statistics (the reference's method bodies, golden) vs the oracle."""
+    z = np.load(os.path.join(GOLD, f"diag_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.diag_inputs(spec)
+    ref_n, tar_n = orc.normalize_rows(c["ref_raw"]), orc.normalize_rows(c["tar_raw"])
+    np.testing.assert_allclose(orc.ref_to_target_similarity(ref_n, tar_n, c["ref_mask"]).numpy(), z["ref_to_target"],
+                               rtol=1e-6, atol=1e-7)
+    st = orc.aposteriori_statistics(ref_n @ tar_n.t(), c["ref_mask"], c["tar_mask"], c["ref_raw"], c["tar_raw"])
+    np.testing.assert_allclose([st["aposteriori_similarity_mean"], st["aposteriori_similarity_max"],
+                                st["aposteriori_similarity_std"], st["embeddings_euclidean_distance"]], z["stats"],
+                               rtol=1e-6, atol=1e-7)
