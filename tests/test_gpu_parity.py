@@ -993,3 +993,36 @@ def test_engine_wire_formats(mb):
         out = eng.run(other)
         for k, v in ref.items():
             assert torch.equal(out[k], v), k
+
+
+@pytest.mark.parametrize("case", ["single", "all_equal", "empty_proposal", "all_empty"])
+def test_fuse_rank_degenerate_inputs(mb, case):
+    """Edge cases the reference leaves to arithmetic: P = 1 (both min-max terms vanish), all scores
+    equal (order = index order), an all-zero proposal (0 / 1e-7 = 0 alignment), no proposal pixel at all."""
+    g, h = 8, 64
+    n = g * g
+    p = 1 if case == "single" else 6
+    masks = cases.blob_masks(p, h, h, 11, 0.05, 0.3)
+    if case == "all_equal":
+        masks[:] = masks[0]
+    if case == "empty_proposal":
+        masks[2] = 0
+    if case == "all_empty":
+        masks[:] = 0
+    rs = np.random.RandomState(3)
+    vva = rs.rand(g, g).astype(np.float32)
+    vta = rs.rand(g, g).astype(np.float32)
+    emd = np.full(p, 0.4) if case in ("all_equal", "all_empty") else rs.rand(p)
+    clip = np.full(p, 0.2, dtype=np.float32) if case in ("all_equal", "all_empty") else rs.rand(p).astype(np.float32)
+    pooled_ref, cov, avv, avt = orc.region_scores(masks, vva, vta, g)
+    want = orc.fuse_scores(emd, clip, cov, avv, avt, 0.85)
+    d = dev()
+    bits = mb.ops.pack_masks(masks.to(d))[None]
+    pooled, area, cnt = mb.ops.pool_packed(bits, h, h, g)
+    sv, st, uc = mb.ops.region_sums(pooled, torch.from_numpy(vva).to(d).reshape(1, n), torch.from_numpy(vta).to(d).reshape(1, n))
+    res = mb.ops.fuse_rank(torch.from_numpy(emd).to(d).reshape(1, p), torch.from_numpy(clip).to(d).reshape(1, p), cnt, sv, st,
+                           uc, None, 0.85, 0.55, 0.95, None)
+    np.testing.assert_allclose(res["scores"][0].cpu().numpy(), want, rtol=RTOL, atol=1e-9)
+    assert_order_matches(res["order"][0].cpu().numpy(), res["scores"][0].cpu().numpy(), orc.stable_rank(want), want)
+    if case in ("all_equal", "all_empty"):
+        np.testing.assert_array_equal(res["order"][0].cpu().numpy(), np.arange(p))
