@@ -42,6 +42,8 @@ constexpr int PG_OFF_BARS = PG_OFF_FLAGS + 128;
 constexpr int PG_SMEM_BYTES = PG_OFF_BARS + 256 + 1024;
 static_assert(PG_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
+// -DMARSB200_GEMM_PROFILE: clock64 stamps of CTA 0 (MMA thread, epilogue warp 0) per tile, read back with
+// marsb200_debug_gemm_profile (profiles/gemm_timeline.py).  Compiled out otherwise.
 #ifdef MARSB200_GEMM_PROFILE
 __device__ long long g_gemm_prof[128];
 #define GP_STAMP(slot) do { if (blockIdx.x == 0) g_gemm_prof[slot] = clock64(); } while (0)
