@@ -1026,3 +1026,23 @@ def test_fuse_rank_degenerate_inputs(mb, case):
     assert_order_matches(res["order"][0].cpu().numpy(), res["scores"][0].cpu().numpy(), orc.stable_rank(want), want)
     if case in ("all_equal", "all_empty"):
         np.testing.assert_array_equal(res["order"][0].cpu().numpy(), np.arange(p))
+
+
+def test_emd_repeatable_and_orientation_free(mb):
+    """The solver's atomics reorder work between runs, the optimum must not move (a race would): three runs of
+    64 LPs agree to 1e-12, and the transposed problem (roles of support rows and proposal patches exchanged, which
+    flips the solver's source / sink orientation) has the same value."""
+    ns, g, p, h = 1, 24, 64, 336
+    cost, support, masks = _emd_inputs(ns, g, p, h, seed=4242)
+    d = dev()
+    n = g * g
+    row_fg = mb.ops.pool_mask(support.to(d), g).reshape(1, -1)
+    pooled, _, cnt = mb.ops.pool_packed(mb.ops.pack_masks(masks.to(d)), h, h, g)
+    runs = [mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], pooled_count=cnt)[0] for _ in range(3)]
+    assert float((runs[0] - runs[1]).abs().max()) < 1e-12 and float((runs[0] - runs[2]).abs().max()) < 1e-12
+    # transposed: cost^T, "support" = patches of proposal i, "proposal" = the support rows
+    sup_bits = mb.ops.pack_masks(row_fg.reshape(1, 1, n))[:, :(n + 31) // 32].contiguous()[None]   # [1, 1, npw]
+    for i in sorted(range(p), key=lambda k: -int(cnt[k]))[:6] + sorted(range(p), key=lambda k: int(cnt[k]))[:6]:
+        rows_i = ((pooled[i][:, None] >> torch.arange(32, device=d, dtype=torch.int32)) & 1).reshape(-1)[:n].to(torch.uint8)
+        flipped = mb.ops.emd_scores(cost.t().contiguous().to(d)[None], rows_i[None], sup_bits)[0, 0]
+        assert abs(float(flipped) - float(runs[0][i])) < 1e-12
