@@ -291,6 +291,32 @@ def run_ours(args):
         elapsed_ms = float(t.item())
     value = total_episodes * args.steps / (elapsed_ms / 1e3)
 
+    # ---- the same device-resident loop fed with lighter proposal formats (uint8 masks, packed bits)
+    def value_variant(kind):
+        if kind == "u8":
+            alt = [dict(b, masks=(b["masks"] > 0).to(torch.uint8)) for b in batches]
+            eng_v = marsb200.RankingEngine(shape, E, cfg, dev, torch.uint8)
+        else:
+            alt = [{k: v for k, v in b.items() if k != "masks"} for b in batches]
+            for a, b in zip(alt, batches):
+                a["mask_bits"] = ops.pack_masks(b["masks"])
+            eng_v = marsb200.RankingEngine(shape, E, cfg, dev, md)
+        for i in range(args.warmup):
+            eng_v.run(alt[i % n_batches])
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(args.steps):
+            eng_v.run(alt[i % n_batches])
+        a1.record()
+        barrier()
+        ms = a0.elapsed_time(a1) / args.steps
+        return {"value": world * E / (ms / 1e3), "unit": "episodes/s", "ms_per_step": ms}
+
+    value_variants = None
+    if md == torch.float32 and not args.no_e2e:
+        value_variants = {"u8_masks": value_variant("u8"), "packed_masks": value_variant("bits")}
+
     # ---- per-kernel timing of the dominant kernels with CUDA events on the launching stream
     def time_kernel(fn, iters):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
@@ -451,7 +477,7 @@ def run_ours(args):
                        "gemm_backend": "tcgen05" if ops.DEFAULT_GEMM == ops.GEMM_TCGEN05 else "simt",
                        "pair_backend": "popc" if ops.DEFAULT_PAIR == ops.PAIR_POPC else "mma",
                        "fused_ingest": bool(args.fused_ingest)},
-            "clocks": clocks, "e2e": e2e, "e2e_variants": e2e_variants,
+            "clocks": clocks, "value_variants": value_variants, "e2e": e2e, "e2e_variants": e2e_variants,
             "gpu_launches": marsb200.kernel_launches_per_run(cfg) * args.steps * world,
             "roofline": roofline, "pairwise": pairwise, "fused_ingest": fused, "full_scoring": full,
             "single_episode_latency": lat, "cpu_baseline": cpu_baseline,

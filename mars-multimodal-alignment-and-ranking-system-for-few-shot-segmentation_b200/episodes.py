@@ -92,7 +92,8 @@ class RankingEngine:
         self.vva = new((e, n), f32)
         self.vta_ref = new((e, nt), f32)
         self.vta = new((e, n), f32)
-        self.pir_ws = ops.pir_workspace(e, max(n, nt), dev)
+        self.pir_ws = ops.pir_workspace(e, n, dev)
+        self.pir_ws_vta = ops.pir_workspace(e, nt, dev)  # own workspace: the two refinements run concurrently
         wpm = ops.words_per_mask(s.H * s.W)
         npw = (n + 31) // 32
         self.bits = new((e, s.P, wpm), i32)
@@ -110,6 +111,8 @@ class RankingEngine:
         self._rle_ws = None
         self._side = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
         self._side2 = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
+        self._side3 = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
+        self._ev_vta = torch.cuda.Event()
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
         self._ev_pack = torch.cuda.Event()
@@ -168,6 +171,14 @@ class RankingEngine:
             with torch.cuda.stream(self._side):
                 self._mask_chain(batch)
                 self._ev_join.record(self._side)
+        if self._side3 is not None:
+            # the vta refinement depends on nothing of the vva chain: its small kernels (box mask, column sums, mat-vecs)
+            # fill the gaps of the other chain's contractions
+            self._side3.wait_event(self._ev_fork)
+            with torch.cuda.stream(self._side3):
+                ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
+                               backend=cfg.gemm_backend, workspace=self.pir_ws_vta, out=self.vta_ref)
+                self._ev_vta.record(self._side3)
         ops.normalize_rows(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
         ops.normalize_rows(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
         ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
@@ -176,8 +187,11 @@ class RankingEngine:
         ops.vva_finalize(self.gemm_out["colstats"], self.row_fg, m, n, out=self.prior)
         ops.pir_refine(self.prior, batch["attn_vva"], s.g, cfg.vva_box_threshold, apply_minmax=True,
                        backend=cfg.gemm_backend, workspace=self.pir_ws, out=self.vva)
-        ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
-                       backend=cfg.gemm_backend, workspace=self.pir_ws, out=self.vta_ref)
+        if self._side3 is not None:
+            main.wait_event(self._ev_vta)
+        else:
+            ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
+                           backend=cfg.gemm_backend, workspace=self.pir_ws_vta, out=self.vta_ref)
         ops.resize_minmax(self.vta_ref.reshape(e, s.gt, s.gt), s.g, True, out=self.vta)
         ops.clip_scores(batch["clip_img"], batch["clip_txt"], out=self.clip)
         if self._side is not None:
