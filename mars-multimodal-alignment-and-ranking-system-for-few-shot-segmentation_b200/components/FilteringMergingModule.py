@@ -9,7 +9,7 @@ and its 3*P device->host copies disappear.
 
 EMD (`ot.emd2`, an exact transport LP per proposal, FilteringMergingModule.py:142-169)
 is solved exactly on the device for all proposals at once (`ops.emd_scores`,
-successive shortest paths on integer flows).  `emd_fn=` (a host solver taking the
+primal-dual method on integer flows).  `emd_fn=` (a host solver taking the
 cost sub-matrix, e.g. a POT wrapper) or precomputed `emd_scores=` override it;
 `_compute_emd` keeps the reference's per-proposal host signature for callers that
 use it directly.
