@@ -90,10 +90,13 @@ int marsb200_match_argmax(const float* sim, const uint8_t* row_mask, int E, int 
 /* Exact rectangular linear-sum assignment: scipy.optimize.linear_sum_assignment(S, maximize=True) of
  * Matcher's forward / reverse patch matching, matcher/Matcher.py:449-450, 471-472.  sim [E, R, C]; row_sel [E, R] and
  * col_sel [E, C] pick the participating rows / columns (NULL = all).  Every element of the smaller side is assigned.
- * row_to_col [E, R]: assigned column per selected row or -1; objective [E]: sum of assigned similarities (fp64);
- * *status: 0 or the size that exceeded the shared-memory state.  Shortest augmenting paths, one CTA per problem. */
+ * t_cap / m_cap bound the number of selected elements on the smaller / larger side the shared-memory state is sized
+ * for (<= 0: min(R, C) / max(R, C)); 28 * t_cap + 23 * m_cap bytes must fit in 220 KB (1369 x 6845, the 5-shot
+ * reverse matching, does).  row_to_col [E, R]: assigned column per selected row or -1; objective [E]: sum of
+ * assigned similarities (fp64); *status: 0 or the size that exceeded the caps.  Shortest augmenting paths
+ * (Jonker-Volgenant), one CTA per problem. */
 int marsb200_lsap(const float* sim, const uint8_t* row_sel, const uint8_t* col_sel, int E, int R, int C, int maximize,
-                  int32_t* row_to_col, double* objective, int32_t* status, void* stream);
+                  int t_cap, int m_cap, int32_t* row_to_col, double* objective, int32_t* status, void* stream);
 
 /* vva = mean_fg*max_fg - mean_bg*max_bg (bg skipped when there is no bg row), then min-max with eps 1e-7.
  * Replaces VisualVisualAlignmentModule.py:82-102.  out [E, N].  Returns an error when an episode has no fg row

@@ -42,7 +42,7 @@ SIGNATURES = {
     "marsb200_pool_mask": (_i, [_p, _i, _l, _i, _i, _i, _p, _p]),
     "marsb200_sim_contract": (_i, [_p, _p, _p, _p, _i, _l, _l, _l, _p, _p, _p, _p, _i, _p]),
     "marsb200_match_argmax": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
-    "marsb200_lsap": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "marsb200_lsap": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "marsb200_vva_finalize": (_i, [_p, _p, _i, _l, _l, _p, _p]),
     "marsb200_attn_mean": (_i, [ctypes.POINTER(_p), _i, _i, _i, _i, _i, _p, _l, _p]),
     "marsb200_pir_workspace_bytes": (_l, [_i, _l]),

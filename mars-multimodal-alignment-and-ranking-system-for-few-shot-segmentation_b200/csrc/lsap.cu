@@ -11,15 +11,19 @@ namespace marsb200 {
 constexpr int LSAP_THREADS = 512;
 constexpr double LSAP_INF = 1e300;
 
+// per source: u, dsrc (f64), id / assigned sink / reached list (i32); per sink: v, dist (f64), id / predecessor /
+// assigned source (u16) and a scanned flag: 23 bytes, so that the 5-shot reverse matching (<= 1369 x 6845) fits
 __host__ __device__ inline size_t lsap_smem_bytes(int t_cap, int m_cap) {
-    return (size_t)t_cap * (2 * 8 + 3 * 4 + 1) + (size_t)m_cap * (3 * 8 + 3 * 4) + 64;
+    return (size_t)t_cap * (2 * 8 + 3 * 4) + (size_t)m_cap * (2 * 8 + 3 * 2 + 1) + 64;
 }
+constexpr unsigned short LSAP_NONE = 0xffff;
 
-__device__ inline void lsap_argmin(const double* key, int M, double& best, int& best_j, double* s_val, int* s_idx) {
+__device__ inline void lsap_argmin(const double* dist, const unsigned char* scanned, int M, double& best, int& best_j,
+                                   double* s_val, int* s_idx) {
     double v = LSAP_INF;
     int j = 0x7fffffff;
     for (int t = threadIdx.x; t < M; t += LSAP_THREADS) {
-        const double k = key[t];
+        const double k = scanned[t] ? LSAP_INF : dist[t];
         if (k < v) {
             v = k;
             j = t;
@@ -62,13 +66,13 @@ __global__ void __launch_bounds__(LSAP_THREADS) lsap_kernel(const float* __restr
     double* dsrc = u + t_cap;                              // [t_cap]
     double* v = dsrc + t_cap;                              // [m_cap]
     double* dist = v + m_cap;                              // [m_cap]
-    double* key = dist + m_cap;                            // [m_cap]
-    int* src_id = reinterpret_cast<int*>(key + m_cap);     // [t_cap] row (or column) index of source i
+    int* src_id = reinterpret_cast<int*>(dist + m_cap);    // [t_cap] row (or column) index of source i
     int* src_sink = src_id + t_cap;                        // [t_cap] sink assigned to source i
     int* list = src_sink + t_cap;                          // [t_cap] reached sources
-    int* sink_id = list + t_cap;                           // [m_cap]
-    int* pred_src = sink_id + m_cap;                       // [m_cap]
-    int* sink_src = pred_src + m_cap;                      // [m_cap] source assigned to sink j, or -1
+    unsigned short* sink_id = reinterpret_cast<unsigned short*>(list + t_cap);  // [m_cap]
+    unsigned short* pred_src = sink_id + m_cap;            // [m_cap]
+    unsigned short* sink_src = pred_src + m_cap;           // [m_cap] source assigned to sink j, or LSAP_NONE
+    unsigned char* scanned = reinterpret_cast<unsigned char*>(sink_src + m_cap);  // [m_cap]
     __shared__ double s_val[2][LSAP_THREADS / 32];
     __shared__ int s_idx[2][LSAP_THREADS / 32];
     __shared__ int s_nr, s_nc, s_nreached;
@@ -104,9 +108,15 @@ __global__ void __launch_bounds__(LSAP_THREADS) lsap_kernel(const float* __restr
     if (tid == 0) {
         int a = 0, b = 0;
         for (int r = 0; r < R; ++r)
-            if (!row_sel || row_sel[e * R + r]) (rows_are_sources ? src_id : sink_id)[a++] = r;
+            if (!row_sel || row_sel[e * R + r]) {
+                if (rows_are_sources) src_id[a++] = r;
+                else sink_id[a++] = (unsigned short)r;
+            }
         for (int c = 0; c < Ccols; ++c)
-            if (!col_sel || col_sel[e * Ccols + c]) (rows_are_sources ? sink_id : src_id)[b++] = c;
+            if (!col_sel || col_sel[e * Ccols + c]) {
+                if (rows_are_sources) sink_id[b++] = (unsigned short)c;
+                else src_id[b++] = c;
+            }
     }
     __syncthreads();
     const double sign = maximize ? -1.0 : 1.0;
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(LSAP_THREADS) lsap_kernel(const float* __restr
     }
     for (int j = tid; j < M; j += LSAP_THREADS) {
         v[j] = 0.0;
-        sink_src[j] = -1;
+        sink_src[j] = LSAP_NONE;
     }
     __syncthreads();
 
@@ -139,8 +149,8 @@ __global__ void __launch_bounds__(LSAP_THREADS) lsap_kernel(const float* __restr
         for (int j = tid; j < M; j += LSAP_THREADS) {
             const double d = cost(r, j) - ur - v[j];
             dist[j] = d;
-            key[j] = d;
-            pred_src[j] = r;
+            scanned[j] = 0;
+            pred_src[j] = (unsigned short)r;
         }
         if (tid == 0) {
             dsrc[r] = 0.0;
@@ -151,23 +161,22 @@ __global__ void __launch_bounds__(LSAP_THREADS) lsap_kernel(const float* __restr
         double D;
         int jstar;
         for (int step = 0;; ++step) {
-            lsap_argmin(key, M, D, jstar, s_val[step & 1], s_idx[step & 1]);
-            const int i = sink_src[jstar];  // assignments only change in the augmentation: uniform
-            if (tid == 0) key[jstar] = LSAP_INF;
+            lsap_argmin(dist, scanned, M, D, jstar, s_val[step & 1], s_idx[step & 1]);
+            const int i = sink_src[jstar] == LSAP_NONE ? -1 : (int)sink_src[jstar];  // only changes in the augmentation
+            if (tid == 0) scanned[jstar] = 1;
             if (i < 0) break;
             if (tid == 0) {
                 dsrc[i] = D;
                 list[s_nreached++] = i;
             }
             const double base = D - u[i];
-            __syncthreads();  // key[jstar] = INF visible before the relaxation reads it
+            __syncthreads();  // scanned[jstar] visible before the relaxation reads it
             for (int j = tid; j < M; j += LSAP_THREADS) {
-                if (key[j] < LSAP_INF) {
+                if (!scanned[j]) {
                     const double nd = base + cost(i, j) - v[j];
                     if (nd < dist[j]) {
                         dist[j] = nd;
-                        key[j] = nd;
-                        pred_src[j] = i;
+                        pred_src[j] = (unsigned short)i;
                     }
                 }
             }
@@ -180,14 +189,14 @@ __global__ void __launch_bounds__(LSAP_THREADS) lsap_kernel(const float* __restr
             u[i] += D - dsrc[i];
         }
         for (int j = tid; j < M; j += LSAP_THREADS)
-            if (key[j] >= LSAP_INF) v[j] -= D - dist[j];
+            if (scanned[j]) v[j] -= D - dist[j];
         __syncthreads();
         if (tid == 0) {  // flip the assignments along the path back to r
             int j = jstar;
             while (true) {
                 const int i = pred_src[j];
                 const int prev = src_sink[i];
-                sink_src[j] = i;
+                sink_src[j] = (unsigned short)i;
                 src_sink[i] = j;
                 if (i == r) break;
                 j = prev;
@@ -220,12 +229,16 @@ __global__ void __launch_bounds__(LSAP_THREADS) lsap_kernel(const float* __restr
 using namespace marsb200;
 
 extern "C" int marsb200_lsap(const float* sim, const uint8_t* row_sel, const uint8_t* col_sel, int E, int R, int C,
-                             int maximize, int32_t* row_to_col, double* objective, int32_t* status, void* stream) {
+                             int maximize, int t_cap, int m_cap, int32_t* row_to_col, double* objective, int32_t* status,
+                             void* stream) {
     MARS_REQUIRE(sim && row_to_col && objective && status, "null pointer");
-    MARS_REQUIRE(E > 0 && R > 0 && C > 0, "shape");
-    const int t_cap = R < C ? R : C, m_cap = R < C ? C : R;
+    MARS_REQUIRE(E > 0 && R > 0 && C > 0 && R <= 65534 && C <= 65534, "shape (R, C <= 65534)");
+    if (t_cap <= 0 || m_cap <= 0) {  // no bound on the selected counts given: size for the whole matrix
+        t_cap = R < C ? R : C;
+        m_cap = R < C ? C : R;
+    }
     const size_t smem = lsap_smem_bytes(t_cap, m_cap);
-    MARS_REQUIRE(smem <= 200 * 1024, "problem too large for the shared-memory state (29*min + 36*max bytes <= 200 KB)");
+    MARS_REQUIRE(smem <= 220 * 1024, "problem too large for the shared-memory state (28*min + 23*max bytes <= 220 KB)");
     cudaStream_t s = as_stream(stream);
     MARS_CUDA_OK(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MARS_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), s));

@@ -172,8 +172,11 @@ def lsap(sim: torch.Tensor, row_sel: Optional[torch.Tensor] = None, col_sel: Opt
     r2c = torch.empty((e, r), device=sim.device, dtype=torch.int32)
     obj = torch.empty((e,), device=sim.device, dtype=torch.float64)
     status = torch.zeros(1, device=sim.device, dtype=torch.int32)
-    check(lib.marsb200_lsap(sim.data_ptr(), _ptr(rs), _ptr(cs), e, r, c, int(maximize), r2c.data_ptr(), obj.data_ptr(),
-                            status.data_ptr(), _stream()))
+    # the solver's state is sized for the selected rows / columns (one small sync, like the reference's host call)
+    nr = r if rs is None else max(1, int((rs != 0).sum(dim=1).max().item()))
+    nc = c if cs is None else max(1, int((cs != 0).sum(dim=1).max().item()))
+    check(lib.marsb200_lsap(sim.data_ptr(), _ptr(rs), _ptr(cs), e, r, c, int(maximize), min(nr, nc), max(nr, nc),
+                            r2c.data_ptr(), obj.data_ptr(), status.data_ptr(), _stream()))
     if check_status and int(status.item()):
         raise _lib.MarsB200Error(f"lsap: a problem of size {int(status.item())} exceeds the shared-memory state")
     return r2c, obj

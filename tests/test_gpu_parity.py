@@ -1046,3 +1046,19 @@ def test_emd_repeatable_and_orientation_free(mb):
         rows_i = ((pooled[i][:, None] >> torch.arange(32, device=d, dtype=torch.int32)) & 1).reshape(-1)[:n].to(torch.uint8)
         flipped = mb.ops.emd_scores(cost.t().contiguous().to(d)[None], rows_i[None], sup_bits)[0, 0]
         assert abs(float(flipped) - float(runs[0][i])) < 1e-12
+
+
+def test_patch_matcher_5shot_full_size(mb):
+    """c3 shape: 5 x 1369 support patches against 1369 query patches.  The reverse assignment is 1369 x 6845, the
+    largest problem the solver's shared-memory state has to hold; compared with the scipy restatement."""
+    shape = mb.EpisodeShape(ns=5, g=37, C=256, P=4, H=518, W=518)
+    ep = mb.make_episode(shape, 21)
+    n = shape.N
+    fs = orc.normalize_rows(ep["feat_s"].reshape(5 * n, shape.C))
+    fq = orc.normalize_rows(ep["feat_q"])
+    pool = orc.pool_mask(ep["support_mask"], shape.g).reshape(-1).float()
+    pts_ref, neg_ref, reduced_ref = orc.matcher_patch_matching(fs, fq, pool, shape.g, 14, (518, 518))
+    res = mb.PatchMatcher(shape.g, 14, (518, 518), dev()).match(fs, fq, pool)
+    assert res["reduced_points_num"] == reduced_ref
+    assert sorted(map(tuple, res["points"].cpu().tolist())) == pts_ref
+    assert sorted(map(tuple, res["points_discarded"].cpu().tolist())) == neg_ref
