@@ -613,7 +613,7 @@ def run_episode(ep: dict, cfg: dict, emd_fn: Optional[Callable] = None) -> dict:
     scores = fuse_scores(emd, clip, cov, avv, avt, cfg["alpha"])
     order = stable_rank(scores)
     out = dict(sim=sim, cost=cost, support_bits=sup_bits, prior=prior, vva=vva, vta=vta,
-               pooled=pooled, coverage=cov, pvv_align=avv, pvt_align=avt, clip=clip,
+               pooled=pooled, coverage=cov, pvv_align=avv, pvt_align=avt, clip=clip, emd=emd,
                scores=scores, order=order)
     nms_thr = cfg.get("nms_iou_threshold")
     sel = merge_select(scores[order], cfg["static_threshold"], cfg["dynamic_threshold"])
