@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_packed_kernel(const uint32_
                                                                    uint32_t* __restrict__ pooled,
                                                                    int32_t* __restrict__ area,
                                                                    int32_t* __restrict__ pooled_count) {
-    extern __shared__ uint32_t s_mem_pool[];
+    extern __shared__ __align__(16) uint32_t s_mem_pool[];
     uint32_t* binrow = s_mem_pool;             // g * rw
     uint32_t* s_pool = binrow + g * rw;        // npw
     int* s_cnt = reinterpret_cast<int*>(s_pool + npw);  // 2
@@ -184,11 +184,18 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_packed_kernel(const uint32_
                 if ((int)y < H) {
                     const int wi0 = (int)(quad - y * (uint32_t)quads_per_row) * 4;
                     const int rb = s_rowbins[y];
+                    my_area += __popc(words[0]) + __popc(words[1]) + __popc(words[2]) + __popc(words[3]);
+                    // rw is a multiple of 4 on this path: one 128-bit read tells whether the bit row already holds
+                    // these pixels (the usual case inside a blob: ~28 image rows share a patch-row bin)
+                    for (int jy = rb & 0xff; jy <= (rb >> 8); ++jy) {
+                        uint32_t* dst = &binrow[jy * rw + wi0];
+                        const uint4 cur = *reinterpret_cast<const uint4*>(dst);
+                        if (((cur.x & words[0]) ^ words[0]) | ((cur.y & words[1]) ^ words[1]) |
+                            ((cur.z & words[2]) ^ words[2]) | ((cur.w & words[3]) ^ words[3])) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (words[k] == 0) continue;
-                        my_area += __popc(words[k]);
-                        for (int jy = rb & 0xff; jy <= (rb >> 8); ++jy) smem_or(&binrow[jy * rw + wi0 + k], words[k]);
+                            for (int k = 0; k < 4; ++k)
+                                if (words[k] & ~(&cur.x)[k]) atomicOr(dst + k, words[k]);
+                        }
                     }
                 }
                 continue;
@@ -550,7 +557,8 @@ int marsb200_pool_packed(const uint32_t* bits, int64_t n, int H, int W, int g, u
     const int64_t wpm = marsb200_words_per_mask((int64_t)H * W);
     MARS_REQUIRE(n < (1ll << 31), "too many masks");
     MARS_REQUIRE((int64_t)H * W < (1ll << 31), "mask too large");
-    const int rw = W / 32 + 2;  // row-aligned bit row: ceil(W/32) words + 1 spill word
+    int rw = W / 32 + 2;  // row-aligned bit row: ceil(W/32) words + 1 spill word
+    if (W % 128 == 0) rw = (rw + 3) / 4 * 4;  // 16-byte aligned bit rows for the 128-bit fast path
     MARS_REQUIRE(g <= 255 && H <= 32768 && W <= 32768, "g <= 255, H, W <= 32768");
     const size_t smem = ((size_t)g * rw + npw + 2) * sizeof(uint32_t) + (size_t)H * sizeof(uint16_t);
     MARS_REQUIRE(smem <= 48 * 1024, "g * W too large for the pooling scratch");
