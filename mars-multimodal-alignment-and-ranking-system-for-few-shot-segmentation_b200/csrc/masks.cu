@@ -301,9 +301,17 @@ __global__ void __launch_bounds__(256) union_count_kernel(const uint32_t* __rest
     const int64_t e = blockIdx.x;
     const uint32_t* base = pooled + e * P * npw;
     const int total = P * npw;
-    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x) {
-        const uint32_t v = base[i0];
-        if (v) smem_or(&s_union[i0 % npw], v);
+    // eight independent loads in flight per thread: one CTA per episode is latency-bound otherwise
+    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            v[u] = i < total ? __ldg(base + i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (v[u]) smem_or(&s_union[(i0 + u * blockDim.x) % npw], v[u]);
     }
     __syncthreads();
     int c = 0;

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(FIN_THREADS) vva_finalize_kernel(const float* 
     __shared__ int s_i[FIN_THREADS / 32];
     const int64_t e = blockIdx.x;
     int t = 0;
+#pragma unroll 8
     for (int64_t m = threadIdx.x; m < M; m += FIN_THREADS) t += row_fg[e * M + m] ? 1 : 0;
     t = fin_block_reduce(t, [](int a, int b) { return a + b; }, s_i);
     const int64_t n_bg = M - t;
@@ -185,12 +186,24 @@ __global__ void __launch_bounds__(FIN_THREADS) vva_finalize_kernel(const float* 
     for (int64_t n = threadIdx.x; n < N; n += FIN_THREADS) {
         float fg_max = -INFINITY, bg_max = -INFINITY;
         double fg_sum = 0.0, bg_sum = 0.0;
-        for (int tm = 0; tm < tiles_m; ++tm) {
-            const float* c = cs + (int64_t)tm * 4 * N + n;
-            fg_max = fmaxf(fg_max, c[0]);
-            fg_sum += (double)c[N];
-            bg_max = fmaxf(bg_max, c[2 * N]);
-            bg_sum += (double)c[3 * N];
+        for (int tm0 = 0; tm0 < tiles_m; tm0 += 4) {  // 16 independent loads in flight (one CTA per episode)
+            float v[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool ok = tm0 + q < tiles_m;
+                const float* c = cs + (int64_t)(ok ? tm0 + q : 0) * 4 * N + n;
+                v[q][0] = ok ? __ldg(c) : -INFINITY;
+                v[q][1] = ok ? __ldg(c + N) : 0.f;
+                v[q][2] = ok ? __ldg(c + 2 * N) : -INFINITY;
+                v[q][3] = ok ? __ldg(c + 3 * N) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // same order as a plain loop over the tiles
+                fg_max = fmaxf(fg_max, v[q][0]);
+                fg_sum += (double)v[q][1];
+                bg_max = fmaxf(bg_max, v[q][2]);
+                bg_sum += (double)v[q][3];
+            }
         }
         // mean * max in float32; with no fg row the reference raises - we emit NaN (0/0)
         float v = (float)(fg_sum / (double)t) * fg_max;
