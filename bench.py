@@ -464,6 +464,10 @@ def run_ours(args):
                                   f"(torch CPU, {cores} threads, EMD excluded)"}
         if full is not None:
             full["cpu_emd"] = cpu_emd_sample(shape, batches[0], args.cpu_emd_lps)
+            per_episode = 1.0 / cpu_baseline["value"] + shape.P / full["cpu_emd"]["lps_per_s"]
+            full["cpu_full_scoring"] = {"value": 1.0 / per_episode, "unit": "episodes/s",
+                                        "how": "extrapolated: host time of one episode without EMD (all cores) plus P "
+                                               "transport LPs at the sampled one-core HiGHS rate"}
 
     if rank == 0:
         print(json.dumps({
