@@ -123,3 +123,21 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_header_is_plain_c():
+    """include/marsb200.h must parse as C99 and as C++ (the C-ABI boundary: no torch or CUDA types in signatures)."""
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "marsb200.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    subprocess.run(["gcc", "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", hdr], check=True)
+    subprocess.run(["g++", "-x", "c++", "-fsyntax-only", "-Wall", "-Werror", hdr], check=True)
+    import re
+
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)  # declarations only, comments stripped
+    for banned in ("torch", "at::", "Tensor", "cudaStream_t", "std::"):
+        assert banned not in code, banned
