@@ -162,11 +162,25 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restr
     const float* a = attn + (e * N + row) * ld;
     float* d = D + (e * N + row) * k_pad;
     float* dl = D_lo + (e * N + row) * k_pad;
+    // the row stays in registers between the two passes (N <= 8 * 256 on this path; longer rows go through D)
+    constexpr int RN_MAX = 8;
+    const bool in_regs = N <= RN_MAX * 256;
+    float vals[RN_MAX];
     double acc = 0.0;
-    for (int c = threadIdx.x; c < N; c += blockDim.x) {
-        const float v = __fdiv_rn(a[c], colsum[e * N + c]);
-        d[c] = v;
-        acc += (double)v;
+    if (in_regs) {
+#pragma unroll
+        for (int k = 0; k < RN_MAX; ++k) {
+            const int c = threadIdx.x + k * 256;
+            vals[k] = c < N ? __fdiv_rn(a[c], colsum[e * N + c]) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < RN_MAX; ++k) acc += (double)vals[k];  // same order as the strided loop below
+    } else {
+        for (int c = threadIdx.x; c < N; c += blockDim.x) {
+            const float v = __fdiv_rn(a[c], colsum[e * N + c]);
+            d[c] = v;
+            acc += (double)v;
+        }
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
@@ -174,6 +188,18 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restr
     double total = 0.0;
     for (int w = 0; w < 8; ++w) total += s_red[w];
     const float rs = (float)total;
+    if (in_regs) {
+#pragma unroll
+        for (int k = 0; k < RN_MAX; ++k) {
+            const int64_t c = threadIdx.x + k * 256;
+            if (c < k_pad) {
+                const float v = c < N ? __fdiv_rn(vals[k], rs) : 0.f;
+                d[c] = v;
+                dl[c] = tf32_residual(v);
+            }
+        }
+        return;
+    }
     for (int64_t c = threadIdx.x; c < k_pad; c += blockDim.x) {
         float v = 0.f;
         if (c < N) v = __fdiv_rn(d[c], rs);
