@@ -93,13 +93,27 @@ pairwise_mma_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int b
         const int rb = bj * PM_ROWS + tid, ra = bi * PM_ROWS + tid;
         const uint4* src_b = reinterpret_cast<const uint4*>(ebits + (int64_t)rb * wpm);
         const uint4* src_a = reinterpret_cast<const uint4*>(ebits + (int64_t)ra * wpm);
+        // the words of k-block i + 2 are requested before k-block i is expanded: with the bits coming from HBM (the
+        // packed masks of a launch exceed the L2) one load latency per k-block would otherwise pace the MMAs
+        constexpr int AHEAD = 2;
+        uint4 qb[AHEAD], qa[AHEAD];
+#pragma unroll
+        for (int a = 0; a < AHEAD; ++a) {
+            qb[a] = (rb < P && a < num_kb) ? __ldg(src_b + kb_begin + a) : make_uint4(0, 0, 0, 0);
+            qa[a] = (!diagonal && ra < P && a < num_kb) ? __ldg(src_a + kb_begin + a) : make_uint4(0, 0, 0, 0);
+        }
         for (int i = 0; i < num_kb; ++i) {
             const int s = i % PM_STAGES;
             const uint32_t phase = (i / PM_STAGES) & 1;
-            const int kb = kb_begin + i;
-            uint4 vb = make_uint4(0, 0, 0, 0), va = make_uint4(0, 0, 0, 0);
-            if (rb < P) vb = __ldg(src_b + kb);
-            if (!diagonal && ra < P) va = __ldg(src_a + kb);
+            const uint4 vb = qb[0], va = qa[0];
+#pragma unroll
+            for (int a = 0; a + 1 < AHEAD; ++a) {
+                qb[a] = qb[a + 1];
+                qa[a] = qa[a + 1];
+            }
+            const int nk = kb_begin + i + AHEAD;
+            qb[AHEAD - 1] = (rb < P && i + AHEAD < num_kb) ? __ldg(src_b + nk) : make_uint4(0, 0, 0, 0);
+            qa[AHEAD - 1] = (!diagonal && ra < P && i + AHEAD < num_kb) ? __ldg(src_a + nk) : make_uint4(0, 0, 0, 0);
             mbar_wait(empty_bar(s), phase ^ 1);
             unsigned char* st = base_ptr + s * PM_STAGE_BYTES;
             expand_row(st, tid, vb);
