@@ -44,6 +44,11 @@ extern "C" {
 
 int marsb200_version(void);
 const char* marsb200_last_error(void);
+/* SMs a launch on `stream` can use: the partition of the stream's CUDA green context, else the device's SM
+ * count.  The persistent tensor-core kernels size their grids with it, so an episode engine can give the HBM-bound
+ * mask ingest and the contractions disjoint SM partitions (no reference counterpart: the reference is single-stream,
+ * main_MARS.py:54-94).  count_host is a HOST pointer. */
+int marsb200_stream_sm_count(void* stream, int* count_host);
 /* words (uint32) per packed mask row for an H*W mask: ceil(HW/32) rounded up to 32 words (128 B) */
 int64_t marsb200_words_per_mask(int64_t hw);
 /* padded extents used by the contraction operands */

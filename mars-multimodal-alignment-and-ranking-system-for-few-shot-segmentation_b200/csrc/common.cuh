@@ -84,6 +84,9 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
     return r;
 }
 
+// SMs a launch on `s` can use (the stream's green-context partition, else the device): stream_sms.cu
+int sms_for_stream(cudaStream_t s, int* out);
+
 // internal back ends shared between translation units
 int pairwise_popc(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s);
 int pairwise_mma(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s);

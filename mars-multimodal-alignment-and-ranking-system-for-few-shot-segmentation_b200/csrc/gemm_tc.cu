@@ -344,13 +344,13 @@ int gemm_tcgen05(const GemmOperand& a, const GemmOperand& b, int E, int64_t M, i
     if ((rc = make_operand_map(&maps[1], a.lo, a, E, K))) return rc;
     if ((rc = make_operand_map(&maps[2], b.p, b, E, K))) return rc;
     if ((rc = make_operand_map(&maps[3], b.lo, b, E, K))) return rc;
-    static int num_sms = 0;
-    if (!num_sms) {
+    static bool configured = false;
+    if (!configured) {
         MARS_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM_BYTES));
-        int dev = 0;
-        MARS_CUDA_OK(cudaGetDevice(&dev));
-        MARS_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
     }
+    int num_sms = 0;  // the stream's partition when it belongs to a green context
+    if ((rc = sms_for_stream(s, &num_sms))) return rc;
     const int tiles_m = (int)ceil_div64(M, GEMM_BM), tiles_n = (int)ceil_div64(N, TC_BN);
     int tiles_per_ep = tiles_m * tiles_n;
     if (ep.symmetric) {

@@ -37,11 +37,25 @@ class RankingConfig:
     emd_m_cap: Optional[int] = None    # max pooled patches of a proposal (default N); smaller -> more LPs per SM
     gemm_backend: Optional[int] = None
     pair_backend: Optional[int] = None
+    # SMs of the `tensor` green-context partition (partition.py); the mask ingest gets the rest of the device and runs
+    # beside the contractions instead of before them.  None = one whole-device timeline (the streams above).
+    tensor_partition_sms: Optional[int] = None
+    partition_chunks: int = 4          # episode chunks pack -> pairwise are pipelined in across the two partitions
+    partition_pairwise_tail: int = 0   # intersections of the last chunks run on the `hbm` partition after the ingest
+    partition_vta_on_hbm: bool = True  # vta refinement on the `hbm` partition after the ingest (else beside the vva chain)
 
 
-def kernel_launches_per_run(cfg: RankingConfig) -> int:
+def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int] = None) -> int:
     """How many of our kernels one `RankingEngine.run` launches (counted from the sequence below)."""
-    n = 2                      # normalize_rows x2
+    n = 0
+    if cfg.tensor_partition_sms and not cfg.fused_ingest:
+        # pack, pool_packed and pairwise run once per episode chunk instead of once per batch
+        k = max(1, cfg.partition_chunks if episodes_per_batch is None else min(cfg.partition_chunks, episodes_per_batch))
+        if episodes_per_batch is not None:
+            per = (episodes_per_batch + k - 1) // k
+            k = (episodes_per_batch + per - 1) // per
+        n += (k - 1) * (2 + (1 if cfg.nms_iou_threshold is not None else 0))
+    n += 2                     # normalize_rows x2
     n += 1                     # pool_mask
     n += 1                     # sim_contract
     n += 1                     # vva_finalize
@@ -117,6 +131,16 @@ class RankingEngine:
         self._ev_join = torch.cuda.Event()
         self._ev_pack = torch.cuda.Event()
         self._ev_pool = torch.cuda.Event()
+        self._part = None
+        if cfg.tensor_partition_sms:
+            from .partition import SmPartition
+
+            self._part = SmPartition(dev, cfg.tensor_partition_sms)
+            self._part_side = self._part.extra_stream("tensor")
+            k = max(1, min(cfg.partition_chunks, e))
+            per = (e + k - 1) // k
+            self._chunks = [(lo, min(lo + per, e)) for lo in range(0, e, per)]
+            self._ev_chunk = [torch.cuda.Event() for _ in self._chunks]
 
     # ------------------------------------------------------------------ the kernel sequence
     def _ingest(self, batch: dict):
@@ -160,9 +184,77 @@ class RankingEngine:
             ops.pairwise_inter(self.bits, backend=cfg.pair_backend, out=self.inter)
             cur.wait_event(self._ev_pool)
 
+    def _run_partitioned(self, batch: dict) -> dict:
+        """The same kernel sequence on two disjoint SM sets.  `hbm` partition: pack (+ pooled bitmaps) of one episode
+        chunk after the other, at the HBM roofline.  `tensor` partition: normalise -> S -> vva / vta refinement first
+        (they do not depend on the masks), then the tensor-core pairwise kernel chunk by chunk as the packed bits
+        arrive, then scoring, ranking and merging.  Both sets are busy for the whole step; on one timeline the ingest
+        and the tensor kernels add up."""
+        s, e, cfg, part = self.shape, self.E, self.cfg, self._part
+        n, m = s.N, s.ns * s.N
+        main = torch.cuda.current_stream()
+        hbm, ten, side = part.hbm_stream, part.tensor_stream, self._part_side
+        self._ev_fork.record(main)
+        for st in (hbm, ten, side):
+            st.wait_event(self._ev_fork)
+        masks = batch["masks"]
+        with torch.cuda.stream(hbm):
+            for (lo, hi), ev in zip(self._chunks, self._ev_chunk):
+                ops.pack_masks(masks[lo:hi], out=self.bits[lo:hi])
+                ev.record(hbm)
+                ops.pool_packed(self.bits[lo:hi], s.H, s.W, s.g, out=tuple(t[lo:hi] for t in self.pool_out))
+            # the last chunks' intersections stay on this partition: their bits only exist when the ingest is over and
+            # the tensor partition still has its own queue to drain
+            tail = self._chunks[len(self._chunks) - cfg.partition_pairwise_tail:] if cfg.partition_pairwise_tail else []
+            if self.inter is not None:
+                for lo, hi in tail:
+                    ops.pairwise_inter(self.bits[lo:hi], backend=cfg.pair_backend, out=self.inter[lo:hi])
+            self._ev_pool.record(hbm)
+        # the vta refinement is independent of everything else: it fills the `hbm` partition once the ingest is done
+        # (the tensor partition is the longer chain) or runs beside the vva chain inside the tensor partition
+        vta_stream = hbm if cfg.partition_vta_on_hbm else side
+        with torch.cuda.stream(vta_stream):
+            ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
+                           backend=cfg.gemm_backend, workspace=self.pir_ws_vta, out=self.vta_ref)
+            self._ev_vta.record(vta_stream)
+        with torch.cuda.stream(ten):
+            ops.normalize_rows(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
+            ops.normalize_rows(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
+            ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
+            ops.sim_contract(self.fs, self.fq, m, n, s.C, want_sim=cfg.want_sim,
+                             want_cost=cfg.want_cost or cfg.emd_on_device, row_fg=self.row_fg, backend=cfg.gemm_backend,
+                             out=self.gemm_out)
+            ops.vva_finalize(self.gemm_out["colstats"], self.row_fg, m, n, out=self.prior)
+            ops.pir_refine(self.prior, batch["attn_vva"], s.g, cfg.vva_box_threshold, apply_minmax=True,
+                           backend=cfg.gemm_backend, workspace=self.pir_ws, out=self.vva)
+            ops.clip_scores(batch["clip_img"], batch["clip_txt"], out=self.clip)
+            if self.inter is not None:
+                for (lo, hi), ev in list(zip(self._chunks, self._ev_chunk))[:len(self._chunks) - len(tail)]:
+                    ten.wait_event(ev)
+                    ops.pairwise_inter(self.bits[lo:hi], backend=cfg.pair_backend, out=self.inter[lo:hi])
+            ten.wait_event(self._ev_vta)
+            ops.resize_minmax(self.vta_ref.reshape(e, s.gt, s.gt), s.g, True, out=self.vta)
+            ten.wait_event(self._ev_pool)
+            ops.region_sums(self.pool_out[0], self.vva, self.vta, out=self.region_out)
+            emd = batch.get("emd")
+            if cfg.emd_on_device:
+                emd = ops.emd_scores(self.gemm_out["cost"], self.row_fg.reshape(e, m), self.pool_out[0],
+                                     t_cap=self.emd_t_cap, m_cap=self.emd_m_cap, workspace=self.emd_ws, out=self.emd_out,
+                                     check=False)
+            ops.fuse_rank(emd, self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
+                          self.region_out[2], self.inter, cfg.alpha, cfg.static_threshold, cfg.dynamic_threshold,
+                          cfg.nms_iou_threshold, out=self.rank_out)
+            ops.merge_masks(self.bits, self.rank_out["flags"], s.H * s.W, want_bits=True,
+                            want_f32=cfg.want_merged_f32, out=self.merge_out)
+            self._ev_join.record(ten)
+        main.wait_event(self._ev_join)
+        return self.outputs()
+
     def run(self, batch: dict) -> dict:
         s, e, cfg = self.shape, self.E, self.cfg
         n, m = s.N, s.ns * s.N
+        if self._part is not None and "masks" in batch and not cfg.fused_ingest:
+            return self._run_partitioned(batch)
         main = torch.cuda.current_stream()
         if self._side is not None:
             # the mask chain is HBM-bound and the alignment chain tensor/L2-bound: let them share the SMs

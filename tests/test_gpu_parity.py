@@ -1062,3 +1062,68 @@ def test_patch_matcher_5shot_full_size(mb):
     assert res["reduced_points_num"] == reduced_ref
     assert sorted(map(tuple, res["points"].cpu().tolist())) == pts_ref
     assert sorted(map(tuple, res["points_discarded"].cpu().tolist())) == neg_ref
+
+
+# ------------------------------------------------------------------ SM partitions (CUDA green contexts)
+def test_stream_sm_count_follows_the_partition(mb):
+    """Persistent kernels size their grids from the stream: whole device on a plain stream, the partition's SMs on a
+    green-context stream."""
+    from marsb200.partition import SmPartition, stream_sm_count
+
+    total = torch.cuda.get_device_properties(dev()).multi_processor_count
+    assert stream_sm_count(torch.cuda.current_stream()) == total
+    assert stream_sm_count(torch.cuda.Stream()) == total
+    part = SmPartition(dev(), 56)
+    try:
+        assert part.tensor_sms >= 56 and part.tensor_sms + part.hbm_sms <= total
+        assert stream_sm_count(part.tensor_stream) == part.tensor_sms
+        assert stream_sm_count(part.hbm_stream) == part.hbm_sms
+        assert stream_sm_count(part.extra_stream("tensor")) == part.tensor_sms
+    finally:
+        part.close()
+
+
+@pytest.mark.parametrize("chunks,vta_on_hbm,tail", [(1, True, 0), (2, False, 1), (3, True, 2)])
+def test_engine_partitioned_matches_one_timeline(mb, chunks, vta_on_hbm, tail):
+    """The two-partition schedule (ingest beside the contractions) is the same arithmetic: every output bit for bit."""
+    shape = mb.EpisodeShape(ns=1, g=12, C=64, P=40, H=160, W=160, gt=9, D=32)
+    eps = [mb.make_episode(shape, 300 + i) for i in range(5)]
+    batch = mb.to_device(mb.stack_episodes(eps), dev())
+    base = mb.RankingEngine(shape, 5, mb.RankingConfig(nms_iou_threshold=0.7), dev())
+    ref = {k: v.clone() for k, v in base.run(batch).items() if v is not None}
+    cfg = mb.RankingConfig(nms_iou_threshold=0.7, tensor_partition_sms=56, partition_chunks=chunks,
+                           partition_vta_on_hbm=vta_on_hbm, partition_pairwise_tail=tail)
+    eng = mb.RankingEngine(shape, 5, cfg, dev())
+    try:
+        for _ in range(2):
+            out = eng.run(batch)
+            torch.cuda.synchronize()
+            for k, v in ref.items():
+                assert torch.equal(out[k], v), k
+    finally:
+        eng._part.close()
+
+
+def test_pack_inside_a_partition_is_bit_exact(mb):
+    """pack_masks / pairwise_inter on a green-context stream (fewer SMs, other grid sizes) against the oracle."""
+    from marsb200.partition import SmPartition
+
+    g = torch.Generator().manual_seed(11)
+    masks = (torch.rand(37, 200, 312, generator=g) < 0.35).float()
+    ref_bits = np_pack(masks.numpy() > 0, mb.ops.words_per_mask(200 * 312))
+    ref_inter = orc.pairwise_intersections(masks)
+    part = SmPartition(dev(), 64)
+    try:
+        x = masks.to(dev())
+        torch.cuda.synchronize()
+        with torch.cuda.stream(part.hbm_stream):
+            bits = mb.ops.pack_masks(x)
+        with torch.cuda.stream(part.tensor_stream):
+            part.tensor_stream.wait_stream(part.hbm_stream)
+            inter = mb.ops.pairwise_inter(bits)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(bits.cpu().numpy().view(np.uint32), ref_bits)
+        got = ref_inter[0] if isinstance(ref_inter, tuple) else ref_inter
+        np.testing.assert_array_equal(inter[0].cpu().numpy(), got.numpy())
+    finally:
+        part.close()
