@@ -39,6 +39,9 @@ def parse_args():
     ap.add_argument("--mask-dtype", default="f32", choices=["f32", "u8"])
     ap.add_argument("--nms", type=float, default=0.7)
     ap.add_argument("--fused-ingest", action="store_true", help="one-pass pack + pairwise kernel")
+    ap.add_argument("--tensor-partition-sms", type=int, default=-1,
+                    help="SMs of the tensor green-context partition for the device-resident loop (0 = one whole-device "
+                         "timeline; -1 = 56 for float32 masks at c2, else 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-emd", action="store_true", help="skip the full-scoring (device EMD) variant")
@@ -247,7 +250,14 @@ def run_ours(args):
     md = torch.float32 if args.mask_dtype == "f32" else torch.uint8
     cfg = marsb200.RankingConfig(nms_iou_threshold=args.nms, fused_ingest=args.fused_ingest)
     E = args.episodes_per_step
-    eng = marsb200.RankingEngine(shape, E, cfg, dev, md)
+    part_sms = args.tensor_partition_sms
+    if part_sms < 0:
+        part_sms = 56 if (md == torch.float32 and args.workload == "c2" and not args.fused_ingest and E >= 8) else 0
+    # the headline loop runs the ingest and the contractions on disjoint SM partitions (same kernels, same results);
+    # the small-batch variants below (e2e, latency, full scoring) stay on one whole-device timeline
+    cfg_main = marsb200.RankingConfig(nms_iou_threshold=args.nms, fused_ingest=args.fused_ingest,
+                                      tensor_partition_sms=part_sms or None)
+    eng = marsb200.RankingEngine(shape, E, cfg_main, dev, md)
 
     # two distinct resident batches, alternated: every step reads inputs far larger than the 126 MB L2
     n_batches = 2
@@ -293,7 +303,10 @@ def run_ours(args):
 
     # ---- the same device-resident loop fed with lighter proposal formats (uint8 masks, packed bits)
     def value_variant(kind):
-        if kind == "u8":
+        if kind == "one_timeline":
+            alt = batches
+            eng_v = marsb200.RankingEngine(shape, E, cfg, dev, md)
+        elif kind == "u8":
             alt = [dict(b, masks=(b["masks"] > 0).to(torch.uint8)) for b in batches]
             eng_v = marsb200.RankingEngine(shape, E, cfg, dev, torch.uint8)
         else:
@@ -316,6 +329,8 @@ def run_ours(args):
     value_variants = None
     if md == torch.float32 and not args.no_e2e:
         value_variants = {"u8_masks": value_variant("u8"), "packed_masks": value_variant("bits")}
+    if part_sms:
+        value_variants = dict(value_variants or {}, one_timeline=value_variant("one_timeline"))
 
     # ---- per-kernel timing of the dominant kernels with CUDA events on the launching stream
     def time_kernel(fn, iters):
@@ -480,9 +495,11 @@ def run_ours(args):
                        "l2": "two resident batches alternate; each step's inputs exceed the 126 MB L2",
                        "gemm_backend": "tcgen05" if ops.DEFAULT_GEMM == ops.GEMM_TCGEN05 else "simt",
                        "pair_backend": "popc" if ops.DEFAULT_PAIR == ops.PAIR_POPC else "mma",
-                       "fused_ingest": bool(args.fused_ingest)},
+                       "fused_ingest": bool(args.fused_ingest),
+                       "sm_partition": ({"tensor_sms": eng._part.tensor_sms, "hbm_sms": eng._part.hbm_sms,
+                                         "chunks": len(eng._chunks)} if eng._part is not None else None)},
             "clocks": clocks, "value_variants": value_variants, "e2e": e2e, "e2e_variants": e2e_variants,
-            "gpu_launches": marsb200.kernel_launches_per_run(cfg) * args.steps * world,
+            "gpu_launches": marsb200.kernel_launches_per_run(cfg_main, E) * args.steps * world,
             "roofline": roofline, "pairwise": pairwise, "fused_ingest": fused, "full_scoring": full,
             "single_episode_latency": lat, "cpu_baseline": cpu_baseline,
         }))

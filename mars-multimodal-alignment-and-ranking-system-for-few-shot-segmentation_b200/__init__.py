@@ -14,6 +14,7 @@ from .components import (FilteringMergingModule, PriorInformationRefinementModul
                          VisualVisualAlignmentModule)
 from .MARS import MARS, build_MARS_fss  # noqa: F401
 from .matcher_scoring import MatcherScorer, PatchMatcher  # noqa: F401
+from .Matcher import Matcher, RobustPromptSampler  # noqa: F401
 from .evaluation import AverageMeter, Evaluator  # noqa: F401
 
 __version__ = "0.1.0"

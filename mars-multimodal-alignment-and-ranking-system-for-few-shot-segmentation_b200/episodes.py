@@ -132,6 +132,7 @@ class RankingEngine:
         self._ev_pack = torch.cuda.Event()
         self._ev_pool = torch.cuda.Event()
         self._part = None
+        self._capturing = False
         if cfg.tensor_partition_sms:
             from .partition import SmPartition
 
@@ -253,7 +254,7 @@ class RankingEngine:
     def run(self, batch: dict) -> dict:
         s, e, cfg = self.shape, self.E, self.cfg
         n, m = s.N, s.ns * s.N
-        if self._part is not None and "masks" in batch and not cfg.fused_ingest:
+        if self._part is not None and "masks" in batch and not cfg.fused_ingest and not self._capturing:
             return self._run_partitioned(batch)
         main = torch.cuda.current_stream()
         if self._side is not None:
@@ -316,6 +317,7 @@ class RankingEngine:
     def capture(self, batch: dict):
         """Capture `run` on static copies of `batch`; `replay(batch)` then refreshes the inputs and replays."""
         self._static = {k: v.clone() for k, v in batch.items()}
+        self._capturing = True  # a graph is one whole-device timeline: green-context streams are not captured
         stream = torch.cuda.Stream(device=self.device)
         stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(stream):
@@ -325,6 +327,7 @@ class RankingEngine:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self.run(self._static)
+        self._capturing = False
         return self
 
     def replay(self, batch: Optional[dict] = None) -> dict:

@@ -45,7 +45,7 @@ class MatcherScorer:
                     shape=(h, w))
 
     # ------------------------------------------------------------------ metric filters (Matcher.py:732-746)
-    def metric_filter(self, res: dict) -> torch.Tensor:
+    def metric_filter(self, res: dict, record: Optional[dict] = None) -> torch.Tensor:
         idx = torch.arange(res["scores"].numel(), device=self.device)
         metrics = {k: res[k] for k in ("purity", "coverage", "emd")}
         for metric in ("coverage", "emd", "purity"):
@@ -53,14 +53,21 @@ class MatcherScorer:
             if thr > 0:
                 t = min(thr, float(metrics[metric].max()))
                 keep = torch.where(metrics[metric] >= t)[0]
+                if record is not None:
+                    record[metric] = keep
                 idx = idx[keep]
                 metrics = {k: v[keep] for k, v in metrics.items()}
         return idx
 
     # ------------------------------------------------------------------ merge rules
-    def merge(self, res: dict) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Returns (merged mask float32 [1,H,W], mean score) like Matcher.mask_generation (:834)."""
-        idx = self.metric_filter(res)
+    def select(self, res: dict) -> dict:
+        """Which masks get merged: metric filters, then the score-filter (:749-787) or the top-k rule (:788-832).
+
+        Returns dict(idx (survivors of the metric filters), chosen (positions in idx), chosen_global (mask indices, in
+        merge order), final_score (numpy float32 for top-k, 0-dim CPU tensor for the score filter, as in the reference),
+        metric_filters, before_score_filtering)."""
+        filters = {}
+        idx = self.metric_filter(res, filters)
         scores = res["scores"][idx]
         cfg = self.score_filter_cfg
         if cfg["score_filter"]:
@@ -70,7 +77,8 @@ class MatcherScorer:
             keep[..., 0] = True
             keep = keep & (norm < cfg["score_norm"])
             chosen = rank[keep][: self.num_merging_mask]
-            final = scores[chosen].mean()
+            final = scores[chosen].mean().cpu()
+            before = min(int(scores.numel()), self.num_merging_mask)
         else:
             topk = min(self.num_merging_mask, scores.numel())
             top_idx = scores.topk(topk)[1]
@@ -79,12 +87,25 @@ class MatcherScorer:
                 top_scores = top_scores / top_scores.max()
             sel = top_scores > cfg["topk_scores_threshold"]
             chosen = top_idx[sel]
-            final = top_scores[sel].mean()
+            final = top_scores[sel].cpu().numpy().mean()
+            before = topk
+        return dict(idx=idx, chosen=chosen, chosen_global=idx[chosen], final_score=final, metric_filters=filters,
+                    before_score_filtering=before)
+
+    def merge_selected(self, res: dict, chosen_global: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """OR of the packed rows of the chosen masks -> (merged bits [1, wpm], merged float32 [1,H,W])."""
         h, w = res["shape"]
         flags = torch.zeros((1, res["bits"].shape[0]), dtype=torch.uint8, device=self.device)
-        flags[0, idx[chosen]] = 3
-        _, merged = ops.merge_masks(res["bits"][None], flags, h * w)
-        return merged.reshape(1, h, w), final
+        flags[0, chosen_global] = 3
+        merged_bits, merged = ops.merge_masks(res["bits"][None], flags, h * w, want_bits=True)
+        return merged_bits, merged.reshape(1, h, w)
+
+    def merge(self, res: dict) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Returns (merged mask float32 [1,H,W], mean score) like Matcher.mask_generation (:834)."""
+        sel = self.select(res)
+        _, merged = self.merge_selected(res, sel["chosen_global"])
+        final = sel["final_score"]
+        return merged, torch.as_tensor(final, device=self.device) if not torch.is_tensor(final) else final.to(self.device)
 
 
 class PatchMatcher:

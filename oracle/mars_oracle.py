@@ -17,7 +17,9 @@ Pinning: ``tests/golden/make_golden.py`` runs the *reference's own modules*
 inputs and commits inputs+outputs under ``tests/golden/``; the CPU test-suite
 checks this oracle against those vectors (alignment prior, prior refinement,
 proposal scoring / merging, evaluator + AverageMeter, SAM-AMG RLE / boxes /
-stability score, torchvision box NMS).  The builder-defined pieces
+stability score, torchvision box NMS, and the whole Matcher ancestry path -
+``set_reference`` -> ``patch_level_matching`` -> ``mask_generation`` with its ``RobustPromptSampler`` - by executing the
+reference's own method bodies, cut out of matcher/Matcher.py with ``ast``).  The builder-defined pieces
 (`pairwise_intersections`, `mask_nms`), the exact-EMD stand-in (POT is not
 installed anywhere we can run) and the Matcher assignment matching (scipy's
 LSAP tie-breaking is implementation-defined; compared by objective value) have
@@ -457,6 +459,121 @@ def matcher_merge_score_filter(scores: torch.Tensor, num_merging_mask: int, scor
     keep = keep * (distances_norm < score_norm)
     idx = rank[keep][:num_merging_mask]
     return idx.numpy(), scores[idx].mean()
+
+
+def _patch_centres(idx, g: int, patch_size: int, input_size):
+    """Unique patch indices -> sorted (x, y) patch-centre pixels inside the image (matcher/Matcher.py:519-543)."""
+    out = set()
+    for p in set(int(i) for i in idx):
+        x, y = (p % g) * patch_size + patch_size // 2, (p // g) * patch_size + patch_size // 2
+        if x < input_size[1] and y < input_size[0]:
+            out.add((x, y))
+    return sorted(out)
+
+
+def matcher_negative_priors(ref_feats: torch.Tensor, tar_feat: torch.Tensor, ref_masks_pool: torch.Tensor, g: int,
+                            patch_size: int, input_size, source: str):
+    """Negative point priors of Matcher (scipy LSAP, the reference's solver).
+
+    ``source="discarded"``: forward matches whose reverse match left the support mask, least similar half
+    (matcher/Matcher.py:304-348).  ``source="cost"``: the bidirectional matching run on ``C = (1 - S) / 2`` with
+    ``maximize=True``, keeping pairs whose reverse match lies outside the mask (:350-417) - including the reference's
+    indexing of the *unfiltered* forward columns with positions of the filtered, sorted costs (:386-398).
+    Returns (sorted (x, y) list or None, reduced_points_num or None).
+    """
+    from scipy.optimize import linear_sum_assignment
+
+    sim = ref_feats @ tar_feat.t()
+    mask = ref_masks_pool.flatten().bool()
+    idx_mask = mask.nonzero()[:, 0]
+    if source == "discarded":
+        s_fwd = sim[mask]
+        fr, fc = linear_sum_assignment(s_fwd.numpy(), maximize=True)
+        sim_f = s_fwd[fr, fc]
+        rr, rc = linear_sum_assignment(sim.t()[fc].numpy(), maximize=True)
+        discarded = torch.isin(torch.as_tensor(rc), idx_mask, invert=True)
+        if (discarded == False).all().item():  # noqa: E712
+            return None, None
+        cols, sims = torch.as_tensor(fc)[discarded], sim_f[discarded]
+        k = len(sims) // 2 if len(sims) > 40 else len(sims)
+        order = torch.sort(sims, descending=False)[1][:k]
+        return _patch_centres(cols[order].tolist(), g, patch_size, input_size), k
+    cost = (1 - sim) / 2
+    fr, fc = linear_sum_assignment(cost.numpy(), maximize=True)
+    cost_f = cost[fr, fc]
+    rr, rc = linear_sum_assignment(cost.t()[fc].numpy(), maximize=True)
+    retain = torch.isin(torch.as_tensor(rc), idx_mask, invert=True)
+    cost_kept = cost_f[retain] if not (retain == False).all().item() else cost_f  # noqa: E712
+    k = len(cost_kept) // 2 if len(cost_kept) > 40 else len(cost_kept)
+    pos = torch.sort(cost_kept, descending=True)[1][:k]
+    return _patch_centres(torch.as_tensor(fc)[pos].tolist(), g, patch_size, input_size), k
+
+
+def matcher_combinations(n: int, k: int):
+    """k-subsets of range(n) ordered by largest element, then recursively (matcher/Matcher.py:1212-1224)."""
+    if k > n:
+        return []
+    if k == 0:
+        return [[]]
+    return [c + [i] for i in range(n) for c in matcher_combinations(i, k - 1)]
+
+
+def matcher_sample_points(points, sample_range, max_iterations: int, negative_points=None, rng=None):
+    """Prompt subsets handed to SAM (matcher/Matcher.py:1226-1296); ``rng`` defaults to the ``random`` module, whose
+    calls are made in the reference's order."""
+    import random as _random
+
+    rng = rng or _random
+    samples, labels = [], []
+    n = len(points)
+    for size in range(min(sample_range[0], n), min(sample_range[1], n) + 1):
+        if n > 8:
+            index = [rng.sample(range(n), size) for _ in range(max_iterations)]
+        else:
+            index = matcher_combinations(n, size)
+        pos = np.take(points, index, axis=0)
+        samples.append(pos)
+        labels.append(np.ones((pos.shape[0], size)))
+        if negative_points is not None:
+            m = len(negative_points)
+            if n > 8 and m > 8:
+                index_neg = [rng.sample(range(m), size) for _ in range(max_iterations)]
+            else:
+                index_neg = [rng.choices(range(m), k=size) for _ in range(len(index))]
+            neg = np.take(negative_points, index_neg, axis=0)
+            samples.append(neg)
+            labels.append(np.zeros((neg.shape[0], size)))
+    if negative_points is None:
+        return samples, labels
+    return ([np.hstack((samples[i], samples[i + 1])) for i in range(0, len(samples), 2)],
+            [np.hstack((labels[i], labels[i + 1])) for i in range(0, len(labels), 2)])
+
+
+def matcher_generate_and_merge(masks: np.ndarray, all_points: np.ndarray, cost: torch.Tensor,
+                               ref_masks_pool: torch.Tensor, g: int, alpha: float, beta: float, exp: float, cfg: dict,
+                               num_merging_mask: int) -> dict:
+    """Scores, filters and merges SAM proposals like Matcher.mask_generation (matcher/Matcher.py:676-834).
+
+    ``masks`` bool ``[n,H,W]``.  EMD per mask on ``cost[support fg][:, pooled mask]`` with the empty-mask rule of
+    :1181-1185 (an empty pooled mask is scored against every patch, area = g*g); returns per-mask (purity, coverage,
+    emd), the merge order (mask indices), the merged mask and the final score."""
+    n = masks.shape[0]
+    pooled = pool_mask(torch.from_numpy(masks), g).reshape(n, -1).bool()
+    pooled[~pooled.any(dim=1)] = True
+    emd = torch.tensor([emd_score(ref_masks_pool, pooled[i], cost) for i in range(n)], dtype=torch.float32)
+    purity, coverage = matcher_mask_scores(masks, all_points, g)
+    for i in range(n):  # the empty-mask rule also changes the purity denominator
+        if not masks[i].any():
+            purity[i] = torch.tensor([0.0 / max(float(pooled[i].sum()), 1.0)])[0] + 1e-6
+    scores = matcher_fuse(emd, purity, coverage, alpha, beta, exp)
+    kept_scores, idx = matcher_metric_filter(scores, dict(purity=purity, coverage=coverage, emd=emd), cfg)
+    if cfg["score_filter"]:
+        chosen, final = matcher_merge_score_filter(kept_scores, num_merging_mask, cfg["score"], cfg["score_norm"])
+    else:
+        chosen, final = matcher_merge_topk(kept_scores, num_merging_mask, cfg["topk_scores_threshold"])
+    order = idx.numpy()[np.atleast_1d(chosen)]
+    merged = masks[order].sum(0) > 0
+    return dict(purity=purity, coverage=coverage, emd=emd, scores=scores, order=order, merged=merged, final=float(final))
 
 
 # --------------------------------------------------------------------------

@@ -230,3 +230,86 @@ def diag_inputs(spec):
     ref_mask = blob_masks(ns, g, g, spec["seed"] + 2, 0.1, 0.4).reshape(ns, n)
     tar_mask = blob_masks(1, g, g, spec["seed"] + 3, 0.1, 0.4).reshape(n)
     return dict(ref_raw=ref_raw, tar_raw=tar_raw, ref_mask=ref_mask, tar_mask=tar_mask)
+
+
+# ---- Matcher.predict through the reference's own methods (matcher/Matcher.py), fake encoder / SAM generator --------
+# All cases use the score-filter merge rule: the reference's top-k branch cannot run (it indexes a [1,H,W] array with
+# (y, x) at Matcher.py:822-827 and raises IndexError), so the top-k rule is checked against the oracle restatement only.
+# With negative priors enabled mask_generation raises as well (:782 iterates a list of point arrays), so those cases
+# switch the flags off after patch_level_matching and hand the first negative set on as plain discarded points.
+MATCHER_CASES = {
+    "g10_1shot_basic": dict(g=10, ps=14, ns=1, C=32, n_masks=14, seed=1201, alpha=1.0, beta=0.0, exp=0.0,
+                           num_merging_mask=5, sample_range=(2, 4), max_iter=6, neg_discarded=False, neg_cost=False,
+                           cfg=dict(emd=0.0, purity=0.0, coverage=0.0, score_filter=True, score=0.5, score_norm=0.05,
+                                    topk_scores_threshold=0.0)),
+    "g12_2shot_filters": dict(g=12, ps=14, ns=2, C=48, n_masks=18, seed=1202, alpha=0.8, beta=0.2, exp=1.0,
+                              num_merging_mask=6, sample_range=(1, 3), max_iter=5, neg_discarded=True, neg_cost=False,
+                              cfg=dict(emd=0.6, purity=0.02, coverage=0.05, score_filter=True, score=0.5,
+                                       score_norm=0.5, topk_scores_threshold=0.0)),
+    "g10_1shot_negcost": dict(g=10, ps=14, ns=1, C=32, n_masks=12, seed=1203, alpha=1.0, beta=0.5, exp=0.5,
+                              num_merging_mask=4, sample_range=(2, 3), max_iter=4, neg_discarded=False, neg_cost=True,
+                              cfg=dict(emd=0.0, purity=0.0, coverage=0.2, score_filter=True, score=0.45,
+                                       score_norm=0.8, topk_scores_threshold=0.0)),
+}
+
+
+def matcher_inputs(spec):
+    """Seeded inputs of a Matcher case: raw patch features, support masks, SAM-style proposals with the prompt points
+    the fake generator reports for them (independent of the sampled prompts, so both sides see the same proposals)."""
+    g, ps, ns, c = spec["g"], spec["ps"], spec["ns"], spec["C"]
+    n, size = g * g, g * ps
+    rs = np.random.RandomState(spec["seed"] + 7)
+    ref_raw = proto_features(ns * n, c, spec["seed"]) * 2.0 + 0.25
+    tar_raw = proto_features(n, c, spec["seed"] + 1) * 2.0 + 0.25
+    ref_masks = blob_masks(ns, size, size, spec["seed"] + 2, 0.08, 0.3).reshape(1, ns, size, size)
+    proposals = blob_masks(spec["n_masks"], size, size, spec["seed"] + 3, 0.01, 0.3).numpy() > 0
+    proposals[1] = False  # an empty proposal: the reference scores it against every patch (Matcher.py:1181-1185)
+    point_coords = [[[int(rs.randint(0, size)), int(rs.randint(0, size))] for _ in range(rs.randint(1, 4))]
+                    for _ in range(spec["n_masks"])]
+    ref_imgs = torch.zeros(1, ns, 3, size, size)
+    tar_img = torch.zeros(1, 3, size, size)
+    return dict(ref_raw=ref_raw, tar_raw=tar_raw, ref_masks=ref_masks, proposals=proposals, point_coords=point_coords,
+                ref_imgs=ref_imgs, tar_img=tar_img)
+
+
+class FakeSamGenerator:
+    """Stands in for SamAutomaticMaskGenerator: fixed proposals, records the prompts it was given."""
+
+    class _Model:
+        mask_threshold = 0.0
+
+    class _Predictor:
+        pass
+
+    def __init__(self, proposals, point_coords):
+        self.proposals, self.point_coords = proposals, point_coords
+        self.predictor = self._Predictor()
+        self.predictor.model = self._Model()
+        self.calls, self.resets = [], 0
+
+    def generate(self, image, select_point_coords=None, select_point_labels=None, select_box=None,
+                 select_mask_input=None):
+        self.calls.append(dict(coords=select_point_coords, labels=select_point_labels, box=select_box))
+        return [dict(segmentation=m, point_coords=pc) for m, pc in zip(self.proposals, self.point_coords)]
+
+    def reset_stored_features(self):
+        self.resets += 1
+
+
+class FakePatchEncoder(torch.nn.Module):
+    """DINOv2-shaped encoder stub: x_prenorm = [cls | patches], support call first, then the query."""
+    family = "vits"
+    num_register_tokens = 0
+
+    def __init__(self, ref_raw, tar_raw, ns, patch_size, embed_dim):
+        super().__init__()
+        n = tar_raw.shape[0]
+        self._feats = [torch.cat([torch.zeros(ns, 1, embed_dim), ref_raw.reshape(ns, n, embed_dim)], dim=1),
+                       torch.cat([torch.zeros(1, 1, embed_dim), tar_raw.reshape(1, n, embed_dim)], dim=1)]
+        self._i = 0
+        self.patch_size, self.embed_dim = patch_size, embed_dim
+
+    def forward_features(self, imgs):
+        out = self._feats[self._i % 2].to(imgs.device)
+        self._i += 1
+        return {"x_prenorm": out}

@@ -13,7 +13,7 @@ is replaced by the exact transport LP of ``oracle/mars_oracle.emd_exact``
 return seeded tensors, so the vectors pin everything the reference computes
 *after* the backbones.
 
-Outputs (small, committed): ``vva_*.npz``, ``pir_*.npz``, ``fm_*.npz``, ``eval_*.npz``, ``amg_*.npz``, ``diag_*.npz``.
+Outputs (small, committed): ``vva_*.npz``, ``pir_*.npz``, ``fm_*.npz``, ``eval_*.npz``, ``amg_*.npz``, ``diag_*.npz``, ``matcher_*.npz``.
 Inputs that would be large are regenerated from the recorded seed by
 ``tests/golden/cases.py`` and guarded by a checksum stored in the fixture.
 """
@@ -235,6 +235,96 @@ def gen_diag(name, spec, ref_root):
                                           stats["aposteriori_similarity_std"], stats["embeddings_euclidean_distance"]]))
 
 
+def load_reference_matcher(ref_root):
+    """`Matcher` and `RobustPromptSampler` of matcher/Matcher.py with every method body as it is in the reference.  The
+    module itself cannot be imported here (matplotlib, timm, POT, segment_anything), so the two class definitions are
+    cut out with `ast` (minus the plotting methods) and executed in a namespace that supplies their imports; `ot.emd2`
+    is the exact transport LP of the oracle (POT is not installed)."""
+    import ast
+    import random
+
+    import cv2
+    import torch.nn.functional as F
+    from scipy.optimize import linear_sum_assignment
+
+    tree = ast.parse(open(os.path.join(ref_root, "matcher", "Matcher.py")).read())
+    skip = {"visualize_internal_state", "set_visualizer_parameters", "positive_prompts_experiment",
+            "negative_prompts_from_discarded_experiment", "negative_prompts_from_cost_experiment"}
+    classes = []
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in ("Matcher", "RobustPromptSampler"):
+            node.body = [b for b in node.body if not (isinstance(b, ast.FunctionDef) and b.name in skip)]
+            classes.append(node)
+    assert len(classes) == 2
+    ot = types.SimpleNamespace(emd2=lambda a, b, M: np.float64(orc.emd_exact(np.asarray(M))))
+    ns_ = {"torch": torch, "F": F, "np": np, "cv2": cv2, "ot": ot, "random": random,
+           "linear_sum_assignment": linear_sum_assignment, "SamAutomaticMaskGenerator": object,
+           "kmeans_pp": None, "__name__": "reference_matcher"}
+    exec(compile(ast.Module(body=classes, type_ignores=[]), "Matcher.py[extract]", "exec"), ns_)
+    return ns_["Matcher"], ns_["RobustPromptSampler"]
+
+
+def gen_matcher(name, spec, ref_root):
+    """Matcher.predict of the reference, method bodies unchanged, on a fake encoder / SAM generator."""
+    import random
+
+    RefMatcher, _ = load_reference_matcher(ref_root)
+    c = cases.matcher_inputs(spec)
+    enc = cases.FakePatchEncoder(c["ref_raw"], c["tar_raw"], spec["ns"], spec["ps"], spec["C"])
+    gen = cases.FakeSamGenerator(c["proposals"], c["point_coords"])
+    size = spec["g"] * spec["ps"]
+    m = RefMatcher(encoder=enc, encoder_transforms=lambda x: x, generator=gen, input_size=size,
+                   sample_range=spec["sample_range"], max_sample_iterations=spec["max_iter"], alpha=spec["alpha"],
+                   beta=spec["beta"], exp=spec["exp"], score_filter_cfg=dict(spec["cfg"]),
+                   num_merging_mask=spec["num_merging_mask"],
+                   use_negative_priors_from_discarded=spec["neg_discarded"],
+                   use_negative_priors_from_cost=spec["neg_cost"], device=torch.device("cpu"))
+    m.set_reference(c["ref_imgs"], c["ref_masks"].clone())
+    m.set_target(c["tar_img"])
+    ref_feats, tar_feat = m.extract_img_feats()
+    pts, neg, box, S, C, reduced, reduced_neg = m.patch_level_matching(ref_feats, tar_feat)
+    m.set_rps()
+    per_mask = []
+    inner = m.rps.get_mask_scores
+
+    def recording(**kw):
+        out = inner(**kw)
+        per_mask.append((float(out[0][0]), float(out[1][0]), float(out[2])))
+        return out
+
+    m.rps.get_mask_scores = recording
+    random.seed(spec["seed"])
+    neg_for_generation = neg
+    if isinstance(neg, list):  # see cases.py: the reference cannot run mask_generation with negative priors enabled
+        m.use_negative_priors_from_discarded = m.use_negative_priors_from_cost = False
+        neg_for_generation = neg[0]
+    merged, final = m.mask_generation(m.tar_img_np, pts, box, pts, m.ref_masks_pool, C, neg_for_generation)
+    # prompt sampling on its own, from a known seed and point set
+    random.seed(spec["seed"] + 1)
+    demo_pts = np.arange(2 * 11).reshape(11, 2)
+    s_many, l_many = m.rps.sample_points(demo_pts, negative_points=demo_pts[:5] + 100)
+    s_few, l_few = m.rps.sample_points(demo_pts[:5])
+
+    def rows(a):
+        a = np.asarray(a).reshape(-1, 2)
+        return a[np.lexsort((a[:, 1], a[:, 0]))].astype(np.int64)
+
+    neg_rows = [rows(x) for x in neg] if isinstance(neg, list) else [rows(neg)]
+    stats = {**m.get_patch_matching_statistics(), **m.get_mask_generation_statistics()}
+    np.savez_compressed(
+        os.path.join(HERE, f"matcher_{name}.npz"), spec=np.asarray(repr(spec)),
+        ref_masks_pool=m.ref_masks_pool.numpy(), points=rows(pts), n_neg_sets=len(neg_rows),
+        **{f"neg{i}": r for i, r in enumerate(neg_rows)}, reduced=int(reduced),
+        reduced_neg=np.asarray([(-1 if r is None else r) for r in reduced_neg], dtype=np.int64),
+        sim=S.numpy(), per_mask=np.asarray(per_mask, dtype=np.float64), merged=merged.numpy() > 0,
+        final=float(final), merged_count=int(m.number_of_merged_masks),
+        masks_to_merge=(m.masks_to_merge.reshape(-1, size, size).numpy() > 0),
+        stats_keys=np.asarray(sorted(stats)), stats_vals=np.asarray([float(stats[k]) for k in sorted(stats)]),
+        sample_many=np.concatenate([x.reshape(-1) for x in s_many]), label_many=np.concatenate([x.reshape(-1) for x in l_many]),
+        sample_few=np.concatenate([x.reshape(-1) for x in s_few]), label_few=np.concatenate([x.reshape(-1) for x in l_few]),
+        combos_5_3=np.asarray(m.rps.combinations(5, 3)))
+
+
 def main():
     ref_root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     install_shims(ref_root)
@@ -251,6 +341,8 @@ def main():
         gen_amg(name, spec, ref_root)
     for name, spec in cases.DIAG_CASES.items():
         gen_diag(name, spec, ref_root)
+    for name, spec in cases.MATCHER_CASES.items():
+        gen_matcher(name, spec, ref_root)
 
 
 if __name__ == "__main__":

@@ -253,6 +253,28 @@ def test_pir_module_fp16_and_3d_maps(mb):
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=RTOL, atol=1e-7)
 
 
+@pytest.mark.parametrize("tokens", [38, 37, 70])
+@pytest.mark.parametrize("regs", [0, 3, 4])
+def test_attn_mean_fp16_layouts(mb, tokens, regs):
+    """fp16 attention maps: the paired-column kernel (even token count) and the scalar one (odd) against the oracle,
+    for even and odd numbers of skipped cls / register tokens."""
+    g = torch.Generator().manual_seed(tokens * 10 + regs)
+    maps = [torch.softmax(2 * torch.randn(1, 3, tokens, tokens, generator=g), dim=-1).half() for _ in range(4)]
+    ref = orc.attention_mean(maps, 3, regs)
+    got = mb.ops.attn_mean([a.to(dev()) for a in maps[-3:]], skip=1 + regs)
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=1e-3, atol=1e-6)  # one fp16 rounding of the mean
+    # a view that starts at an odd element: not 4-byte aligned, takes the scalar kernel, same numbers
+    flat = torch.zeros(3 * tokens * tokens + 1, dtype=torch.float16, device=dev())
+    shifted = []
+    for a in maps[-3:]:
+        buf = flat.clone()
+        buf[1:] = a.reshape(-1).to(dev())
+        shifted.append(buf[1:].view(3, tokens, tokens))
+    again = mb.ops.attn_mean(shifted, skip=1 + regs)
+    assert torch.equal(again, got)
+
+
 def test_resize_minmax(mb):
     x = torch.rand(3, 33, 33, generator=torch.Generator().manual_seed(3))
     out = mb.ops.resize_minmax(x.to(dev()), 37).reshape(3, 37, 37).cpu()
@@ -1127,3 +1149,113 @@ def test_pack_inside_a_partition_is_bit_exact(mb):
         np.testing.assert_array_equal(inter[0].cpu().numpy(), got.numpy())
     finally:
         part.close()
+
+
+# ------------------------------------------------------------------ Matcher drop-in against the reference's own methods
+@pytest.mark.parametrize("name", list(cases.MATCHER_CASES))
+def test_matcher_dropin_matches_reference(mb, name):
+    """marsb200.Matcher (same constructor and method signatures) against golden vectors produced by the reference's
+    Matcher / RobustPromptSampler method bodies on the same fake encoder and SAM generator."""
+    import random
+
+    z = np.load(os.path.join(GOLD, f"matcher_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.matcher_inputs(spec)
+    g, ps, size = spec["g"], spec["ps"], spec["g"] * spec["ps"]
+    enc = cases.FakePatchEncoder(c["ref_raw"], c["tar_raw"], spec["ns"], ps, spec["C"])
+    gen = cases.FakeSamGenerator(c["proposals"], c["point_coords"])
+    m = mb.Matcher(encoder=enc, encoder_transforms=lambda x: x, generator=gen, input_size=size,
+                   sample_range=spec["sample_range"], max_sample_iterations=spec["max_iter"], alpha=spec["alpha"],
+                   beta=spec["beta"], exp=spec["exp"], score_filter_cfg=dict(spec["cfg"]),
+                   num_merging_mask=spec["num_merging_mask"], use_negative_priors_from_discarded=spec["neg_discarded"],
+                   use_negative_priors_from_cost=spec["neg_cost"], device=dev())
+    m.set_reference(c["ref_imgs"], c["ref_masks"].clone())
+    m.set_target(c["tar_img"])
+    np.testing.assert_array_equal(m.ref_masks_pool.cpu().numpy(), z["ref_masks_pool"])
+    ref_feats, tar_feat = m.extract_img_feats()
+    pts, neg, box, S, C, reduced, reduced_neg = m.patch_level_matching(ref_feats, tar_feat)
+    np.testing.assert_allclose(S.cpu().numpy(), z["sim"], rtol=RTOL, atol=3e-6)
+    np.testing.assert_allclose(C.cpu().numpy(), (1 - z["sim"]) / 2, rtol=RTOL, atol=3e-6)
+
+    def rows(a):
+        a = np.asarray(a).reshape(-1, 2)
+        return a[np.lexsort((a[:, 1], a[:, 0]))].astype(np.int64)
+
+    np.testing.assert_array_equal(rows(pts), z["points"])
+    assert reduced == int(z["reduced"]) and box is None
+    neg_sets = neg if isinstance(neg, list) else [neg]
+    assert len(neg_sets) == int(z["n_neg_sets"])
+    np.testing.assert_array_equal(rows(neg_sets[0]), z["neg0"])
+    assert [(-1 if r is None else r) for r in reduced_neg] == z["reduced_neg"].tolist()
+    stats = dict(zip([str(k) for k in z["stats_keys"]], z["stats_vals"]))
+    for k, v in m.get_patch_matching_statistics().items():
+        assert v == stats[k], k
+
+    # mask generation: the reference cannot run it with negative priors switched on (cases.py), mirror the fixture
+    m.set_rps()
+    neg_for_generation = neg
+    if isinstance(neg, list):
+        m.use_negative_priors_from_discarded = m.use_negative_priors_from_cost = False
+        neg_for_generation = neg[0]
+    random.seed(spec["seed"])
+    merged, final = m.mask_generation(m.tar_img_np, pts, box, pts, m.ref_masks_pool, C, neg_for_generation)
+    assert merged.shape == (1, size, size) and merged.dtype == torch.float32 and merged.is_cuda
+    res = m.rps.batch_mask_scores(c["proposals"], pts, C, m.ref_masks_pool, spec["alpha"], spec["beta"], spec["exp"])
+    np.testing.assert_allclose(res["purity"].cpu().numpy(), z["per_mask"][:, 0], rtol=RTOL)
+    np.testing.assert_allclose(res["coverage"].cpu().numpy(), z["per_mask"][:, 1], rtol=RTOL)
+    np.testing.assert_allclose(res["emd"].cpu().numpy(), z["per_mask"][:, 2], rtol=RTOL)
+    np.testing.assert_array_equal(merged.cpu().numpy() > 0, z["merged"])
+    np.testing.assert_array_equal(m.get_masks_to_merge().cpu().numpy() > 0, z["masks_to_merge"])
+    assert abs(float(final) - float(z["final"])) <= RTOL * abs(float(z["final"]))
+    assert m.number_of_merged_masks == int(z["merged_count"])
+    got = m.get_mask_generation_statistics()
+    for k in ("number_of_masks_before_score_filtering", "number_of_points_usable_for_prediction",
+              "number_of_points_used_for_prediction", "positive_points_inside_mask", "negative_points_inside_mask",
+              "ratio_points_used_vs_usable", "ratio_negative_vs_positive_points_inside_mask"):
+        assert got[k] == pytest.approx(stats[k]), k
+    assert m.get_unfiltered_generated_masks().shape == (spec["n_masks"], size, size)
+    # the single-mask entry point of the sampler returns the reference's 6-tuple
+    pur, cov, emd_score, p_out, labels, ori = m.rps.get_mask_scores(points=pts, masks=c["proposals"][3][None],
+                                                                   all_points=pts, emd_cost=C,
+                                                                   ref_masks_pool=m.ref_masks_pool)
+    assert abs(float(pur[0]) - z["per_mask"][3, 0]) <= RTOL * z["per_mask"][3, 0] + 1e-9
+    assert abs(emd_score - z["per_mask"][3, 2]) <= RTOL and labels.shape == (len(pts),)
+    # predict() = the same stages end to end; clear() resets the state and the generator
+    m2 = mb.Matcher(encoder=cases.FakePatchEncoder(c["ref_raw"], c["tar_raw"], spec["ns"], ps, spec["C"]),
+                    encoder_transforms=lambda x: x, generator=gen, input_size=size, sample_range=spec["sample_range"],
+                    max_sample_iterations=spec["max_iter"], alpha=spec["alpha"], beta=spec["beta"], exp=spec["exp"],
+                    score_filter_cfg=dict(spec["cfg"]), num_merging_mask=spec["num_merging_mask"], device=dev())
+    m2.set_reference(c["ref_imgs"], c["ref_masks"].clone())
+    m2.set_target(c["tar_img"])
+    pred, score = m2.predict()
+    np.testing.assert_array_equal(pred.cpu().numpy() > 0, z["merged"])
+    assert abs(float(score) - float(z["final"])) <= RTOL * abs(float(z["final"]))
+    m2.clear()
+    assert m2.S is None and m2.ref_masks_pool is None and gen.resets == 1
+
+
+def test_matcher_dropin_topk_rule_and_empty_reference(mb):
+    """The top-k merge rule (the reference's own branch raises IndexError in its diagnostics, Matcher.py:822-827) against
+    the oracle restatement, and the all-zero support mask rule of set_reference (:150-154)."""
+    spec = dict(cases.MATCHER_CASES["g10_1shot_basic"])
+    spec["cfg"] = dict(spec["cfg"], score_filter=False, topk_scores_threshold=0.99)
+    c = cases.matcher_inputs(spec)
+    g, ps, size = spec["g"], spec["ps"], spec["g"] * spec["ps"]
+    gen = cases.FakeSamGenerator(c["proposals"], c["point_coords"])
+    m = mb.Matcher(encoder=cases.FakePatchEncoder(c["ref_raw"], c["tar_raw"], 1, ps, spec["C"]),
+                   encoder_transforms=lambda x: x, generator=gen, input_size=size, sample_range=spec["sample_range"],
+                   max_sample_iterations=spec["max_iter"], score_filter_cfg=spec["cfg"], num_merging_mask=5, device=dev())
+    m.set_reference(c["ref_imgs"], torch.zeros_like(c["ref_masks"]))
+    pool = m.ref_masks_pool.cpu().reshape(g, g)
+    assert pool.sum() == 4 and pool[g // 2 - 1:g // 2 + 1, g // 2 - 1:g // 2 + 1].all()  # rows 63..76 touch 2 x 2 patches
+    m.set_reference(c["ref_imgs"], c["ref_masks"].clone())
+    m.set_target(c["tar_img"])
+    pred, score = m.predict()
+    ref_n, tar_n = orc.normalize_rows(c["ref_raw"]), orc.normalize_rows(c["tar_raw"])
+    pooled = orc.pool_mask(c["ref_masks"][0], g).reshape(-1).float()
+    _, cost = orc.similarity_and_cost(ref_n, tar_n)
+    pts, _, _ = orc.matcher_patch_matching(ref_n, tar_n, pooled, g, ps, (size, size))
+    out = orc.matcher_generate_and_merge(c["proposals"], np.asarray(pts), cost, pooled, g, 1.0, 0.0, 0.0, spec["cfg"], 5)
+    np.testing.assert_array_equal(pred.cpu().numpy()[0] > 0, out["merged"])
+    assert abs(float(score) - out["final"]) <= RTOL * abs(out["final"])
+    assert m.number_of_merged_masks == len(out["order"])

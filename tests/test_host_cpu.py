@@ -141,3 +141,31 @@ def test_header_is_plain_c():
     code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)  # declarations only, comments stripped
     for banned in ("torch", "at::", "Tensor", "cudaStream_t", "std::"):
         assert banned not in code, banned
+
+
+def test_prompt_sampler_reproduces_reference_stream():
+    """RobustPromptSampler.combinations / sample_points of the drop-in against the golden vectors made by the reference's
+    own class with the same `random` seed (host-side logic, no device needed)."""
+    import ast
+    import random
+    import sys
+
+    import marsb200
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+
+    for name in cases.MATCHER_CASES:
+        z = np.load(os.path.join(ROOT, "tests", "golden", f"matcher_{name}.npz"))
+        spec = ast.literal_eval(str(z["spec"]))
+        rps = marsb200.RobustPromptSampler(spec["g"], spec["sample_range"], spec["max_iter"], device="cpu")
+        np.testing.assert_array_equal(np.asarray(rps.combinations(5, 3)), z["combos_5_3"])
+        assert rps.combinations(3, 4) == [] and rps.combinations(4, 0) == [[]]
+        random.seed(spec["seed"] + 1)
+        demo = np.arange(22).reshape(11, 2)
+        s_many, l_many = rps.sample_points(demo, negative_points=demo[:5] + 100)
+        s_few, l_few = rps.sample_points(demo[:5])
+        np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in s_many]), z["sample_many"])
+        np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in l_many]), z["label_many"])
+        np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in s_few]), z["sample_few"])
+        np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in l_few]), z["label_few"])

@@ -146,3 +146,50 @@ def test_matcher_diagnostics_match_reference(name):
     np.testing.assert_allclose([st["aposteriori_similarity_mean"], st["aposteriori_similarity_max"],
                                 st["aposteriori_similarity_std"], st["embeddings_euclidean_distance"]], z["stats"],
                                rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", list(cases.MATCHER_CASES))
+def test_matcher_pipeline_matches_reference(name):
+    """Matcher.set_reference / patch_level_matching / mask_generation / RobustPromptSampler (the reference's method
+    bodies, golden) vs the oracle restatement."""
+    import random
+
+    z = np.load(os.path.join(GOLD, f"matcher_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.matcher_inputs(spec)
+    g, ps, ns = spec["g"], spec["ps"], spec["ns"]
+    size = g * ps
+    pooled = orc.pool_mask(c["ref_masks"][0], g).reshape(-1).float()
+    np.testing.assert_array_equal(pooled.numpy(), z["ref_masks_pool"])
+    ref_n, tar_n = orc.normalize_rows(c["ref_raw"]), orc.normalize_rows(c["tar_raw"])
+    sim, cost = orc.similarity_and_cost(ref_n, tar_n)
+    np.testing.assert_allclose(sim.numpy(), z["sim"], rtol=1e-5, atol=1e-6)
+    pts, discarded, reduced = orc.matcher_patch_matching(ref_n, tar_n, pooled, g, ps, (size, size))
+    np.testing.assert_array_equal(np.asarray(pts), z["points"])
+    assert reduced == int(z["reduced"])
+    if spec["neg_discarded"] or spec["neg_cost"]:
+        neg, k = orc.matcher_negative_priors(ref_n, tar_n, pooled, g, ps, (size, size),
+                                             "discarded" if spec["neg_discarded"] else "cost")
+        np.testing.assert_array_equal(np.asarray(neg), z["neg0"])
+        assert k == int(z["reduced_neg"][0])
+    else:
+        np.testing.assert_array_equal(np.asarray(discarded), z["neg0"])
+    out = orc.matcher_generate_and_merge(c["proposals"], z["points"], cost, pooled, g, spec["alpha"], spec["beta"],
+                                         spec["exp"], spec["cfg"], spec["num_merging_mask"])
+    np.testing.assert_allclose(out["purity"].numpy(), z["per_mask"][:, 0], rtol=1e-6)
+    np.testing.assert_allclose(out["coverage"].numpy(), z["per_mask"][:, 1], rtol=1e-6)
+    np.testing.assert_allclose(out["emd"].numpy(), z["per_mask"][:, 2], rtol=1e-6)
+    np.testing.assert_array_equal(c["proposals"][out["order"]], z["masks_to_merge"])
+    np.testing.assert_array_equal(out["merged"], z["merged"][0])
+    assert abs(out["final"] - float(z["final"])) < 1e-6
+    assert len(out["order"]) == int(z["merged_count"])
+    # prompt sampling: same `random` stream, same subsets
+    np.testing.assert_array_equal(np.asarray(orc.matcher_combinations(5, 3)), z["combos_5_3"])
+    random.seed(spec["seed"] + 1)
+    demo = np.arange(22).reshape(11, 2)
+    s_many, l_many = orc.matcher_sample_points(demo, spec["sample_range"], spec["max_iter"], negative_points=demo[:5] + 100)
+    s_few, l_few = orc.matcher_sample_points(demo[:5], spec["sample_range"], spec["max_iter"])
+    np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in s_many]), z["sample_many"])
+    np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in l_many]), z["label_many"])
+    np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in s_few]), z["sample_few"])
+    np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in l_few]), z["label_few"])
