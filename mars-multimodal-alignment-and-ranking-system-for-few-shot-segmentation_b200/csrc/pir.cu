@@ -174,7 +174,9 @@ __global__ void colsum_final_kernel(const double* __restrict__ partial, int N, f
     double cs = 0.0;
 #pragma unroll
     for (int s = 0; s < COLSUM_SPLITS; ++s) cs += partial[(e * COLSUM_SPLITS + s) * N + col];
-    colsum[e * N + col] = (float)cs;
+    // stored as the correctly rounded reciprocal: the row kernel multiplies (its two IEEE divisions per element made it
+    // instruction-issue bound: 70 % issue-active, 3.5 TB/s); a * rcp(c) differs from a / c by less than two ulp
+    colsum[e * N + col] = __frcp_rn((float)cs);
 }
 
 __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restrict__ attn, int64_t ld, int N,
@@ -195,13 +197,13 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restr
 #pragma unroll
         for (int k = 0; k < RN_MAX; ++k) {
             const int c = threadIdx.x + k * 256;
-            vals[k] = c < N ? __fdiv_rn(a[c], colsum[e * N + c]) : 0.f;
+            vals[k] = c < N ? a[c] * colsum[e * N + c] : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < RN_MAX; ++k) acc += (double)vals[k];  // same order as the strided loop below
     } else {
         for (int c = threadIdx.x; c < N; c += blockDim.x) {
-            const float v = __fdiv_rn(a[c], colsum[e * N + c]);
+            const float v = a[c] * colsum[e * N + c];
             d[c] = v;
             acc += (double)v;
         }
@@ -211,13 +213,13 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restr
     __syncthreads();
     double total = 0.0;
     for (int w = 0; w < 8; ++w) total += s_red[w];
-    const float rs = (float)total;
+    const float rs = __frcp_rn((float)total);  // reciprocal of the row sum
     if (in_regs) {
 #pragma unroll
         for (int k = 0; k < RN_MAX; ++k) {
             const int64_t c = threadIdx.x + k * 256;
             if (c < k_pad) {
-                const float v = c < N ? __fdiv_rn(vals[k], rs) : 0.f;
+                const float v = c < N ? vals[k] * rs : 0.f;
                 d[c] = v;
                 dl[c] = tf32_residual(v);
             }
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const float* __restr
     }
     for (int64_t c = threadIdx.x; c < k_pad; c += blockDim.x) {
         float v = 0.f;
-        if (c < N) v = __fdiv_rn(d[c], rs);
+        if (c < N) v = d[c] * rs;
         d[c] = v;
         dl[c] = tf32_residual(v);
     }
