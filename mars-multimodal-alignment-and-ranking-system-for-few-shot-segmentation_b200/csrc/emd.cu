@@ -163,6 +163,39 @@ __global__ void __launch_bounds__(256) emd_sizes_kernel(const uint8_t* __restric
     if (lane == 0) key[lp] = (int64_t)t * m;
 }
 
+// Proposals of one episode with the same pooled bitmap are the same LP (same support rows, same columns): only the
+// first one is solved, the others copy its value.  SAM proposals that differ by a few pixels pool to identical
+// bitmaps all the time.  One warp per LP compares against the earlier LPs of the episode with the same size key.
+__global__ void __launch_bounds__(256) emd_dedupe_kernel(const uint32_t* __restrict__ pooled, int P, int npw, int64_t total,
+                                                          const int64_t* __restrict__ key, int32_t* __restrict__ dup_of) {
+    const int lane = threadIdx.x & 31;
+    const int64_t lp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (lp >= total) return;
+    const int64_t first = lp / P * P;
+    const int64_t mine = key[lp];
+    int32_t found = -1;
+    for (int64_t q = first; q < lp && found < 0; ++q) {
+        if (key[q] != mine) continue;
+        bool same = true;
+        for (int w = lane; w < npw; w += 32) same &= pooled[lp * npw + w] == pooled[q * npw + w];
+        if (__all_sync(0xffffffffu, same)) found = (int32_t)q;
+    }
+    if (lane == 0) dup_of[lp] = found;
+}
+
+// duplicates sort last and are skipped by the solver: their key becomes negative after every warp has read the keys
+__global__ void __launch_bounds__(256) emd_mark_dups_kernel(int64_t total, const int32_t* __restrict__ dup_of,
+                                                             int64_t* __restrict__ key) {
+    const int64_t lp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp < total && dup_of[lp] >= 0) key[lp] = -1;
+}
+
+__global__ void __launch_bounds__(256) emd_copy_dups_kernel(int64_t total, const int32_t* __restrict__ dup_of,
+                                                             double* __restrict__ out) {
+    const int64_t lp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp < total && dup_of[lp] >= 0) out[lp] = out[dup_of[lp]];
+}
+
 __global__ void __launch_bounds__(256) emd_rank_kernel(const int64_t* __restrict__ key, int64_t total,
                                                         int32_t* __restrict__ order, int32_t* __restrict__ counter) {
     __shared__ int64_t s_key[256];
@@ -311,7 +344,8 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
                                                            const uint32_t* __restrict__ pooled, int P, int64_t m_rows,
                                                            int N, int npw, int t_cap, int m_cap, int total_lps,
                                                            const int32_t* __restrict__ order, int32_t* __restrict__ counter,
-                                                           double* __restrict__ out, int* __restrict__ status) {
+                                                           const int32_t* __restrict__ dup_of, double* __restrict__ out,
+                                                           int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char emd_smem_raw[];
     // sources: the support rows (<= t_cap) or, transposed, a proposal with fewer than t_cap / 3 patches; sinks: either side
     EmdSmem s = emd_carve(emd_smem_raw, t_cap, max(t_cap, m_cap));
@@ -331,6 +365,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
         __syncthreads();
         const int64_t lp = s_lp;
         if (lp < 0) return;
+        if (dup_of[lp] >= 0) continue;  // same pooled bitmap as an earlier proposal of the episode: copied afterwards
 #ifdef MARSB200_EMD_PROFILE
         long long ep_acc[16] = {0};
         long long ep_last = clock64();
@@ -571,7 +606,7 @@ int64_t marsb200_emd_workspace_bytes(int E, int P, int N, int t_cap, int m_cap) 
     if (E <= 0 || P <= 0 || N <= 0 || t_cap <= 0) return 0;
     (void)m_cap;
     const int64_t lps = (int64_t)E * P;
-    return (lps * 8 + lps * 4 + 256 + 255) / 256 * 256;
+    return (lps * 8 + lps * 4 + lps * 4 + 256 + 255) / 256 * 256;  // size keys, order, duplicate links, queue head
 }
 
 int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t* pooled, int E, int P, int64_t m_rows,
@@ -601,14 +636,21 @@ int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t
     const int npw = ceil_div(N, 32);
     int64_t* key = reinterpret_cast<int64_t*>(workspace);
     int32_t* order = reinterpret_cast<int32_t*>(key + lps);
-    int32_t* counter = order + lps;
+    int32_t* dup_of = order + lps;
+    int32_t* counter = dup_of + lps;
     emd_sizes_kernel<<<(unsigned)ceil_div64(lps * 32, 256), 256, 0, s>>>(row_fg, pooled, P, m_rows, npw, lps, key);
+    MARS_LAUNCH_OK();
+    emd_dedupe_kernel<<<(unsigned)ceil_div64(lps * 32, 256), 256, 0, s>>>(pooled, P, npw, lps, key, dup_of);
+    MARS_LAUNCH_OK();
+    emd_mark_dups_kernel<<<(unsigned)ceil_div64(lps, 256), 256, 0, s>>>(lps, dup_of, key);
     MARS_LAUNCH_OK();
     emd_rank_kernel<<<(unsigned)ceil_div64(lps, 256), 256, 0, s>>>(key, lps, order, counter);
     MARS_LAUNCH_OK();
     const unsigned grid = (unsigned)std::min<int64_t>(lps, (int64_t)num_sms * emd_ctas_per_sm(t_cap, m_cap));
     emd_kernel<<<grid, EMD_THREADS, smem, s>>>(cost, row_fg, pooled, P, m_rows, N, npw, t_cap, m_cap, (int)lps, order,
-                                               counter, out, status);
+                                               counter, dup_of, out, status);
+    MARS_LAUNCH_OK();
+    emd_copy_dups_kernel<<<(unsigned)ceil_div64(lps, 256), 256, 0, s>>>(lps, dup_of, out);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }

@@ -68,7 +68,7 @@ def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int
     n += 1                     # pool_packed
     n += 2                     # region sums + union count
     if cfg.emd_on_device:
-        n += 3                 # exact EMD: problem sizes, processing order, the solver (one CTA per proposal)
+        n += 6                 # exact EMD: problem sizes, duplicate links + marks, processing order, the solver, copies
     n += 1                     # clip scores
     n += 1                     # fuse / rank / nms / select
     n += 1                     # merge

@@ -826,6 +826,33 @@ def test_emd_tight_caps_more_sources_than_sinks(mb):
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
 
 
+def test_emd_duplicate_proposals_share_one_lp(mb):
+    """Proposals of an episode with the same pooled bitmap (exact copies, one-pixel shifts, two empty masks) are one LP:
+    solved once, copied to the others - same values as solving each, per episode (a copy in ANOTHER episode has another
+    cost matrix and is not linked)."""
+    ns, g, p, h = 1, 12, 12, 168
+    d = dev()
+    costs, fgs, pooleds, wants = [], [], [], []
+    for e in range(2):
+        cost, support, masks = _emd_inputs(ns, g, p, h, seed=640 + e)
+        masks[5] = masks[2]
+        masks[9] = masks[2]
+        masks[7] = torch.roll(masks[4], 1, dims=1)  # usually the same pooled bitmap, sometimes not: both are fine
+        masks[3] = 0
+        masks[11] = 0
+        sup = orc.pool_mask(support, g).reshape(-1)
+        pm = orc.pool_mask(masks, g).reshape(p, -1)
+        wants.append([1.0 if not pm[i].any() else orc.emd_score(sup, pm[i], cost) for i in range(p)])
+        costs.append(cost)
+        fgs.append(mb.ops.pool_mask(support.to(d), g).reshape(-1))
+        pooleds.append(mb.ops.pool_packed(mb.ops.pack_masks(masks.to(d)), h, h, g)[0])
+    got = mb.ops.emd_scores(torch.stack(costs).to(d), torch.stack(fgs), torch.stack(pooleds)).cpu().numpy()
+    np.testing.assert_allclose(got, np.asarray(wants), rtol=0, atol=1e-9)
+    for e in range(2):
+        assert got[e, 5] == got[e, 2] == got[e, 9] and got[e, 3] == got[e, 11] == 1.0
+    assert got[0, 2] != got[1, 2]
+
+
 def test_emd_square_case_equals_assignment(mb):
     """T == M: the transport LP is an assignment problem; compare with scipy's exact LSAP at a larger size."""
     from scipy.optimize import linear_sum_assignment
