@@ -219,7 +219,7 @@ def run_reference(args):
     value = len(times) / total
     cores = os.cpu_count() or 1
     sample = f"{len(times)} episodes of {args.workload}, one per step, torch CPU with {cores} threads, EMD excluded"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "episodes_per_sec", "value": value, "unit": "episodes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -485,7 +485,7 @@ def run_ours(args):
                                                "transport LPs at the sampled one-core HiGHS rate"}
 
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "episodes_per_sec", "value": value, "unit": "episodes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+fp32(3xtf32)",
@@ -494,7 +494,8 @@ def run_ours(args):
                        "input_bytes_per_step_per_gpu": bytes_per_step,
                        "l2": "two resident batches alternate; each step's inputs exceed the 126 MB L2",
                        "gemm_backend": "tcgen05" if ops.DEFAULT_GEMM == ops.GEMM_TCGEN05 else "simt",
-                       "pair_backend": "popc" if ops.DEFAULT_PAIR == ops.PAIR_POPC else "mma",
+                       "pair_backend": {ops.PAIR_POPC: "popc", ops.PAIR_MMA: "mma (kind::i8)", ops.PAIR_FP4: "fp4 (kind::mxf4)",
+                                        ops.PAIR_AUTO: "auto: kind::mxf4 for P <= 256, kind::i8 above"}[ops.DEFAULT_PAIR],
                        "fused_ingest": bool(args.fused_ingest),
                        "sm_partition": ({"tensor_sms": eng._part.tensor_sms, "hbm_sms": eng._part.hbm_sms,
                                          "chunks": len(eng._chunks)} if eng._part is not None else None)},
@@ -507,7 +508,22 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_RESULT_STREAM = None
+
+
+def emit(line: str) -> None:
+    """The one JSON line of the contract, on the process's original stdout."""
+    out = _RESULT_STREAM or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL prints its version there) goes to
+    # stderr for the rest of the run
+    sys.stdout.flush()
+    _RESULT_STREAM = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

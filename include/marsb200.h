@@ -41,6 +41,8 @@ extern "C" {
 /* pairwise-intersection back ends */
 #define MARSB200_PAIR_POPC 0 /* shared-memory tiled AND + popcount */
 #define MARSB200_PAIR_MMA 1  /* bits expanded to int8 in shared memory, tcgen05 kind::i8 into TMEM */
+#define MARSB200_PAIR_FP4 2  /* P <= 256: bits expanded to e2m1 nibbles, tcgen05 kind::mxf4 with unit scale factors */
+#define MARSB200_PAIR_AUTO 3 /* FP4 when P <= 256 and HW < 2^24, int8 otherwise (same counts, bit for bit) */
 
 int marsb200_version(void);
 const char* marsb200_last_error(void);

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libmarsb200.so")
 
 MASK_F32, MASK_U8 = 0, 1
 GEMM_TCGEN05, GEMM_SIMT = 0, 1
-PAIR_POPC, PAIR_MMA = 0, 1
+PAIR_POPC, PAIR_MMA, PAIR_FP4, PAIR_AUTO = 0, 1, 2, 3
 
 
 class MarsB200Error(RuntimeError):

@@ -90,5 +90,6 @@ int sms_for_stream(cudaStream_t s, int* out);
 // internal back ends shared between translation units
 int pairwise_popc(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s);
 int pairwise_mma(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s);
+int pairwise_fp4(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s);
 
 }  // namespace marsb200

@@ -13,19 +13,19 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import GEMM_SIMT, GEMM_TCGEN05, MASK_F32, MASK_U8, PAIR_MMA, PAIR_POPC, check, lib
+from ._lib import GEMM_SIMT, GEMM_TCGEN05, MASK_F32, MASK_U8, PAIR_AUTO, PAIR_FP4, PAIR_MMA, PAIR_POPC, check, lib
 
 __all__ = [
     "words_per_mask", "pad_rows", "pad_k", "normalize_rows", "pool_mask", "sim_contract", "match_argmax", "mutual_matches", "lsap", "vva_finalize",
     "attn_mean", "pir_refine", "resize_minmax", "pack_masks", "pack_pairwise", "pool_packed", "region_sums", "pairwise_inter",
     "emd_scores", "clip_scores", "fuse_rank", "merge_masks", "points_in_masks", "matcher_scores", "eval_areas", "eval_accumulate", "eval_iou", "rle_decode", "mask_boxes", "stability_score", "box_nms", "masked_feature_means", "masked_sim_stats", "masked_row_mean",
-    "GEMM_TCGEN05", "GEMM_SIMT", "PAIR_POPC", "PAIR_MMA",
+    "GEMM_TCGEN05", "GEMM_SIMT", "PAIR_POPC", "PAIR_MMA", "PAIR_FP4", "PAIR_AUTO",
 ]
 
 # default back ends (module-level so tests can pin either one)
 # (MARSB200_GEMM=simt / MARSB200_PAIR=popc|mma select the validation kernels, for debugging only)
 DEFAULT_GEMM = GEMM_SIMT if os.environ.get("MARSB200_GEMM", "") == "simt" else GEMM_TCGEN05
-DEFAULT_PAIR = PAIR_POPC if os.environ.get("MARSB200_PAIR", "") == "popc" else PAIR_MMA
+DEFAULT_PAIR = {"popc": PAIR_POPC, "mma": PAIR_MMA, "fp4": PAIR_FP4}.get(os.environ.get("MARSB200_PAIR", ""), PAIR_AUTO)
 
 
 def _stream() -> int:

@@ -101,18 +101,38 @@ def test_pooling_matches_adaptive_max_pool(mb, h, g):
     np.testing.assert_array_equal(cnt.cpu().numpy(), ref.sum(1))
 
 
-@pytest.mark.parametrize("p,h", [(9, 100), (64, 140), (130, 200), (257, 64), (300, 96), (600, 64)])
-@pytest.mark.parametrize("backend", [0, 1], ids=["popc", "mma"])
+@pytest.mark.parametrize("p,h", [(9, 100), (64, 140), (130, 200), (256, 72), (257, 64), (300, 96), (600, 64)])
+@pytest.mark.parametrize("backend", [0, 1, 2, 3], ids=["popc", "mma", "fp4", "auto"])
 def test_pairwise_intersections_bit_exact(mb, p, h, backend):
     masks = cases.blob_masks(p, h, h, seed=p, min_frac=0.01, max_frac=0.3, dup_every=7)
     inter_ref, area_ref = orc.pairwise_intersections(masks)
     bits = mb.ops.pack_masks(masks.to(dev()))[None]
+    if backend == mb.ops.PAIR_FP4 and p > 256:  # one 256-row block only: refused, never silently something else
+        with pytest.raises(mb.MarsB200Error, match="256"):
+            mb.ops.pairwise_inter(bits, backend=backend)
+        return
     inter = mb.ops.pairwise_inter(bits, backend=backend)[0].cpu()
     assert torch.equal(inter, inter_ref)
     assert torch.equal(torch.diagonal(inter), area_ref)
 
 
-@pytest.mark.parametrize("backend", [0, 1], ids=["popc", "mma"])
+def test_pairwise_fp4_counts_are_exact_at_full_size(mb):
+    """Block-scaled FP4 products of 0/1 values accumulate in fp32: exact up to 2^24 pixels.  Dense and all-ones masks at
+    1024 x 1024 (every count = 2^20) against the int8 tensor-core kernel; sparse structured masks against popcount."""
+    d = dev()
+    g = torch.Generator(device=d).manual_seed(5)
+    m = (torch.rand(2, 256, 1024, 1024, device=d, generator=g) < 0.6).to(torch.uint8)
+    m[1, :40] = 1
+    m[0, 7] = 0
+    bits = mb.ops.pack_masks(m)
+    del m
+    fp4 = mb.ops.pairwise_inter(bits, backend=mb.ops.PAIR_FP4)
+    assert torch.equal(fp4, mb.ops.pairwise_inter(bits, backend=mb.ops.PAIR_MMA))
+    assert int(fp4[1, 3, 17]) == 1024 * 1024 and int(fp4[0, 7].abs().sum()) == 0
+    assert torch.equal(fp4[:, :32, :32], mb.ops.pairwise_inter(bits[:, :32].contiguous(), backend=mb.ops.PAIR_POPC))
+
+
+@pytest.mark.parametrize("backend", [0, 1, 2], ids=["popc", "mma", "fp4"])
 def test_pairwise_batched_episodes(mb, backend):
     masks = cases.blob_masks(3 * 20, 96, 96, seed=77).reshape(3, 20, 96, 96)
     bits = mb.ops.pack_masks(masks.to(dev()))
