@@ -169,3 +169,16 @@ def test_prompt_sampler_reproduces_reference_stream():
         np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in l_many]), z["label_many"])
         np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in s_few]), z["sample_few"])
         np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in l_few]), z["label_few"])
+
+
+def test_launch_count_follows_the_schedule():
+    """bench.py reports gpu_launches from this count: chunked pack / pool / pairwise on SM partitions, six EMD kernels."""
+    import marsb200
+    from marsb200 import RankingConfig, kernel_launches_per_run
+
+    base = kernel_launches_per_run(RankingConfig(nms_iou_threshold=0.7))
+    assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=0.7, tensor_partition_sms=56), 16) == base + 3 * 3
+    assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=0.7, tensor_partition_sms=56, partition_chunks=8), 2) == base + 3
+    assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=None, tensor_partition_sms=56), 16) == \
+        kernel_launches_per_run(RankingConfig(nms_iou_threshold=None)) + 2 * 3
+    assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=0.7, emd_on_device=True)) == base + 6
