@@ -252,12 +252,14 @@ def run_ours(args):
     E = args.episodes_per_step
     part_sms = args.tensor_partition_sms
     if part_sms < 0:
-        part_sms = 56 if (md == torch.float32 and args.workload == "c2" and not args.fused_ingest and E >= 8) else 0
-    # the headline loop runs the ingest and the contractions on disjoint SM partitions (same kernels, same results);
-    # the small-batch variants below (e2e, latency, full scoring) stay on one whole-device timeline
+        part_sms = 64 if (md == torch.float32 and args.workload == "c2" and not args.fused_ingest and E >= 8) else 0
+    # the headline loop runs the ingest and the contractions on disjoint SM partitions (same kernels, same results) and
+    # two buffer sets take the steps in turn, so the ingest of step i + 1 overlaps the scoring tail of step i; the
+    # small-batch variants below (e2e, latency, full scoring) stay on one whole-device timeline
     cfg_main = marsb200.RankingConfig(nms_iou_threshold=args.nms, fused_ingest=args.fused_ingest,
-                                      tensor_partition_sms=part_sms or None)
-    eng = marsb200.RankingEngine(shape, E, cfg_main, dev, md)
+                                      tensor_partition_sms=part_sms or None, partition_vta_on_hbm=False)
+    pipe = marsb200.PipelinedRanking(shape, E, cfg_main, dev, md, depth=2) if part_sms else None
+    eng = pipe.engines[0] if pipe is not None else marsb200.RankingEngine(shape, E, cfg_main, dev, md)
 
     # two distinct resident batches, alternated: every step reads inputs far larger than the 126 MB L2
     n_batches = 2
@@ -274,14 +276,30 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i):
-        out = eng.run(batches[i % n_batches])
+    def finish(ticket):
+        # results of a pipelined step: join it on this stream, then (multi-GPU) all-gather its records
+        if pipe is not None:
+            pipe.result(ticket)
         if world > 1:
-            marsb200.gather_records(eng.records(), total_episodes)
-        return out
+            marsb200.gather_records((pipe.engine(ticket) if pipe is not None else eng).records(), total_episodes)
 
-    for i in range(args.warmup):
-        step(i)
+    def run_steps(n):
+        """n steps back to back; with the pipeline the results of step i are collected after step i + 1 is enqueued,
+        the last one before returning (so every step's work and gather lie inside the caller's timed region)."""
+        prev = None
+        for i in range(n):
+            if pipe is not None:
+                ticket = pipe.submit(batches[i % n_batches])
+                if prev is not None:
+                    finish(prev)
+                prev = ticket
+            else:
+                eng.run(batches[i % n_batches])
+                finish(None)
+        if prev is not None:
+            finish(prev)
+
+    run_steps(args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -289,8 +307,7 @@ def run_ours(args):
     barrier()
     w0 = time.perf_counter()
     start.record()
-    for i in range(args.steps):
-        step(i)
+    run_steps(args.steps)
     stop.record()
     barrier()
     sampler.windows.append((w0, time.perf_counter()))
@@ -499,7 +516,8 @@ def run_ours(args):
                                         ops.PAIR_AUTO: "auto: kind::mxf4 for P <= 256, kind::i8 above"}[ops.DEFAULT_PAIR],
                        "fused_ingest": bool(args.fused_ingest),
                        "sm_partition": ({"tensor_sms": eng._part.tensor_sms, "hbm_sms": eng._part.hbm_sms,
-                                         "chunks": len(eng._chunks)} if eng._part is not None else None)},
+                                         "chunks": len(eng._chunks), "pipeline_depth": len(pipe.engines)}
+                                        if pipe is not None else None)},
             "clocks": clocks, "value_variants": value_variants, "e2e": e2e, "e2e_variants": e2e_variants,
             "gpu_launches": marsb200.kernel_launches_per_run(cfg_main, E) * args.steps * world,
             "roofline": roofline, "pairwise": pairwise, "fused_ingest": fused, "full_scoring": full,

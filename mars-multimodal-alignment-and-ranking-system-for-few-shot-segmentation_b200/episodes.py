@@ -77,7 +77,7 @@ def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int
 
 class RankingEngine:
     def __init__(self, shape: EpisodeShape, episodes_per_batch: int, cfg: RankingConfig, device,
-                 mask_dtype=torch.float32):
+                 mask_dtype=torch.float32, partition=None):
         if torch.device(device).type != "cuda":
             raise RuntimeError("RankingEngine needs a CUDA device (marsb200 has no CPU path)")
         self.shape, self.E, self.cfg, self.device = shape, episodes_per_batch, cfg, torch.device(device)
@@ -136,8 +136,12 @@ class RankingEngine:
         if cfg.tensor_partition_sms:
             from .partition import SmPartition
 
-            self._part = SmPartition(dev, cfg.tensor_partition_sms)
-            self._part_side = self._part.extra_stream("tensor")
+            # engines of one pipeline (PipelinedRanking) share the partition and its streams
+            self._part = partition if partition is not None else SmPartition(dev, cfg.tensor_partition_sms)
+            if not hasattr(self._part, "side_stream"):
+                self._part.side_stream = self._part.extra_stream("tensor")
+            self._part_side = self._part.side_stream
+            self._pending = False  # a partitioned step has been enqueued and not yet joined
             k = max(1, min(cfg.partition_chunks, e))
             per = (e + k - 1) // k
             self._chunks = [(lo, min(lo + per, e)) for lo in range(0, e, per)]
@@ -185,7 +189,7 @@ class RankingEngine:
             ops.pairwise_inter(self.bits, backend=cfg.pair_backend, out=self.inter)
             cur.wait_event(self._ev_pool)
 
-    def _run_partitioned(self, batch: dict) -> dict:
+    def _run_partitioned(self, batch: dict, wait: bool = True) -> dict:
         """The same kernel sequence on two disjoint SM sets.  `hbm` partition: pack (+ pooled bitmaps) of one episode
         chunk after the other, at the HBM roofline.  `tensor` partition: normalise -> S -> vva / vta refinement first
         (they do not depend on the masks), then the tensor-core pairwise kernel chunk by chunk as the packed bits
@@ -195,6 +199,9 @@ class RankingEngine:
         n, m = s.N, s.ns * s.N
         main = torch.cuda.current_stream()
         hbm, ten, side = part.hbm_stream, part.tensor_stream, self._part_side
+        if self._pending:  # this buffer set is reused: the previous step that ran in it must have drained
+            for st in (hbm, ten, side):
+                st.wait_event(self._ev_join)
         self._ev_fork.record(main)
         for st in (hbm, ten, side):
             st.wait_event(self._ev_fork)
@@ -248,14 +255,24 @@ class RankingEngine:
             ops.merge_masks(self.bits, self.rank_out["flags"], s.H * s.W, want_bits=True,
                             want_f32=cfg.want_merged_f32, out=self.merge_out)
             self._ev_join.record(ten)
-        main.wait_event(self._ev_join)
+        self._pending = True
+        if wait:
+            self.join()
         return self.outputs()
 
-    def run(self, batch: dict) -> dict:
+    def join(self) -> dict:
+        """Orders the current stream after the step enqueued by `run(..., wait=False)`; returns its outputs."""
+        if self._part is not None and self._pending:
+            torch.cuda.current_stream().wait_event(self._ev_join)
+        return self.outputs()
+
+    def run(self, batch: dict, wait: bool = True) -> dict:
+        """Enqueues one step.  With `wait=False` (partitioned schedule only) the current stream is NOT ordered after the
+        step - `join()` does that - so the next step's ingest can start while this one's tail is still running."""
         s, e, cfg = self.shape, self.E, self.cfg
         n, m = s.N, s.ns * s.N
         if self._part is not None and "masks" in batch and not cfg.fused_ingest and not self._capturing:
-            return self._run_partitioned(batch)
+            return self._run_partitioned(batch, wait)
         main = torch.cuda.current_stream()
         if self._side is not None:
             # the mask chain is HBM-bound and the alignment chain tensor/L2-bound: let them share the SMs
@@ -350,6 +367,37 @@ class RankingEngine:
                           r["scores"].float().view(torch.uint8).reshape(e, -1),
                           r["flags"].reshape(e, -1),
                           r["summary"].view(torch.uint8).reshape(e, -1)], dim=1).contiguous()
+
+
+class PipelinedRanking:
+    """Software pipeline over steps: `depth` buffer sets (RankingEngines) share one SM partition and take the steps in
+    turn, so the ingest of step i + 1 runs on the `hbm` partition while the tensor partition is still scoring step i.
+    `submit(batch)` enqueues a step and returns its ticket; `result(ticket)` orders the current stream after that step
+    and returns its outputs (valid until the same buffer set is submitted again, `depth` steps later)."""
+
+    def __init__(self, shape: EpisodeShape, episodes_per_batch: int, cfg: RankingConfig, device, mask_dtype=torch.float32,
+                 depth: int = 2):
+        if not cfg.tensor_partition_sms:
+            raise ValueError("PipelinedRanking needs cfg.tensor_partition_sms (the two-partition schedule)")
+        first = RankingEngine(shape, episodes_per_batch, cfg, device, mask_dtype)
+        self.engines = [first] + [RankingEngine(shape, episodes_per_batch, cfg, device, mask_dtype, partition=first._part)
+                                  for _ in range(depth - 1)]
+        self._next = 0
+
+    def submit(self, batch: dict) -> int:
+        ticket = self._next
+        self.engines[ticket % len(self.engines)].run(batch, wait=False)
+        self._next += 1
+        return ticket
+
+    def engine(self, ticket: int) -> "RankingEngine":
+        return self.engines[ticket % len(self.engines)]
+
+    def result(self, ticket: int) -> dict:
+        return self.engine(ticket).join()
+
+    def close(self):
+        self.engines[0]._part.close()
 
 
 def decode_records(records: torch.Tensor, p: int) -> dict:

@@ -1306,3 +1306,34 @@ def test_matcher_dropin_topk_rule_and_empty_reference(mb):
     np.testing.assert_array_equal(pred.cpu().numpy()[0] > 0, out["merged"])
     assert abs(float(score) - out["final"]) <= RTOL * abs(out["final"])
     assert m.number_of_merged_masks == len(out["order"])
+
+
+def test_pipelined_steps_match_one_timeline(mb):
+    """PipelinedRanking: two buffer sets on one SM partition, step i + 1 enqueued before step i is joined - every
+    step's outputs still equal the one-timeline engine's, bit for bit, and a buffer set is only reused after its
+    previous step has drained."""
+    shape = mb.EpisodeShape(ns=1, g=12, C=64, P=40, H=160, W=160, gt=9, D=32)
+    batches = [mb.to_device(mb.stack_episodes([mb.make_episode(shape, 500 + 4 * b + i) for i in range(4)]), dev())
+               for b in range(3)]
+    base = mb.RankingEngine(shape, 4, mb.RankingConfig(nms_iou_threshold=0.7), dev())
+    refs = [{k: v.clone() for k, v in base.run(b).items() if v is not None} for b in batches]
+    cfg = mb.RankingConfig(nms_iou_threshold=0.7, tensor_partition_sms=64, partition_chunks=2, partition_vta_on_hbm=False)
+    pipe = mb.PipelinedRanking(shape, 4, cfg, dev(), depth=2)
+    try:
+        prev = None
+        for i in range(7):
+            t = pipe.submit(batches[i % 3])
+            if prev is not None:
+                out = pipe.result(prev)
+                torch.cuda.synchronize()
+                for k, v in refs[prev % 3].items():
+                    assert torch.equal(out[k], v), (prev, k)
+                rec = mb.decode_records(pipe.engine(prev).records().cpu(), shape.P)
+                assert torch.equal(rec["order"], refs[prev % 3]["order"].cpu())
+            prev = t
+        out = pipe.result(prev)
+        torch.cuda.synchronize()
+        for k, v in refs[prev % 3].items():
+            assert torch.equal(out[k], v), (prev, k)
+    finally:
+        pipe.close()
