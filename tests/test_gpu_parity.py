@@ -1267,6 +1267,19 @@ def test_matcher_dropin_matches_reference(mb, name):
                                                                    ref_masks_pool=m.ref_masks_pool)
     assert abs(float(pur[0]) - z["per_mask"][3, 0]) <= RTOL * z["per_mask"][3, 0] + 1e-9
     assert abs(emd_score - z["per_mask"][3, 2]) <= RTOL and labels.shape == (len(pts),)
+    # diagnostics getters of the class (row A13) on the state this run left behind
+    ref_n, tar_n = orc.normalize_rows(c["ref_raw"]), orc.normalize_rows(c["tar_raw"])
+    pooled_ref = torch.from_numpy(z["ref_masks_pool"])
+    r2t = m.get_ref_to_target_similarity(ref_feats, tar_feat, m.ref_masks_pool)
+    np.testing.assert_allclose(r2t.reshape(-1).cpu().numpy(),
+                               orc.ref_to_target_similarity(ref_n, tar_n, pooled_ref.reshape(spec["ns"], -1)).reshape(-1).numpy(),
+                               rtol=RTOL, atol=1e-6)
+    st = m.get_aposteriori_statistics(merged)
+    tar_pool = orc.pool_mask(torch.from_numpy(z["merged"]).float(), g).reshape(-1)
+    want = orc.aposteriori_statistics(ref_n @ tar_n.t(), pooled_ref, tar_pool, c["ref_raw"], c["tar_raw"])
+    for k, v in want.items():
+        assert st[k] == pytest.approx(v, rel=1e-3, abs=1e-5), k
+    assert m.get_similarities()[0].shape[0] == int(pooled_ref.sum())
     # predict() = the same stages end to end; clear() resets the state and the generator
     m2 = mb.Matcher(encoder=cases.FakePatchEncoder(c["ref_raw"], c["tar_raw"], spec["ns"], ps, spec["C"]),
                     encoder_transforms=lambda x: x, generator=gen, input_size=size, sample_range=spec["sample_range"],
