@@ -260,6 +260,12 @@ class RankingEngine:
             self.join()
         return self.outputs()
 
+    def close(self) -> None:
+        """Releases the SM partition (green contexts and their streams) of an engine that owns one."""
+        if self._part is not None:
+            self._part.close()
+            self._part = None
+
     def join(self) -> dict:
         """Orders the current stream after the step enqueued by `run(..., wait=False)`; returns its outputs."""
         if self._part is not None and self._pending:
