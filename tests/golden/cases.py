@@ -313,3 +313,22 @@ class FakePatchEncoder(torch.nn.Module):
         out = self._feats[self._i % 2].to(imgs.device)
         self._i += 1
         return {"x_prenorm": out}
+
+
+# ---- MARS.predict end to end through the reference's own MARS / VisualVisualAlignmentModule / FilteringMergingModule ----
+MARS_CASES = {
+    "g10_2shot": dict(vva="g10_2shot", P=14, gt=8, D=24, seed=2101, alpha=0.85, static=0.55, dynamic=0.95, description=""),
+    "g10_allfg": dict(vva="g10_allfg", P=9, gt=7, D=16, seed=2102, alpha=0.7, static=0.4, dynamic=0.9,
+                      description="seen from above"),
+}
+
+
+def mars_inputs(spec):
+    v = VVA_CASES[spec["vva"]]
+    c = vva_inputs(v)
+    gen = _gen(spec["seed"])
+    masks = blob_masks(spec["P"], v["H"], v["H"], seed=spec["seed"] + 1, min_frac=0.02, max_frac=0.3)
+    vta_raw = torch.rand(spec["gt"], spec["gt"], generator=gen)
+    clip_img = torch.nn.functional.normalize(torch.randn(spec["P"], spec["D"], generator=gen), dim=1)
+    clip_txt = torch.nn.functional.normalize(torch.randn(spec["D"], generator=gen), dim=0)
+    return dict(c, masks=masks, vta_raw=vta_raw, clip_img=clip_img, clip_txt=clip_txt)

@@ -13,7 +13,7 @@ is replaced by the exact transport LP of ``oracle/mars_oracle.emd_exact``
 return seeded tensors, so the vectors pin everything the reference computes
 *after* the backbones.
 
-Outputs (small, committed): ``vva_*.npz``, ``pir_*.npz``, ``fm_*.npz``, ``eval_*.npz``, ``amg_*.npz``, ``diag_*.npz``, ``matcher_*.npz``.
+Outputs (small, committed): ``vva_*.npz``, ``pir_*.npz``, ``fm_*.npz``, ``eval_*.npz``, ``amg_*.npz``, ``diag_*.npz``, ``matcher_*.npz``, ``mars_*.npz``.
 Inputs that would be large are regenerated from the recorded seed by
 ``tests/golden/cases.py`` and guarded by a checksum stored in the fixture.
 """
@@ -325,6 +325,54 @@ def gen_matcher(name, spec, ref_root):
         combos_5_3=np.asarray(m.rps.combinations(5, 3)))
 
 
+def gen_mars(name, spec, ref_root):
+    """MARS.predict (mars/MARS.py:33-104, class body cut out with `ast`: the module imports nltk / CLIP / Grad-CAM) with
+    the reference's own VisualVisualAlignmentModule and FilteringMergingModule underneath, fake backbones, a fake text
+    retriever and a fake visual-text alignment component.  `ot.emd2` = the exact LP of the oracle (install_shims)."""
+    import ast
+    import time
+    from typing import Optional
+
+    import torch.nn.functional as F
+    from mars.components.FilteringMergingModule import FilteringMergingModule
+    from mars.components.VisualVisualAlignmentModule import VisualVisualAlignmentModule
+
+    tree = ast.parse(open(os.path.join(ref_root, "mars", "MARS.py")).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "MARS"]
+    ns_ = {"torch": torch, "F": F, "time": time, "Optional": Optional, "TextRetrieverModule": object,
+           "VisualTextAlignmentModule": object, "VisualVisualAlignmentModule": VisualVisualAlignmentModule,
+           "FilteringMergingModule": FilteringMergingModule}
+    exec(compile(ast.Module(body=cls, type_ignores=[]), "MARS.py[extract]", "exec"), ns_)
+    v = cases.VVA_CASES[spec["vva"]]
+    c = cases.mars_inputs(spec)
+    regs, cdim, h = v["regs"], v["C"], v["H"]
+    ns = c["feat_s"].shape[0]
+    pad = lambda f: torch.cat([torch.full((f.shape[0], 1 + regs, cdim), 7.0), f], dim=1)
+    vva_mod = VisualVisualAlignmentModule(
+        model=FakeDino([pad(c["feat_s"]), pad(c["feat_q"][None])], c["attn_maps"], cdim), model_transforms=lambda x: x,
+        model_patch_size=14, model_embedding_spatial_dimensions=v["g"], model_num_regs=regs,
+        vva_refinement_box_threshold=v["thr"], last_n_attention_maps_for_refinement=v["last_n"], device="cpu")
+    fm = FilteringMergingModule(
+        alpha_clip_model=FakeAlphaClip(c["clip_img"], c["clip_txt"]), img_transforms=lambda x: torch.zeros(3, 8, 8),
+        mask_transforms=lambda m: torch.from_numpy(m)[None].float(), alpha=spec["alpha"],
+        static_threshold=spec["static"], dynamic_threshold=spec["dynamic"], device="cpu")
+    seen = {}
+    inner = fm.compute
+
+    def recording(**kw):
+        seen.update(vva=kw["vva"].clone(), vta=kw["vta"].clone(), text=list(kw["text"]), g=kw["patch_features_spatial_dimension"])
+        return inner(**kw)
+
+    fm.compute = recording
+    text = types.SimpleNamespace(get_conceptual_information=lambda support_images, support_masks: ("thing", spec["description"]))
+    vta = types.SimpleNamespace(compute=lambda query_image, fg_label, bg_labels: c["vta_raw"])
+    mars = ns_["MARS"](text, vta, vva_mod, fm)
+    pred = mars.predict(torch.zeros(1, ns, 3, h, h), c["support_mask"][None], torch.zeros(1, 3, h, h), c["masks"])
+    np.savez_compressed(os.path.join(HERE, f"mars_{name}.npz"), spec=np.asarray(repr(spec)), merged=pred.numpy() > 0,
+                        vva=seen["vva"].numpy(), vta=seen["vta"].numpy(), text=np.asarray(seen["text"][0]), g=seen["g"])
+    print("mars", name, pred.shape, int((pred > 0).sum()), seen["text"])
+
+
 def main():
     ref_root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     install_shims(ref_root)
@@ -343,6 +391,8 @@ def main():
         gen_diag(name, spec, ref_root)
     for name, spec in cases.MATCHER_CASES.items():
         gen_matcher(name, spec, ref_root)
+    for name, spec in cases.MARS_CASES.items():
+        gen_mars(name, spec, ref_root)
 
 
 if __name__ == "__main__":

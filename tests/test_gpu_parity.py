@@ -618,6 +618,59 @@ def test_mars_predict_dropin(mb):
     assert vva_mod.cost_matrix is None
 
 
+@pytest.mark.parametrize("name", list(cases.MARS_CASES))
+def test_mars_predict_matches_reference_end_to_end(mb, name):
+    """The drop-in MARS / VisualVisualAlignmentModule / FilteringMergingModule (EMD solved on the device) against the
+    golden output of the reference's own classes run end to end on the same fake backbones (tests/golden/mars_*.npz)."""
+    z = np.load(os.path.join(GOLD, f"mars_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    v = cases.VVA_CASES[spec["vva"]]
+    c = cases.mars_inputs(spec)
+    g, h, cdim, regs = v["g"], v["H"], v["C"], v["regs"]
+    ns = c["feat_s"].shape[0]
+
+    class FakeDino(torch.nn.Module):
+        embed_dim = cdim
+
+        def __init__(self):
+            super().__init__()
+            pad = lambda f: torch.cat([torch.full((f.shape[0], 1 + regs, cdim), 7.0), f], dim=1).to(dev())
+            self.feats = [pad(c["feat_s"]), pad(c["feat_q"][None])]
+
+        def forward_features(self, imgs):
+            return {"x_prenorm": self.feats.pop(0)}
+
+        def get_last_self_attention(self, img):
+            return tuple(a.to(dev()) for a in c["attn_maps"])
+
+    class FakeText:
+        def get_conceptual_information(self, support_images, support_masks):
+            return "thing", spec["description"]
+
+    class FakeVTA:
+        def compute(self, query_image, fg_label, bg_labels):
+            return c["vta_raw"]
+
+    vva_mod = mb.VisualVisualAlignmentModule(FakeDino(), lambda x: x, 14, g, regs, v["thr"], v["last_n"], dev())
+    fm = mb.FilteringMergingModule(None, None, None, alpha=spec["alpha"], static_threshold=spec["static"],
+                                   dynamic_threshold=spec["dynamic"], device=dev())
+    seen = {}
+    orig = fm.compute
+
+    def compute(**kw):
+        seen.update(vva=kw["vva"], vta=kw["vta"], text=kw["text"])
+        return orig(alphaclip_feats=(c["clip_img"], c["clip_txt"]), **kw)
+
+    fm.compute = compute
+    mars = mb.MARS(FakeText(), FakeVTA(), vva_mod, fm)
+    pred = mars.predict(torch.zeros(1, ns, 3, h, h), c["support_mask"][None], torch.zeros(1, 3, h, h), c["masks"])
+    np.testing.assert_allclose(seen["vva"].reshape(g, g).cpu().numpy(), z["vva"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(seen["vta"].reshape(g, g).cpu().numpy(), z["vta"], rtol=RTOL, atol=1e-6)
+    assert seen["text"] == [str(z["text"])]
+    assert pred.shape == (h, h) and pred.dtype == torch.float32
+    np.testing.assert_array_equal(pred.cpu().numpy() > 0, z["merged"])
+
+
 @pytest.mark.parametrize("mode", ["topk", "score_filter", "metric_filter"])
 def test_matcher_scorer_merge(mb, mode):
     """MatcherScorer against the oracle restatement of matcher/Matcher.py:719-834."""

@@ -193,3 +193,34 @@ def test_matcher_pipeline_matches_reference(name):
     np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in l_many]), z["label_many"])
     np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in s_few]), z["sample_few"])
     np.testing.assert_array_equal(np.concatenate([x.reshape(-1) for x in l_few]), z["label_few"])
+
+
+@pytest.mark.parametrize("name", list(cases.MARS_CASES))
+def test_mars_predict_end_to_end_matches_reference(name):
+    """MARS.predict of the reference (its own MARS / VisualVisualAlignmentModule / FilteringMergingModule classes on
+    fake backbones, exact LP for ot.emd2) against the oracle's composition of the same stage, end to end: refined vva,
+    resized + min-max vta, the AlphaCLIP text and the merged mask."""
+    z = np.load(os.path.join(GOLD, f"mars_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    v = cases.VVA_CASES[spec["vva"]]
+    c = cases.mars_inputs(spec)
+    g = v["g"]
+    assert int(z["g"]) == g
+    fs, fq = orc.normalize_rows(c["feat_s"]), orc.normalize_rows(c["feat_q"])
+    _, cost = orc.similarity_and_cost(fs.reshape(-1, fs.shape[-1]), fq)
+    bits = orc.pool_mask(c["support_mask"], g).reshape(-1)
+    prior = orc.vva_prior(fs, fq, bits, g)
+    attn = orc.attention_mean(c["attn_maps"], v["last_n"], v["regs"])
+    vva = orc.minmax(orc.pir_refine(prior, attn, v["thr"]))
+    vta = orc.minmax(orc.nearest_resize(c["vta_raw"], (g, g)))
+    np.testing.assert_allclose(vva.numpy(), z["vva"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(vta.numpy(), z["vta"], rtol=1e-6, atol=1e-7)
+    text = "a thing." if spec["description"] == "" else f"a thing, {spec['description']}."
+    assert str(z["text"]) == text
+    pooled, cov, avv, avt = orc.region_scores(c["masks"], vva.numpy(), vta.numpy(), g)
+    emd = np.asarray([orc.emd_score(bits, torch.from_numpy(pm), cost) for pm in pooled])
+    scores = orc.fuse_scores(emd, orc.clip_scores(c["clip_img"], c["clip_txt"]), cov, avv, avt, spec["alpha"])
+    order = orc.stable_rank(scores)
+    sel = orc.merge_select(scores[order], spec["static"], spec["dynamic"])
+    merged = orc.merge_masks(c["masks"], order[sel])
+    np.testing.assert_array_equal(merged.numpy() > 0, z["merged"])
