@@ -19,7 +19,8 @@ checks this oracle against those vectors (alignment prior, prior refinement,
 proposal scoring / merging, evaluator + AverageMeter, SAM-AMG RLE / boxes /
 stability score, torchvision box NMS, and the whole Matcher ancestry path -
 ``set_reference`` -> ``patch_level_matching`` -> ``mask_generation`` with its ``RobustPromptSampler`` - by executing the
-reference's own method bodies, cut out of matcher/Matcher.py with ``ast``).  The builder-defined pieces
+reference's own method bodies, cut out of matcher/Matcher.py with ``ast`` - and ``MARS.predict`` end to end through the
+reference's ``MARS``, ``VisualVisualAlignmentModule`` and ``FilteringMergingModule`` classes).  The builder-defined pieces
 (`pairwise_intersections`, `mask_nms`), the exact-EMD stand-in (POT is not
 installed anywhere we can run) and the Matcher assignment matching (scipy's
 LSAP tie-breaking is implementation-defined; compared by objective value) have
