@@ -167,25 +167,49 @@ def workload_description(shape, args):
             f"pairwise intersections + IoU-NMS {args.nms}, fuse/rank, merge; EMD scores are an input")
 
 
+def workload_config(shape, args):
+    """The `config` object of the JSON line: the workload only, identical for both arms (how each arm schedules it is
+    reported under `schedule`)."""
+    return {"workload": workload_description(shape, args), "shots": shape.ns, "patches": shape.N, "feature_width": shape.C,
+            "proposals": shape.P, "proposal_resolution": [shape.H, shape.W], "mask_format": args.mask_dtype,
+            "nms_iou_threshold": args.nms, "emd": "input vector",
+            "l2": "inputs larger than L2: two resident batches alternate, each step reads far more than the 126 MB L2"}
+
+
+def load_synthetic():
+    """The synthetic-episode generator (pure torch) loaded by path: the reference arm must not import the product
+    package (importing `marsb200` maps libmarsb200.so)."""
+    import importlib.util
+
+    path = os.path.join(ROOT, "mars-multimodal-alignment-and-ranking-system-for-few-shot-segmentation_b200", "synthetic.py")
+    spec = importlib.util.spec_from_file_location("marsb200_synthetic_standalone", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def oracle_cfg(shape, args):
+    return dict(g=shape.g, vva_box_threshold=0.8, vta_box_threshold=0.4, alpha=0.85, static_threshold=0.55,
+                dynamic_threshold=0.95, nms_iou_threshold=args.nms)
+
+
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_episodes(shape, args, n_episodes, device_for_generation):
-    """Run the oracle port on `n_episodes` episodes with all host threads; returns (seconds per episode list)."""
-    import marsb200
+def cpu_reference_episodes(shape, args, episodes):
+    """Run the oracle port on the given CPU episodes (dicts of CPU tensors) with all host threads; returns
+    (seconds per episode, oracle results)."""
     from oracle import mars_oracle as orc
 
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = dict(g=shape.g, vva_box_threshold=0.8, vta_box_threshold=0.4, alpha=0.85, static_threshold=0.55,
-               dynamic_threshold=0.95, nms_iou_threshold=args.nms)
-    md = torch.float32 if args.mask_dtype == "f32" else torch.uint8
-    times = []
-    for i in range(n_episodes):
-        ep = marsb200.make_episode(shape, 10_000 + i, device_for_generation, md)
-        ep = {k: v.cpu() for k, v in ep.items()}
+    cfg = oracle_cfg(shape, args)
+    times, results = [], []
+    for ep in episodes:
+        ep = dict(ep)
         ep["masks"] = ep["masks"].float()  # the reference's wire format
         t0 = time.perf_counter()
-        orc.run_episode(ep, cfg)
+        results.append(orc.run_episode(ep, cfg))
         times.append(time.perf_counter() - t0)
-    return times
+    return times, results
 
 
 def cpu_emd_sample(shape, batch, n_lps):
@@ -206,15 +230,17 @@ def cpu_emd_sample(shape, batch, n_lps):
 
 
 def run_reference(args):
+    """The reference arm: the reference's algorithm (oracle port) on the host cores only.  Nothing of the product is
+    imported and CUDA is never initialised: episodes are generated on the CPU (two distinct ones, alternated)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import marsb200
-
-    shape = marsb200.CONFIGS[args.workload]
-    gen_dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    cpu_reference_episodes(shape, args, min(args.warmup, 1), gen_dev)  # one warm-up episode is enough on the CPU
-    times = cpu_reference_episodes(shape, args, args.steps, gen_dev)
+    syn = load_synthetic()
+    shape = syn.CONFIGS[args.workload]
+    md = torch.float32 if args.mask_dtype == "f32" else torch.uint8
+    eps = [syn.make_episode(shape, 10_000 + i, "cpu", md) for i in range(2)]
+    cpu_reference_episodes(shape, args, eps[:1])  # one warm-up episode is enough on the CPU
+    times, _ = cpu_reference_episodes(shape, args, [eps[i % 2] for i in range(args.steps)])
     total = sum(times)
     value = len(times) / total
     cores = os.cpu_count() or 1
@@ -223,7 +249,8 @@ def run_reference(args):
         "impl": "reference", "metric": "episodes_per_sec", "value": value, "unit": "episodes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": workload_description(shape, args)},
+        "config": workload_config(shape, args),
+        "schedule": {"episodes_per_step": 1, "device": "host CPU", "threads": cores},
         "cpu_baseline": {"value": value, "unit": "episodes/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -494,13 +521,39 @@ def run_ours(args):
         del eng_f
 
     clocks = sampler.stop()
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times = cpu_reference_episodes(shape, args, args.cpu_sample_episodes, dev)
+        # the CPU baseline runs on the SAME episodes the timed loop ranked (the first ones of resident batch 0) and
+        # doubles as the checker of what that loop produced: one more step of the timed schedule, then
+        # order / scores / intersections / keep-set / selection / merged mask against the oracle
+        n_chk = min(args.cpu_sample_episodes, E)
+        if pipe is not None:
+            out = pipe.result(pipe.submit(batches[0]))
+        else:
+            out = eng.run(batches[0])
+        torch.cuda.synchronize()
+        keys = ("row_fg", "prior", "vva", "vta", "pooled", "clip", "inter", "area", "scores", "order", "flags", "merged_bits")
+        got = {k: out[k][:n_chk].cpu() for k in keys if out.get(k) is not None}
+        eps_cpu = [{k: v[i].cpu() for k, v in batches[0].items()} for i in range(n_chk)]
+        times, refs = cpu_reference_episodes(shape, args, eps_cpu)
         cores = os.cpu_count() or 1
         cpu_baseline = {"value": len(times) / sum(times), "unit": "episodes/s", "cores": cores, "kind": "port",
                         "sample": f"{len(times)} episodes of {args.workload} through oracle.run_episode "
-                                  f"(torch CPU, {cores} threads, EMD excluded)"}
+                                  f"(torch CPU, {cores} threads, EMD excluded): the first episodes of the timed loop's "
+                                  f"resident batch 0"}
+        from oracle import compare
+
+        fails, swaps = [], 0
+        for i in range(n_chk):
+            res = compare.compare_episode(refs[i], {k: v[i] for k, v in got.items()}, eps_cpu[i]["masks"].float(),
+                                          oracle_cfg(shape, args))
+            fails += [f"episode {i}: {f}" for f in res["failures"]]
+            swaps += res["tie_swaps"]
+        parity = {"episodes": n_chk, "ok": not fails, "tie_swaps_within_tolerance": swaps, "failures": fails[:8],
+                  "checked": "support bits, prior, vva, vta, pooled bitmaps, clip, intersections, areas (bit-exact), "
+                             "scores (1e-4 rel), order, NMS keep-set, selection, merged mask (bit-exact) of the schedule "
+                             "the headline times"}
+        del got, eps_cpu, refs
         if full is not None:
             full["cpu_emd"] = cpu_emd_sample(shape, batches[0], args.cpu_emd_lps)
             per_episode = 1.0 / cpu_baseline["value"] + shape.P / full["cpu_emd"]["lps_per_s"]
@@ -514,9 +567,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+fp32(3xtf32)",
             "data": "synthetic",
-            "config": {"workload": workload_description(shape, args), "episodes_per_step_per_gpu": E,
-                       "input_bytes_per_step_per_gpu": bytes_per_step,
-                       "l2": "two resident batches alternate; each step's inputs exceed the 126 MB L2",
+            "config": workload_config(shape, args),
+            "schedule": {"episodes_per_step_per_gpu": E, "input_bytes_per_step_per_gpu": bytes_per_step,
                        "gemm_backend": "tcgen05" if ops.DEFAULT_GEMM == ops.GEMM_TCGEN05 else "simt",
                        "pair_backend": {ops.PAIR_POPC: "popc", ops.PAIR_MMA: "mma (kind::i8)", ops.PAIR_FP4: "fp4 (kind::mxf4)",
                                         ops.PAIR_AUTO: "auto: kind::mxf4 for P <= 256, kind::i8 above"}[ops.DEFAULT_PAIR],
@@ -527,7 +579,7 @@ def run_ours(args):
             "clocks": clocks, "value_variants": value_variants, "e2e": e2e, "e2e_variants": e2e_variants,
             "gpu_launches": marsb200.kernel_launches_per_run(cfg_main, E) * args.steps * world,
             "roofline": roofline, "pairwise": pairwise, "fused_ingest": fused, "full_scoring": full,
-            "single_episode_latency": lat, "cpu_baseline": cpu_baseline,
+            "single_episode_latency": lat, "cpu_baseline": cpu_baseline, "parity_checked": parity,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -130,6 +130,14 @@ int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, 
                         int apply_minmax, float* out, uint8_t* box_out, void* workspace, int64_t workspace_bytes,
                         int backend, void* stream);
 
+/* The box list behind the box mask: `_scoremap2bbox(scoremap, multi_contour_eval=True)` of
+ * PriorInformationRefinementModule.py:91-122.  prior [E, g*g]; boxes_out [E, g*g, 4] int32 (x0, y0, x1, y1) with the
+ * reference's clip x1 = min(x + w, g - 1), one per 8-connected component in raster order of its first pixel;
+ * count_out [E].  Hole contours (OpenCV RETR_TREE lists them too) are nested in their component's box and never change
+ * the mask, so they are not listed. */
+int marsb200_scoremap_boxes(const float* prior, int E, int g, double box_threshold, int32_t* boxes_out,
+                            int32_t* count_out, void* stream);
+
 /* Nearest-neighbour resize of [E, gs, gs] maps to [E, gd, gd] followed by min-max (eps 1e-7).
  * Replaces mars/MARS.py:77-82. */
 int marsb200_resize_minmax(const float* src, int E, int gs, int gd, int apply_minmax, float* out, void* stream);

@@ -59,10 +59,45 @@ class MARS:
         self.visual_visual_alignment_component.clear()
 
 
-def build_MARS_fss(args, text_retriever_component, visual_text_alignment_component, dino_model, dino_transforms,
-                   alpha_clip_model, alpha_clip_transforms, mask_generator=None):
-    """Assemble MARS from already-loaded PyTorch producers (the reference's builder loads them from disk,
-    mars/MARS.py:110-116; checkpoint loading is outside this package)."""
+def build_MARS_fss(args, text_retriever_component=None, visual_text_alignment_component=None, dino_model=None,
+                   dino_transforms=None, alpha_clip_model=None, alpha_clip_transforms=None, mask_generator=None):
+    """Assemble MARS (mars/MARS.py:110-116).
+
+    `build_MARS_fss(args)` - the reference's one-argument form: the PyTorch producers (ViP-LLaVA text retriever,
+    CLIP Grad-CAM component, DINOv2, AlphaCLIP) are loaded with the reference's own loaders, which must be importable
+    (the reference checkout on `sys.path`); the ranking components on top are this package's.  Any producer passed
+    explicitly is used as given, so already-loaded models are never loaded twice."""
+    import os
+
+    need_ref = [n for n, v in (("text retriever", text_retriever_component), ("visual-text component", visual_text_alignment_component),
+                               ("DINOv2", dino_model), ("AlphaCLIP", alpha_clip_model)) if v is None]
+    if need_ref:
+        try:  # mars/MARS.py:9-10, VisualVisualAlignmentModule.py:133-154, FilteringMergingModule.py:222-230
+            if text_retriever_component is None:
+                from mars.components.TextRetrieverModule import build_text_retriever_component
+                text_retriever_component = build_text_retriever_component(args=args)
+            if visual_text_alignment_component is None:
+                from mars.components.VisualTextAlignmentModule import build_visual_text_alignment_component
+                visual_text_alignment_component = build_visual_text_alignment_component(args=args)
+            if dino_model is None or alpha_clip_model is None:
+                from utils.backbone_loader import BackboneLoader
+            if dino_model is None:
+                weights = 'dinov2_vitl14_reg4_pretrain.pth' if args.num_regs == 4 else 'dinov2_vitl14_pretrain.pth'
+                dino_model, dino_transforms = BackboneLoader.load_backbone(
+                    backbone_name='dinov2', backbone_size=args.dino_backbone, device=args.device,
+                    backbone_weights_path=os.path.join(args.models_path, weights),
+                    encoder_kwargs=dict(img_size=args.input_size, patch_size=14, init_values=1e-5, ffn_layer='mlp',
+                                        block_chunks=0, num_register_tokens=args.num_regs, qkv_bias=True, proj_bias=True,
+                                        ffn_bias=True))
+            if alpha_clip_model is None:
+                alpha_clip_model, alpha_clip_transforms = BackboneLoader.load_backbone(
+                    backbone_name='alphaclip', backbone_size='ViT-L/14@336px', device=args.device,
+                    backbone_weights_path=os.path.join(args.models_path, 'clip_l14_336_grit_20m_4xe.pth'),
+                    encoder_kwargs={'device': args.device, 'download_root': args.models_path})
+        except ImportError as ex:
+            raise ImportError(f"build_MARS_fss(args): the {', '.join(need_ref)} producer(s) were not passed and the reference's "
+                              f"loaders are not importable ({ex}); put the reference checkout on sys.path or pass the "
+                              f"loaded PyTorch producers explicitly") from ex
     vva = VisualVisualAlignmentModule(
         model=dino_model, model_transforms=dino_transforms, model_patch_size=14,
         model_embedding_spatial_dimensions=args.input_size // 14, model_num_regs=args.num_regs,

@@ -32,9 +32,22 @@ class PriorInformationRefinementModule:
         return out.reshape(shape)
 
     def _scoremap2bbox(self, scoremap, multi_contour_eval: bool = False):
-        """Box mask the kernel builds for `scoremap` (uint8 [g,g]); the reference returns the box list instead."""
-        prior = torch.as_tensor(scoremap, dtype=torch.float32, device=self.device)
+        """`(boxes ndarray [k, 4] of (x0, y0, x1, y1), k)` like the reference (:91-122): one box per 8-connected
+        component of `uint8(scoremap * 255) > int(threshold * max)`, with the reference's clip `x1 = min(x + w, W - 1)`;
+        `[[0, 0, 0, 0]], 1` when nothing passes the threshold.  Computed by the same kernel that builds the box mask
+        inside `compute`.  Two documented differences to OpenCV's contour list: hole contours (nested in their
+        component's box, so they never change the mask) are not listed, and with `multi_contour_eval=False` the
+        component with the largest BOX area stands in for `cv2.contourArea` (the pipeline always passes True, :53-56)."""
+        import numpy as np
+
+        prior = torch.as_tensor(np.asarray(scoremap, dtype=np.float32), device=self.device)
         g = prior.shape[-1]
-        eye = torch.eye(g * g, device=self.device)[None]
-        _, box = ops.pir_refine(prior.reshape(1, -1), eye, g, self.threshold, want_box=True)
-        return box.reshape(g, g)
+        boxes, count = ops.scoremap_boxes(prior.reshape(1, -1), g, self.threshold)
+        k = int(count[0])
+        if k == 0:
+            return np.asarray([[0, 0, 0, 0]]), 1
+        out = boxes[0, :k].cpu().numpy().astype(np.int64)
+        if not multi_contour_eval:
+            area = (out[:, 2] - out[:, 0] + 1) * (out[:, 3] - out[:, 1] + 1)
+            return out[int(np.argmax(area))][None], 1
+        return out, k

@@ -1,6 +1,7 @@
 // Shared helpers for the marsb200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -32,6 +33,43 @@ inline int fail(int code, const char* fmt, const char* a = "", long long b = 0, 
 #define MARS_LAUNCH_OK() MARS_CUDA_OK(cudaGetLastError())
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Per-device, thread-safe "done once" flags and cached attributes.  Function attributes
+// (cudaFuncAttributeMaxDynamicSharedMemorySize) and the SM count belong to a DEVICE, not to the process: a host
+// process that drives several GPUs (or several host threads) must configure each device it touches.
+constexpr int MARS_MAX_DEVICES = 64;
+struct PerDeviceOnce {
+    std::atomic<int> done[MARS_MAX_DEVICES];
+};
+// Runs `fn` (-> cudaError_t) the first time the calling thread's current device meets `flag`; racing threads may both
+// run it (the configured attributes are idempotent), later calls cost one relaxed load.
+template <typename Fn>
+static inline cudaError_t per_device_once(PerDeviceOnce& flag, Fn fn) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= MARS_MAX_DEVICES) return fn();
+    if (flag.done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    e = fn();
+    if (e == cudaSuccess) flag.done[dev].store(1, std::memory_order_release);
+    return e;
+}
+// SM count of the calling thread's current device (cached per device)
+static inline cudaError_t device_sm_count(int* out) {
+    static std::atomic<int> cached[MARS_MAX_DEVICES];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool ok = dev >= 0 && dev < MARS_MAX_DEVICES;
+    int v = ok ? cached[dev].load(std::memory_order_acquire) : 0;
+    if (!v) {
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        if (ok) cached[dev].store(v, std::memory_order_release);
+    }
+    *out = v;
+    return cudaSuccess;
+}
 
 __host__ __device__ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

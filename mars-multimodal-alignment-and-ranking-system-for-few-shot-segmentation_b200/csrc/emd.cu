@@ -624,12 +624,8 @@ int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t
     const size_t smem = emd_smem_bytes(t_cap, std::max(t_cap, m_cap));
     MARS_REQUIRE(smem <= 200 * 1024, "t_cap + N too large for the shared-memory state");
     cudaStream_t s = as_stream(stream);
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        MARS_CUDA_OK(cudaGetDevice(&dev));
-        MARS_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int num_sms = 0;
+    MARS_CUDA_OK(device_sm_count(&num_sms));
     MARS_CUDA_OK(cudaFuncSetAttribute(emd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MARS_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
     const int64_t lps = (int64_t)E * P;

@@ -344,11 +344,10 @@ int gemm_tcgen05(const GemmOperand& a, const GemmOperand& b, int E, int64_t M, i
     if ((rc = make_operand_map(&maps[1], a.lo, a, E, K))) return rc;
     if ((rc = make_operand_map(&maps[2], b.p, b, E, K))) return rc;
     if ((rc = make_operand_map(&maps[3], b.lo, b, E, K))) return rc;
-    static bool configured = false;
-    if (!configured) {
-        MARS_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM_BYTES));
-        configured = true;
-    }
+    static PerDeviceOnce configured;  // the attribute is per device
+    MARS_CUDA_OK(per_device_once(configured, [] {
+        return cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM_BYTES);
+    }));
     int num_sms = 0;  // the stream's partition when it belongs to a green context
     if ((rc = sms_for_stream(s, &num_sms))) return rc;
     const int tiles_m = (int)ceil_div64(M, GEMM_BM), tiles_n = (int)ceil_div64(N, TC_BN);

@@ -201,15 +201,16 @@ extern "C" int marsb200_pack_pairwise(const void* masks, int mask_dtype, int E, 
     }
     const int total_kb = (int)(wpm / 4);
     // all CTAs resident at once (1 per SM): split the pixels so that E * ksplit <= 148
-    int ksplit = std::max(1, std::min(total_kb, 148 / E));
+    int device_sms = 148;
+    MARS_CUDA_OK(device_sm_count(&device_sms));
+    int ksplit = std::max(1, std::min(total_kb, device_sms / E));
     int kb_per_split = ceil_div(total_kb, ksplit);
     ksplit = ceil_div(total_kb, kb_per_split);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MARS_CUDA_OK(cudaFuncSetAttribute(pack_pairwise_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM_BYTES));
-        MARS_CUDA_OK(cudaFuncSetAttribute(pack_pairwise_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM_BYTES));
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_set;  // the attribute is per device
+    MARS_CUDA_OK(per_device_once(attr_set, [] {
+        cudaError_t e = cudaFuncSetAttribute(pack_pairwise_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM_BYTES);
+        return e != cudaSuccess ? e : cudaFuncSetAttribute(pack_pairwise_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM_BYTES);
+    }));
     MARS_CUDA_OK(cudaMemsetAsync(inter, 0, sizeof(int32_t) * (size_t)E * P * P, s));
     if (P == FZ_ROWS && HW % 1024 == 0)
         pack_pairwise_f32_kernel<true><<<dim3(ksplit, E), FZ_THREADS, FZ_SMEM_BYTES, s>>>((const float*)masks, P, HW, wpm,

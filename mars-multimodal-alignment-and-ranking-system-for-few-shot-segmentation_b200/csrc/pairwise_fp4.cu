@@ -209,11 +209,10 @@ int pairwise_fp4(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter
     if (P > PF_ROWS) return fail(MARSB200_ERR_UNSUPPORTED, "%s: at most 256 proposals (%lld given)", "pairwise_fp4", P);
     if (wpm * 32 >= (1ll << 24)) return fail(MARSB200_ERR_UNSUPPORTED, "%s: masks of 2^24 pixels or more", "pairwise_fp4");
     const int total_kb = (int)(wpm / 8);
-    static bool configured = false;
-    if (!configured) {
-        MARS_CUDA_OK(cudaFuncSetAttribute(pairwise_fp4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BYTES));
-        configured = true;
-    }
+    static PerDeviceOnce configured;  // the attribute is per device
+    MARS_CUDA_OK(per_device_once(configured, [] {
+        return cudaFuncSetAttribute(pairwise_fp4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BYTES);
+    }));
     int num_sms = 0;
     if (int rc = sms_for_stream(s, &num_sms)) return rc;
     const int waves = ceil_div(E, num_sms);

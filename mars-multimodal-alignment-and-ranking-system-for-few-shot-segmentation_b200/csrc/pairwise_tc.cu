@@ -201,11 +201,10 @@ int pairwise_mma(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter
     const int blocks = ceil_div(P, PM_ROWS);
     const int pairs = blocks * (blocks + 1) / 2;
     const int total_kb = (int)(wpm / 4);
-    static bool configured = false;
-    if (!configured) {
-        MARS_CUDA_OK(cudaFuncSetAttribute(pairwise_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PM_SMEM_BYTES));
-        configured = true;
-    }
+    static PerDeviceOnce configured;  // the attribute is per device
+    MARS_CUDA_OK(per_device_once(configured, [] {
+        return cudaFuncSetAttribute(pairwise_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PM_SMEM_BYTES);
+    }));
     int num_sms = 0;  // the stream's partition when it belongs to a green context
     if (int rc = sms_for_stream(s, &num_sms)) return rc;
     // one CTA per SM (all of TMEM, 193 KB of shared memory): split the pixels so that the launch fills whole waves

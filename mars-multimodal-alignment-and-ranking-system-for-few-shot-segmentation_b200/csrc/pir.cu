@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(256) attn_mean_h2_kernel(AttnPtrs maps, int n_
 // 91-122).  Writes B (uint8, optional) and v = B * prior.
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) box_mask_kernel(const float* __restrict__ prior, int g, double threshold,
-                                                       uint8_t* __restrict__ box_out, float* __restrict__ v_out) {
+                                                       uint8_t* __restrict__ box_out, float* __restrict__ v_out,
+                                                       int32_t* __restrict__ boxes_out, int32_t* __restrict__ count_out) {
     extern __shared__ int s_mem[];
     const int n = g * g;
     int* label = s_mem;          // n
@@ -144,7 +145,22 @@ __global__ void __launch_bounds__(256) box_mask_kernel(const float* __restrict__
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         if (box_out) box_out[e * n + i] = (uint8_t)boxm[i];
-        v_out[e * n + i] = boxm[i] ? p[i] : 0.f;
+        if (v_out) v_out[e * n + i] = boxm[i] ? p[i] : 0.f;
+    }
+    // optional box list (the reference's `_scoremap2bbox` return value, :112-122): one (x0, y0, x1, y1) per component,
+    // clipped like the fill above, in raster order of each component's first pixel.  Diagnostic output, off the hot path.
+    if (boxes_out && threadIdx.x == 0) {
+        int k = 0;
+        for (int i = 0; i < n; ++i) {
+            if (label[i] != i) continue;
+            int32_t* b = boxes_out + ((int64_t)e * n + k) * 4;
+            b[0] = bx0[i];
+            b[1] = by0[i];
+            b[2] = min(bx1[i] + 1, g - 1);
+            b[3] = min(by1[i] + 1, g - 1);
+            ++k;
+        }
+        count_out[e] = k;
     }
 }
 
@@ -320,6 +336,18 @@ int marsb200_attn_mean(const void* const* maps_host, int n_maps, int dtype, int 
     return MARSB200_OK;
 }
 
+int marsb200_scoremap_boxes(const float* prior, int E, int g, double box_threshold, int32_t* boxes_out,
+                            int32_t* count_out, void* stream) {
+    MARS_REQUIRE(prior && boxes_out && count_out, "null pointer");
+    MARS_REQUIRE(E > 0 && E <= 65535 && g > 0 && g <= 96, "shape (g <= 96)");
+    const size_t smem = (size_t)6 * g * g * sizeof(int);
+    if (smem > 48 * 1024)
+        MARS_CUDA_OK(cudaFuncSetAttribute(box_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    box_mask_kernel<<<E, 256, smem, as_stream(stream)>>>(prior, g, box_threshold, nullptr, nullptr, boxes_out, count_out);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
 int64_t marsb200_pir_workspace_bytes(int E, int64_t N) {
     if (E <= 0 || N <= 0) return 0;
     return carve(nullptr, E, N).bytes;
@@ -341,7 +369,7 @@ int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, 
     const size_t smem = (size_t)6 * N * sizeof(int);
     if (smem > 48 * 1024)
         MARS_CUDA_OK(cudaFuncSetAttribute(box_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    box_mask_kernel<<<E, 256, smem, s>>>(prior, g, box_threshold, box_out, w.v);
+    box_mask_kernel<<<E, 256, smem, s>>>(prior, g, box_threshold, box_out, w.v, nullptr, nullptr);
     MARS_LAUNCH_OK();
 
     colsum_partial_kernel<<<dim3(ceil_div(N, 128), COLSUM_SPLITS, E), 128, 0, s>>>(attn, ld_attn, N, w.partial);

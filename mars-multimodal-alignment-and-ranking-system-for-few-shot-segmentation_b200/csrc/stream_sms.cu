@@ -12,16 +12,13 @@ typedef CUresult (*StreamGetGreenCtxFn)(CUstream, CUgreenCtx*);
 typedef CUresult (*GreenCtxGetDevResourceFn)(CUgreenCtx, CUdevResource*, CUdevResourceType);
 
 int sms_for_stream(cudaStream_t stream, int* out) {
-    static int device_sms = 0;
+    int device_sms = 0;  // of the calling thread's current device (cached per device)
+    MARS_CUDA_OK(device_sm_count(&device_sms));
+    // driver entry points are process-wide; the lookup is idempotent, the flag is published last
     static StreamGetGreenCtxFn get_green = nullptr;
     static GreenCtxGetDevResourceFn get_res = nullptr;
-    static bool looked_up = false;
-    if (!device_sms) {
-        int dev = 0;
-        MARS_CUDA_OK(cudaGetDevice(&dev));
-        MARS_CUDA_OK(cudaDeviceGetAttribute(&device_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    if (!looked_up) {
+    static std::atomic<bool> looked_up{false};
+    if (!looked_up.load(std::memory_order_acquire)) {
         void *p0 = nullptr, *p1 = nullptr;
         cudaDriverEntryPointQueryResult q0, q1;
         if (cudaGetDriverEntryPoint("cuStreamGetGreenCtx", &p0, cudaEnableDefault, &q0) == cudaSuccess &&
@@ -32,7 +29,7 @@ int sms_for_stream(cudaStream_t stream, int* out) {
             get_res = reinterpret_cast<GreenCtxGetDevResourceFn>(p1);
         }
         (void)cudaGetLastError();
-        looked_up = true;
+        looked_up.store(true, std::memory_order_release);
     }
     *out = device_sms;
     if (!get_green || !stream) return MARSB200_OK;

@@ -236,6 +236,18 @@ def pir_refine(prior: torch.Tensor, attn: torch.Tensor, g: int, box_threshold: f
     return (out, box) if want_box else out
 
 
+def scoremap_boxes(prior: torch.Tensor, g: int, box_threshold: float):
+    """prior [E, g*g] -> (boxes int32 [E, g*g, 4] as (x0, y0, x1, y1), count int32 [E]): the per-component boxes behind
+    the PIR box mask (PriorInformationRefinementModule.py:91-122)."""
+    prior = _cuda(prior, torch.float32, "prior").reshape(-1, g * g)
+    e, n = prior.shape
+    boxes = torch.zeros((e, n, 4), device=prior.device, dtype=torch.int32)
+    count = torch.zeros((e,), device=prior.device, dtype=torch.int32)
+    check(lib.marsb200_scoremap_boxes(prior.data_ptr(), e, g, float(box_threshold), boxes.data_ptr(), count.data_ptr(),
+                                      _stream()))
+    return boxes, count
+
+
 def resize_minmax(src: torch.Tensor, gd: int, apply_minmax=True, out=None) -> torch.Tensor:
     src = _cuda(src, torch.float32, "src")
     gs = src.shape[-1]

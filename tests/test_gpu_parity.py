@@ -12,6 +12,7 @@ import pytest
 import torch
 
 import cases
+from oracle import compare
 from oracle import mars_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -263,6 +264,31 @@ def test_pir_matches_reference(mb, name, backend):
     np.testing.assert_allclose(out.reshape(g, g).cpu().numpy(), z["refined"], rtol=RTOL, atol=1e-7)
 
 
+@pytest.mark.parametrize("name", list(cases.PIR_CASES))
+def test_scoremap2bbox_returns_the_reference_boxes(mb, name):
+    """`_scoremap2bbox` keeps the reference's return type (boxes ndarray, count): every box is one of OpenCV's boxes of
+    the golden run (which may list hole contours in addition) and together they fill the same mask."""
+    z = np.load(os.path.join(GOLD, f"pir_{name}.npz"))
+    spec = ast.literal_eval(str(z["spec"]))
+    c = cases.pir_inputs(spec)
+    g = spec["g"]
+    pir = mb.PriorInformationRefinementModule(spec["thr"], spec["last_n"], dev(), num_regs=spec["regs"])
+    boxes, cnt = pir._scoremap2bbox(scoremap=c["prior"].numpy(), multi_contour_eval=True)
+    assert isinstance(boxes, np.ndarray) and boxes.shape == (cnt, 4)
+    gold = {tuple(int(v) for v in b) for b in z["boxes"][: int(z["cnt"])]}
+    assert {tuple(int(v) for v in b) for b in boxes} <= gold
+    b_ref, b_got = np.zeros((g, g), dtype=np.uint8), np.zeros((g, g), dtype=np.uint8)
+    for x0, y0, x1, y1 in z["boxes"][: int(z["cnt"])]:
+        b_ref[y0:y1, x0:x1] = 1
+    for x0, y0, x1, y1 in boxes:
+        b_got[y0:y1, x0:x1] = 1
+    np.testing.assert_array_equal(b_got, b_ref)
+    one, k = pir._scoremap2bbox(scoremap=c["prior"].numpy(), multi_contour_eval=False)
+    assert k == 1 and one.shape == (1, 4)
+    none, k0 = mb.PriorInformationRefinementModule(1.0, 1, dev())._scoremap2bbox(np.zeros((g, g), np.float32), True)
+    assert k0 == 1 and none.tolist() == [[0, 0, 0, 0]]
+
+
 def test_pir_module_fp16_and_3d_maps(mb):
     spec = cases.PIR_CASES["g33_border"]
     c = cases.pir_inputs(spec)
@@ -383,38 +409,18 @@ def _run_engine(mb, shape, n_ep, cfg, mask_dtype=torch.float32, seed0=0):
     return eps, eng, {k: (v.cpu() if v is not None else None) for k, v in out.items()}
 
 
-def _check_episode(mb, shape, cfg, ep, out, e):
-    ocfg = dict(g=shape.g, vva_box_threshold=cfg.vva_box_threshold, vta_box_threshold=cfg.vta_box_threshold,
-                alpha=cfg.alpha, static_threshold=cfg.static_threshold, dynamic_threshold=cfg.dynamic_threshold,
-                nms_iou_threshold=cfg.nms_iou_threshold)
-    ep = dict(ep)
+def _check_episode(mb, shape, cfg, ep, out, e, emd_fn=None):
+    """One episode of a device batch against `orc.run_episode` (oracle/compare.py): maps and scores within RTOL,
+    integer outputs bit-exact; the NMS keep-set, the selection and the merged mask are ALWAYS checked - on the device's
+    own order when a tolerated tie swapped two ranks."""
+    ocfg = compare.oracle_config(cfg, shape.g)
+    ep = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in ep.items()}
     ep["masks"] = ep["masks"].float()
-    ref = orc.run_episode(ep, ocfg)
-    n = shape.N
-    np.testing.assert_array_equal(out["row_fg"][e].reshape(-1).numpy() > 0, ref["support_bits"].numpy())
-    np.testing.assert_allclose(out["prior"][e].numpy(), ref["prior"].reshape(-1).numpy(), rtol=RTOL, atol=2e-5)
-    np.testing.assert_allclose(out["vva"][e].numpy(), ref["vva"].reshape(-1).numpy(), rtol=RTOL, atol=5e-5)
-    np.testing.assert_allclose(out["vta"][e].numpy(), ref["vta"].reshape(-1).numpy(), rtol=RTOL, atol=5e-5)
-    np.testing.assert_array_equal(unpack_pooled(out["pooled"][e], n), ref["pooled"].reshape(shape.P, -1))
-    np.testing.assert_allclose(out["clip"][e].numpy(), ref["clip"], rtol=RTOL, atol=1e-6)
-    if cfg.nms_iou_threshold is not None:
-        assert torch.equal(out["inter"][e], ref["inter"])
-        assert torch.equal(out["area"][e], ref["area"])
-    assert_order_matches(out["order"][e].numpy(), out["scores"][e].numpy(), ref["order"], ref["scores"])
-    if np.array_equal(out["order"][e].numpy(), ref["order"]):
-        flags = out["flags"][e].numpy()
-        if cfg.nms_iou_threshold is not None:
-            np.testing.assert_array_equal((flags & 1).astype(bool), ref["keep"])
-        sel = np.zeros(shape.P, dtype=bool)
-        sel[ref["selected"]] = True
-        # selection compares scores against thresholds; allow a flip only for a score within tolerance of the bound
-        top = ref["scores"][ref["order"][0]]
-        bound = cfg.dynamic_threshold * top if top < cfg.static_threshold else cfg.static_threshold
-        diff = np.nonzero(((flags & 2) > 0) != sel)[0]
-        assert all(abs(ref["scores"][i] - bound) <= RTOL * bound for i in diff)
-        if len(diff) == 0:
-            np.testing.assert_array_equal(out["merged"][e].reshape(shape.H, shape.W).numpy() > 0,
-                                          ref["merged"].numpy() > 0)
+    ref = orc.run_episode(ep, ocfg, emd_fn=emd_fn)
+    got = {k: (v[e] if v is not None else None) for k, v in out.items()}
+    res = compare.compare_episode(ref, got, ep["masks"], ocfg, rtol=RTOL)
+    assert res["ok"], res["failures"]
+    return ref, res
 
 
 @pytest.mark.parametrize("nms", [None, 0.7])
@@ -481,6 +487,113 @@ def test_full_size_properties_c2(mb):
     assert torch.equal(area2, area)
     ref_pool = torch.nn.functional.adaptive_max_pool2d(masks[:8, None], (shape.g, shape.g)).flatten(1) > 0
     np.testing.assert_array_equal(unpack_pooled(pooled[:8], shape.N), ref_pool.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------ BASELINE configs at FULL size
+def _cpu_out(out, keys=("row_fg", "prior", "vva", "vta", "pooled", "clip", "inter", "area", "scores", "order", "flags",
+                         "merged_bits", "emd")):
+    return {k: (out[k].cpu() if out.get(k) is not None else None) for k in keys}
+
+
+@pytest.mark.parametrize("mask_dtype", [torch.float32, torch.uint8])
+def test_engine_c2_full_against_oracle(mb, mask_dtype):
+    """BASELINE config 2 at full size (1-shot, N=1369, C=1024, P=256 at 1024x1024, IoU-NMS 0.7): two whole episodes
+    through RankingEngine against orc.run_episode - maps, pooled bitmaps, all 65 536 intersections, scores, order,
+    keep-set, selection and the merged mask (mars/MARS.py:62-101, FilteringMergingModule.py:59-140)."""
+    shape = mb.CONFIGS["c2"]
+    cfg = mb.RankingConfig(nms_iou_threshold=0.7, want_merged_f32=False)
+    batch = mb.stack_episodes([mb.make_episode(shape, 9000 + i, dev(), mask_dtype) for i in range(2)])
+    eng = mb.RankingEngine(shape, 2, cfg, dev(), mask_dtype)
+    out = eng.run(batch)
+    torch.cuda.synchronize()
+    out = _cpu_out(out)
+    for e in range(2):
+        _check_episode(mb, shape, cfg, {k: v[e] for k, v in batch.items()}, out, e)
+
+
+def test_engine_c2_full_pipelined_bench_schedule(mb):
+    """The exact schedule bench.py times: PipelinedRanking, 16 c2 episodes per step on two SM partitions, two buffer
+    sets, two resident batches alternating.  After three steps the records of steps 1 and 2 (first and last episode of
+    each) equal the oracle's results for those episodes."""
+    shape = mb.CONFIGS["c2"]
+    E = 16
+    cfg = mb.RankingConfig(nms_iou_threshold=0.7, tensor_partition_sms=64, partition_vta_on_hbm=False)
+    batches = [mb.stack_episodes([mb.make_episode(shape, 9200 + b * E + i, dev()) for i in range(E)]) for b in range(2)]
+    pipe = mb.PipelinedRanking(shape, E, cfg, dev(), depth=2)
+    try:
+        tickets = [pipe.submit(batches[0]), pipe.submit(batches[1])]
+        pipe.result(tickets[0])
+        tickets.append(pipe.submit(batches[0]))  # reuses buffer set 0 after its first step drained
+        for t in tickets[1:]:
+            out = pipe.result(t)
+            torch.cuda.synchronize()
+            rec = mb.decode_records(pipe.engine(t).records().cpu(), shape.P)
+            full = _cpu_out(out)
+            assert torch.equal(rec["order"], full["order"]) and torch.equal(rec["flags"], full["flags"])
+            for e in (0, E - 1):
+                _check_episode(mb, shape, cfg, {k: v[e] for k, v in batches[t % 2].items()}, full, e)
+    finally:
+        pipe.close()
+
+
+def test_engine_c3_full_against_oracle(mb):
+    """BASELINE config 3 at full size: 5-shot (6845 support rows), P=512 at 518x518 - one whole episode against the
+    oracle (P > 256: the intersections take the multi-block tensor-core path), plus the transport LPs of 16 proposals
+    solved on the device against the oracle's exact LP (FilteringMergingModule.py:142-169)."""
+    shape = mb.CONFIGS["c3"]
+    cfg = mb.RankingConfig(nms_iou_threshold=0.7, want_cost=True, want_merged_f32=False)
+    eps, eng, out = _run_engine(mb, shape, 1, cfg, seed0=9100)
+    ref, _ = _check_episode(mb, shape, cfg, eps[0], out, 0)
+    # 16 proposals spread over the size range (every 32nd of the proposals sorted by pooled patch count)
+    counts = ref["pooled"].reshape(shape.P, -1).sum(1)
+    pick = np.argsort(counts, kind="stable")[15::32][:16]
+    d = dev()
+    pooled = eng.pool_out[0][0][torch.as_tensor(pick, device=d)][None].contiguous()
+    t_fg = int(ref["support_bits"].sum())
+    emd = mb.ops.emd_scores(eng.gemm_out["cost"], eng.row_fg.reshape(1, -1), pooled, t_cap=(t_fg + 63) // 64 * 64)
+    torch.cuda.synchronize()
+    want = np.asarray([orc.emd_score(ref["support_bits"], torch.from_numpy(ref["pooled"][i]), ref["cost"]) for i in pick])
+    np.testing.assert_allclose(emd[0].cpu().numpy(), want, rtol=0, atol=2e-5)  # costs differ by ~1e-6 (3xTF32 vs MKL)
+
+
+def test_mask_chain_c4_full_against_oracle(mb):
+    """BASELINE config 4 at full size: P=1000 at 1024x1024 - all 10^6 intersections of the tensor-core kernel against
+    the oracle's blockwise exact contraction, then the NMS keep-set, selection and merged mask."""
+    shape = mb.CONFIGS["c4"]
+    d = dev()
+    gen = torch.Generator(device=d).manual_seed(4004)
+    from marsb200.synthetic import random_masks
+
+    masks = random_masks(shape.P, shape.H, shape.W, gen, d, dtype=torch.uint8)
+    bits = mb.ops.pack_masks(masks)[None]
+    inter = mb.ops.pairwise_inter(bits)
+    masks_cpu = masks.cpu()
+    inter_ref, area_ref = orc.pairwise_intersections(masks_cpu)
+    assert torch.equal(inter[0].cpu(), inter_ref)
+    p = shape.P
+    rs = np.random.RandomState(11)
+    scores = rs.rand(p)
+    cnt = torch.ones((1, p), dtype=torch.int32, device=d)
+    sv = torch.as_tensor(2 * scores, dtype=torch.float32, device=d).reshape(1, p)
+    uc = torch.ones((1,), dtype=torch.int32, device=d)
+    zero = torch.zeros((1, p), device=d)
+    res = mb.ops.fuse_rank(zero.double(), zero, cnt, sv, sv, uc, inter, alpha=1.0, static_threshold=0.9,
+                           dynamic_threshold=0.5, nms_iou_threshold=0.7)
+    s32 = (2 * scores).astype(np.float32).astype(np.float64) / (1e-7 + 1)
+    fused = (s32 + s32) / 4
+    order_expected = orc.stable_rank(fused)
+    np.testing.assert_array_equal(res["order"][0].cpu().numpy(), order_expected)
+    keep_expected = orc.mask_nms(order_expected, inter_ref, area_ref, 0.7)
+    flags = res["flags"][0].cpu().numpy()
+    np.testing.assert_array_equal((flags & 1).astype(bool), keep_expected)
+    sel_expected = np.zeros(p, dtype=bool)
+    sel_ranked = orc.merge_select(fused[order_expected], 0.9, 0.5) & keep_expected[order_expected]
+    sel_expected[order_expected[sel_ranked]] = True
+    np.testing.assert_array_equal((flags & 2) > 0, sel_expected)
+    merged_bits, _ = mb.ops.merge_masks(bits, res["flags"], shape.H * shape.W, want_bits=True, want_f32=False)
+    ref = orc.merge_masks(masks_cpu, np.nonzero(sel_expected)[0])
+    got = compare.unpack_bits(merged_bits.cpu().reshape(1, -1), shape.H * shape.W)[0]
+    np.testing.assert_array_equal(got, ref.reshape(-1).numpy() > 0)
 
 
 # ------------------------------------------------------------------------------------------ Matcher / evaluator
