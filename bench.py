@@ -43,6 +43,8 @@ def parse_args():
                     help="SMs of the tensor green-context partition for the device-resident loop (0 = one whole-device "
                          "timeline; -1 = 56 for float32 masks at c2, else 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify-gather", action="store_true", help="skip the multi-GPU check of the gathered record table")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short c1 / c3 / c4 runs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-emd", action="store_true", help="skip the full-scoring (device EMD) variant")
     ap.add_argument("--cpu-emd-lps", type=int, default=4, help="transport LPs timed on the host for the EMD baseline")
@@ -50,13 +52,24 @@ def parse_args():
     return ap.parse_args()
 
 
+def kernel_source_sha16(source="masks.cu"):
+    """sha256 (first 16 hex digits) of the CUDA source that holds the kernel: ties an ncu capture to the code it measured."""
+    import hashlib
+
+    path = os.path.join(ROOT, "mars-multimodal-alignment-and-ranking-system-for-few-shot-segmentation_b200", "csrc", source)
+    with open(path, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()[:16]
+
+
 def ncu_traffic_bytes(kernel, workload, episodes, mask_dtype):
-    """dram read+write bytes per launch of `kernel` from the committed `ncu --set full` capture, or None."""
+    """dram read+write bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json),
+    or None when no capture of THIS version of the kernel source exists (a stale capture says nothing about new code)."""
     try:
+        sha = kernel_source_sha16()
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             for row in json.load(f):
                 if (row["kernel"], row["workload"], row["episodes_per_launch"], row["mask_dtype"]) == \
-                        (kernel, workload, episodes, mask_dtype):
+                        (kernel, workload, episodes, mask_dtype) and row.get("source_sha16") == sha:
                     return row["dram_read_bytes"] + row["dram_write_bytes"]
     except Exception:
         pass
@@ -415,40 +428,81 @@ def run_ours(args):
              "achieved_gbs": pack_bytes / (fused_ms / 1e3) / 1e9, "frac_of_hbm_peak": pack_bytes / (fused_ms / 1e3) / 1e9 / peak,
              "unordered_pairs_per_s": pairs / (fused_ms / 1e3)}
 
-    # ---- end to end: pinned host inputs -> H2D -> ranking -> D2H of the result records, every step
-    def run_e2e(e2e_dtype, wire="dense"):
-        Ee = args.e2e_episodes_per_step
-        eng2 = marsb200.RankingEngine(shape, Ee, cfg, dev, e2e_dtype)
+    # ---- end to end: pinned host inputs -> H2D -> ranking -> D2H of the result records, every step.
+    # Two buffer sets (pinned host records, device inputs, engine) take the steps in turn: the H2D copy of step i + 1 runs on
+    # a copy stream while step i computes, the D2H of step i's records runs behind its compute on a third stream and the host
+    # reads them one step later.  Every byte of every step's inputs crosses PCIe inside the timed region (or, for the
+    # `backbone_resident` variants, every byte of the PROPOSALS: in the reference pipeline the DINOv2 / CLIP tensors are
+    # produced on the GPU and only the proposals are loaded from disk, main_MARS.py:62).
+    rle_cache = {}
+
+    def run_e2e(e2e_dtype, wire="dense", episodes=None, resident_backbone=False):
+        Ee = episodes or args.e2e_episodes_per_step
+        engs = [marsb200.RankingEngine(shape, Ee, cfg, dev, e2e_dtype) for _ in range(2)]
         host = {k: v[:Ee].cpu() for k, v in batches[0].items()}
         if wire == "rle":  # SAM's own output format: uncompressed COCO RLE, decoded on the device
-            counts, offsets = marsb200.masks_to_rle(host.pop("masks").reshape(-1, shape.H, shape.W))
-            host["mask_rle_counts"], host["mask_rle_offsets"] = counts, offsets
+            if Ee not in rle_cache:
+                rle_cache[Ee] = marsb200.masks_to_rle(host["masks"].reshape(-1, shape.H, shape.W))
+            host.pop("masks")
+            host["mask_rle_counts"], host["mask_rle_offsets"] = rle_cache[Ee]
         elif wire == "bits":  # proposals kept bit-packed by the producer
             host["mask_bits"] = ops.pack_masks(batches[0]["masks"][:Ee]).cpu()
             host.pop("masks")
         else:
             host["masks"] = host["masks"].to(e2e_dtype)
-        host = {k: v.pin_memory() for k, v in host.items()}
-        dev_in = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
-        rec_host = torch.empty((Ee, eng2.record_bytes()), dtype=torch.uint8).pin_memory()
+        mask_keys = [k for k in host if k.startswith("mask")]
+        moved = mask_keys if resident_backbone else list(host)
+        fixed = {k: host[k].to(dev) for k in host if k not in moved}  # produced on the device by the backbones
+        host = {k: host[k].pin_memory() for k in moved}
+        dev_in = [dict({k: torch.empty_like(v, device=dev) for k, v in host.items()}, **fixed) for _ in range(2)]
+        rec_host = [torch.empty((Ee, engs[0].record_bytes()), dtype=torch.uint8).pin_memory() for _ in range(2)]
         h2d = sum(v.numel() * v.element_size() for v in host.values())
-        d2h = rec_host.numel()
+        d2h = rec_host[0].numel()
+        main = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        ev_in = [torch.cuda.Event() for _ in range(2)]     # inputs of the set have landed
+        ev_done = [torch.cuda.Event() for _ in range(2)]   # the step that used the set has been computed
+        ev_out = [torch.cuda.Event() for _ in range(2)]    # its records are in host memory
 
-        def e2e_step():
-            for k in host:
-                dev_in[k].copy_(host[k], non_blocking=True)
-            eng2.run(dev_in)
-            rec_host.copy_(eng2.records(), non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller reads the result on the host
+        def upload(i):
+            b = i % 2
+            s_in.wait_event(ev_done[b])  # the set's previous step no longer reads these inputs
+            with torch.cuda.stream(s_in):
+                for k in host:
+                    dev_in[b][k].copy_(host[k], non_blocking=True)
+                ev_in[b].record(s_in)
 
-        for _ in range(args.warmup):
-            e2e_step()
+        def loop(n):
+            for b in range(2):
+                ev_done[b].record(main)
+            upload(0)
+            for i in range(n):
+                b = i % 2
+                if i + 1 < n:
+                    upload(i + 1)
+                main.wait_event(ev_in[b])
+                main.wait_event(ev_out[b])  # the records of the set's previous step have left the device
+                engs[b].run(dev_in[b])
+                rec = engs[b].records()
+                ev_done[b].record(main)
+                s_out.wait_event(ev_done[b])
+                with torch.cuda.stream(s_out):
+                    rec_host[b].copy_(rec, non_blocking=True)
+                    ev_out[b].record(s_out)
+                rec.record_stream(s_out)
+                if i >= 1:
+                    ev_out[(i - 1) % 2].synchronize()  # the caller reads step i - 1's result on the host
+            ev_out[(n - 1) % 2].synchronize()
+
+        for b in range(2):
+            ev_out[b].record(s_out)
+        loop(max(2, args.warmup))
         barrier()
         s2, t2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         s2.record()
-        for _ in range(args.steps):
-            e2e_step()
+        loop(args.steps)
+        main.wait_stream(s_out)
         t2.record()
         barrier()
         sampler.windows.append((w0, time.perf_counter()))
@@ -459,15 +513,24 @@ def run_ours(args):
             ms2 = float(t.item())
         return {"value": world * Ee * args.steps / (ms2 / 1e3), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "episodes_per_step": Ee, "ms_per_step": ms2 / args.steps,
+                "pcie_gbs": h2d * args.steps / (ms2 / 1e3) / 1e9,
+                "inputs_over_pcie": "proposals only (backbone tensors produced on the device)" if resident_backbone
+                                    else "every input of the step",
                 "host_mask_format": {"dense": "f32" if e2e_dtype == torch.float32 else "u8", "rle": "uncompressed COCO RLE",
                                      "bits": "packed bits"}[wire]}
 
     e2e, e2e_variants = None, None
     if not args.no_e2e:
         e2e = run_e2e(md)
+        e2e["note"] = ("PCIe-bound: the reference's float32 wire format is 1.1 GB per episode; `pcie_gbs` is the achieved "
+                       "host-to-device rate (H2D of step i + 1 overlaps the compute of step i)")
         if md == torch.float32:  # the same call with lighter proposal wire formats (PCIe carries far fewer bytes)
-            e2e_variants = {"u8_host_masks": run_e2e(torch.uint8), "rle_host_masks": run_e2e(md, "rle"),
-                            "packed_host_masks": run_e2e(md, "bits")}
+            Ev = min(E, 16)
+            e2e_variants = {"u8_host_masks": run_e2e(torch.uint8, episodes=4),
+                            "rle_host_masks": run_e2e(md, "rle", episodes=Ev),
+                            "packed_host_masks": run_e2e(md, "bits", episodes=Ev),
+                            "rle_host_masks_backbone_resident": run_e2e(md, "rle", episodes=Ev, resident_backbone=True),
+                            "packed_host_masks_backbone_resident": run_e2e(md, "bits", episodes=Ev, resident_backbone=True)}
 
     # ---- single-episode latency (the reference ranks one episode at a time, main_MARS.py:54-94): eager launches
     # and one CUDA-graph replay of the same kernel sequence
@@ -519,6 +582,74 @@ def run_ours(args):
                 "episodes_per_step": Ef, "ms_per_step": ms3, "value": world * Ef / (ms3 / 1e3), "unit": "episodes/s",
                 "emd_kernel_ms": emd_ms, "emd_lps_per_s": Ef * shape.P / (emd_ms / 1e3), "emd_m_cap": m_cap, "emd_t_cap": t_cap}
         del eng_f
+
+    # ---- the gathered record table equals the rank-local results (multi-GPU only): rank 0 regenerates every other rank's
+    # batch 0 from its seeds, ranks it locally and compares with that rank's slice of the all-gathered table
+    gather_check = None
+    if world > 1 and not args.no_verify_gather:
+        if pipe is not None:
+            out = pipe.result(pipe.submit(batches[0]))
+            local = pipe.engine(pipe._next - 1).records().clone()
+        else:
+            eng.run(batches[0])
+            local = eng.records().clone()
+        table = marsb200.gather_records(local, total_episodes)
+        torch.cuda.synchronize()
+        ok_local = bool(torch.equal(table[rank * E:(rank + 1) * E], local))
+        bad = []
+        if rank == 0:
+            chk = marsb200.RankingEngine(shape, E, cfg, dev, md)
+            for r in range(1, world):
+                eps = [marsb200.make_episode(shape, (r * n_batches + 0) * E + i, dev, md) for i in range(E)]
+                chk.run(marsb200.stack_episodes(eps))
+                del eps
+                if not torch.equal(table[r * E:(r + 1) * E], chk.records()):
+                    bad.append(r)
+            del chk
+        flag = torch.tensor([0 if ok_local else 1], device=dev)
+        dist.all_reduce(flag)
+        gather_check = {"ranks": world, "episodes": total_episodes, "ok": bool(flag.item() == 0) and not bad,
+                        "ranks_with_wrong_slices": bad,
+                        "how": "every rank: own slice of the gathered table == local records; rank 0: recomputed every other "
+                               "rank's episodes from their seeds on its own GPU, bit-equal records"}
+
+    # ---- the other BASELINE configs, device-resident, one timeline, a few steps each (driver-visible)
+    def other_config(name, episodes, mask_dt):
+        shp = marsb200.CONFIGS[name]
+        dt = torch.float32 if mask_dt == "f32" else torch.uint8
+        bs = [marsb200.stack_episodes([marsb200.make_episode(shp, 777 + (rank * 2 + b) * episodes + i, dev, dt)
+                                       for i in range(episodes)]) for b in range(2)]
+        en = marsb200.RankingEngine(shp, episodes, cfg, dev, dt)
+        for i in range(3):
+            en.run(bs[i % 2])
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(3):
+            en.run(bs[i % 2])
+        a1.record()
+        barrier()
+        ms = a0.elapsed_time(a1) / 3
+        pk = time_kernel(lambda i: ops.pack_masks(bs[i % 2]["masks"], out=en.bits), 4)
+        pr = time_kernel(lambda i: ops.pairwise_inter(en.bits, backend=cfg.pair_backend, out=en.inter), 4)
+        hw_, wpm_ = shp.H * shp.W, ops.words_per_mask(shp.H * shp.W)
+        pack_b = episodes * shp.P * (hw_ * (4 if dt == torch.float32 else 1) + wpm_ * 4)
+        prs = episodes * shp.P * (shp.P + 1) // 2
+        res = {"episodes_per_step": episodes, "mask_format": mask_dt, "value": world * episodes / (ms / 1e3),
+               "unit": "episodes/s", "ms_per_step": ms, "proposals": shp.P, "shots": shp.ns,
+               "resolution": [shp.H, shp.W],
+               "pack_kernel": {"ms": pk, "gbs": pack_b / (pk / 1e3) / 1e9, "frac_of_hbm_peak": pack_b / (pk / 1e3) / 1e9 / peak},
+               "pairwise_kernel": {"ms": pr, "unordered_pairs_per_s": prs / (pr / 1e3),
+                                   "backend": "kind::mxf4" if shp.P <= 256 else "kind::i8"},
+               "dominant_kernel": "pack_masks" if pk >= pr else "pairwise_inter"}
+        del en, bs
+        torch.cuda.empty_cache()
+        return res
+
+    other = None
+    if args.workload == "c2" and not args.no_other_configs:
+        other = {"c1": other_config("c1", 16, "f32"), "c3": other_config("c3", 8, "f32"),
+                 "c4": other_config("c4", 2, "f32")}
 
     clocks = sampler.stop()
     cpu_baseline, parity = None, None
@@ -580,6 +711,7 @@ def run_ours(args):
             "gpu_launches": marsb200.kernel_launches_per_run(cfg_main, E) * args.steps * world,
             "roofline": roofline, "pairwise": pairwise, "fused_ingest": fused, "full_scoring": full,
             "single_episode_latency": lat, "cpu_baseline": cpu_baseline, "parity_checked": parity,
+            "gather_verified": gather_check, "other_configs": other,
         }))
     if world > 1:
         dist.destroy_process_group()

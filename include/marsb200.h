@@ -179,11 +179,15 @@ int marsb200_pack_pairwise(const void* masks, int mask_dtype, int E, int P, int6
  * matcher/Matcher.py:1187-1194, solved exactly on integer flows (primal-dual method: multi-source shortest-path
  * phases, all sinks at the minimum distance settled per step), one CTA per proposal, largest problems first.
  * cost [E, m_rows, N] fp32 ((1 - S) / 2 from marsb200_sim_contract); row_fg [E, m_rows] uint8; pooled [E, P, ceil(N/32)].
- * t_cap / m_cap bound the number of fg rows / of pooled patches per proposal the shared-memory state and the
- * workspace are sized for (m_cap <= 0 means N; a smaller m_cap lets more problems share an SM).  *status receives 0,
- * the needed t_cap, or (1 << 24) + needed m_cap if a problem exceeded the caps (its score is NaN), -1 on an internal
- * capacity fault.  An empty proposal or empty support scores 1.0 (zero transport).  workspace: 256-byte aligned. */
-int64_t marsb200_emd_workspace_bytes(int E, int P, int N, int t_cap, int m_cap);
+ * t_cap / m_cap size the FAST PATH (solver state in shared memory): the number of fg rows / of pooled patches per proposal
+ * it is laid out for (<= 0: all rows / N; clamped to what fits 200 KB; a smaller m_cap lets more problems share an SM).
+ * A problem beyond those caps is not an error: it is queued for a second launch of the same solver whose state lives in a
+ * per-CTA slab of the workspace (global memory), sized for ANY problem of the episode shape - so, like ot.emd2, there is no
+ * capacity limit (5-shot episodes with large support masks included) up to the 16-bit index range (about 8000 fg rows;
+ * beyond it the score is NaN and *status receives the row count, or (1 << 24) + the patch count).  *status: 0 = every
+ * problem solved, -1 = internal capacity fault (score NaN).  An empty proposal or empty support scores 1.0 (zero
+ * transport).  workspace: 256-byte aligned, marsb200_emd_workspace_bytes(E, P, N, m_rows, t_cap, m_cap) bytes. */
+int64_t marsb200_emd_workspace_bytes(int E, int P, int N, int64_t m_rows, int t_cap, int m_cap);
 int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t* pooled, int E, int P, int64_t m_rows,
                         int N, int t_cap, int m_cap, void* workspace, int64_t workspace_bytes, double* out,
                         int32_t* status, void* stream);
@@ -201,7 +205,8 @@ int marsb200_clip_scores(const float* img, const float* txt, int E, int P, int D
  * the reference); the AlphaCLIP min-max is evaluated in fp32 exactly as the reference's numpy does.
  * Outputs: scores [E,P] fp64 by proposal index; order [E,P] int32 (rank -> index);
  * flags [E,P] uint8 by proposal index (bit0 = kept by NMS, bit1 = selected for the merge);
- * summary [E,4] int32 = {n_kept, n_selected, top_index, 0}. */
+ * summary [E,4] int32 = {n_kept, n_selected, top_index, n_nonfinite}: n_nonfinite counts proposals whose fused score is
+ * NaN / inf (a NaN input score); they rank last and the caller should treat the episode as failed. */
 int marsb200_fuse_rank(const double* emd, const float* clip, const int32_t* pooled_count, const float* sum_vva,
                        const float* sum_vta, const int32_t* union_count, const int32_t* inter, int E, int P,
                        double alpha, double static_threshold, double dynamic_threshold, float nms_iou_threshold,

@@ -55,7 +55,7 @@ SIGNATURES = {
     "marsb200_region_sums": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "marsb200_pairwise_inter": (_i, [_p, _i, _i, _l, _p, _i, _p]),
     "marsb200_pack_pairwise": (_i, [_p, _i, _i, _i, _l, _p, _p, _i, _p]),
-    "marsb200_emd_workspace_bytes": (_l, [_i, _i, _i, _i, _i]),
+    "marsb200_emd_workspace_bytes": (_l, [_i, _i, _i, _l, _i, _i]),
     "marsb200_emd_scores": (_i, [_p, _p, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p, _p, _p]),
     "marsb200_clip_scores": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "marsb200_fuse_rank": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _d, _d, _d, _f, _p, _p, _p, _p, _p]),

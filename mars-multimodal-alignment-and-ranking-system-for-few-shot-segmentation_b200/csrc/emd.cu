@@ -37,6 +37,7 @@ __device__ long long g_emd_prof[16];
 constexpr int EMD_THREADS = 256;
 constexpr int EMD_WARPS = EMD_THREADS / 32;
 constexpr double EMD_INF = 1e300;
+constexpr int EMD_GLOBAL_CTAS = 148;  // CTAs (and state slabs) of the global-state launch
 
 __host__ __device__ inline int emd_pool_nodes(int t_cap, int n_cap) { return 2 * (t_cap + n_cap) + 64; }
 
@@ -197,10 +198,9 @@ __global__ void __launch_bounds__(256) emd_copy_dups_kernel(int64_t total, const
 }
 
 __global__ void __launch_bounds__(256) emd_rank_kernel(const int64_t* __restrict__ key, int64_t total,
-                                                        int32_t* __restrict__ order, int32_t* __restrict__ counter) {
+                                                        int32_t* __restrict__ order) {
     __shared__ int64_t s_key[256];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *counter = 0;
     const int64_t mine = i < total ? key[i] : 0;
     int64_t rank = 0;
     for (int64_t k0 = 0; k0 < total; k0 += 256) {
@@ -277,22 +277,34 @@ __device__ inline void scan_sources(const EmdSmem& s, const float* __restrict__ 
                         }
                     }
             }
-            // remainder: one source at a time, still EMD_SPT gathers in flight
-            for (; k < n; k += lanes) {
-                const int i = list[k];
-                const int off = s.soff[i];
-                const double ui = s.u[i];
-                float cv[EMD_SPT];
+            // remainder: one more chunk with the missing sources masked out (one round trip to L2, not one per source)
+            if (k < n) {
+                int idx[EMD_CHUNK];
+                int off[EMD_CHUNK];
+                double ui[EMD_CHUNK];
+                bool has[EMD_CHUNK];
 #pragma unroll
-                for (int t = 0; t < EMD_SPT; ++t) cv[t] = live[t] ? col[t][off] : 0.f;
-#pragma unroll
-                for (int t = 0; t < EMD_SPT; ++t) {
-                    const double d = (double)cv[t] - ui;
-                    if (d < best[t]) {
-                        best[t] = d;
-                        best_i[t] = i;
-                    }
+                for (int q = 0; q < EMD_CHUNK; ++q) {
+                    has[q] = k + q * lanes < n;
+                    idx[q] = has[q] ? list[k + q * lanes] : 0;
+                    off[q] = s.soff[idx[q]];
+                    ui[q] = s.u[idx[q]];
                 }
+                float cv[EMD_SPT][EMD_CHUNK];
+#pragma unroll
+                for (int t = 0; t < EMD_SPT; ++t)
+#pragma unroll
+                    for (int q = 0; q < EMD_CHUNK; ++q) cv[t][q] = (live[t] && has[q]) ? col[t][off[q]] : 0.f;
+#pragma unroll
+                for (int t = 0; t < EMD_SPT; ++t)
+#pragma unroll
+                    for (int q = 0; q < EMD_CHUNK; ++q) {
+                        const double d = (double)cv[t][q] - ui[q];
+                        if (has[q] && d < best[t]) {
+                            best[t] = d;
+                            best_i[t] = idx[q];
+                        }
+                    }
             }
         }
 #pragma unroll
@@ -340,27 +352,36 @@ __device__ inline void expand_feeders(const EmdSmem& s, int j, double d, int* nn
     }
 }
 
+// gstate == nullptr (GLOBAL_STATE false): the fast path, solver state in shared memory, sized by (t_cap, m_cap); a problem that exceeds the caps
+// is appended to the overflow list instead of being solved.  GLOBAL_STATE = true: the same solver with its state in a
+// per-CTA slab of global memory (L2-resident), sized for ANY problem of the episode shape (t_cap = all support rows,
+// m_cap = N); it only walks the overflow list, so it costs one empty launch when nothing overflowed.  Together: no capacity
+// limit below the 16-bit index range, like the reference's ot.emd2 (FilteringMergingModule.py:162-166).
 __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __restrict__ cost, const uint8_t* __restrict__ row_fg,
                                                            const uint32_t* __restrict__ pooled, int P, int64_t m_rows,
                                                            int N, int npw, int t_cap, int m_cap, int total_lps,
                                                            const int32_t* __restrict__ order, int32_t* __restrict__ counter,
                                                            const int32_t* __restrict__ dup_of, double* __restrict__ out,
-                                                           int* __restrict__ status) {
+                                                           int* __restrict__ status, int32_t* __restrict__ ovf_count,
+                                                           int32_t* __restrict__ ovf_list, unsigned char* __restrict__ gstate,
+                                                           size_t gstate_stride) {
     extern __shared__ __align__(16) unsigned char emd_smem_raw[];
+    const bool GLOBAL_STATE = gstate != nullptr;  // (a runtime flag: nvcc 12.9 aborts on this kernel as a template)
     // sources: the support rows (<= t_cap) or, transposed, a proposal with fewer than t_cap / 3 patches; sinks: either side
-    EmdSmem s = emd_carve(emd_smem_raw, t_cap, max(t_cap, m_cap));
+    EmdSmem s = emd_carve(GLOBAL_STATE ? gstate + (size_t)blockIdx.x * gstate_stride : emd_smem_raw, t_cap, max(t_cap, m_cap));
     __shared__ unsigned long long s_val[EMD_WARPS];
     __shared__ double s_acc[EMD_WARPS];
     __shared__ int s_warp[EMD_WARPS];
-    __shared__ int s_lp, s_ndef, s_nnew, s_left, s_free, s_fault;
+    __shared__ int s_lp, s_ndef, s_nnew, s_left, s_free, s_fault, s_open;
     const int tid = threadIdx.x;
     const int pool = emd_pool_nodes(t_cap, max(t_cap, m_cap));
+    const int n_queue = GLOBAL_STATE ? *ovf_count : total_lps;  // written by the fast-path launch before this one starts
 
     while (true) {
         __syncthreads();
         if (tid == 0) {
             const int q = atomicAdd(counter, 1);
-            s_lp = q < total_lps ? order[q] : -1;
+            s_lp = q < n_queue ? (GLOBAL_STATE ? ovf_list[q] : order[q]) : -1;
         }
         __syncthreads();
         const int64_t lp = s_lp;
@@ -386,7 +407,8 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
         if (T0 > t_cap || M0 > m_cap) {
             if (tid == 0) {
                 out[lp] = nan("");
-                atomicMax(status, T0 > t_cap ? T0 : (1 << 24) + M0);  // tells the host the capacity it needs
+                if (GLOBAL_STATE) atomicMax(status, T0 > t_cap ? T0 : (1 << 24) + M0);  // beyond the 16-bit index range
+                else ovf_list[atomicAdd(ovf_count, 1)] = (int32_t)lp;                   // solved by the global-state launch
             }
             continue;
         }
@@ -432,7 +454,15 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
                 s.dsrc[i] = 0.0;
                 s.pred_sink[i] = -1;
             }
-            for (int j = tid; j < M; j += EMD_THREADS) s.scanned[j] = 0;
+            int open_local = 0;
+            for (int j = tid; j < M; j += EMD_THREADS) {
+                s.scanned[j] = 0;
+                open_local += s.demand[j] > 0 ? 1 : 0;
+            }
+            if (tid == 0) s_open = 0;
+            __syncthreads();
+            open_local = warp_sum(open_local);
+            if ((tid & 31) == 0 && open_local) atomicAdd(&s_open, open_local);  // unscanned sinks with open demand
             scan_sources<true>(s, C, M, s.newlist, nroots, lanes, 0.0, first_phase);
             if (first_phase) {
                 // row reduction: u_i = min_j (c_ij - v_j) >= 0 makes one more arc per source tight before the first
@@ -471,10 +501,26 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
                 EP_LAP(3);  // settle
                 const int ndef = s_ndef;
                 if (ndef > 0) {
-                    // ---- augment along the tree path of every settled sink with open demand (sequential: paths share arcs)
+                    // ---- augment along the tree path of every settled sink with open demand (sequential: paths share arcs).
+                    // Most attempts of the later phases find their root spent or a tree arc emptied: those are filtered
+                    // out in parallel first (capacities only shrink within a phase, so a dead path stays dead) and marked
+                    // by complementing the sink index.
+                    for (int b = tid; b < ndef; b += EMD_THREADS) {
+                        const int j = s.batch[b];
+                        int delta = s.demand[j];
+                        int i = s.pred_src[j];
+                        while (delta > 0 && s.pred_sink[i] >= 0) {
+                            delta = min(delta, (int)s.capflow[i]);
+                            i = s.pred_src[s.pred_sink[i]];
+                        }
+                        if (delta <= 0 || s.supply[i] <= 0) s.batch[b] = (short)~j;
+                    }
+                    __syncthreads();
                     if (tid == 0) {
+                        s_open -= ndef;
                         for (int b = 0; b < ndef; ++b) {
                             const int j = s.batch[b];
+                            if (j < 0) continue;
                             int delta = s.demand[j];
                             int i = s.pred_src[j];
                             while (s.pred_sink[i] >= 0) {
@@ -531,8 +577,13 @@ __global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __rest
                         }
                     }
                     __syncthreads();
-                    if (s_left <= 0 || s_fault) break;
-                    for (int b = tid; b < ndef; b += EMD_THREADS) expand_feeders(s, s.batch[b], dmin, &s_nnew);
+                    // the phase ends when the flow is complete or no unscanned sink has open demand left: later waves could
+                    // not augment anything (dual update with D = this wave's distance, unscanned nodes keep their duals)
+                    if (s_left <= 0 || s_fault || s_open <= 0) break;
+                    for (int b = tid; b < ndef; b += EMD_THREADS) {
+                        const int j = s.batch[b];
+                        expand_feeders(s, j < 0 ? ~j : j, dmin, &s_nnew);
+                    }
                     __syncthreads();
                 }
                 EP_LAP(4);  // augment
@@ -601,50 +652,85 @@ static int emd_ctas_per_sm(int t_cap, int m_cap) {  // 64 registers x 256 thread
     return (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
 }
 
-// Workspace: size keys, processing order, queue head (the flows and duals live in shared memory).
-int64_t marsb200_emd_workspace_bytes(int E, int P, int N, int t_cap, int m_cap) {
-    if (E <= 0 || P <= 0 || N <= 0 || t_cap <= 0) return 0;
+constexpr size_t EMD_SMEM_LIMIT = 200 * 1024;
+constexpr int EMD_INDEX_LIMIT = 32767;  // 16-bit node / row indices
+
+// Largest t <= t_cap whose state (with m_cap sinks) fits the shared-memory fast path.
+static int emd_fast_t_cap(int t_cap, int m_cap) {
+    int t = std::max(1, t_cap);
+    while (t > 1 && (emd_smem_bytes(t, std::max(t, m_cap)) > EMD_SMEM_LIMIT ||
+                     emd_pool_nodes(t, std::max(t, m_cap)) > EMD_INDEX_LIMIT))
+        t = t - std::max(1, t / 16);
+    return t;
+}
+// Caps of the global-state launch: every problem of the episode shape, as far as 16-bit indices reach.
+static int emd_full_t_cap(int64_t m_rows, int N) {
+    int t = (int)std::min<int64_t>(m_rows, EMD_INDEX_LIMIT);
+    while (t > 1 && emd_pool_nodes(t, std::max(t, N)) > EMD_INDEX_LIMIT) t = t - std::max(1, t / 64);
+    return t;
+}
+static size_t emd_gstate_stride(int64_t m_rows, int N) {
+    const int t = emd_full_t_cap(m_rows, N);
+    return (emd_smem_bytes(t, std::max(t, N)) + 255) / 256 * 256;
+}
+
+// Workspace: size keys, processing order, duplicate links, overflow list, two queue heads + the overflow count, and one
+// state slab per SM for the global-state launch (the fast path keeps flows and duals in shared memory).
+int64_t marsb200_emd_workspace_bytes(int E, int P, int N, int64_t m_rows, int t_cap, int m_cap) {
+    if (E <= 0 || P <= 0 || N <= 0 || m_rows <= 0) return 0;
+    (void)t_cap;
     (void)m_cap;
     const int64_t lps = (int64_t)E * P;
-    return (lps * 8 + lps * 4 + lps * 4 + 256 + 255) / 256 * 256;  // size keys, order, duplicate links, queue head
+    const int64_t head = (lps * 8 + lps * 4 + lps * 4 + lps * 4 + 256 + 255) / 256 * 256;
+    return head + (int64_t)EMD_GLOBAL_CTAS * (int64_t)emd_gstate_stride(m_rows, N);
 }
 
 int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t* pooled, int E, int P, int64_t m_rows,
                         int N, int t_cap, int m_cap, void* workspace, int64_t workspace_bytes, double* out,
                         int32_t* status, void* stream) {
     MARS_REQUIRE(cost && row_fg && pooled && workspace && out && status, "null pointer");
-    MARS_REQUIRE(E > 0 && P > 0 && m_rows > 0 && N > 0 && t_cap > 0 && t_cap <= 32767 && N <= 32767 && m_rows <= 32767,
-                 "shape");
+    MARS_REQUIRE(E > 0 && P > 0 && m_rows > 0 && N > 0 && N <= 32767 && m_rows <= 32767, "shape");
     MARS_REQUIRE((int64_t)E * P < (1ll << 31), "too many problems");
     if (m_cap <= 0 || m_cap > N) m_cap = N;
-    MARS_REQUIRE(workspace_bytes >= marsb200_emd_workspace_bytes(E, P, N, t_cap, m_cap), "workspace too small");
+    if (t_cap <= 0 || t_cap > m_rows) t_cap = (int)m_rows;
+    MARS_REQUIRE(workspace_bytes >= marsb200_emd_workspace_bytes(E, P, N, m_rows, t_cap, m_cap), "workspace too small");
     MARS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
-    MARS_REQUIRE(emd_pool_nodes(t_cap, std::max(t_cap, m_cap)) <= 32767, "t_cap + N too large for 16-bit flow-node indices");
     MARS_REQUIRE(m_rows * (int64_t)N < (1ll << 31), "cost matrix too large for 32-bit offsets");
+    // (t_cap, m_cap) size the shared-memory fast path; what does not fit it is solved by the global-state launch
+    t_cap = emd_fast_t_cap(t_cap, m_cap);
     const size_t smem = emd_smem_bytes(t_cap, std::max(t_cap, m_cap));
-    MARS_REQUIRE(smem <= 200 * 1024, "t_cap + N too large for the shared-memory state");
     cudaStream_t s = as_stream(stream);
     int num_sms = 0;
     MARS_CUDA_OK(device_sm_count(&num_sms));
     MARS_CUDA_OK(cudaFuncSetAttribute(emd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MARS_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
     const int64_t lps = (int64_t)E * P;
     const int npw = ceil_div(N, 32);
     int64_t* key = reinterpret_cast<int64_t*>(workspace);
     int32_t* order = reinterpret_cast<int32_t*>(key + lps);
     int32_t* dup_of = order + lps;
-    int32_t* counter = dup_of + lps;
+    int32_t* ovf_list = dup_of + lps;
+    int32_t* counter = ovf_list + lps;  // [0] fast-path queue head, [1] overflow count, [2] global-state queue head
+    const int64_t head = (lps * 8 + lps * 4 + lps * 4 + lps * 4 + 256 + 255) / 256 * 256;
+    unsigned char* gstate = reinterpret_cast<unsigned char*>(workspace) + head;
+    MARS_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+    MARS_CUDA_OK(cudaMemsetAsync(counter, 0, 4 * sizeof(int32_t), s));
     emd_sizes_kernel<<<(unsigned)ceil_div64(lps * 32, 256), 256, 0, s>>>(row_fg, pooled, P, m_rows, npw, lps, key);
     MARS_LAUNCH_OK();
     emd_dedupe_kernel<<<(unsigned)ceil_div64(lps * 32, 256), 256, 0, s>>>(pooled, P, npw, lps, key, dup_of);
     MARS_LAUNCH_OK();
     emd_mark_dups_kernel<<<(unsigned)ceil_div64(lps, 256), 256, 0, s>>>(lps, dup_of, key);
     MARS_LAUNCH_OK();
-    emd_rank_kernel<<<(unsigned)ceil_div64(lps, 256), 256, 0, s>>>(key, lps, order, counter);
+    emd_rank_kernel<<<(unsigned)ceil_div64(lps, 256), 256, 0, s>>>(key, lps, order);
     MARS_LAUNCH_OK();
     const unsigned grid = (unsigned)std::min<int64_t>(lps, (int64_t)num_sms * emd_ctas_per_sm(t_cap, m_cap));
     emd_kernel<<<grid, EMD_THREADS, smem, s>>>(cost, row_fg, pooled, P, m_rows, N, npw, t_cap, m_cap, (int)lps, order,
-                                               counter, dup_of, out, status);
+                                                      counter, dup_of, out, status, counter + 1, ovf_list, nullptr, 0);
+    MARS_LAUNCH_OK();
+    // problems beyond the fast path's caps (none in the usual case: the launch finds an empty list and returns)
+    const int t_full = emd_full_t_cap(m_rows, N);
+    emd_kernel<<<EMD_GLOBAL_CTAS, EMD_THREADS, 0, s>>>(cost, row_fg, pooled, P, m_rows, N, npw, t_full, N, (int)lps, order,
+                                                            counter + 2, dup_of, out, status, counter + 1, ovf_list, gstate,
+                                                            emd_gstate_stride(m_rows, N));
     MARS_LAUNCH_OK();
     emd_copy_dups_kernel<<<(unsigned)ceil_div64(lps, 256), 256, 0, s>>>(lps, dup_of, out);
     MARS_LAUNCH_OK();

@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
     __shared__ double s_scratch_d[FUSE_THREADS / 32];
     __shared__ float s_scratch_f[FUSE_THREADS / 32];
     __shared__ int s_counts[2];
+    __shared__ int s_nonfinite;  // proposals whose fused score is NaN / inf (e.g. a NaN EMD input): reported in summary[3]
+    if (threadIdx.x == 0) s_nonfinite = 0;
 
     const int64_t e = blockIdx.x;
     const int tid = threadIdx.x;
@@ -98,7 +100,9 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
             const float cn = __fdiv_rn(clip[p] - cmin, c_den);
             const double sc = (((en + (double)cn) + pvv) + pvt) / 4.0;
             scores[e * P + p] = sc;
-            s_key[p] = sc;
+            const bool finite = isfinite(sc);
+            if (!finite) atomicAdd(&s_nonfinite, 1);
+            s_key[p] = finite ? sc : -INFINITY;  // a NaN key would make the sort inconsistent: such proposals rank last
             s_idx[p] = p;
         } else {
             s_key[p] = -INFINITY;
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
         summary[e * 4 + 0] = s_counts[0];
         summary[e * 4 + 1] = s_counts[1];
         summary[e * 4 + 2] = s_idx[0];
-        summary[e * 4 + 3] = 0;
+        summary[e * 4 + 3] = s_nonfinite;
     }
 }
 

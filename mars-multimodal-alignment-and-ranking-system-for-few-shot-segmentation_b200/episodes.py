@@ -33,8 +33,10 @@ class RankingConfig:
     overlap_streams: bool = True       # mask chain (HBM-bound) on a second stream beside the contractions
     fused_ingest: bool = False         # one-pass pack + pairwise kernel (owns all TMEM: cannot overlap the contractions)
     emd_on_device: bool = False        # solve the P transport LPs per episode on the device instead of taking batch["emd"]
-    emd_t_cap: Optional[int] = None    # max fg support rows the EMD workspace is sized for (default min(ns*N, 2048))
-    emd_m_cap: Optional[int] = None    # max pooled patches of a proposal (default N); smaller -> more LPs per SM
+    # fast-path sizing of the EMD solver (state in shared memory); problems beyond it take its global-state launch, so
+    # these are performance hints, never capacity limits
+    emd_t_cap: Optional[int] = None    # fg support rows (default min(ns*N, 2048))
+    emd_m_cap: Optional[int] = None    # pooled patches of a proposal (default N); smaller -> more LPs per SM
     gemm_backend: Optional[int] = None
     pair_backend: Optional[int] = None
     # SMs of the `tensor` green-context partition (partition.py); the mask ingest gets the rest of the device and runs
@@ -99,9 +101,10 @@ class RankingEngine:
         if cfg.emd_on_device:
             self.emd_t_cap = cfg.emd_t_cap or min(m, 2048)
             self.emd_m_cap = min(cfg.emd_m_cap or n, n)
-            nbytes = int(ops.lib.marsb200_emd_workspace_bytes(e, s.P, n, self.emd_t_cap, self.emd_m_cap))
+            nbytes = int(ops.lib.marsb200_emd_workspace_bytes(e, s.P, n, m, self.emd_t_cap, self.emd_m_cap))
             self.emd_ws = new((nbytes,), u8)
             self.emd_out = new((e, s.P), torch.float64)
+            self.emd_status = torch.zeros(1, device=dev, dtype=i32)  # persistent: read by check_status()
         self.prior = new((e, n), f32)
         self.vva = new((e, n), f32)
         self.vta_ref = new((e, nt), f32)
@@ -248,7 +251,7 @@ class RankingEngine:
             if cfg.emd_on_device:
                 emd = ops.emd_scores(self.gemm_out["cost"], self.row_fg.reshape(e, m), self.pool_out[0],
                                      t_cap=self.emd_t_cap, m_cap=self.emd_m_cap, workspace=self.emd_ws, out=self.emd_out,
-                                     check=False)
+                                     check=False, status=self.emd_status)
             ops.fuse_rank(emd, self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
                           self.region_out[2], self.inter, cfg.alpha, cfg.static_threshold, cfg.dynamic_threshold,
                           cfg.nms_iou_threshold, out=self.rank_out)
@@ -318,7 +321,8 @@ class RankingEngine:
         emd = batch.get("emd")
         if cfg.emd_on_device:
             emd = ops.emd_scores(self.gemm_out["cost"], self.row_fg.reshape(e, m), self.pool_out[0], t_cap=self.emd_t_cap,
-                                 m_cap=self.emd_m_cap, workspace=self.emd_ws, out=self.emd_out, check=False)
+                                 m_cap=self.emd_m_cap, workspace=self.emd_ws, out=self.emd_out, check=False,
+                                 status=self.emd_status)
         ops.fuse_rank(emd, self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
                       self.region_out[2], self.inter, cfg.alpha, cfg.static_threshold, cfg.dynamic_threshold,
                       cfg.nms_iou_threshold, out=self.rank_out)
@@ -332,9 +336,19 @@ class RankingEngine:
                    sum_vva=self.region_out[0], sum_vta=self.region_out[1], union_count=self.region_out[2],
                    inter=self.inter, clip=self.clip, merged_bits=self.merge_out["bits"],
                    merged=self.merge_out.get("f32"), sim=self.gemm_out.get("sim"), cost=self.gemm_out.get("cost"),
-                   emd=self.emd_out if self.cfg.emd_on_device else None)
+                   emd=self.emd_out if self.cfg.emd_on_device else None,
+                   emd_status=self.emd_status if self.cfg.emd_on_device else None)
         out.update(self.rank_out)
         return out
+
+    def check_status(self) -> None:
+        """Host-side check of the last step (one small device->host read, so it is not part of `run`): raises if the EMD
+        solver reported a fault or if a fused score came out non-finite (`summary[:, 3]`, set by fuse_rank)."""
+        if self.cfg.emd_on_device:
+            ops.raise_on_emd_status(int(self.emd_status.item()))
+        bad = torch.nonzero(self.rank_out["summary"][:, 3]).reshape(-1)
+        if bad.numel():
+            raise ops.MarsB200Error(f"non-finite fused scores in episodes {bad.tolist()} of the batch")
 
     # ------------------------------------------------------------------ CUDA graph replay
     def capture(self, batch: dict):

@@ -335,13 +335,14 @@ def pack_pairwise(masks: torch.Tensor, backend=None, out=None):
 # ----------------------------------------------------------------------------- A7
 def emd_scores(cost: torch.Tensor, row_fg: torch.Tensor, pooled: torch.Tensor, t_cap: Optional[int] = None,
                m_cap: Optional[int] = None, pooled_count: Optional[torch.Tensor] = None, workspace=None, out=None,
-               check=True) -> torch.Tensor:
+               check=True, status: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Exact `1 - emd2` of every proposal: cost [E, m_rows, N] fp32, row_fg [E, m_rows] u8, pooled [E, P, npw].
 
-    `t_cap` (max fg support rows) and `m_cap` (max pooled patches of a proposal) size the solver's state; when
-    omitted they are read from `row_fg` / `pooled_count` - one small device->host sync, like the reference's own host
-    EMD (`m_cap` falls back to N without `pooled_count`).  With `check` the status word is read back and an exception
-    raised if a problem exceeded the caps.
+    `t_cap` (fg support rows) and `m_cap` (pooled patches of a proposal) size the solver's shared-memory fast path; a
+    problem beyond them is solved by the global-state launch (slower, any size), so they are performance hints, not
+    limits.  When omitted they are read from `row_fg` / `pooled_count` - one small device->host sync, like the
+    reference's own host EMD (`m_cap` falls back to N without `pooled_count`).  `status` (int32 [1], optional) receives
+    the solver's status word; with `check` it is read back and an exception raised on a fault.
     """
     cost = _cuda(cost, torch.float32, "cost")
     if cost.dim() == 2:
@@ -355,25 +356,30 @@ def emd_scores(cost: torch.Tensor, row_fg: torch.Tensor, pooled: torch.Tensor, t
     if m_cap is None:
         m_cap = n if pooled_count is None else max(1, int(pooled_count.max().item()))
     m_cap = min(int(m_cap), n)
-    nbytes = int(lib.marsb200_emd_workspace_bytes(e, p, n, t_cap, m_cap))
+    nbytes = int(lib.marsb200_emd_workspace_bytes(e, p, n, m_rows, t_cap, m_cap))
     if workspace is None or workspace.numel() < nbytes:
         workspace = torch.empty(nbytes, device=cost.device, dtype=torch.uint8)
     if out is None:
         out = torch.empty((e, p), device=cost.device, dtype=torch.float64)
-    status = torch.zeros(1, device=cost.device, dtype=torch.int32)
+    if status is None:
+        status = torch.zeros(1, device=cost.device, dtype=torch.int32)
     check_rc = lib.marsb200_emd_scores(cost.data_ptr(), row_fg.data_ptr(), pooled.data_ptr(), e, p, m_rows, n, t_cap,
                                        m_cap, workspace.data_ptr(), workspace.numel(), out.data_ptr(),
                                        status.data_ptr(), _stream())
     _lib.check(check_rc)
     if check:
-        need = int(status.item())
-        if need < 0:
-            raise _lib.MarsB200Error("emd_scores: internal flow-node pool exhausted")
-        if need >= (1 << 24):
-            raise _lib.MarsB200Error(f"emd_scores: a proposal covers {need - (1 << 24)} patches > m_cap={m_cap}")
-        if need:
-            raise _lib.MarsB200Error(f"emd_scores: an episode has {need} foreground support rows > t_cap={t_cap}")
+        raise_on_emd_status(int(status.item()))
     return out
+
+
+def raise_on_emd_status(need: int) -> None:
+    """Turns the EMD solver's status word (include/marsb200.h) into an exception."""
+    if need < 0:
+        raise _lib.MarsB200Error("emd_scores: internal flow-node pool exhausted")
+    if need >= (1 << 24):
+        raise _lib.MarsB200Error(f"emd_scores: a proposal covers {need - (1 << 24)} patches, beyond the 16-bit index range")
+    if need:
+        raise _lib.MarsB200Error(f"emd_scores: an episode has {need} foreground support rows, beyond the 16-bit index range")
 
 
 # ----------------------------------------------------------------------------- A8 / A10 / A11

@@ -989,10 +989,48 @@ def test_emd_caps_and_larger_problems(mb):
     big = sorted(range(p), key=lambda i: -int(cnt[i]))[:3]
     want = np.asarray([orc.emd_score(sup, pm[i], cost) for i in big])
     np.testing.assert_allclose(full.cpu().numpy()[big], want, rtol=0, atol=1e-9)
-    with pytest.raises(mb.MarsB200Error, match="m_cap"):
-        mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], m_cap=int(cnt.max()) - 1)
-    with pytest.raises(mb.MarsB200Error, match="t_cap"):
-        mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], t_cap=int(row_fg.sum()) - 1)
+    # caps size the shared-memory fast path only: problems beyond them are solved by the global-state launch, bit for bit
+    # the same values (same solver, other memory), never an error (the reference's ot.emd2 has no capacity limit)
+    small_m = mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], m_cap=int(cnt.max()) // 2)[0]
+    small_t = mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], t_cap=int(row_fg.sum()) // 3)[0]
+    assert torch.equal(small_m, full) and torch.equal(small_t, full)
+
+
+def test_emd_5shot_large_support_masks_take_the_global_state_path(mb):
+    """a 5-shot episode whose objects cover most of the image has more foreground support rows (here ~4700)
+    than the shared-memory state can hold (~2400): the drop-in must still score it, like ot.emd2 does
+    (FilteringMergingModule.py:142-169).  Values against the oracle's exact LP on two proposals."""
+    ns, g, h, p = 5, 37, 148, 6
+    gen = torch.Generator().manual_seed(77)
+    n = g * g
+    fs = orc.normalize_rows(torch.randn(ns * n, 32, generator=gen))
+    fq = orc.normalize_rows(torch.randn(n, 32, generator=gen))
+    _, cost = orc.similarity_and_cost(fs, fq)
+    support = torch.zeros(ns, h, h)
+    support[:, 10:140, 8:132] = 1.0  # ~70 % of every shot
+    masks = cases.blob_masks(p, h, h, seed=5, min_frac=0.002, max_frac=0.02)
+    d = dev()
+    row_fg = mb.ops.pool_mask(support.to(d), g).reshape(1, -1)
+    t_fg = int(row_fg.sum())
+    assert t_fg > 2600
+    bits = mb.ops.pack_masks(masks.to(d))
+    pooled, _, cnt = mb.ops.pool_packed(bits, h, h, g)
+    got = mb.ops.emd_scores(cost.to(d)[None], row_fg, pooled[None], pooled_count=cnt)[0].cpu().numpy()
+    assert np.isfinite(got).all()
+    sup = orc.pool_mask(support, g).reshape(-1)
+    pm = orc.pool_mask(masks, g).reshape(p, -1)
+    small = sorted(range(p), key=lambda i: int(cnt[i]))[:2]
+    want = np.asarray([orc.emd_score(sup, pm[i], cost) for i in small])
+    np.testing.assert_allclose(got[small], want, rtol=0, atol=1e-9)
+    # the same through the drop-in module (it used to raise 't_cap + N too large for the shared-memory state')
+    fm = mb.FilteringMergingModule(alpha_clip_model=None, img_transforms=None, mask_transforms=None, alpha=0.85,
+                                   static_threshold=0.55, dynamic_threshold=0.95, device=d)
+    gen2 = torch.Generator().manual_seed(3)
+    img = torch.nn.functional.normalize(torch.randn(p, 16, generator=gen2), dim=1)
+    txt = torch.nn.functional.normalize(torch.randn(16, generator=gen2), dim=0)
+    ranked = fm._score_proposals(torch.zeros(1, 3, h, h), masks, support[None], cost, g, torch.rand(g, g, generator=gen2),
+                                 torch.rand(g, g, generator=gen2), ["x"], alphaclip_feats=(img, txt))
+    assert len(ranked) == p and all(np.isfinite(float(sc)) for _, sc in ranked)
 
 
 def test_emd_tight_caps_more_sources_than_sinks(mb):
@@ -1037,6 +1075,35 @@ def test_emd_duplicate_proposals_share_one_lp(mb):
     for e in range(2):
         assert got[e, 5] == got[e, 2] == got[e, 9] and got[e, 3] == got[e, 11] == 1.0
     assert got[0, 2] != got[1, 2]
+
+
+@pytest.mark.parametrize("t,m", [(6, 4), (4, 6), (9, 6), (10, 4), (7, 5), (12, 8), (15, 10), (8, 12), (20, 3), (1, 7)])
+def test_emd_rectangular_equals_expanded_assignment(mb, t, m):
+    """Device EMD against an INDEPENDENT exact solver on rectangular problems: the T x M uniform-marginal LP expanded to
+    an lcm(T, M)^2 assignment and solved by scipy's LSAP (no LP solver, no shared code with the oracle's HiGHS path)."""
+    import math
+
+    from scipy.optimize import linear_sum_assignment
+
+    g = 5
+    n = g * g
+    rs = np.random.RandomState(1000 * t + m)
+    cost = ((1 - rs.uniform(-0.2, 0.9, size=(n, n))) / 2).astype(np.float32)
+    rows = np.sort(rs.choice(n, t, replace=False))
+    cols = np.sort(rs.choice(n, m, replace=False))
+    row_fg = torch.zeros(1, n, dtype=torch.uint8)
+    row_fg[0, rows] = 1
+    word = np.zeros(1, dtype=np.uint32)
+    for c in cols:
+        word[0] |= np.uint32(1) << np.uint32(c)
+    pooled = torch.from_numpy(word.view(np.int32)).reshape(1, 1, 1)
+    got = float(mb.ops.emd_scores(torch.from_numpy(cost).to(dev())[None], row_fg.to(dev()), pooled.to(dev()))[0, 0])
+    big = math.lcm(t, m)
+    sub = cost[rows][:, cols].astype(np.float64)
+    exp = np.repeat(np.repeat(sub, big // t, axis=0), big // m, axis=1)
+    r, c = linear_sum_assignment(exp)
+    want = 1.0 - exp[r, c].sum() / big
+    assert abs(got - want) < 1e-12
 
 
 def test_emd_square_case_equals_assignment(mb):

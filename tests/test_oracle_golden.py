@@ -224,3 +224,27 @@ def test_mars_predict_end_to_end_matches_reference(name):
     sel = orc.merge_select(scores[order], spec["static"], spec["dynamic"])
     merged = orc.merge_masks(c["masks"], order[sel])
     np.testing.assert_array_equal(merged.numpy() > 0, z["merged"])
+
+
+def _emd_by_assignment(cost: np.ndarray) -> float:
+    """Independent exact solver for the uniform-marginal transport LP: expand the T x M problem to an L x L assignment
+    (L = lcm(T, M); source i appears L/T times, sink j L/M times, every unit carries mass 1/L) and solve it with scipy's
+    LSAP.  The expansion is exact: a transport plan with rational entries of denominator L is a sum of L unit matchings."""
+    import math
+
+    from scipy.optimize import linear_sum_assignment
+
+    t, m = cost.shape
+    big = math.lcm(t, m)
+    exp = np.repeat(np.repeat(np.asarray(cost, dtype=np.float64), big // t, axis=0), big // m, axis=1)
+    r, c = linear_sum_assignment(exp)
+    return float(exp[r, c].sum() / big)
+
+
+@pytest.mark.parametrize("t,m", [(6, 4), (4, 6), (9, 6), (10, 4), (7, 5), (12, 8), (15, 10), (8, 12), (5, 5), (1, 7), (13, 1)])
+def test_exact_emd_rectangular_cross_check(t, m):
+    """The oracle's HiGHS transport LP (stand-in for ot.emd2, FilteringMergingModule.py:162-166) against an independent
+    exact solver on RECTANGULAR problems (only the square case was cross-checked)."""
+    rs = np.random.RandomState(100 * t + m)
+    cost = ((1 - rs.uniform(-0.2, 0.9, size=(t, m))) / 2).astype(np.float32)
+    assert abs(orc.emd_exact(cost) - _emd_by_assignment(cost)) < 1e-12
