@@ -195,6 +195,9 @@ int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t
 /* ---- A8: AlphaCLIP cosine scores -----------------------------------------------------------
  * clip[e,p] = img[e,p,:] . txt[e,:].  Replaces img_feats @ text_feats.T, FilteringMergingModule.py:97. */
 int marsb200_clip_scores(const float* img, const float* txt, int E, int P, int D, float* out, void* stream);
+/* The same with float16 features (AlphaCLIP runs in half precision on a GPU, :189,195): fp32 accumulation, ONE rounding to
+ * float16 like a half-precision matmul; out holds the float16 values as float32. */
+int marsb200_clip_scores_f16(const void* img_f16, const void* txt_f16, int E, int P, int D, float* out, void* stream);
 
 /* ---- A8 + A10 + A11: fuse, rank, NMS, select ------------------------------------------------
  * score = (minmax(emd) + minmax(clip) + a*pvv+(1-a)*cov + a*pvt+(1-a)*cov) / 4, stable descending
@@ -202,7 +205,10 @@ int marsb200_clip_scores(const float* img, const float* txt, int E, int P, int D
  * static/dynamic threshold selection.  Replaces FilteringMergingModule.py:118-138 and :213-217; the NMS is
  * builder-defined with the semantics of torchvision nms (segment_anything/automatic_mask_generator.py:370-376).
  * emd is fp64 (the reference's 1 - ot.emd2 is a float64) and alpha / thresholds are doubles (Python floats in
- * the reference); the AlphaCLIP min-max is evaluated in fp32 exactly as the reference's numpy does.
+ * the reference); the AlphaCLIP min-max is evaluated in the feature dtype exactly as the reference's numpy does:
+ * clip_f16 = 0: float32 scores; clip_f16 = 1: `clip` holds float16 values (marsb200_clip_scores_f16) and the min-max and
+ * the first addition of the fusion are float16 operations with NumPy's promotion rules (FilteringMergingModule.py:97,
+ * 126-136 as run on a GPU, where AlphaCLIP is half precision).
  * Outputs: scores [E,P] fp64 by proposal index; order [E,P] int32 (rank -> index);
  * flags [E,P] uint8 by proposal index (bit0 = kept by NMS, bit1 = selected for the merge);
  * summary [E,4] int32 = {n_kept, n_selected, top_index, n_nonfinite}: n_nonfinite counts proposals whose fused score is
@@ -210,7 +216,7 @@ int marsb200_clip_scores(const float* img, const float* txt, int E, int P, int D
 int marsb200_fuse_rank(const double* emd, const float* clip, const int32_t* pooled_count, const float* sum_vva,
                        const float* sum_vta, const int32_t* union_count, const int32_t* inter, int E, int P,
                        double alpha, double static_threshold, double dynamic_threshold, float nms_iou_threshold,
-                       double* scores, int32_t* order, uint8_t* flags, int32_t* summary, void* stream);
+                       int clip_f16, double* scores, int32_t* order, uint8_t* flags, int32_t* summary, void* stream);
 
 /* OR of the selected packed masks and expansion to the float32 [H,W] map the reference returns.
  * Replaces (torch.sum(torch.stack(ranked_masks), 0) > 0).float(), FilteringMergingModule.py:219, and the

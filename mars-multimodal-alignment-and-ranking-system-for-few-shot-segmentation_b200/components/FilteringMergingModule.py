@@ -13,6 +13,11 @@ primal-dual method on integer flows).  `emd_fn=` (a host solver taking the
 cost sub-matrix, e.g. a POT wrapper) or precomputed `emd_scores=` override it;
 `_compute_emd` keeps the reference's per-proposal host signature for callers that
 use it directly.
+
+AlphaCLIP features in float16 (what the reference's own producer code returns on a
+GPU) select the float16 score sequence of the reference: float16 dot products,
+float16 min-max (with NumPy's weak-scalar rule for the 1e-7), float16 first addition,
+float64 afterwards; float32 features select the float32 sequence.
 """
 from typing import Callable, Optional
 
@@ -120,7 +125,13 @@ class FilteringMergingModule:
             img = self._compute_alphaclip_vis_feats(query_img[0], mask_proposals)
         else:
             img, txt = alphaclip_feats
-        clip = ops.clip_scores(img.to(dev).float()[None], txt.to(dev).float().reshape(1, -1))
+        # AlphaCLIP runs in half precision on a GPU (FilteringMergingModule.py:189,195): with float16 features the reference's
+        # dot products, their min-max and the first addition of the fusion are float16 arithmetic (:97,126-136); the
+        # kernels reproduce that sequence.  float32 features take the float32 sequence.
+        clip_f16 = img.dtype == torch.float16 and txt.dtype == torch.float16
+        if not clip_f16:
+            img, txt = img.float(), txt.float()
+        clip = ops.clip_scores(img.to(dev)[None], txt.to(dev).reshape(1, -1))
         if emd_scores is None:
             sup = ops.pool_mask(support_mask.to(dev).permute(1, 0, 2, 3), g).reshape(-1)
             if self.emd_fn is None:
@@ -132,7 +143,7 @@ class FilteringMergingModule:
             emd = torch.as_tensor(np.asarray(emd_scores, dtype=np.float64), device=dev).reshape(1, p)
         inter = ops.pairwise_inter(bits) if self.nms_iou_threshold is not None else None
         res = ops.fuse_rank(emd, clip, cnt, sv, st, uc, inter, self.alpha, self.static_threshold,
-                            self.dynamic_threshold, self.nms_iou_threshold)
+                            self.dynamic_threshold, self.nms_iou_threshold, clip_f16=clip_f16)
         res.update(bits=bits, pooled=pooled, area=area, pooled_count=cnt, inter=inter, clip=clip)
         self.last = res
 

@@ -277,34 +277,22 @@ __device__ inline void scan_sources(const EmdSmem& s, const float* __restrict__ 
                         }
                     }
             }
-            // remainder: one more chunk with the missing sources masked out (one round trip to L2, not one per source)
-            if (k < n) {
-                int idx[EMD_CHUNK];
-                int off[EMD_CHUNK];
-                double ui[EMD_CHUNK];
-                bool has[EMD_CHUNK];
+            // remainder: one source at a time, still EMD_SPT gathers in flight
+            for (; k < n; k += lanes) {
+                const int i = list[k];
+                const int off = s.soff[i];
+                const double ui = s.u[i];
+                float cv[EMD_SPT];
 #pragma unroll
-                for (int q = 0; q < EMD_CHUNK; ++q) {
-                    has[q] = k + q * lanes < n;
-                    idx[q] = has[q] ? list[k + q * lanes] : 0;
-                    off[q] = s.soff[idx[q]];
-                    ui[q] = s.u[idx[q]];
-                }
-                float cv[EMD_SPT][EMD_CHUNK];
+                for (int t = 0; t < EMD_SPT; ++t) cv[t] = live[t] ? col[t][off] : 0.f;
 #pragma unroll
-                for (int t = 0; t < EMD_SPT; ++t)
-#pragma unroll
-                    for (int q = 0; q < EMD_CHUNK; ++q) cv[t][q] = (live[t] && has[q]) ? col[t][off[q]] : 0.f;
-#pragma unroll
-                for (int t = 0; t < EMD_SPT; ++t)
-#pragma unroll
-                    for (int q = 0; q < EMD_CHUNK; ++q) {
-                        const double d = (double)cv[t][q] - ui[q];
-                        if (has[q] && d < best[t]) {
-                            best[t] = d;
-                            best_i[t] = idx[q];
-                        }
+                for (int t = 0; t < EMD_SPT; ++t) {
+                    const double d = (double)cv[t] - ui;
+                    if (d < best[t]) {
+                        best[t] = d;
+                        best_i[t] = i;
                     }
+                }
             }
         }
 #pragma unroll

@@ -1,5 +1,7 @@
 // Score fusion, stable ranking, greedy IoU-NMS and merge selection (one CTA per episode), plus
 // the AlphaCLIP cosine scores.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace marsb200 {
@@ -17,6 +19,26 @@ __global__ void clip_scores_kernel(const float* __restrict__ img, const float* _
     acc = warp_sum(acc);
     if (lane == 0) out[wg] = (float)acc;
 }
+
+// float16 features (the reference's AlphaCLIP runs in half precision on a GPU, FilteringMergingModule.py:189,195): the dot
+// product is accumulated in fp32 and rounded to float16 once, like a half-precision matmul; `out` holds that float16 value.
+__global__ void clip_scores_f16_kernel(const __half* __restrict__ img, const __half* __restrict__ txt, int64_t total, int P,
+                                       int D, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wg >= total) return;
+    const int64_t e = wg / P;
+    const __half* a = img + wg * D;
+    const __half* t = txt + e * D;
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc = fmaf(__half2float(a[d]), __half2float(t[d]), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[wg] = __half2float(__float2half_rn(acc));
+}
+
+// one float16 operation the way NumPy evaluates it: operands are float16 values, the operation runs in float32 and the
+// result is rounded to float16 (round to nearest even)
+__device__ __forceinline__ float h_rn(float x) { return __half2float(__float2half_rn(x)); }
 
 // block-wide reductions through shared memory (blockDim.x == FUSE_THREADS)
 constexpr int FUSE_THREADS = 1024;
@@ -43,7 +65,7 @@ __device__ __forceinline__ bool ranks_before(double sa, int ia, double sb, int i
 __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
     const double* __restrict__ emd, const float* __restrict__ clip, const int32_t* __restrict__ pooled_count,
     const float* __restrict__ sum_vva, const float* __restrict__ sum_vta, const int32_t* __restrict__ union_count,
-    const int32_t* __restrict__ inter, int P, int n2, int use_bitmask, double alpha, double static_thr, double dynamic_thr,
+    const int32_t* __restrict__ inter, int P, int n2, int use_bitmask, int clip_f16, double alpha, double static_thr, double dynamic_thr,
     float nms_thr, double* __restrict__ scores, int32_t* __restrict__ order, uint8_t* __restrict__ flags,
     int32_t* __restrict__ summary) {
     extern __shared__ unsigned char smem_raw[];
@@ -84,7 +106,8 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
     cmax = block_reduce(cmax, [](float a, float b) { return fmaxf(a, b); }, s_scratch_f);
 
     const double e_den = 1e-7 + emax - emin;         // float64, FilteringMergingModule.py:131
-    const float c_den = (1e-7f + cmax) - cmin;       // evaluated in the feature dtype (float32), :132
+    // evaluated in the feature dtype, :132 - float32, or float16 (`1e-7` is a weak Python scalar: 1.19e-7 as a half)
+    const float c_den = clip_f16 ? h_rn(h_rn(h_rn(1e-7f) + cmax) - cmin) : (1e-7f + cmax) - cmin;
     const double u_den = 1e-7 + (double)union_count[e];
 
     // ---- fused score per proposal
@@ -97,8 +120,17 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
             const double pvv = alpha * avv + (1.0 - alpha) * cov;
             const double pvt = alpha * avt + (1.0 - alpha) * cov;
             const double en = (emd[p] - emin) / e_den;
-            const float cn = __fdiv_rn(clip[p] - cmin, c_den);
-            const double sc = (((en + (double)cn) + pvv) + pvt) / 4.0;
+            double sc;
+            if (clip_f16) {
+                // NumPy's types at :136 - Python float + float16 array: the float is cast to float16 and the sum is a
+                // float16 operation; adding the np.float64 pvv / pvt then promotes to float64
+                const float cn = h_rn(__fdiv_rn(h_rn(clip[p] - cmin), c_den));
+                const float first = h_rn(__half2float(__double2half(en)) + cn);
+                sc = (((double)first + pvv) + pvt) / 4.0;
+            } else {
+                const float cn = __fdiv_rn(clip[p] - cmin, c_den);
+                sc = (((en + (double)cn) + pvv) + pvt) / 4.0;
+            }
             scores[e * P + p] = sc;
             const bool finite = isfinite(sc);
             if (!finite) atomicAdd(&s_nonfinite, 1);
@@ -246,10 +278,20 @@ int marsb200_clip_scores(const float* img, const float* txt, int E, int P, int D
     return MARSB200_OK;
 }
 
+int marsb200_clip_scores_f16(const void* img, const void* txt, int E, int P, int D, float* out, void* stream) {
+    MARS_REQUIRE(img && txt && out, "null pointer");
+    MARS_REQUIRE(E > 0 && P > 0 && D > 0, "shape");
+    const int64_t total = (int64_t)E * P;
+    clip_scores_f16_kernel<<<(unsigned)ceil_div64(total, 8), 256, 0, as_stream(stream)>>>(
+        static_cast<const __half*>(img), static_cast<const __half*>(txt), total, P, D, out);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
 int marsb200_fuse_rank(const double* emd, const float* clip, const int32_t* pooled_count, const float* sum_vva,
                        const float* sum_vta, const int32_t* union_count, const int32_t* inter, int E, int P,
                        double alpha, double static_threshold, double dynamic_threshold, float nms_iou_threshold,
-                       double* scores, int32_t* order, uint8_t* flags, int32_t* summary, void* stream) {
+                       int clip_f16, double* scores, int32_t* order, uint8_t* flags, int32_t* summary, void* stream) {
     MARS_REQUIRE(emd && clip && pooled_count && sum_vva && sum_vta && union_count, "null input");
     MARS_REQUIRE(scores && order && flags && summary, "null output");
     MARS_REQUIRE(E > 0 && P > 0 && P <= 8192, "shape (P <= 8192)");
@@ -264,7 +306,7 @@ int marsb200_fuse_rank(const double* emd, const float* clip, const int32_t* pool
     if (smem > 48 * 1024)
         MARS_CUDA_OK(cudaFuncSetAttribute(fuse_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fuse_rank_kernel<<<E, FUSE_THREADS, smem, as_stream(stream)>>>(emd, clip, pooled_count, sum_vva, sum_vta,
-                                                                   union_count, inter, P, n2, use_bitmask, alpha, static_threshold,
+                                                                   union_count, inter, P, n2, use_bitmask, clip_f16 ? 1 : 0, alpha, static_threshold,
                                                                    dynamic_threshold, nms_iou_threshold, scores, order,
                                                                    flags, summary);
     MARS_LAUNCH_OK();

@@ -384,20 +384,25 @@ def raise_on_emd_status(need: int) -> None:
 
 # ----------------------------------------------------------------------------- A8 / A10 / A11
 def clip_scores(img: torch.Tensor, txt: torch.Tensor, out=None) -> torch.Tensor:
-    img = _cuda(img, torch.float32, "img")
+    """img [E, P, D] . txt [E, D] -> [E, P] float32.  float16 features (the reference's AlphaCLIP on a GPU) give the
+    float16-rounded dot products of a half-precision matmul, stored as float32 - pass `clip_f16=True` to `fuse_rank`."""
+    half = img.dtype == torch.float16
+    img = _cuda(img, torch.float16 if half else torch.float32, "img")
     if img.dim() == 2:
         img = img[None]
     e, p, d = img.shape
-    txt = _cuda(txt, torch.float32, "txt").reshape(e, d)
+    txt = _cuda(txt, torch.float16 if half else torch.float32, "txt").reshape(e, d)
     if out is None:
         out = torch.empty((e, p), device=img.device, dtype=torch.float32)
-    check(lib.marsb200_clip_scores(img.data_ptr(), txt.data_ptr(), e, p, d, out.data_ptr(), _stream()))
+    fn = lib.marsb200_clip_scores_f16 if half else lib.marsb200_clip_scores
+    check(fn(img.data_ptr(), txt.data_ptr(), e, p, d, out.data_ptr(), _stream()))
     return out
 
 
 def fuse_rank(emd, clip, pooled_count, sum_vva, sum_vta, union_count, inter, alpha, static_threshold,
-              dynamic_threshold, nms_iou_threshold=None, out=None):
-    """Returns dict(scores [E,P] f64, order [E,P] i32, flags [E,P] u8, summary [E,4] i32)."""
+              dynamic_threshold, nms_iou_threshold=None, out=None, clip_f16=False):
+    """Returns dict(scores [E,P] f64, order [E,P] i32, flags [E,P] u8, summary [E,4] i32).  `clip_f16`: `clip` holds
+    float16 values and the fusion follows NumPy's float16 sequence (include/marsb200.h)."""
     e, p = clip.shape
     dev = clip.device
     emd = _cuda(emd, torch.float64, "emd").reshape(e, p)
@@ -410,7 +415,7 @@ def fuse_rank(emd, clip, pooled_count, sum_vva, sum_vta, union_count, inter, alp
     check(lib.marsb200_fuse_rank(emd.data_ptr(), clip.data_ptr(), pooled_count.data_ptr(), sum_vva.data_ptr(),
                                  sum_vta.data_ptr(), union_count.data_ptr(), _ptr(inter) if use_nms else None, e, p,
                                  float(alpha), float(static_threshold), float(dynamic_threshold),
-                                 float(nms_iou_threshold) if use_nms else -1.0, out["scores"].data_ptr(),
+                                 float(nms_iou_threshold) if use_nms else -1.0, int(bool(clip_f16)), out["scores"].data_ptr(),
                                  out["order"].data_ptr(), out["flags"].data_ptr(), out["summary"].data_ptr(), _stream()))
     return out
 

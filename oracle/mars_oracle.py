@@ -266,13 +266,28 @@ def fuse_scores(emd_scores, clip_scores, coverage, pvv_align, pvt_align, alpha: 
 
     ``pvv = a*align + (1-a)*coverage`` (FilteringMergingModule.py:118-119),
     min-max of the EMD and AlphaCLIP scores over the proposals (:126-132; the
-    AlphaCLIP min-max is evaluated in the feature dtype, float32 in this
-    oracle), mean of the four (:136).
+    AlphaCLIP min-max is evaluated in the feature dtype), mean of the four (:136).
+
+    float32 AlphaCLIP scores (the primary oracle): float32 min-max, float64 sum.
+    float16 AlphaCLIP scores (the reference as run on a GPU: features are ``.half()``, :189,195, and
+    ``(img_feats @ text_feats.T).cpu().numpy()`` is a float16 array, :97): the expressions of :126-136 are
+    evaluated with the reference's own operand types - Python floats for the EMD (POT returns a Python float), NumPy
+    float16 for AlphaCLIP, np.float64 for pvv / pvt - so NumPy's promotion rules (a Python float is weak: ``1e-7 + max``
+    and ``emd_n + clip_n`` are float16 operations) apply exactly as they do in the reference.
     """
-    emd = np.asarray(emd_scores, dtype=np.float64)
-    clip = np.asarray(clip_scores, dtype=np.float32).reshape(-1)
     pvv = alpha * np.asarray(pvv_align) + (1 - alpha) * np.asarray(coverage)
     pvt = alpha * np.asarray(pvt_align) + (1 - alpha) * np.asarray(coverage)
+    if np.asarray(clip_scores).dtype == np.float16:
+        emd = [float(v) for v in np.asarray(emd_scores, dtype=np.float64)]
+        clip = [np.asarray([v], dtype=np.float16) for v in np.asarray(clip_scores).reshape(-1)]  # shape-(1,) arrays, :97
+        min_emd, max_emd = min(emd), max(emd)
+        min_c, max_c = min(clip), max(clip)
+        emd_n = [(v - min_emd) / (1e-7 + max_emd - min_emd) for v in emd]
+        clip_n = [(v - min_c) / (1e-7 + max_c - min_c) for v in clip]
+        out = [(emd_n[i] + clip_n[i] + np.float64(pvv[i]) + np.float64(pvt[i])) / 4 for i in range(len(emd))]
+        return np.asarray([float(np.asarray(v).reshape(-1)[0]) for v in out], dtype=np.float64)
+    emd = np.asarray(emd_scores, dtype=np.float64)
+    clip = np.asarray(clip_scores, dtype=np.float32).reshape(-1)
     emd_n = (emd - emd.min()) / (EPS + emd.max() - emd.min())
     clip_n = (clip - clip.min()) / (np.float32(EPS) + clip.max() - clip.min())
     return (emd_n + clip_n.astype(np.float64) + pvv + pvt) / 4

@@ -66,11 +66,12 @@ def proto_features(rows, c, seed, n_proto=8):
     return 0.6 * protos[k] + 0.8 * torch.randn(rows, c, generator=g)
 
 
-def attention_stack(layers, heads, tokens, seed, four_d=True):
+def attention_stack(layers, heads, tokens, seed, four_d=True, sharp=2.0):
+    """`sharp` scales the logits: 2.0 = diffuse attention, 12.0 = near-one-hot rows (peaky)."""
     g = _gen(seed)
     maps = []
     for _ in range(layers):
-        a = torch.softmax(2.0 * torch.randn(heads, tokens, tokens, generator=g), dim=-1)
+        a = torch.softmax(sharp * torch.randn(heads, tokens, tokens, generator=g), dim=-1)
         maps.append(a[None] if four_d else a)
     return maps
 
@@ -105,6 +106,12 @@ PIR_CASES = {
     "g33_border": dict(seed=22, g=33, regs=0, layers=1, heads=2, last_n=8, thr=0.4, kind="border", four_d=False),
     "g9_flat": dict(seed=23, g=9, regs=2, layers=1, heads=1, last_n=1, thr=0.8, kind="flat", four_d=True),
     "g16_rand": dict(seed=24, g=16, regs=1, layers=3, heads=2, last_n=2, thr=0.6, kind="rand", four_d=True),
+    # adversarial for the R (R (B*p)) evaluation order: near-one-hot attention rows and a prior whose range is
+    # 2 % of its mean, so the final min-max amplifies any rounding difference ~50x
+    "g14_peaky_lowrange": dict(seed=25, g=14, regs=0, layers=2, heads=2, last_n=2, thr=0.4, kind="lowrange", four_d=True,
+                               sharp=12.0),
+    # the same attention at the native grid with a random prior
+    "g37_peaky": dict(seed=26, g=37, regs=4, layers=1, heads=2, last_n=1, thr=0.8, kind="rand", four_d=True, sharp=10.0),
 }
 
 
@@ -125,13 +132,16 @@ def pir_inputs(spec):
         prior[10:20, 10:20] = 0.7
         prior[13:17, 13:17] = 0.05    # a hole inside a component
         prior[14:16, 14:16] = 0.75    # an island inside the hole
+    elif spec["kind"] == "lowrange":
+        prior = 0.6 + 0.012 * rs.rand(g, g)  # every pixel above the threshold: one component, box clipped at the border
     elif spec["kind"] == "flat":
         prior = np.zeros((g, g))      # no pixel above the threshold -> no contour -> B == 0
     else:
         prior = rs.rand(g, g)
     prior = torch.from_numpy(np.clip(prior, 0, 1).astype(np.float32))
     tokens = 1 + spec["regs"] + g * g
-    return dict(prior=prior, attn_maps=attention_stack(spec["layers"], spec["heads"], tokens, seed + 2, spec["four_d"]))
+    return dict(prior=prior, attn_maps=attention_stack(spec["layers"], spec["heads"], tokens, seed + 2, spec["four_d"],
+                                                       spec.get("sharp", 2.0)))
 
 
 # ---------------------------------------------------------------- FM cases
@@ -142,6 +152,17 @@ FM_CASES = {
     "g37_native": dict(seed=32, g=37, H=518, ns=2, P=6, D=48, alpha=0.85, static=0.55, dynamic=0.95, dup_every=0, small_support=True),
     # high static threshold -> the dynamic branch of the merge is taken
     "g10_dynamic": dict(seed=33, g=10, H=140, ns=1, P=12, D=16, alpha=0.7, static=0.99, dynamic=0.8, dup_every=5),
+    # every proposal is the same mask: all four scores tie, min-max gives 0 / 1e-7, the stable rule keeps index order
+    "g8_identical": dict(seed=34, g=8, H=112, ns=1, P=6, D=16, alpha=0.85, static=0.55, dynamic=0.95, dup_every=0,
+                         identical=True),
+    # 1024 -> 37 pooling (28/29-pixel bins that overlap by one pixel): proposal 0 is the single pixel (27, 27), which lies
+    # in the overlap of bins 0 and 1 on both axes (4 patches); proposal 1 is the single pixel (28, 28) (1 patch)
+    "g37_onepixel_1024": dict(seed=35, g=37, H=1024, ns=1, P=5, D=16, alpha=0.85, static=0.55, dynamic=0.95, dup_every=0,
+                              onepixel=True),
+    # AlphaCLIP features in float16, as the reference runs them on a GPU (FilteringMergingModule.py:97,126-136,189,195):
+    # the dot products, their min-max and the first addition of the fusion are float16 arithmetic in NumPy
+    "g10_clipfp16": dict(seed=36, g=10, H=140, ns=1, P=14, D=64, alpha=0.85, static=0.55, dynamic=0.95, dup_every=0,
+                         clip_fp16=True),
 }
 
 
@@ -155,6 +176,13 @@ def fm_inputs(spec):
         support = blob_masks(ns, h, h, seed + 2, 0.01, 0.03)
     else:
         support = blob_masks(ns, h, h, seed + 2, 0.05, 0.25)
+    if spec.get("identical"):
+        masks = masks[:1].repeat(p, 1, 1).contiguous()
+    if spec.get("onepixel"):
+        masks[0] = 0
+        masks[0, 27, 27] = 1
+        masks[1] = 0
+        masks[1, 28, 28] = 1
     fs = torch.nn.functional.normalize(proto_features(ns * n, 24, seed + 3), dim=1)
     fq = torch.nn.functional.normalize(proto_features(n, 24, seed + 4), dim=1)
     cost = (1 - fs @ fq.T) / 2
@@ -162,7 +190,22 @@ def fm_inputs(spec):
     txt = torch.nn.functional.normalize(torch.randn(d, generator=gen), dim=0)
     vva = torch.rand(g, g, generator=gen)
     vta = torch.rand(g, g, generator=gen)
+    if spec.get("clip_fp16"):
+        img, txt = img.half(), txt.half()
     return dict(masks=masks, support_mask=support, cost=cost.contiguous(), clip_img=img, clip_txt=txt, vva=vva, vta=vta)
+
+
+def alphaclip_as_seen(c):
+    """The AlphaCLIP (image, text) features as the reference's dot product sees them: its producer code re-normalises
+    what the model returns in the feature dtype (FilteringMergingModule.py:179,201).  The float32 fixtures hold already
+    normalised features (the step is an identity up to 1 ulp and was generated without it); for float16 features the
+    half-precision normalisation is part of the input the fixture pins."""
+    img, txt = c["clip_img"], c["clip_txt"]
+    if img.dtype == torch.float16:
+        img = img / img.norm(dim=-1, keepdim=True)
+        txt = txt.reshape(1, -1)
+        txt = (txt / txt.norm(dim=-1, keepdim=True)).reshape(-1)
+    return img, txt
 
 
 # ---- evaluator / AverageMeter (SURVEY 8f-3): episodes of (prediction, ground truth, ignore band, class id)

@@ -119,6 +119,10 @@ def gen_fm(name, spec):
     from mars.components.FilteringMergingModule import FilteringMergingModule
 
     c = cases.fm_inputs(spec)
+    if spec.get("clip_fp16"):
+        # POT's ot.emd2 returns a Python float for NumPy inputs; with float16 AlphaCLIP scores that matters: NumPy adds a
+        # (weak) Python float to a float16 array IN float16, an np.float64 would promote the sum
+        sys.modules["ot"].emd2 = lambda a, b, M: float(orc.emd_exact(np.asarray(M)))
     model = FakeAlphaClip(c["clip_img"], c["clip_txt"])
     mod = FilteringMergingModule(
         alpha_clip_model=model, img_transforms=lambda x: torch.zeros(3, 8, 8),
@@ -144,6 +148,8 @@ def gen_fm(name, spec):
                         emd=np.asarray(emd, dtype=np.float64),
                         merged_bits=np.packbits(merged.numpy() > 0), merged_shape=np.asarray(merged.shape))
     print("fm", name, order[:8], scores[:4])
+    if spec.get("clip_fp16"):
+        sys.modules["ot"].emd2 = lambda a, b, M: np.float64(orc.emd_exact(np.asarray(M)))
 
 
 def gen_eval(name, spec):

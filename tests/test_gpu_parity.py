@@ -262,6 +262,12 @@ def test_pir_matches_reference(mb, name, backend):
         b_ref[y0:y1, x0:x1] = 1
     np.testing.assert_array_equal(box.reshape(g, g).cpu().numpy(), b_ref)
     np.testing.assert_allclose(out.reshape(g, g).cpu().numpy(), z["refined"], rtol=RTOL, atol=1e-7)
+    # what the pipeline consumes is the min-max of this map (VisualVisualAlignmentModule.py:102, mars/MARS.py:82): the
+    # R (R (B*p)) evaluation order must survive that amplification too - the peaky / low-range cases are built for it
+    mm = mb.ops.pir_refine(c["prior"].reshape(1, -1).to(dev()), attn[None], g, spec["thr"], apply_minmax=True, backend=backend)
+    ref = z["refined"].astype(np.float32)
+    ref_mm = (ref - ref.min()) / (np.float32(1e-7) + ref.max() - ref.min())
+    np.testing.assert_allclose(mm.reshape(g, g).cpu().numpy(), ref_mm, rtol=RTOL, atol=2e-5)
 
 
 @pytest.mark.parametrize("name", list(cases.PIR_CASES))
@@ -340,7 +346,7 @@ def test_filtering_merging_module_matches_reference(mb, name):
                                     dynamic_threshold=spec["dynamic"], device=dev())
     kw = dict(query_img=torch.zeros(1, 3, h, h), mask_proposals=c["masks"], support_mask=c["support_mask"][None],
               cost_matrix=c["cost"].to(dev()), patch_features_spatial_dimension=spec["g"], vva=c["vva"], vta=c["vta"],
-              text=["a thing."], emd_scores=z["emd"], alphaclip_feats=(c["clip_img"], c["clip_txt"]))
+              text=["a thing."], emd_scores=z["emd"], alphaclip_feats=cases.alphaclip_as_seen(c))
     ranked = mod._score_proposals(**kw)
     order = [[i for i in range(spec["P"]) if m.data_ptr() == c["masks"][i].data_ptr()][0] for m, _ in ranked]
     scores_by_index_ref = np.empty(spec["P"])

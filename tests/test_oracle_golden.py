@@ -62,7 +62,7 @@ def test_filtering_merging_matches_reference(name):
     sup = orc.pool_mask(c["support_mask"], g).reshape(-1)
     emd = np.asarray([orc.emd_score(sup, torch.from_numpy(pm), c["cost"]) for pm in pooled])
     np.testing.assert_allclose(emd, z["emd"], rtol=0, atol=1e-9)
-    clip = orc.clip_scores(c["clip_img"], c["clip_txt"])
+    clip = orc.clip_scores(*cases.alphaclip_as_seen(c))
     scores = orc.fuse_scores(z["emd"], clip, cov, avv, avt, spec["alpha"])
     order = orc.stable_rank(scores)
     np.testing.assert_array_equal(order, z["order"])
