@@ -34,7 +34,11 @@ __device__ long long g_emd_prof[16];
 #define EP_COUNT(slot) do { } while (0)
 #endif
 
-constexpr int EMD_THREADS = 256;
+#ifndef MARSB200_EMD_THREADS
+#define MARSB200_EMD_THREADS 256
+#endif
+constexpr int EMD_THREADS = MARSB200_EMD_THREADS;
+constexpr int EMD_MAX_CTAS = 1024 / EMD_THREADS;  // resident CTAs per SM the register file allows at 64 registers per thread
 constexpr int EMD_WARPS = EMD_THREADS / 32;
 constexpr double EMD_INF = 1e300;
 constexpr int EMD_GLOBAL_CTAS = 148;  // CTAs (and state slabs) of the global-state launch
@@ -345,7 +349,7 @@ __device__ inline void expand_feeders(const EmdSmem& s, int j, double d, int* nn
 // per-CTA slab of global memory (L2-resident), sized for ANY problem of the episode shape (t_cap = all support rows,
 // m_cap = N); it only walks the overflow list, so it costs one empty launch when nothing overflowed.  Together: no capacity
 // limit below the 16-bit index range, like the reference's ot.emd2 (FilteringMergingModule.py:162-166).
-__global__ void __launch_bounds__(EMD_THREADS, 4) emd_kernel(const float* __restrict__ cost, const uint8_t* __restrict__ row_fg,
+__global__ void __launch_bounds__(EMD_THREADS, EMD_MAX_CTAS) emd_kernel(const float* __restrict__ cost, const uint8_t* __restrict__ row_fg,
                                                            const uint32_t* __restrict__ pooled, int P, int64_t m_rows,
                                                            int N, int npw, int t_cap, int m_cap, int total_lps,
                                                            const int32_t* __restrict__ order, int32_t* __restrict__ counter,
@@ -637,7 +641,7 @@ extern "C" {
 
 static int emd_ctas_per_sm(int t_cap, int m_cap) {  // 64 registers x 256 threads: at most 4 by the register file
     const size_t smem = emd_smem_bytes(t_cap, std::max(t_cap, m_cap));
-    return (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
+    return (int)std::max<size_t>(1, std::min<size_t>(EMD_MAX_CTAS, (size_t)(227 * 1024) / (smem + 1024)));
 }
 
 constexpr size_t EMD_SMEM_LIMIT = 200 * 1024;

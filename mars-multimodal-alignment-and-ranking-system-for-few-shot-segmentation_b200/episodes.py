@@ -45,6 +45,7 @@ class RankingConfig:
     partition_chunks: int = 4          # episode chunks pack -> pairwise are pipelined in across the two partitions
     partition_pairwise_tail: int = 0   # intersections of the last chunks run on the `hbm` partition after the ingest
     partition_vta_on_hbm: bool = True  # vta refinement on the `hbm` partition after the ingest (else beside the vva chain)
+    partition_pool_on_tensor: bool = False  # pooled bitmaps of a chunk on the `tensor` partition (the `hbm` one only packs)
 
 
 def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int] = None) -> int:
@@ -213,7 +214,8 @@ class RankingEngine:
             for (lo, hi), ev in zip(self._chunks, self._ev_chunk):
                 ops.pack_masks(masks[lo:hi], out=self.bits[lo:hi])
                 ev.record(hbm)
-                ops.pool_packed(self.bits[lo:hi], s.H, s.W, s.g, out=tuple(t[lo:hi] for t in self.pool_out))
+                if not cfg.partition_pool_on_tensor:
+                    ops.pool_packed(self.bits[lo:hi], s.H, s.W, s.g, out=tuple(t[lo:hi] for t in self.pool_out))
             # the last chunks' intersections stay on this partition: their bits only exist when the ingest is over and
             # the tensor partition still has its own queue to drain
             tail = self._chunks[len(self._chunks) - cfg.partition_pairwise_tail:] if cfg.partition_pairwise_tail else []
@@ -239,9 +241,14 @@ class RankingEngine:
             ops.pir_refine(self.prior, batch["attn_vva"], s.g, cfg.vva_box_threshold, apply_minmax=True,
                            backend=cfg.gemm_backend, workspace=self.pir_ws, out=self.vva)
             ops.clip_scores(batch["clip_img"], batch["clip_txt"], out=self.clip)
-            if self.inter is not None:
-                for (lo, hi), ev in list(zip(self._chunks, self._ev_chunk))[:len(self._chunks) - len(tail)]:
+            n_front = len(self._chunks) - len(tail)
+            for k, ((lo, hi), ev) in enumerate(zip(self._chunks, self._ev_chunk)):
+                on_tensor = self.inter is not None and k < n_front
+                if on_tensor or cfg.partition_pool_on_tensor:
                     ten.wait_event(ev)
+                if cfg.partition_pool_on_tensor:
+                    ops.pool_packed(self.bits[lo:hi], s.H, s.W, s.g, out=tuple(t[lo:hi] for t in self.pool_out))
+                if on_tensor:
                     ops.pairwise_inter(self.bits[lo:hi], backend=cfg.pair_backend, out=self.inter[lo:hi])
             ten.wait_event(self._ev_vta)
             ops.resize_minmax(self.vta_ref.reshape(e, s.gt, s.gt), s.g, True, out=self.vta)
