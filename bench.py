@@ -322,12 +322,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if world > 1:  # every engine's fuse / rank kernel writes its records into its rank's slice of an all-gather table
+        for en in (pipe.engines if pipe is not None else [eng]):
+            en.attach_gather_table(world, rank)
+
     def finish(ticket):
-        # results of a pipelined step: join it on this stream, then (multi-GPU) all-gather its records
+        # results of a pipelined step: join it on this stream, then (multi-GPU) all-gather its records, in place
         if pipe is not None:
             pipe.result(ticket)
         if world > 1:
-            marsb200.gather_records((pipe.engine(ticket) if pipe is not None else eng).records(), total_episodes)
+            (pipe.engine(ticket) if pipe is not None else eng).gather()
 
     def run_steps(n):
         """n steps back to back; with the pipeline the results of step i are collected after step i + 1 is enqueued,
@@ -589,11 +593,12 @@ def run_ours(args):
     if world > 1 and not args.no_verify_gather:
         if pipe is not None:
             out = pipe.result(pipe.submit(batches[0]))
-            local = pipe.engine(pipe._next - 1).records().clone()
+            en = pipe.engine(pipe._next - 1)
         else:
             eng.run(batches[0])
-            local = eng.records().clone()
-        table = marsb200.gather_records(local, total_episodes)
+            en = eng
+        local = en.records().clone()
+        table = en.gather().clone()  # the same in-place collective the timed loop runs
         torch.cuda.synchronize()
         ok_local = bool(torch.equal(table[rank * E:(rank + 1) * E], local))
         bad = []

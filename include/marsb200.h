@@ -212,11 +212,18 @@ int marsb200_clip_scores_f16(const void* img_f16, const void* txt_f16, int E, in
  * Outputs: scores [E,P] fp64 by proposal index; order [E,P] int32 (rank -> index);
  * flags [E,P] uint8 by proposal index (bit0 = kept by NMS, bit1 = selected for the merge);
  * summary [E,4] int32 = {n_kept, n_selected, top_index, n_nonfinite}: n_nonfinite counts proposals whose fused score is
- * NaN / inf (a NaN input score); they rank last and the caller should treat the episode as failed. */
+ * NaN / inf (a NaN input score); they rank last and the caller should treat the episode as failed.
+ * record: optional [E, record_stride] bytes, see marsb200_record_bytes. */
 int marsb200_fuse_rank(const double* emd, const float* clip, const int32_t* pooled_count, const float* sum_vva,
                        const float* sum_vta, const int32_t* union_count, const int32_t* inter, int E, int P,
                        double alpha, double static_threshold, double dynamic_threshold, float nms_iou_threshold,
-                       int clip_f16, double* scores, int32_t* order, uint8_t* flags, int32_t* summary, void* stream);
+                       int clip_f16, double* scores, int32_t* order, uint8_t* flags, int32_t* summary, uint8_t* record,
+                       int64_t record_stride, void* stream);
+/* Bytes of one episode's result record: order int32[P] | score float32[P] | flags uint8[P rounded up to 4] | summary
+ * int32[4].  When `record` is given (row e at record + e * record_stride, 4-byte aligned) marsb200_fuse_rank writes the
+ * record itself, so the rows can BE a rank's slice of the all-gather table (the only collective of the path
+ * gathers these records; nothing is copied or concatenated before it). */
+int64_t marsb200_record_bytes(int P);
 
 /* OR of the selected packed masks and expansion to the float32 [H,W] map the reference returns.
  * Replaces (torch.sum(torch.stack(ranked_masks), 0) > 0).float(), FilteringMergingModule.py:219, and the

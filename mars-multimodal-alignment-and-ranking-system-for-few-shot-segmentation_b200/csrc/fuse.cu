@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
     const float* __restrict__ sum_vva, const float* __restrict__ sum_vta, const int32_t* __restrict__ union_count,
     const int32_t* __restrict__ inter, int P, int n2, int use_bitmask, int clip_f16, double alpha, double static_thr, double dynamic_thr,
     float nms_thr, double* __restrict__ scores, int32_t* __restrict__ order, uint8_t* __restrict__ flags,
-    int32_t* __restrict__ summary) {
+    int32_t* __restrict__ summary, uint8_t* __restrict__ record, int64_t record_stride) {
     extern __shared__ unsigned char smem_raw[];
     double* s_key = reinterpret_cast<double*>(smem_raw);               // n2
     int* s_idx = reinterpret_cast<int*>(s_key + n2);                   // n2
@@ -83,6 +83,12 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
 
     const int64_t e = blockIdx.x;
     const int tid = threadIdx.x;
+    // optional result record of the episode (the row of the all-gather table, episodes.py):
+    // order int32[P] | score float32[P] | flags uint8[pad4(P)] | summary int32[4]
+    int32_t* rec_order = record ? reinterpret_cast<int32_t*>(record + e * record_stride) : nullptr;
+    float* rec_score = record ? reinterpret_cast<float*>(record + e * record_stride + 4 * (int64_t)P) : nullptr;
+    uint8_t* rec_flags = record ? record + e * record_stride + 8 * (int64_t)P : nullptr;
+    int32_t* rec_summary = record ? reinterpret_cast<int32_t*>(record + e * record_stride + 8 * (int64_t)P + ((P + 3) & ~3)) : nullptr;
     emd += e * P;
     clip += e * P;
     pooled_count += e * P;
@@ -132,6 +138,7 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
                 sc = (((en + (double)cn) + pvv) + pvt) / 4.0;
             }
             scores[e * P + p] = sc;
+            if (rec_score) rec_score[p] = (float)sc;
             const bool finite = isfinite(sc);
             if (!finite) atomicAdd(&s_nonfinite, 1);
             s_key[p] = finite ? sc : -INFINITY;  // a NaN key would make the sort inconsistent: such proposals rank last
@@ -167,6 +174,7 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
     for (int r = tid; r < P; r += FUSE_THREADS) {
         const int p = s_idx[r];
         order[e * P + r] = p;
+        if (rec_order) rec_order[r] = p;
         s_rank[p] = r;
         s_removed[r] = 0;  // indexed by proposal below; cleared for all P entries here
     }
@@ -245,6 +253,7 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
         const bool keep = !do_nms || !s_removed[p];
         const bool sel = keep && (s_key[s_rank[p]] >= bound);
         flags[e * P + p] = (keep ? 1 : 0) | (sel ? 2 : 0);
+        if (rec_flags) rec_flags[p] = (keep ? 1 : 0) | (sel ? 2 : 0);
         kept += keep;
         selected += sel;
     }
@@ -260,6 +269,12 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
         summary[e * 4 + 1] = s_counts[1];
         summary[e * 4 + 2] = s_idx[0];
         summary[e * 4 + 3] = s_nonfinite;
+        if (rec_summary) {
+            rec_summary[0] = s_counts[0];
+            rec_summary[1] = s_counts[1];
+            rec_summary[2] = s_idx[0];
+            rec_summary[3] = s_nonfinite;
+        }
     }
 }
 
@@ -288,13 +303,18 @@ int marsb200_clip_scores_f16(const void* img, const void* txt, int E, int P, int
     return MARSB200_OK;
 }
 
+int64_t marsb200_record_bytes(int P) { return P <= 0 ? 0 : 8 * (int64_t)P + ((P + 3) & ~3) + 16; }
+
 int marsb200_fuse_rank(const double* emd, const float* clip, const int32_t* pooled_count, const float* sum_vva,
                        const float* sum_vta, const int32_t* union_count, const int32_t* inter, int E, int P,
                        double alpha, double static_threshold, double dynamic_threshold, float nms_iou_threshold,
-                       int clip_f16, double* scores, int32_t* order, uint8_t* flags, int32_t* summary, void* stream) {
+                       int clip_f16, double* scores, int32_t* order, uint8_t* flags, int32_t* summary, uint8_t* record,
+                       int64_t record_stride, void* stream) {
     MARS_REQUIRE(emd && clip && pooled_count && sum_vva && sum_vta && union_count, "null input");
     MARS_REQUIRE(scores && order && flags && summary, "null output");
     MARS_REQUIRE(E > 0 && P > 0 && P <= 8192, "shape (P <= 8192)");
+    MARS_REQUIRE(!record || (record_stride >= marsb200_record_bytes(P) && record_stride % 4 == 0 &&
+                             (reinterpret_cast<uintptr_t>(record) & 3) == 0), "record row: >= marsb200_record_bytes(P), 4-byte aligned");
     int n2 = 1;
     while (n2 < P) n2 <<= 1;
     size_t smem = (size_t)n2 * (sizeof(double) + sizeof(int)) + (size_t)P * (2 * sizeof(int) + 1) + 16;
@@ -308,7 +328,7 @@ int marsb200_fuse_rank(const double* emd, const float* clip, const int32_t* pool
     fuse_rank_kernel<<<E, FUSE_THREADS, smem, as_stream(stream)>>>(emd, clip, pooled_count, sum_vva, sum_vta,
                                                                    union_count, inter, P, n2, use_bitmask, clip_f16 ? 1 : 0, alpha, static_threshold,
                                                                    dynamic_threshold, nms_iou_threshold, scores, order,
-                                                                   flags, summary);
+                                                                   flags, summary, record, record_stride);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }

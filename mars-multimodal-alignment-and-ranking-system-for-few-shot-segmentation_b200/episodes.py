@@ -121,6 +121,10 @@ class RankingEngine:
         self.clip = new((e, s.P), f32)
         self.rank_out = dict(scores=new((e, s.P), torch.float64), order=new((e, s.P), i32),
                              flags=new((e, s.P), u8), summary=new((e, 4), i32))
+        # result records [E, record_bytes], written by fuse_rank itself; `attach_gather_table` re-points this at the rank's
+        # slice of the all-gather table so that nothing is copied before the collective
+        self.record_buf = new((e, ops.record_bytes(s.P)), u8)
+        self._gather_table = None
         self.merge_out = dict(bits=new((e, wpm), i32))
         if cfg.want_merged_f32:
             self.merge_out["f32"] = new((e, s.H * s.W), f32)
@@ -261,7 +265,7 @@ class RankingEngine:
                                      check=False, status=self.emd_status)
             ops.fuse_rank(emd, self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
                           self.region_out[2], self.inter, cfg.alpha, cfg.static_threshold, cfg.dynamic_threshold,
-                          cfg.nms_iou_threshold, out=self.rank_out)
+                          cfg.nms_iou_threshold, out=self.rank_out, record=self.record_buf)
             ops.merge_masks(self.bits, self.rank_out["flags"], s.H * s.W, want_bits=True,
                             want_f32=cfg.want_merged_f32, out=self.merge_out)
             self._ev_join.record(ten)
@@ -332,7 +336,7 @@ class RankingEngine:
                                  status=self.emd_status)
         ops.fuse_rank(emd, self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
                       self.region_out[2], self.inter, cfg.alpha, cfg.static_threshold, cfg.dynamic_threshold,
-                      cfg.nms_iou_threshold, out=self.rank_out)
+                      cfg.nms_iou_threshold, out=self.rank_out, record=self.record_buf)
         ops.merge_masks(self.bits, self.rank_out["flags"], s.H * s.W, want_bits=True,
                         want_f32=cfg.want_merged_f32, out=self.merge_out)
         return self.outputs()
@@ -383,17 +387,33 @@ class RankingEngine:
 
     # ------------------------------------------------------------------ result records
     def record_bytes(self) -> int:
-        p = self.shape.P
-        return 4 * p + 4 * p + p + 16
+        return ops.record_bytes(self.shape.P)
 
     def records(self) -> torch.Tensor:
-        """Fixed-size per-episode result records [E, record_bytes] uint8: order, score (f32), flags, summary."""
-        r = self.rank_out
+        """Fixed-size per-episode result records [E, record_bytes] uint8 (order int32[P] | score float32[P] | flags
+        uint8[pad4(P)] | summary int32[4]), written by the fuse / rank kernel of the last step: no copy, no concatenation.
+        The tensor is the engine's own buffer (or its slice of the gather table) - clone it to keep it across steps."""
+        return self.record_buf
+
+    def attach_gather_table(self, world_size: int, rank: int) -> torch.Tensor:
+        """Allocates the all-gather table [world_size * E, record_bytes] and makes this rank's slice the buffer the fuse /
+        rank kernel writes the records into; `gather()` then runs the collective in place."""
+        if self._graph is not None:
+            raise RuntimeError("attach_gather_table must precede capture(): the graph holds the record pointer")
         e = self.E
-        return torch.cat([r["order"].view(torch.uint8).reshape(e, -1),
-                          r["scores"].float().view(torch.uint8).reshape(e, -1),
-                          r["flags"].reshape(e, -1),
-                          r["summary"].view(torch.uint8).reshape(e, -1)], dim=1).contiguous()
+        self._gather_table = torch.empty((world_size * e, self.record_bytes()), device=self.device, dtype=torch.uint8)
+        self.record_buf = self._gather_table[rank * e:(rank + 1) * e]
+        return self._gather_table
+
+    def gather(self, group=None) -> torch.Tensor:
+        """The path's only collective: all-gather of the result records, in place in the table this engine's kernels wrote
+        their slice of (NCCL over NVLink on GPUs)."""
+        import torch.distributed as dist
+
+        if self._gather_table is None:
+            raise RuntimeError("call attach_gather_table(world_size, rank) first")
+        dist.all_gather_into_tensor(self._gather_table, self.record_buf, group=group)
+        return self._gather_table
 
 
 class PipelinedRanking:
@@ -428,12 +448,13 @@ class PipelinedRanking:
 
 
 def decode_records(records: torch.Tensor, p: int) -> dict:
-    """Inverse of `RankingEngine.records` (works on CPU or CUDA tensors)."""
+    """Splits result records [n, record_bytes] (CPU or CUDA) into order / scores / flags / summary."""
     n = records.shape[0]
+    fl = (p + 3) // 4 * 4
     order = records[:, :4 * p].contiguous().view(torch.int32).reshape(n, p)
     scores = records[:, 4 * p:8 * p].contiguous().view(torch.float32).reshape(n, p)
     flags = records[:, 8 * p:9 * p]
-    summary = records[:, 9 * p:9 * p + 16].contiguous().view(torch.int32).reshape(n, 4)
+    summary = records[:, 8 * p + fl:8 * p + fl + 16].contiguous().view(torch.int32).reshape(n, 4)
     return dict(order=order, scores=scores, flags=flags, summary=summary)
 
 

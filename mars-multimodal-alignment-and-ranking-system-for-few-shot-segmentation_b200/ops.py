@@ -400,9 +400,10 @@ def clip_scores(img: torch.Tensor, txt: torch.Tensor, out=None) -> torch.Tensor:
 
 
 def fuse_rank(emd, clip, pooled_count, sum_vva, sum_vta, union_count, inter, alpha, static_threshold,
-              dynamic_threshold, nms_iou_threshold=None, out=None, clip_f16=False):
+              dynamic_threshold, nms_iou_threshold=None, out=None, clip_f16=False, record=None):
     """Returns dict(scores [E,P] f64, order [E,P] i32, flags [E,P] u8, summary [E,4] i32).  `clip_f16`: `clip` holds
-    float16 values and the fusion follows NumPy's float16 sequence (include/marsb200.h)."""
+    float16 values and the fusion follows NumPy's float16 sequence (include/marsb200.h).  `record`: optional uint8
+    [E, >= record_bytes(P)] rows (may be a slice of a larger table) the kernel also writes the result records into."""
     e, p = clip.shape
     dev = clip.device
     emd = _cuda(emd, torch.float64, "emd").reshape(e, p)
@@ -416,8 +417,13 @@ def fuse_rank(emd, clip, pooled_count, sum_vva, sum_vta, union_count, inter, alp
                                  sum_vta.data_ptr(), union_count.data_ptr(), _ptr(inter) if use_nms else None, e, p,
                                  float(alpha), float(static_threshold), float(dynamic_threshold),
                                  float(nms_iou_threshold) if use_nms else -1.0, int(bool(clip_f16)), out["scores"].data_ptr(),
-                                 out["order"].data_ptr(), out["flags"].data_ptr(), out["summary"].data_ptr(), _stream()))
+                                 out["order"].data_ptr(), out["flags"].data_ptr(), out["summary"].data_ptr(),
+                                 _ptr(record), 0 if record is None else record.stride(0), _stream()))
     return out
+
+
+def record_bytes(p: int) -> int:
+    return int(lib.marsb200_record_bytes(int(p)))
 
 
 def merge_masks(bits: torch.Tensor, flags: torch.Tensor, hw: int, want_bits=False, want_f32=True, out=None):

@@ -458,8 +458,13 @@ def test_engine_graph_replay_matches_eager(mb):
     torch.cuda.synchronize()
     for k, v in eager.items():
         assert torch.equal(v, replay[k]), k
+    # the result records are written by the fuse / rank kernel itself (no concatenation): every field equals the outputs
     rec = mb.decode_records(eng.records().cpu(), shape.P)
     assert torch.equal(rec["order"], replay["order"].cpu())
+    assert torch.equal(rec["scores"], replay["scores"].float().cpu())
+    assert torch.equal(rec["flags"], replay["flags"].cpu())
+    assert torch.equal(rec["summary"], replay["summary"].cpu())
+    assert eng.records().shape == (2, mb.ops.record_bytes(shape.P))
 
 
 def test_full_size_properties_c2(mb):

@@ -49,13 +49,16 @@ def test_shard_ranges_cover_everything():
 def test_record_roundtrip():
     from marsb200 import decode_records
 
-    p, e = 5, 3
+    p, e = 5, 3  # the flags section is padded to a multiple of 4 bytes (marsb200_record_bytes)
     order = torch.arange(e * p, dtype=torch.int32).reshape(e, p)
     scores = torch.rand(e, p)
     flags = torch.randint(0, 4, (e, p), dtype=torch.uint8)
     summary = torch.arange(e * 4, dtype=torch.int32).reshape(e, 4)
-    rec = torch.cat([order.view(torch.uint8).reshape(e, -1), scores.view(torch.uint8).reshape(e, -1), flags,
+    pad = torch.zeros((e, (p + 3) // 4 * 4 - p), dtype=torch.uint8)
+    rec = torch.cat([order.view(torch.uint8).reshape(e, -1), scores.view(torch.uint8).reshape(e, -1), flags, pad,
                      summary.view(torch.uint8).reshape(e, -1)], dim=1)
+    from marsb200 import ops
+    assert rec.shape[1] == ops.record_bytes(p)
     d = decode_records(rec, p)
     assert torch.equal(d["order"], order) and torch.equal(d["scores"], scores)
     assert torch.equal(d["flags"], flags) and torch.equal(d["summary"], summary)
@@ -74,6 +77,74 @@ def _gather_worker(rank, world, port, n_ep, q):
     if rank == 0:
         q.put(out.numpy())
     dist.destroy_process_group()
+
+
+def _fake_records(rank, e, p):
+    """What fuse_rank writes for `e` episodes of rank `rank` (layout of marsb200_record_bytes), built with numpy."""
+    rs = np.random.RandomState(100 + rank)
+    fl = (p + 3) // 4 * 4
+    rec = np.zeros((e, 8 * p + fl + 16), dtype=np.uint8)
+    fields = []
+    for i in range(e):
+        order = rs.permutation(p).astype(np.int32)
+        score = rs.rand(p).astype(np.float32)
+        flags = rs.randint(0, 4, p).astype(np.uint8)
+        summary = np.asarray([int((flags & 1).sum()), int((flags & 2).sum() // 2), int(order[0]), 0], dtype=np.int32)
+        rec[i, :4 * p] = order.view(np.uint8)
+        rec[i, 4 * p:8 * p] = score.view(np.uint8)
+        rec[i, 8 * p:9 * p] = flags
+        rec[i, 8 * p + fl:] = summary.view(np.uint8)
+        fields.append((order, score, flags, summary))
+    return rec, fields
+
+
+def _inplace_gather_worker(rank, world, port, e, p, q):
+    """The engine's pattern (RankingEngine.attach_gather_table / gather): every rank's kernels write its slice of ONE
+    table, the all-gather runs in place on it."""
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rec, _ = _fake_records(rank, e, p)
+    table = torch.zeros((world * e, rec.shape[1]), dtype=torch.uint8)
+    mine = table[rank * e:(rank + 1) * e]
+    mine.copy_(torch.from_numpy(rec))  # stands in for fuse_rank writing the records
+    dist.all_gather_into_tensor(table, mine)
+    q.put((rank, table.numpy().copy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("p", [12, 10])  # 10: the flags section is padded to a multiple of 4 bytes
+def test_two_rank_inplace_gather_of_result_records(p):
+    """world_size-2 gloo run: the gathered table on EVERY rank equals the concatenation of the rank-local records, and
+    decode_records splits it back into the fields each rank produced."""
+    import torch.multiprocessing as mp
+
+    import marsb200
+
+    e, world = 3, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + p
+    procs = [ctx.Process(target=_inplace_gather_worker, args=(r, world, port, e, p, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    want = np.concatenate([_fake_records(r, e, p)[0] for r in range(world)])
+    assert want.shape[1] == marsb200.ops.record_bytes(p)
+    for r in range(world):
+        np.testing.assert_array_equal(got[r], want)
+    d = marsb200.decode_records(torch.from_numpy(want), p)
+    for r in range(world):
+        for i, (order, score, flags, summary) in enumerate(_fake_records(r, e, p)[1]):
+            k = r * e + i
+            np.testing.assert_array_equal(d["order"][k].numpy(), order)
+            np.testing.assert_array_equal(d["scores"][k].numpy(), score)
+            np.testing.assert_array_equal(d["flags"][k].numpy(), flags)
+            np.testing.assert_array_equal(d["summary"][k].numpy(), summary)
 
 
 @pytest.mark.parametrize("n_ep", [8, 7])
