@@ -447,6 +447,45 @@ class PipelinedRanking:
         self.engines[0]._part.close()
 
 
+class InterleavedRanking:
+    """Two (or more) one-timeline engines on their own streams taking the steps in turn: the low-occupancy tail of step i
+    (one-CTA-per-episode kernels: box mask, fuse / rank / NMS, selection) overlaps the contractions and the ingest of
+    step i + 1.  The schedule for proposal formats whose ingest is cheap (uint8 masks, packed bits, RLE), where no SM
+    partition pays; same interface as `PipelinedRanking`."""
+
+    def __init__(self, shape: EpisodeShape, episodes_per_batch: int, cfg: RankingConfig, device, mask_dtype=torch.float32,
+                 depth: int = 2):
+        if cfg.tensor_partition_sms:
+            raise ValueError("InterleavedRanking runs whole-device engines (use PipelinedRanking with SM partitions)")
+        self.engines = [RankingEngine(shape, episodes_per_batch, cfg, device, mask_dtype) for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
+        self._fork = [torch.cuda.Event() for _ in range(depth)]
+        self._done = [torch.cuda.Event() for _ in range(depth)]
+        self._next = 0
+
+    def submit(self, batch: dict) -> int:
+        ticket = self._next
+        k = ticket % len(self.engines)
+        main = torch.cuda.current_stream()
+        self._fork[k].record(main)           # the batch (and whatever produced it) is ready on the caller's stream
+        self.streams[k].wait_event(self._fork[k])
+        with torch.cuda.stream(self.streams[k]):
+            self.engines[k].run(batch)
+            self._done[k].record(self.streams[k])
+        self._next += 1
+        return ticket
+
+    def engine(self, ticket: int) -> "RankingEngine":
+        return self.engines[ticket % len(self.engines)]
+
+    def result(self, ticket: int) -> dict:
+        torch.cuda.current_stream().wait_event(self._done[ticket % len(self.engines)])
+        return self.engine(ticket).outputs()
+
+    def close(self):
+        pass
+
+
 def decode_records(records: torch.Tensor, p: int) -> dict:
     """Splits result records [n, record_bytes] (CPU or CUDA) into order / scores / flags / summary."""
     n = records.shape[0]

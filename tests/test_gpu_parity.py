@@ -1594,3 +1594,28 @@ def test_pipelined_steps_match_one_timeline(mb):
             assert torch.equal(out[k], v), (prev, k)
     finally:
         pipe.close()
+
+
+def test_interleaved_engines_match_one_timeline(mb):
+    """InterleavedRanking (two whole-device engines on two streams, the schedule of the uint8 / packed / RLE variants):
+    step i + 1 is enqueued before step i is joined; every step's outputs equal the single engine's, bit for bit."""
+    shape = mb.EpisodeShape(ns=1, g=12, C=64, P=40, H=160, W=160, gt=9, D=32)
+    cfg = mb.RankingConfig(nms_iou_threshold=0.7)
+    batches = [mb.to_device(mb.stack_episodes([mb.make_episode(shape, 700 + 4 * b + i, "cpu", torch.uint8) for i in range(4)]), dev())
+               for b in range(3)]
+    base = mb.RankingEngine(shape, 4, cfg, dev(), torch.uint8)
+    refs = [{k: v.clone() for k, v in base.run(b).items() if v is not None} for b in batches]
+    inter = mb.InterleavedRanking(shape, 4, cfg, dev(), torch.uint8, depth=2)
+    prev = None
+    for i in range(7):
+        t = inter.submit(batches[i % 3])
+        if prev is not None:
+            out = inter.result(prev)
+            torch.cuda.synchronize()
+            for k, v in refs[prev % 3].items():
+                assert torch.equal(out[k], v), (prev, k)
+        prev = t
+    out = inter.result(prev)
+    torch.cuda.synchronize()
+    for k, v in refs[prev % 3].items():
+        assert torch.equal(out[k], v), (prev, k)
