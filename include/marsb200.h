@@ -154,6 +154,15 @@ int marsb200_pack_masks(const void* masks, int mask_dtype, int64_t n, int64_t HW
 int marsb200_pool_packed(const uint32_t* bits, int64_t n, int H, int W, int g, uint32_t* pooled, int32_t* area,
                          int32_t* pooled_count, void* stream);
 
+/* Ingest + pooling in ONE pass over the masks: bits = marsb200_pack_masks(masks) and (pooled, area, pooled_count) =
+ * marsb200_pool_packed(bits) - the pooling runs on the packed words while they are still in registers, so the packed
+ * bits are never read back (W % 32 == 0 and at most 2048 patches; any other geometry runs the two kernels internally, so
+ * the call is always valid and the results are always identical).  Replaces the per-proposal adaptive_max_pool2d loop of
+ * FilteringMergingModule.py:103-110 together with the ingest of the proposal tensors (main_MARS.py:62).
+ * masks [n, H, W] float32 / uint8; bits [n, wpm]; pooled [n, ceil(g*g/32)]; area, pooled_count [n]. */
+int marsb200_pack_pool_masks(const void* masks, int mask_dtype, int64_t n, int H, int W, int g, uint32_t* bits,
+                             uint32_t* pooled, int32_t* area, int32_t* pooled_count, void* stream);
+
 /* Per-proposal sums of the vva / vta maps under the pooled bitmap and the pooled size of the
  * proposal union.  Replaces FilteringMergingModule.py:77-81,108-110.
  * pooled [E, P, npw]; vva, vta [E, N]; sum_vva, sum_vta [E, P] fp32; union_count [E] int32. */

@@ -265,6 +265,156 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_packed_kernel(const uint32_
 }
 
 // --------------------------------------------------------------------------------------------
+// Fused ingest + pooling (W % 32 == 0, at most 2048 patches): the vector pack kernels with a pooling epilogue on the
+// words that are still in registers - the packed bits are not read again (pool_packed_kernel re-reads all of them) and
+// one launch per chunk disappears.  A block covers 8192 (f32) / 16384 (u8) consecutive pixels of ONE mask, i.e. a few
+// image rows: its patches fall into at most a few words of the pooled bitmap, OR-ed into global memory once per block
+// (and only by blocks that saw a set pixel).  Same bin rule as pool_packed_kernel, bit-identical results.
+// --------------------------------------------------------------------------------------------
+constexpr int FUSED_POOL_WORDS = 64;
+
+__device__ __forceinline__ void pool_word(uint32_t word, uint32_t px0, int H, int W, int g, uint32_t* s_pool) {
+    // `word` = 32 pixels of one image row starting at flat pixel index px0 (W % 32 == 0); word != 0
+    const int y = (int)(px0 / (uint32_t)W);
+    const int x0 = (int)(px0 - (uint32_t)y * (uint32_t)W);
+    const int c_lo = bin_lo_of32(x0 + __ffs(word) - 1, W, g);   // lowest bin of the first set pixel
+    const int c_hi = bin_hi_of32(x0 + 31 - __clz(word), W, g);  // highest bin of the last set pixel
+    const int r_lo = bin_lo_of32(y, H, g), r_hi = bin_hi_of32(y, H, g);
+    for (int c = c_lo; c <= c_hi; ++c) {
+        const int lo = max(bin_start32(c, W, g) - x0, 0), hi = min(bin_end32(c, W, g) - x0, 32);  // window inside the word
+        const uint32_t window = (hi - lo) >= 32 ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+        if (word & window)
+            for (int r = r_lo; r <= r_hi; ++r) {
+                const int b = r * g + c;
+                smem_or(&s_pool[b >> 5], 1u << (b & 31));
+            }
+    }
+}
+
+__device__ __forceinline__ void pool_flush(const uint32_t* s_pool, int s_area, int64_t m, int npw,
+                                           uint32_t* __restrict__ pooled, int32_t* __restrict__ area) {
+    if ((int)threadIdx.x < npw && s_pool[threadIdx.x]) atomicOr(&pooled[m * npw + threadIdx.x], s_pool[threadIdx.x]);
+    if (threadIdx.x == 0 && s_area) atomicAdd(&area[m], s_area);
+}
+
+__global__ void __launch_bounds__(PACK_THREADS, 6) pack_pool_f32_kernel(const float* __restrict__ masks, int64_t n, int64_t HW,
+                                                                      int64_t wpm, uint32_t* __restrict__ bits, int chunks,
+                                                                      int H, int W, int g, int npw,
+                                                                      uint32_t* __restrict__ pooled,
+                                                                      int32_t* __restrict__ area) {
+    __shared__ uint32_t s_pool[FUSED_POOL_WORDS];
+    __shared__ int s_area;
+    const int64_t blk = blockIdx.x;
+    const int64_t m = blk / chunks;
+    const int chunk = (int)(blk % chunks);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PX_PER_BLOCK = PACK_THREADS * PACK_UNROLL_F32 * 4;
+    const int64_t px_base = (int64_t)chunk * PX_PER_BLOCK + (int64_t)warp * (PACK_UNROLL_F32 * 128);
+    const float* src = masks + m * HW;
+
+    uint4 v[PACK_UNROLL_F32];
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL_F32; ++u) {
+        const int64_t px = px_base + u * 128 + lane * 4;
+        v[u] = (px < HW) ? ldg_stream_u4(src + px) : make_uint4(0, 0, 0, 0);
+    }
+    if (threadIdx.x < FUSED_POOL_WORDS) s_pool[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_area = 0;
+    __syncthreads();  // (the loads above are in flight meanwhile)
+    uint32_t word[PACK_UNROLL_F32];
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL_F32; ++u) {
+        uint32_t nib = (__uint_as_float(v[u].x) > 0.f ? 1u : 0u) | (__uint_as_float(v[u].y) > 0.f ? 2u : 0u) |
+                       (__uint_as_float(v[u].z) > 0.f ? 4u : 0u) | (__uint_as_float(v[u].w) > 0.f ? 8u : 0u);
+        uint32_t w = nib << (4 * (lane & 7));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        word[u] = w;
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL_F32; ++u) {
+        uint32_t got = __shfl_sync(0xffffffffu, word[u], (lane & 3) * 8);
+        if ((lane >> 2) == u) out = got;
+    }
+    const int64_t w_idx = px_base / 32 + lane;
+    int my_area = 0;
+    if (lane < PACK_UNROLL_F32 * 4 && w_idx < wpm) {
+        bits[m * wpm + w_idx] = out;
+        if (out) {
+            my_area = __popc(out);
+            pool_word(out, (uint32_t)(w_idx * 32), H, W, g, s_pool);
+        }
+    }
+    my_area = warp_sum(my_area);
+    if (lane == 0 && my_area) atomicAdd(&s_area, my_area);
+    __syncthreads();
+    pool_flush(s_pool, s_area, m, npw, pooled, area);
+}
+
+__global__ void __launch_bounds__(PACK_THREADS) pack_pool_u8_kernel(const uint8_t* __restrict__ masks, int64_t n, int64_t HW,
+                                                                     int64_t wpm, uint32_t* __restrict__ bits, int chunks,
+                                                                     int H, int W, int g, int npw,
+                                                                     uint32_t* __restrict__ pooled,
+                                                                     int32_t* __restrict__ area) {
+    __shared__ uint32_t s_pool[FUSED_POOL_WORDS];
+    __shared__ int s_area;
+    const int64_t blk = blockIdx.x;
+    const int64_t m = blk / chunks;
+    const int chunk = (int)(blk % chunks);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PX_PER_BLOCK = PACK_THREADS * PACK_UNROLL * 16;
+    const int64_t px_base = (int64_t)chunk * PX_PER_BLOCK + (int64_t)warp * (PACK_UNROLL * 512);
+    const uint8_t* src = masks + m * HW;
+
+    uint4 v[PACK_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL; ++u) {
+        const int64_t px = px_base + u * 512 + lane * 16;
+        v[u] = (px < HW) ? ldg_stream_u4(src + px) : make_uint4(0, 0, 0, 0);
+    }
+    if (threadIdx.x < FUSED_POOL_WORDS) s_pool[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_area = 0;
+    __syncthreads();
+    int my_area = 0;
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL; ++u) {
+        auto nib = [](uint32_t x) -> uint32_t {
+            uint32_t mbits = __vcmpgtu4(x, 0u) & 0x01010101u;
+            return (mbits * 0x01020408u) >> 24 & 0xfu;
+        };
+        uint32_t half = nib(v[u].x) | (nib(v[u].y) << 4) | (nib(v[u].z) << 8) | (nib(v[u].w) << 12);
+        uint32_t w = half << (16 * (lane & 1));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        const int64_t w_idx = px_base / 32 + u * 16 + (lane >> 1);
+        if ((lane & 1) == 0 && w_idx < wpm) {
+            bits[m * wpm + w_idx] = w;
+            if (w) {
+                my_area += __popc(w);
+                pool_word(w, (uint32_t)(w_idx * 32), H, W, g, s_pool);
+            }
+        }
+    }
+    my_area = warp_sum(my_area);
+    if (lane == 0 && my_area) atomicAdd(&s_area, my_area);
+    __syncthreads();
+    pool_flush(s_pool, s_area, m, npw, pooled, area);
+}
+
+// pooled patch count of every mask: one warp per mask
+__global__ void __launch_bounds__(256) pooled_count_kernel(const uint32_t* __restrict__ pooled, int64_t n, int npw,
+                                                            int32_t* __restrict__ pooled_count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (m >= n) return;
+    int c = 0;
+    for (int w = lane; w < npw; w += 32) c += __popc(pooled[m * npw + w]);
+    c = warp_sum(c);
+    if (lane == 0) pooled_count[m] = c;
+}
+
+// --------------------------------------------------------------------------------------------
 // region sums: one warp per proposal; union count: one block per episode.
 // --------------------------------------------------------------------------------------------
 __global__ void region_sums_kernel(const uint32_t* __restrict__ pooled, int64_t total, int P, int N, int npw,
@@ -575,6 +725,42 @@ int marsb200_pool_packed(const uint32_t* bits, int64_t n, int H, int W, int g, u
     MARS_REQUIRE(smem <= 48 * 1024, "g * W too large for the pooling scratch");
     pool_packed_kernel<<<(unsigned)n, POOL_THREADS, smem, as_stream(stream)>>>(bits, n, H, W, g, wpm, npw, rw, pooled,
                                                                              area, pooled_count);
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
+int marsb200_pack_pool_masks(const void* masks, int mask_dtype, int64_t n, int H, int W, int g, uint32_t* bits,
+                             uint32_t* pooled, int32_t* area, int32_t* pooled_count, void* stream) {
+    MARS_REQUIRE(masks && bits && pooled && area && pooled_count, "null pointer");
+    MARS_REQUIRE(n > 0 && H > 0 && W > 0 && g > 0 && g <= H && g <= W, "shape");
+    MARS_REQUIRE(mask_dtype == MARSB200_MASK_F32 || mask_dtype == MARSB200_MASK_U8, "mask_dtype");
+    const int64_t HW = (int64_t)H * W;
+    const int64_t wpm = marsb200_words_per_mask(HW);
+    const int npw = ceil_div(g * g, 32);
+    const bool aligned = (reinterpret_cast<uintptr_t>(masks) & 15) == 0;
+    const bool vec = aligned && (mask_dtype == MARSB200_MASK_F32 ? HW % 4 == 0 : HW % 16 == 0);
+    const bool fusable = vec && W % 32 == 0 && npw <= FUSED_POOL_WORDS && H <= 32768 && W <= 32768 && g <= 255 &&
+                         HW < (1ll << 31);
+    if (!fusable) {  // any other geometry: the two kernels (same results)
+        if (int rc = marsb200_pack_masks(masks, mask_dtype, n, HW, bits, stream)) return rc;
+        return marsb200_pool_packed(bits, n, H, W, g, pooled, area, pooled_count, stream);
+    }
+    cudaStream_t s = as_stream(stream);
+    MARS_CUDA_OK(cudaMemsetAsync(pooled, 0, sizeof(uint32_t) * (size_t)n * npw, s));
+    MARS_CUDA_OK(cudaMemsetAsync(area, 0, sizeof(int32_t) * (size_t)n, s));
+    if (mask_dtype == MARSB200_MASK_F32) {
+        const int chunks = (int)ceil_div64(wpm * 32, PACK_THREADS * PACK_UNROLL_F32 * 4);
+        MARS_REQUIRE(n * chunks < (1ll << 31), "grid too large");
+        pack_pool_f32_kernel<<<(unsigned)(n * chunks), PACK_THREADS, 0, s>>>((const float*)masks, n, HW, wpm, bits, chunks, H,
+                                                                           W, g, npw, pooled, area);
+    } else {
+        const int chunks = (int)ceil_div64(wpm * 32, PACK_THREADS * PACK_UNROLL * 16);
+        MARS_REQUIRE(n * chunks < (1ll << 31), "grid too large");
+        pack_pool_u8_kernel<<<(unsigned)(n * chunks), PACK_THREADS, 0, s>>>((const uint8_t*)masks, n, HW, wpm, bits, chunks, H,
+                                                                          W, g, npw, pooled, area);
+    }
+    MARS_LAUNCH_OK();
+    pooled_count_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, s>>>(pooled, n, npw, pooled_count);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }

@@ -57,7 +57,7 @@ def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int
         if episodes_per_batch is not None:
             per = (episodes_per_batch + k - 1) // k
             k = (episodes_per_batch + per - 1) // per
-        n += (k - 1) * (2 + (1 if cfg.nms_iou_threshold is not None else 0))
+        n += (k - 1) * (2 + (1 if cfg.nms_iou_threshold is not None else 0))  # pack+pool, pooled counts, pairwise
     n += 2                     # normalize_rows x2
     n += 1                     # pool_mask
     n += 1                     # sim_contract
@@ -65,10 +65,10 @@ def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int
     n += 2 * (1 + 3 + 1 + 2)   # two PIR passes: box mask, colsum x2 + rownorm, contraction, two mat-vecs
     n += 1                     # min-max of the refined vva
     n += 1                     # resize + min-max of the vta
-    n += 1                     # pack (memset not counted)
+    n += 1                     # pack + pooled bitmaps, one pass (memsets not counted)
     if cfg.nms_iou_threshold is not None and not cfg.fused_ingest:
         n += 1                 # pairwise intersections (part of the pack kernel with fused_ingest)
-    n += 1                     # pool_packed
+    n += 1                     # pooled patch counts (or pool_packed when the geometry is not fusable)
     n += 2                     # region sums + union count
     if cfg.emd_on_device:
         n += 6                 # exact EMD: problem sizes, duplicate links + marks, processing order, the solver, copies
@@ -180,6 +180,12 @@ class RankingEngine:
             ops.pack_pairwise(batch["masks"], backend=cfg.pair_backend, out=(self.bits, self.inter))
             ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
             return
+        if "masks" in batch:
+            # dense masks: packed bits and pooled bitmaps come out of ONE pass over the masks (ops.pack_pool)
+            ops.pack_pool(batch["masks"], s.g, out_bits=self.bits, out_pool=self.pool_out)
+            if self.inter is not None:
+                ops.pairwise_inter(self.bits, backend=cfg.pair_backend, out=self.inter)
+            return
         self._ingest(batch)
         if self.inter is None:
             ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
@@ -216,10 +222,11 @@ class RankingEngine:
         masks = batch["masks"]
         with torch.cuda.stream(hbm):
             for (lo, hi), ev in zip(self._chunks, self._ev_chunk):
-                ops.pack_masks(masks[lo:hi], out=self.bits[lo:hi])
+                if cfg.partition_pool_on_tensor:
+                    ops.pack_masks(masks[lo:hi], out=self.bits[lo:hi])
+                else:  # packed bits + pooled bitmaps in one pass over the chunk's masks
+                    ops.pack_pool(masks[lo:hi], s.g, out_bits=self.bits[lo:hi], out_pool=tuple(t[lo:hi] for t in self.pool_out))
                 ev.record(hbm)
-                if not cfg.partition_pool_on_tensor:
-                    ops.pool_packed(self.bits[lo:hi], s.H, s.W, s.g, out=tuple(t[lo:hi] for t in self.pool_out))
             # the last chunks' intersections stay on this partition: their bits only exist when the ingest is over and
             # the tensor partition still has its own queue to drain
             tail = self._chunks[len(self._chunks) - cfg.partition_pairwise_tail:] if cfg.partition_pairwise_tail else []

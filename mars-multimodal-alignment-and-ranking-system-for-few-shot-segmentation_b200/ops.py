@@ -286,6 +286,28 @@ def pool_packed(bits: torch.Tensor, h: int, w: int, g: int, out=None):
     return pooled, area, cnt
 
 
+def pack_pool(masks: torch.Tensor, g: int, out_bits=None, out_pool=None):
+    """masks [..., H, W] -> (bits [..., wpm], (pooled, area, pooled_count)) in one pass over the masks: `pack_masks`
+    followed by `pool_packed`, with the pooling done on the packed words while they are in registers (one kernel when
+    W % 32 == 0, else the two kernels - identical results either way)."""
+    m, dt = _mask_tensor(masks)
+    h, w = m.shape[-2:]
+    lead = tuple(m.shape[:-2])
+    n = m.numel() // (h * w)
+    wpm = words_per_mask(h * w)
+    npw = (g * g + 31) // 32
+    if out_bits is None:
+        out_bits = torch.empty(lead + (wpm,), device=m.device, dtype=torch.int32)
+    if out_pool is None:
+        out_pool = (torch.empty(lead + (npw,), device=m.device, dtype=torch.int32),
+                    torch.empty(lead, device=m.device, dtype=torch.int32),
+                    torch.empty(lead, device=m.device, dtype=torch.int32))
+    pooled, area, cnt = out_pool
+    check(lib.marsb200_pack_pool_masks(m.data_ptr(), dt, n, h, w, g, out_bits.data_ptr(), pooled.data_ptr(), area.data_ptr(),
+                                       cnt.data_ptr(), _stream()))
+    return out_bits, (pooled, area, cnt)
+
+
 def region_sums(pooled: torch.Tensor, vva: torch.Tensor, vta: torch.Tensor, out=None):
     """pooled [E, P, npw]; vva/vta [E, N] -> (sum_vva [E,P], sum_vta [E,P], union_count [E])."""
     e, p, _ = pooled.shape

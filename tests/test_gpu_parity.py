@@ -79,6 +79,38 @@ def test_pack_masks_bit_exact(mb, shape, dtype):
     np.testing.assert_array_equal(bits.cpu().numpy().view(np.uint32), np_pack(m.numpy(), wpm))
 
 
+@pytest.mark.parametrize("h,w,g,dtype", [
+    (1024, 1024, 37, torch.float32),   # c2 / c4 geometry: overlapping 28/29-pixel bins
+    (1024, 1024, 37, torch.uint8),
+    (96, 64, 5, torch.float32),        # rows shorter than a warp's 1024 pixels: a warp covers many rows
+    (100, 128, 7, torch.uint8),
+    (33, 32, 4, torch.float32),        # one word per row
+    (518, 544, 37, torch.float32),     # W % 32 == 0 but H*W not a multiple of the block size
+    (518, 518, 37, torch.float32),     # W % 32 != 0: the call falls back to the two kernels
+    (140, 140, 10, torch.uint8),
+])
+def test_fused_pack_pool_equals_pack_then_pool(mb, h, w, g, dtype):
+    """ops.pack_pool (one pass: packed bits + pooled bitmaps from the words in registers) against pack_masks followed by
+    pool_packed, bit for bit, and the pooled bitmaps against adaptive_max_pool2d (FilteringMergingModule.py:103-107)."""
+    n = 9
+    masks = cases.blob_masks(n, h, w, seed=h + w + g, min_frac=0.002, max_frac=0.3)
+    masks[0] = 0                       # empty mask
+    masks[1] = 0
+    masks[1, h - 1, w - 1] = 1         # last pixel only
+    masks[2] = 1                       # full mask
+    x = masks.to(dev()).to(dtype)
+    bits_ref = mb.ops.pack_masks(x)
+    pooled_ref, area_ref, cnt_ref = mb.ops.pool_packed(bits_ref, h, w, g)
+    bits, (pooled, area, cnt) = mb.ops.pack_pool(x, g)
+    assert torch.equal(bits, bits_ref) and torch.equal(pooled, pooled_ref)
+    assert torch.equal(area, area_ref) and torch.equal(cnt, cnt_ref)
+    want = torch.nn.functional.adaptive_max_pool2d(masks[:, None], (g, g)).flatten(1) > 0
+    np.testing.assert_array_equal(unpack_pooled(pooled, g * g), want.numpy())
+    # a second call into the same output buffers (the engine reuses them every step) gives the same result
+    bits2, (pooled2, area2, cnt2) = mb.ops.pack_pool(x, g, out_bits=bits, out_pool=(pooled, area, cnt))
+    assert torch.equal(pooled2, pooled_ref) and torch.equal(area2, area_ref) and torch.equal(cnt2, cnt_ref)
+
+
 def test_pack_nonbinary_values(mb):
     """Pixels are set iff value > 0 (the reference pools and thresholds with `> 0`)."""
     m = torch.tensor([[[0.0, 0.5, -1.0, 2.0, 1e-30, -0.0, 255.0, 0.0]]])
