@@ -417,9 +417,9 @@ __global__ void __launch_bounds__(256) pooled_count_kernel(const uint32_t* __res
 // --------------------------------------------------------------------------------------------
 // region sums: one warp per proposal; union count: one block per episode.
 // --------------------------------------------------------------------------------------------
-__global__ void region_sums_kernel(const uint32_t* __restrict__ pooled, int64_t total, int P, int N, int npw,
-                                   const float* __restrict__ vva, const float* __restrict__ vta,
-                                   float* __restrict__ sum_vva, float* __restrict__ sum_vta) {
+__device__ __forceinline__ void region_sums_block(const uint32_t* __restrict__ pooled, int64_t total, int P, int N, int npw,
+                                                  const float* __restrict__ vva, const float* __restrict__ vta,
+                                                  float* __restrict__ sum_vva, float* __restrict__ sum_vta) {
     const int lane = threadIdx.x & 31;
     const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wg >= total) return;
@@ -446,12 +446,11 @@ __global__ void region_sums_kernel(const uint32_t* __restrict__ pooled, int64_t 
 
 // 256 threads per episode: thread t ORs word (t % 64 ...) over a slice of the proposals, then a
 // shared-memory OR per word and a popcount.
-__global__ void __launch_bounds__(256) union_count_kernel(const uint32_t* __restrict__ pooled, int P, int npw,
-                                                          int32_t* __restrict__ union_count) {
+__device__ __forceinline__ void union_count_block(const uint32_t* __restrict__ pooled, int64_t e, int P, int npw,
+                                                  int32_t* __restrict__ union_count) {
     extern __shared__ uint32_t s_union[];  // npw words + 1 counter
     for (int i = threadIdx.x; i <= npw; i += blockDim.x) s_union[i] = 0;
     __syncthreads();
-    const int64_t e = blockIdx.x;
     const uint32_t* base = pooled + e * P * npw;
     const int total = P * npw;
     // eight independent loads in flight per thread: one CTA per episode is latency-bound otherwise
@@ -473,6 +472,17 @@ __global__ void __launch_bounds__(256) union_count_kernel(const uint32_t* __rest
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(reinterpret_cast<int*>(&s_union[npw]), c);
     __syncthreads();
     if (threadIdx.x == 0) union_count[e] = (int)s_union[npw];
+}
+
+// One launch for both: the first `region_blocks` blocks compute the per-proposal region sums (8 proposals each), the
+// remaining E blocks the union patch count of one episode each.
+__global__ void __launch_bounds__(256) region_union_kernel(const uint32_t* __restrict__ pooled, int64_t total, int P, int N,
+                                                           int npw, const float* __restrict__ vva,
+                                                           const float* __restrict__ vta, float* __restrict__ sum_vva,
+                                                           float* __restrict__ sum_vta, int32_t* __restrict__ union_count,
+                                                           unsigned region_blocks) {
+    if (blockIdx.x < region_blocks) region_sums_block(pooled, total, P, N, npw, vva, vta, sum_vva, sum_vta);
+    else union_count_block(pooled, (int64_t)(blockIdx.x - region_blocks), P, npw, union_count);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -771,10 +781,9 @@ int marsb200_region_sums(const uint32_t* pooled, int E, int P, int N, const floa
     MARS_REQUIRE(E > 0 && P > 0 && N > 0, "shape");
     const int npw = ceil_div(N, 32);
     const int64_t total = (int64_t)E * P;
-    region_sums_kernel<<<(unsigned)ceil_div64(total, 8), 256, 0, as_stream(stream)>>>(pooled, total, P, N, npw, vva, vta,
-                                                                                      sum_vva, sum_vta);
-    MARS_LAUNCH_OK();
-    union_count_kernel<<<E, 256, (npw + 1) * sizeof(uint32_t), as_stream(stream)>>>(pooled, P, npw, union_count);
+    const unsigned region_blocks = (unsigned)ceil_div64(total, 8);
+    region_union_kernel<<<region_blocks + (unsigned)E, 256, (npw + 1) * sizeof(uint32_t), as_stream(stream)>>>(
+        pooled, total, P, N, npw, vva, vta, sum_vva, sum_vta, union_count, region_blocks);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }
