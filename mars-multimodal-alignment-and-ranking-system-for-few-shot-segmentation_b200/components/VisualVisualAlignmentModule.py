@@ -18,7 +18,7 @@ from .PriorInformationRefinementModule import PriorInformationRefinementModule
 class VisualVisualAlignmentModule:
     def __init__(self, model: nn.Module, model_transforms, model_patch_size: int,
                  model_embedding_spatial_dimensions: int, model_num_regs: int, vva_refinement_box_threshold: float,
-                 last_n_attention_maps_for_refinement: int, device):
+                 last_n_attention_maps_for_refinement: int, device, matrices_on_cpu: bool = False):
         self.model = model
         self.model_transforms = model_transforms
         self.model_patch_size = model_patch_size
@@ -29,6 +29,10 @@ class VisualVisualAlignmentModule:
             box_threshold=vva_refinement_box_threshold,
             last_n_attention_maps_for_refinement=last_n_attention_maps_for_refinement,
             device=device, num_regs=model_num_regs)
+        # the reference moves `similarity_matrix` / `cost_matrix` to the CPU (VisualVisualAlignmentModule.py:69-70) because its
+        # EMD runs on the host; here the consumer (FilteringMergingModule) is on the device, so they stay there by default.
+        # `matrices_on_cpu=True` restores the reference's placement for callers that index them with CPU tensors.
+        self.matrices_on_cpu = matrices_on_cpu
         self.similarity_matrix = None
         self.cost_matrix = None
 
@@ -51,8 +55,8 @@ class VisualVisualAlignmentModule:
             # the reference fails here too: max over an empty foreground (VisualVisualAlignmentModule.py:82)
             raise RuntimeError("empty pooled support mask: no foreground support patch")
         res = ops.sim_contract(fs, fq, m, n, c, want_sim=True, want_cost=True, row_fg=row_fg)
-        self.similarity_matrix = res["sim"][0]
-        self.cost_matrix = res["cost"][0]
+        self.similarity_matrix = res["sim"][0].cpu() if self.matrices_on_cpu else res["sim"][0]
+        self.cost_matrix = res["cost"][0].cpu() if self.matrices_on_cpu else res["cost"][0]
         if not bool((row_fg == 0).any()):
             print("[VVA] - No background VVA computed, only foreground VVA.")
         prior = ops.vva_finalize(res["colstats"], row_fg, m, n).reshape(g, g)

@@ -32,6 +32,7 @@ class RankingConfig:
     want_merged_f32: bool = True       # the float32 [H, W] map the reference returns
     overlap_streams: bool = True       # mask chain (HBM-bound) on a second stream beside the contractions
     fused_ingest: bool = False         # one-pass pack + pairwise kernel (owns all TMEM: cannot overlap the contractions)
+    fused_pool: bool = False           # one-pass pack + pooled bitmaps (ops.pack_pool); measured slower than the two kernels
     emd_on_device: bool = False        # solve the P transport LPs per episode on the device instead of taking batch["emd"]
     # fast-path sizing of the EMD solver (state in shared memory); problems beyond it take its global-state launch, so
     # these are performance hints, never capacity limits
@@ -57,7 +58,7 @@ def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int
         if episodes_per_batch is not None:
             per = (episodes_per_batch + k - 1) // k
             k = (episodes_per_batch + per - 1) // per
-        n += (k - 1) * (2 + (1 if cfg.nms_iou_threshold is not None else 0))  # pack+pool, pooled counts, pairwise
+        n += (k - 1) * (2 + (1 if cfg.nms_iou_threshold is not None else 0))  # pack, pool_packed, pairwise
     n += 2                     # normalize_rows x2
     n += 1                     # pool_mask
     n += 1                     # sim_contract
@@ -65,11 +66,11 @@ def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int
     n += 2 * (1 + 3 + 1 + 2)   # two PIR passes: box mask, colsum x2 + rownorm, contraction, two mat-vecs
     n += 1                     # min-max of the refined vva
     n += 1                     # resize + min-max of the vta
-    n += 1                     # pack + pooled bitmaps, one pass (memsets not counted)
+    n += 1                     # pack (memset not counted)
     if cfg.nms_iou_threshold is not None and not cfg.fused_ingest:
         n += 1                 # pairwise intersections (part of the pack kernel with fused_ingest)
-    n += 1                     # pooled patch counts (or pool_packed when the geometry is not fusable)
-    n += 2                     # region sums + union count
+    n += 1                     # pool_packed
+    n += 1                     # region sums + union count (one launch)
     if cfg.emd_on_device:
         n += 6                 # exact EMD: problem sizes, duplicate links + marks, processing order, the solver, copies
     n += 1                     # clip scores
@@ -180,8 +181,10 @@ class RankingEngine:
             ops.pack_pairwise(batch["masks"], backend=cfg.pair_backend, out=(self.bits, self.inter))
             ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
             return
-        if "masks" in batch:
-            # dense masks: packed bits and pooled bitmaps come out of ONE pass over the masks (ops.pack_pool)
+        if "masks" in batch and cfg.fused_pool:
+            # dense masks: packed bits and pooled bitmaps out of ONE pass over the masks (ops.pack_pool).  Measured slower
+            # than the two kernels on B200 (the pooling epilogue costs the ingest kernel its load rate), so off
+            # by default
             ops.pack_pool(batch["masks"], s.g, out_bits=self.bits, out_pool=self.pool_out)
             if self.inter is not None:
                 ops.pairwise_inter(self.bits, backend=cfg.pair_backend, out=self.inter)
@@ -222,11 +225,14 @@ class RankingEngine:
         masks = batch["masks"]
         with torch.cuda.stream(hbm):
             for (lo, hi), ev in zip(self._chunks, self._ev_chunk):
-                if cfg.partition_pool_on_tensor:
-                    ops.pack_masks(masks[lo:hi], out=self.bits[lo:hi])
-                else:  # packed bits + pooled bitmaps in one pass over the chunk's masks
+                if cfg.fused_pool and not cfg.partition_pool_on_tensor:
                     ops.pack_pool(masks[lo:hi], s.g, out_bits=self.bits[lo:hi], out_pool=tuple(t[lo:hi] for t in self.pool_out))
+                    ev.record(hbm)
+                    continue
+                ops.pack_masks(masks[lo:hi], out=self.bits[lo:hi])
                 ev.record(hbm)
+                if not cfg.partition_pool_on_tensor:
+                    ops.pool_packed(self.bits[lo:hi], s.H, s.W, s.g, out=tuple(t[lo:hi] for t in self.pool_out))
             # the last chunks' intersections stay on this partition: their bits only exist when the ingest is over and
             # the tensor partition still has its own queue to drain
             tail = self._chunks[len(self._chunks) - cfg.partition_pairwise_tail:] if cfg.partition_pairwise_tail else []
