@@ -134,16 +134,11 @@ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
-// minimum of dist over the unscanned sinks a thread owns (j = tid, tid + EMD_THREADS, ...)
-__device__ inline double own_min_key(const EmdSmem& s, int M) {
+// block-wide minimum of dist over the unscanned sinks; every thread gets the result
+__device__ inline double block_min_key(const EmdSmem& s, int M, unsigned long long* s_val) {
     double v = EMD_INF;
     for (int j = threadIdx.x; j < M; j += EMD_THREADS)
         if (!s.scanned[j]) v = fmin(v, s.dist[j]);
-    return v;
-}
-
-// block-wide minimum of the threads' values; every thread gets the result
-__device__ inline double block_min_key(double v, unsigned long long* s_val) {
     // warp minimum with two integer reductions (high word, then low word among the lanes that hold the minimum high word)
     const unsigned long long k = dkey(v);
     const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
@@ -235,7 +230,7 @@ constexpr int EMD_CHUNK = 4;
 
 template <bool INIT>
 __device__ inline void scan_sources(const EmdSmem& s, const float* __restrict__ cmat, int M, const short* list,
-                                    int n, int lanes, double dbase, bool first_phase, double* own_min = nullptr) {
+                                    int n, int lanes, double dbase, bool first_phase) {
     const int tid = threadIdx.x;
     const int sub = tid & (lanes - 1);
     const int groups = EMD_THREADS / lanes;
@@ -329,7 +324,6 @@ __device__ inline void scan_sources(const EmdSmem& s, const float* __restrict__ 
                     if (nd < s.dist[j]) {
                         s.dist[j] = nd;
                         s.pred_src[j] = (short)best_i[t];
-                        if (own_min) *own_min = fmin(*own_min, nd);  // lanes == 1: sink j belongs to this thread
                     }
                 }
             }
@@ -482,34 +476,19 @@ __global__ void __launch_bounds__(EMD_THREADS, EMD_MAX_CTAS) emd_kernel(const fl
             EP_LAP(1);  // phase init
 
             double D = 0.0;
-            // With one thread per sink (lanes == 1) a thread keeps the minimum distance of ITS unscanned sinks in a
-            // register across the waves: the settle pass and the relaxation below update it, so the arg-min of a wave is
-            // one block reduction instead of another pass over the sinks, and only the threads that hold the minimum
-            // walk their sinks to settle them.
-            const bool cached = lanes == 1;
-            double own_min = cached ? own_min_key(s, M) : 0.0;
             while (true) {
                 EP_COUNT(9);
                 // ---- wave: settle every unscanned sink at the minimum distance
-                const double dmin = block_min_key(cached ? own_min : own_min_key(s, M), s_val);
+                const double dmin = block_min_key(s, M, s_val);
                 EP_LAP(2);  // argmin
                 if (dmin >= EMD_INF) break;  // every sink is scanned
                 D = dmin;
-                if (!cached || own_min == dmin) {
-                    double rest = EMD_INF;
-                    for (int j = tid; j < M; j += EMD_THREADS)
-                        if (!s.scanned[j]) {
-                            const double dj = s.dist[j];
-                            if (dj == dmin) {
-                                s.scanned[j] = 1;
-                                if (s.demand[j] > 0) s.batch[atomicAdd(&s_ndef, 1)] = (short)j;  // open demand: augment first
-                                else expand_feeders(s, j, dmin, &s_nnew);  // its flow arcs cannot change in this wave
-                            } else {
-                                rest = fmin(rest, dj);
-                            }
-                        }
-                    own_min = rest;
-                }
+                for (int j = tid; j < M; j += EMD_THREADS)
+                    if (!s.scanned[j] && s.dist[j] == dmin) {
+                        s.scanned[j] = 1;
+                        if (s.demand[j] > 0) s.batch[atomicAdd(&s_ndef, 1)] = (short)j;  // open demand: augment first
+                        else expand_feeders(s, j, dmin, &s_nnew);  // its flow arcs cannot change in this wave
+                    }
                 __syncthreads();
                 EP_LAP(3);  // settle
                 const int ndef = s_ndef;
@@ -602,7 +581,7 @@ __global__ void __launch_bounds__(EMD_THREADS, EMD_MAX_CTAS) emd_kernel(const fl
                 EP_LAP(4);  // augment
                 const int nnew = s_nnew;
                 // ---- relax every unscanned sink against the newly reached sources
-                if (nnew > 0) scan_sources<false>(s, C, M, s.newlist, nnew, lanes, dmin, false, cached ? &own_min : nullptr);
+                if (nnew > 0) scan_sources<false>(s, C, M, s.newlist, nnew, lanes, dmin, false);
                 __syncthreads();  // everyone has read the counters; the next wave's settle pass starts after another barrier
                 if (tid == 0) {
                     s_ndef = 0;
