@@ -66,25 +66,61 @@ __global__ void __launch_bounds__(RLE_THREADS) rle_fill_kernel(const int32_t* __
     if (tid == 0 && s_base != HW) atomicExch(status, 1);  // the counts must cover the image exactly
 }
 
-// colbits [n][W][H/32] -> bits [n][H][W/32] (+ zero padding words up to wpm); one warp per 32 x 32 tile
+// colbits [n][W][H/32] -> bits [n][H][W/32] (+ zero padding words up to wpm).  One CTA transposes a block of 8 x 8 tiles of
+// 32 x 32 bits (256 columns x 256 rows): thread t reads the 8 consecutive words of column x0 + t (one 32-byte sector), the
+// tiles are transposed with ballots out of shared memory, thread t writes the 8 consecutive words of row y0 + t.  Every
+// global access is a full sector (the one-warp-per-tile version read and wrote 4 useful bytes per sector).
+constexpr int BT_TILES = 8;
+
 __global__ void __launch_bounds__(256) bit_transpose_kernel(const uint32_t* __restrict__ colbits, int H, int W, int64_t wpm,
                                                             uint32_t* __restrict__ bits) {
-    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t s_in[32 * BT_TILES][BT_TILES + 1];   // [column][tile row], padded against bank conflicts
+    __shared__ uint32_t s_out[32 * BT_TILES][BT_TILES + 1];  // [row][tile column]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hw32 = H >> 5, ww32 = W >> 5;
-    const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t tiles_per_mask = (int64_t)hw32 * ww32;
+    const int bx = blockIdx.x % ((ww32 + BT_TILES - 1) / BT_TILES), by = blockIdx.x / ((ww32 + BT_TILES - 1) / BT_TILES);
     const int64_t m = blockIdx.y;
-    if (tile >= tiles_per_mask) return;
-    const int ty = (int)(tile / ww32), tx = (int)(tile % ww32);
-    // lane = column x0 + lane: its word holds rows y0 .. y0 + 31
-    const uint32_t col = colbits[(m * W + (int64_t)tx * 32 + lane) * hw32 + ty];
-    uint32_t row = 0;
+    const int tx0 = bx * BT_TILES, ty0 = by * BT_TILES;
+    {   // column x0 + tid: words ty0 .. ty0 + 7
+        const int x = tx0 * 32 + tid;
+        const uint32_t* src = colbits + (m * W + x) * hw32 + ty0;
+        if (x < W && (hw32 & 3) == 0 && ty0 + BT_TILES <= hw32) {  // 16-byte aligned: two 128-bit loads
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(src)), b = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+            s_in[tid][0] = a.x; s_in[tid][1] = a.y; s_in[tid][2] = a.z; s_in[tid][3] = a.w;
+            s_in[tid][4] = b.x; s_in[tid][5] = b.y; s_in[tid][6] = b.z; s_in[tid][7] = b.w;
+        } else {
 #pragma unroll
-    for (int b = 0; b < 32; ++b) {
-        const uint32_t r = __ballot_sync(0xffffffffu, (col >> b) & 1u);  // row y0 + b: bit x = lane's bit b
-        if (lane == b) row = r;
+            for (int k = 0; k < BT_TILES; ++k) s_in[tid][k] = (x < W && ty0 + k < hw32) ? src[k] : 0u;
+        }
     }
-    bits[m * wpm + ((int64_t)ty * 32 + lane) * ww32 + tx] = row;
+    __syncthreads();
+    // warp w owns tile row ty0 + w; for each tile column the 32 lanes (= 32 columns) transpose their word with ballots
+#pragma unroll 2
+    for (int k = 0; k < BT_TILES; ++k) {
+        const uint32_t col = s_in[k * 32 + lane][warp];
+        uint32_t row = 0;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const uint32_t r = __ballot_sync(0xffffffffu, (col >> b) & 1u);  // row y0 + b: bit x = lane's bit b
+            if (lane == b) row = r;
+        }
+        s_out[warp * 32 + lane][k] = row;
+    }
+    __syncthreads();
+    {   // row y0 + tid: words tx0 .. tx0 + 7
+        const int y = ty0 * 32 + tid;
+        if (y < H) {
+            uint32_t* dst = bits + m * wpm + (int64_t)y * ww32 + tx0;
+            if ((ww32 & 3) == 0 && (wpm & 3) == 0 && tx0 + BT_TILES <= ww32) {
+                reinterpret_cast<uint4*>(dst)[0] = make_uint4(s_out[tid][0], s_out[tid][1], s_out[tid][2], s_out[tid][3]);
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(s_out[tid][4], s_out[tid][5], s_out[tid][6], s_out[tid][7]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < BT_TILES; ++k)
+                    if (tx0 + k < ww32) dst[k] = s_out[tid][k];
+            }
+        }
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -304,9 +340,8 @@ int marsb200_rle_decode(const int32_t* counts, const int64_t* offsets, int64_t n
     if (wpm * 32 != hw) MARS_CUDA_OK(cudaMemsetAsync(bits, 0, (size_t)(n * wpm * 4), s));  // padding words
     rle_fill_kernel<<<(unsigned)n, RLE_THREADS, 0, s>>>(counts, offsets, hw, col_words, (uint32_t*)workspace, status);
     MARS_LAUNCH_OK();
-    const int64_t tiles = (int64_t)(H / 32) * (W / 32);
-    bit_transpose_kernel<<<dim3((unsigned)ceil_div64(tiles * 32, 256), (unsigned)n), 256, 0, s>>>(
-        (const uint32_t*)workspace, H, W, wpm, bits);
+    const unsigned blocks = (unsigned)(ceil_div(H / 32, BT_TILES) * ceil_div(W / 32, BT_TILES));
+    bit_transpose_kernel<<<dim3(blocks, (unsigned)n), 256, 0, s>>>((const uint32_t*)workspace, H, W, wpm, bits);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }
