@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(RLE_THREADS) rle_fill_kernel(const int32_t* __
 
 // colbits [n][W][H/32] -> bits [n][H][W/32] (+ zero padding words up to wpm).  One CTA transposes a block of 8 x 8 tiles of
 // 32 x 32 bits (256 columns x 256 rows): thread t reads the 8 consecutive words of column x0 + t (one 32-byte sector), the
-// tiles are transposed with ballots out of shared memory, thread t writes the 8 consecutive words of row y0 + t.  Every
+// tiles are transposed with warp shuffles out of shared memory, thread t writes the 8 consecutive words of row y0 + t.  Every
 // global access is a full sector (the one-warp-per-tile version read and wrote 4 useful bytes per sector).
 constexpr int BT_TILES = 8;
 
@@ -97,14 +97,18 @@ __global__ void __launch_bounds__(256) bit_transpose_kernel(const uint32_t* __re
     // warp w owns tile row ty0 + w; for each tile column the 32 lanes (= 32 columns) transpose their word with ballots
 #pragma unroll 2
     for (int k = 0; k < BT_TILES; ++k) {
-        const uint32_t col = s_in[k * 32 + lane][warp];
-        uint32_t row = 0;
+        // 32 x 32 bit transpose across the warp in five exchange steps (block swaps of 16, 8, 4, 2, 1): lane l enters with
+        // column x0 + l (bit b = row y0 + b) and leaves with row y0 + l (bit b = column x0 + b).  ~30 instructions per tile;
+        // the 32-ballot version this replaces was issue-bound at 0.8 TB/s.
+        uint32_t a = s_in[k * 32 + lane][warp];
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
-            const uint32_t r = __ballot_sync(0xffffffffu, (col >> b) & 1u);  // row y0 + b: bit x = lane's bit b
-            if (lane == b) row = r;
+        for (int j = 16; j >= 1; j >>= 1) {
+            const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, a, j);
+            if ((lane & j) == 0) a ^= (((a >> j) ^ o) & m) << j;
+            else a ^= ((o >> j) ^ a) & m;
         }
-        s_out[warp * 32 + lane][k] = row;
+        s_out[warp * 32 + lane][k] = a;
     }
     __syncthreads();
     {   // row y0 + tid: words tx0 .. tx0 + 7
