@@ -52,20 +52,26 @@ def parse_args():
     return ap.parse_args()
 
 
-def kernel_source_sha16(source="masks.cu"):
-    """sha256 (first 16 hex digits) of the CUDA source that holds the kernel: ties an ncu capture to the code it measured."""
+def kernel_source_sha16(kernel="pack_f32_vec_kernel", source="masks.cu"):
+    """sha256 (first 16 hex digits) of the CUDA source of ONE kernel (its `__global__` definition up to the closing brace
+    at column 0, plus the tuning constants above it): ties an ncu capture to the code it measured without going stale when
+    an unrelated kernel of the same file changes."""
     import hashlib
+    import re
 
     path = os.path.join(ROOT, "mars-multimodal-alignment-and-ranking-system-for-few-shot-segmentation_b200", "csrc", source)
-    with open(path, "rb") as f:
-        return hashlib.sha256(f.read()).hexdigest()[:16]
+    with open(path) as f:
+        text = f.read()
+    m = re.search(r"__global__[^;{]*\b" + re.escape(kernel) + r"\s*\(.*?\n}\n", text, re.S)
+    consts = "".join(re.findall(r"^constexpr int PACK_\w+ = [^;]+;$", text, re.M))
+    return hashlib.sha256(((m.group(0) if m else text) + consts).encode()).hexdigest()[:16]
 
 
 def ncu_traffic_bytes(kernel, workload, episodes, mask_dtype):
     """dram read+write bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json),
     or None when no capture of THIS version of the kernel source exists (a stale capture says nothing about new code)."""
     try:
-        sha = kernel_source_sha16()
+        sha = kernel_source_sha16(kernel)
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             for row in json.load(f):
                 if (row["kernel"], row["workload"], row["episodes_per_launch"], row["mask_dtype"]) == \

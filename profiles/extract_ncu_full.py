@@ -44,8 +44,10 @@ def main():
             if r[hdr.index("Kernel Name")].startswith(kern):
                 best = r  # the last captured launch of the kernel
         if best is not None:
-            src = os.path.join(ROOT, "mars-multimodal-alignment-and-ranking-system-for-few-shot-segmentation_b200", "csrc", "masks.cu")
-            sha = hashlib.sha256(open(src, "rb").read()).hexdigest()[:16]
+            sys.path.insert(0, ROOT)
+            import bench  # the same hash bench.py checks
+
+            sha = bench.kernel_source_sha16(kern)
             path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             table = [row for row in json.load(open(path))
                      if (row["kernel"], row["workload"], row["episodes_per_launch"], row["mask_dtype"]) != (kern, workload, episodes, dtype)]
