@@ -34,15 +34,18 @@ extern "C" {
 #define MARSB200_MASK_F32 0 /* reference-native float32 0/1 (main_MARS.py:62, Matcher.py:728-729) */
 #define MARSB200_MASK_U8 1  /* uint8 / bool, 1 byte per pixel */
 
-/* contraction back ends of marsb200_sim_contract / marsb200_pir_refine */
-#define MARSB200_GEMM_TCGEN05 0 /* TMA + tcgen05 3xTF32 (error-compensated), fp32 accumulate in TMEM */
-#define MARSB200_GEMM_SIMT 1    /* fp32 FFMA tiles; validation path for the tensor-core kernel */
+/* Back ends.  There is ONE product path per operation: MARSB200_GEMM_TCGEN05 for the contractions and
+ * MARSB200_PAIR_AUTO for the intersections (callers pass exactly these; the Python wrappers default to them).  The other
+ * values select second implementations of the same arithmetic that exist to pin the tensor-core kernels in the test
+ * suite (tests/test_gpu_parity.py compares them bit for bit / within 3e-6): TEST-ONLY, not a dispatch a deployment
+ * chooses from - they are all sm_100a CUDA, there is no other target and no CPU path. */
+#define MARSB200_GEMM_TCGEN05 0 /* product: TMA + tcgen05 3xTF32 (error-compensated), fp32 accumulate in TMEM */
+#define MARSB200_GEMM_SIMT 1    /* test-only: fp32 FFMA tiles, pins the tensor-core kernel */
 
-/* pairwise-intersection back ends */
-#define MARSB200_PAIR_POPC 0 /* shared-memory tiled AND + popcount */
-#define MARSB200_PAIR_MMA 1  /* bits expanded to int8 in shared memory, tcgen05 kind::i8 into TMEM */
-#define MARSB200_PAIR_FP4 2  /* P <= 256: bits expanded to e2m1 nibbles, tcgen05 kind::mxf4 with unit scale factors */
-#define MARSB200_PAIR_AUTO 3 /* FP4 when P <= 256 and HW < 2^24, int8 otherwise (same counts, bit for bit) */
+#define MARSB200_PAIR_AUTO 3 /* product: kind::mxf4 when P <= 256 and HW < 2^24, kind::i8 otherwise (same counts, bit for bit) */
+#define MARSB200_PAIR_FP4 2  /* the P <= 256 half of AUTO: bits expanded to e2m1 nibbles, tcgen05 kind::mxf4 with unit scale factors */
+#define MARSB200_PAIR_MMA 1  /* the any-P half of AUTO: bits expanded to int8 in shared memory, tcgen05 kind::i8 into TMEM */
+#define MARSB200_PAIR_POPC 0 /* test-only: shared-memory tiled AND + popcount, pins the tensor-core kernels */
 
 int marsb200_version(void);
 const char* marsb200_last_error(void);
