@@ -253,3 +253,27 @@ def test_launch_count_follows_the_schedule():
     assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=None, tensor_partition_sms=56), 16) == \
         kernel_launches_per_run(RankingConfig(nms_iou_threshold=None)) + 2 * 3
     assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=0.7, emd_on_device=True)) == base + 6
+
+
+def test_build_mars_fss_one_argument_form_needs_the_reference_loaders():
+    """`build_MARS_fss(args)` (the reference's signature, mars/MARS.py:110-116) loads the PyTorch producers with the
+    reference's own loaders; without the reference checkout on sys.path it must say so instead of failing obscurely."""
+    import types
+
+    import marsb200
+
+    args = types.SimpleNamespace(input_size=518, num_regs=4, device="cuda:0", models_path="/nonexistent",
+                                 dino_backbone="vitl14", vva_refinement_box_threshold=0.8,
+                                 last_n_attn_for_vva_refinement=24, alpha_coverage=0.85, static_threshold=0.55,
+                                 dynamic_threshold=0.95)
+    with pytest.raises(ImportError, match="reference"):
+        marsb200.build_MARS_fss(args)
+
+
+def test_record_layout_matches_the_header():
+    """marsb200_record_bytes: order int32[P] | score float32[P] | flags uint8[P rounded up to 4] | summary int32[4]."""
+    from marsb200 import ops
+
+    for p in (1, 3, 4, 10, 256, 1000):
+        assert ops.record_bytes(p) == 8 * p + (p + 3) // 4 * 4 + 16
+        assert ops.record_bytes(p) % 4 == 0
