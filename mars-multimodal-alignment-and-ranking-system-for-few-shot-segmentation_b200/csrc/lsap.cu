@@ -54,54 +54,6 @@ __device__ inline void lsap_argmin(const double* dist, const unsigned char* scan
     }
 }
 
-// Block-wide smallest and second smallest of key(j) over j in [0, M): (v1, j1) = minimum (lowest j among equals), v2 = the
-// smallest key over j != j1 (at j2).  Used by the augmenting row reduction.
-template <typename Key>
-__device__ inline void lsap_argmin2(int M, Key key, double& v1, int& j1, double& v2, int& j2, double* s_a, int* s_ja,
-                                    double* s_b, int* s_jb) {
-    double a = LSAP_INF, b = LSAP_INF;
-    int ja = 0x7fffffff, jb = 0x7fffffff;
-    auto push = [&](double k, int j) {  // insert (k, j) into the running (a, ja) <= (b, jb) pair
-        if (k < a || (k == a && j < ja)) {
-            b = a;
-            jb = ja;
-            a = k;
-            ja = j;
-        } else if (k < b || (k == b && j < jb)) {
-            b = k;
-            jb = j;
-        }
-    };
-    for (int j = threadIdx.x; j < M; j += LSAP_THREADS) push(key(j), j);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double oa = __shfl_xor_sync(0xffffffffu, a, o), ob = __shfl_xor_sync(0xffffffffu, b, o);
-        const int oja = __shfl_xor_sync(0xffffffffu, ja, o), ojb = __shfl_xor_sync(0xffffffffu, jb, o);
-        if (oja != 0x7fffffff) push(oa, oja);
-        if (ojb != 0x7fffffff) push(ob, ojb);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        s_a[threadIdx.x >> 5] = a;
-        s_ja[threadIdx.x >> 5] = ja;
-        s_b[threadIdx.x >> 5] = b;
-        s_jb[threadIdx.x >> 5] = jb;
-    }
-    __syncthreads();
-    a = LSAP_INF;
-    b = LSAP_INF;
-    ja = jb = 0x7fffffff;
-#pragma unroll
-    for (int w = 0; w < LSAP_THREADS / 32; ++w) {
-        if (s_ja[w] != 0x7fffffff) push(s_a[w], s_ja[w]);
-        if (s_jb[w] != 0x7fffffff) push(s_b[w], s_jb[w]);
-    }
-    v1 = a;
-    j1 = ja;
-    v2 = b;
-    j2 = jb;
-    __syncthreads();  // the scratch arrays may be reused right away
-}
-
 // sim [E, R, C]; row_sel [E, R] / col_sel [E, C] choose the participating rows / columns (null = all).
 // row_to_col [E, R]: assigned column of each selected row or -1; objective [E]: sum of the assigned similarities.
 __global__ void __launch_bounds__(LSAP_THREADS) lsap_kernel(const float* __restrict__ sim, const uint8_t* __restrict__ row_sel,
@@ -192,65 +144,7 @@ __global__ void __launch_bounds__(LSAP_THREADS) lsap_kernel(const float* __restr
     }
     __syncthreads();
 
-    // ---- augmenting row reduction (Jonker & Volgenant 1987, step 3): for a free source i take the smallest and second
-    // smallest of c_ij - v_j; the best sink j1 becomes i's, its dual drops by the difference (so the arc is tight at
-    // u_i = second smallest and every reduced cost stays >= 0) and its previous owner is freed - and, if the drop was
-    // strict, processed next.  One block reduction per step instead of a shortest-path search; two passes over the free
-    // list leave only the contested sources for the search below.  A sink's dual only changes when it is assigned and an
-    // assigned sink never becomes free again, so unassigned sinks keep dual 0 (the inequality side of the rectangular
-    // problem).
-    __shared__ double s_a2[LSAP_THREADS / 32], s_b2[LSAP_THREADS / 32];
-    __shared__ int s_ja2[LSAP_THREADS / 32], s_jb2[LSAP_THREADS / 32];
-    __shared__ int s_cur, s_k, s_nfree, s_nnext, s_steps;
-    if (M >= 2) {
-        for (int pass = 0; pass < 2; ++pass) {
-            if (tid == 0) {  // free list of this pass (ascending), the next pass's list grows behind it in `list`
-                int n = 0;
-                for (int i = 0; i < T; ++i)
-                    if (src_sink[i] < 0) list[n++] = i;
-                s_nfree = n;
-                s_k = 0;
-                s_cur = n > 0 ? list[0] : -1;
-                s_steps = 0;
-            }
-            __syncthreads();
-            while (s_cur >= 0) {  // uniform: shared state only changes between barriers
-                const int i = s_cur;
-                const double ui = 0.0;  // keys are c_ij - v_j (u_i is being set by this step)
-                double v1, v2;
-                int j1, j2;
-                lsap_argmin2(M, [&](int j) { return cost(i, j) - ui - v[j]; }, v1, j1, v2, j2, s_a2, s_ja2, s_b2, s_jb2);
-                if (tid == 0) {
-                    int owner = sink_src[j1] == LSAP_NONE ? -1 : (int)sink_src[j1];
-                    const bool strict = v1 < v2;
-                    if (strict) {
-                        v[j1] -= v2 - v1;
-                    } else if (owner >= 0) {  // tie: leave the taken sink alone if the runner-up is as good
-                        j1 = j2;
-                        owner = sink_src[j1] == LSAP_NONE ? -1 : (int)sink_src[j1];
-                    }
-                    u[i] = v2;
-                    src_sink[i] = j1;
-                    sink_src[j1] = (unsigned short)i;
-                    int next = -1;
-                    if (owner >= 0) {
-                        src_sink[owner] = -1;
-                        if (strict && ++s_steps < 4 * T) next = owner;  // freed by a strict drop: handle it right away
-                    }
-                    if (next < 0) {
-                        ++s_k;
-                        next = s_k < s_nfree ? list[s_k] : -1;
-                    }
-                    s_cur = next;
-                }
-                __syncthreads();
-            }
-            __syncthreads();
-        }
-    }
-
     for (int r = 0; r < T; ++r) {
-        if (src_sink[r] >= 0) continue;  // assigned by the row reduction (uniform: shared state)
         const double ur = u[r];
         for (int j = tid; j < M; j += LSAP_THREADS) {
             const double d = cost(r, j) - ur - v[j];
