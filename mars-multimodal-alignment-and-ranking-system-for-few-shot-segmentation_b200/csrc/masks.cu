@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_packed_kernel(const uint32_
     const uint4* row = reinterpret_cast<const uint4*>(bits + m * wpm);
     const int quads = (int)(wpm / 4);
     const int quads_per_row = (W % 128 == 0) ? W / 128 : 0;  // > 0 selects the word-aligned fast path
+    const int qpr_shift = (quads_per_row > 0 && (quads_per_row & (quads_per_row - 1)) == 0) ? __ffs(quads_per_row) - 1 : -1;
     int my_area = 0;
     for (int q0 = threadIdx.x; q0 < quads; q0 += POOL_THREADS * POOL_UNROLL) {
         uint4 v[POOL_UNROLL];
@@ -190,7 +191,8 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_packed_kernel(const uint32_
             const uint32_t quad = (uint32_t)(q0 + u * POOL_THREADS);
             if (quads_per_row > 0) {
                 // W % 128 == 0: the four words sit in one image row, word-aligned with the bit rows
-                const uint32_t y = quad / (uint32_t)quads_per_row;
+                // quads_per_row is a power of two for the usual widths (1024 -> 8): a shift instead of a division
+                const uint32_t y = qpr_shift >= 0 ? (quad >> qpr_shift) : quad / (uint32_t)quads_per_row;
                 if ((int)y < H) {
                     const int wi0 = (int)(quad - y * (uint32_t)quads_per_row) * 4;
                     const int rb = s_rowbins[y];
