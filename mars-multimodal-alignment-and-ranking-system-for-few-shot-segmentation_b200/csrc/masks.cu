@@ -687,8 +687,21 @@ extern "C" {
 
 int64_t marsb200_words_per_mask(int64_t hw) { return ceil_div64(ceil_div64(hw, 32), 32) * 32; }
 
+// The ingest kernels (no shared memory) and pool_packed_kernel (~8 KB per CTA) ask for the SAME L1 / shared-memory split:
+// CTAs of two kernels only share an SM when their carveouts agree, and the episode engine runs the
+// issue-bound pooling of one chunk beside the load-path-bound ingest of the next on one SM partition.
+static cudaError_t set_ingest_carveouts() {
+    const int pct = 50;
+    cudaError_t e = cudaFuncSetAttribute(pack_f32_vec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pack_u8_vec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pool_packed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    return e;
+}
+static PerDeviceOnce g_ingest_carveouts;
+
 int marsb200_pack_masks(const void* masks, int mask_dtype, int64_t n, int64_t HW, uint32_t* bits, void* stream) {
     MARS_REQUIRE(masks && bits, "null pointer");
+    MARS_CUDA_OK(per_device_once(g_ingest_carveouts, set_ingest_carveouts));
     MARS_REQUIRE(n > 0 && HW > 0, "empty input");
     MARS_REQUIRE(mask_dtype == MARSB200_MASK_F32 || mask_dtype == MARSB200_MASK_U8, "mask_dtype");
     const int64_t wpm = marsb200_words_per_mask(HW);
@@ -742,6 +755,7 @@ int marsb200_pool_packed(const uint32_t* bits, int64_t n, int H, int W, int g, u
     MARS_REQUIRE(g <= 255 && H <= 32768 && W <= 32768, "g <= 255, H, W <= 32768");
     const size_t smem = ((size_t)g * rw + npw + 2) * sizeof(uint32_t) + (size_t)H * sizeof(uint16_t);
     MARS_REQUIRE(smem <= 48 * 1024, "g * W too large for the pooling scratch");
+    MARS_CUDA_OK(per_device_once(g_ingest_carveouts, set_ingest_carveouts));
     pool_packed_kernel<<<(unsigned)n, POOL_THREADS, smem, as_stream(stream)>>>(bits, n, H, W, g, wpm, npw, rw, pooled,
                                                                              area, pooled_count);
     MARS_LAUNCH_OK();

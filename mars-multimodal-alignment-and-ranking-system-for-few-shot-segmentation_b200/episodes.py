@@ -47,6 +47,7 @@ class RankingConfig:
     partition_pairwise_tail: int = 0   # intersections of the last chunks run on the `hbm` partition after the ingest
     partition_vta_on_hbm: bool = True  # vta refinement on the `hbm` partition after the ingest (else beside the vva chain)
     partition_pool_on_tensor: bool = False  # pooled bitmaps of a chunk on the `tensor` partition (the `hbm` one only packs)
+    partition_pool_side_stream: bool = False  # pooled bitmaps on a second stream of the `hbm` partition, beside the next chunk's pack
 
 
 def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int] = None) -> int:
@@ -150,6 +151,8 @@ class RankingEngine:
             if not hasattr(self._part, "side_stream"):
                 self._part.side_stream = self._part.extra_stream("tensor")
             self._part_side = self._part.side_stream
+            if cfg.partition_pool_side_stream and not hasattr(self._part, "hbm_side_stream"):
+                self._part.hbm_side_stream = self._part.extra_stream("hbm")
             self._pending = False  # a partitioned step has been enqueued and not yet joined
             k = max(1, min(cfg.partition_chunks, e))
             per = (e + k - 1) // k
@@ -216,11 +219,12 @@ class RankingEngine:
         n, m = s.N, s.ns * s.N
         main = torch.cuda.current_stream()
         hbm, ten, side = part.hbm_stream, part.tensor_stream, self._part_side
+        streams = (hbm, ten, side) + ((part.hbm_side_stream,) if cfg.partition_pool_side_stream else ())
         if self._pending:  # this buffer set is reused: the previous step that ran in it must have drained
-            for st in (hbm, ten, side):
+            for st in streams:
                 st.wait_event(self._ev_join)
         self._ev_fork.record(main)
-        for st in (hbm, ten, side):
+        for st in streams:
             st.wait_event(self._ev_fork)
         masks = batch["masks"]
         with torch.cuda.stream(hbm):
@@ -231,7 +235,14 @@ class RankingEngine:
                     continue
                 ops.pack_masks(masks[lo:hi], out=self.bits[lo:hi])
                 ev.record(hbm)
-                if not cfg.partition_pool_on_tensor:
+                if cfg.partition_pool_side_stream and not cfg.partition_pool_on_tensor:
+                    # pooling is issue-bound, the ingest load-path-bound: the pooled bitmaps of this chunk are computed
+                    # on a second stream of the same partition while the next chunk is being packed
+                    hs = part.hbm_side_stream
+                    hs.wait_event(ev)
+                    with torch.cuda.stream(hs):
+                        ops.pool_packed(self.bits[lo:hi], s.H, s.W, s.g, out=tuple(t[lo:hi] for t in self.pool_out))
+                elif not cfg.partition_pool_on_tensor:
                     ops.pool_packed(self.bits[lo:hi], s.H, s.W, s.g, out=tuple(t[lo:hi] for t in self.pool_out))
             # the last chunks' intersections stay on this partition: their bits only exist when the ingest is over and
             # the tensor partition still has its own queue to drain
@@ -239,6 +250,9 @@ class RankingEngine:
             if self.inter is not None:
                 for lo, hi in tail:
                     ops.pairwise_inter(self.bits[lo:hi], backend=cfg.pair_backend, out=self.inter[lo:hi])
+            if cfg.partition_pool_side_stream and not cfg.partition_pool_on_tensor:
+                self._ev_pack.record(part.hbm_side_stream)
+                hbm.wait_event(self._ev_pack)  # the pooled bitmaps of every chunk are done
             self._ev_pool.record(hbm)
         # the vta refinement is independent of everything else: it fills the `hbm` partition once the ingest is done
         # (the tensor partition is the longer chain) or runs beside the vva chain inside the tensor partition
