@@ -133,6 +133,18 @@ int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, 
                         int apply_minmax, float* out, uint8_t* box_out, void* workspace, int64_t workspace_bytes,
                         int backend, void* stream);
 
+/* The same in stages, so that a scheduler can hoist what does not depend on the prior: MARSB200_PIR_NORMALISE (column /
+ * row normalisation of the attention into the operand arrays of the workspace; needs only `attn`), MARSB200_PIR_CONTRACT
+ * (G = D D^T; needs only the workspace) and MARSB200_PIR_APPLY (box mask from the prior, the two mat-vecs, optional
+ * min-max).  Stages of one refinement must run in this order on the same workspace; marsb200_pir_refine = all three. */
+#define MARSB200_PIR_NORMALISE 1
+#define MARSB200_PIR_CONTRACT 2
+#define MARSB200_PIR_APPLY 4
+#define MARSB200_PIR_ALL 7
+int marsb200_pir_stages(const float* prior, const float* attn, int64_t ld_attn, int E, int g, double box_threshold,
+                        int apply_minmax, float* out, uint8_t* box_out, void* workspace, int64_t workspace_bytes,
+                        int backend, int stages, void* stream);
+
 /* The box list behind the box mask: `_scoremap2bbox(scoremap, multi_contour_eval=True)` of
  * PriorInformationRefinementModule.py:91-122.  prior [E, g*g]; boxes_out [E, g*g, 4] int32 (x0, y0, x1, y1) with the
  * reference's clip x1 = min(x + w, g - 1), one per 8-connected component in raster order of its first pixel;

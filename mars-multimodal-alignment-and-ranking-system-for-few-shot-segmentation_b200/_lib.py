@@ -48,6 +48,7 @@ SIGNATURES = {
     "marsb200_attn_mean": (_i, [ctypes.POINTER(_p), _i, _i, _i, _i, _i, _p, _l, _p]),
     "marsb200_pir_workspace_bytes": (_l, [_i, _l]),
     "marsb200_pir_refine": (_i, [_p, _p, _l, _i, _i, _d, _i, _p, _p, _p, _l, _i, _p]),
+    "marsb200_pir_stages": (_i, [_p, _p, _l, _i, _i, _d, _i, _p, _p, _p, _l, _i, _i, _p]),
     "marsb200_scoremap_boxes": (_i, [_p, _i, _i, _d, _p, _p, _p]),
     "marsb200_resize_minmax": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "marsb200_pack_masks": (_i, [_p, _i, _l, _l, _p, _p]),

@@ -356,7 +356,16 @@ int64_t marsb200_pir_workspace_bytes(int E, int64_t N) {
 int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, int E, int g, double box_threshold,
                         int apply_minmax, float* out, uint8_t* box_out, void* workspace, int64_t workspace_bytes,
                         int backend, void* stream) {
-    MARS_REQUIRE(prior && attn && out && workspace, "null pointer");
+    return marsb200_pir_stages(prior, attn, ld_attn, E, g, box_threshold, apply_minmax, out, box_out, workspace,
+                               workspace_bytes, backend, MARSB200_PIR_ALL, stream);
+}
+
+int marsb200_pir_stages(const float* prior, const float* attn, int64_t ld_attn, int E, int g, double box_threshold,
+                        int apply_minmax, float* out, uint8_t* box_out, void* workspace, int64_t workspace_bytes,
+                        int backend, int stages, void* stream) {
+    MARS_REQUIRE(workspace && (stages & MARSB200_PIR_ALL) != 0, "null workspace / no stage selected");
+    MARS_REQUIRE(!(stages & MARSB200_PIR_NORMALISE) || attn, "the normalise stage needs the attention matrix");
+    MARS_REQUIRE(!(stages & MARSB200_PIR_APPLY) || (prior && out), "the apply stage needs the prior and the output");
     MARS_REQUIRE(E > 0 && E <= 65535 && g > 0 && g <= 96, "shape (g <= 96)");
     const int N = g * g;
     MARS_REQUIRE(ld_attn >= N, "ld_attn");
@@ -366,19 +375,22 @@ int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, 
     cudaStream_t s = as_stream(stream);
     const int64_t n_pad = marsb200_pad_rows(N), k_pad = marsb200_pad_k(N);
 
-    const size_t smem = (size_t)6 * N * sizeof(int);
-    if (smem > 48 * 1024)
-        MARS_CUDA_OK(cudaFuncSetAttribute(box_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    box_mask_kernel<<<E, 256, smem, s>>>(prior, g, box_threshold, box_out, w.v, nullptr, nullptr);
-    MARS_LAUNCH_OK();
-
-    colsum_partial_kernel<<<dim3(ceil_div(N, 128), COLSUM_SPLITS, E), 128, 0, s>>>(attn, ld_attn, N, w.partial);
-    MARS_LAUNCH_OK();
-    colsum_final_kernel<<<dim3(ceil_div(N, 128), E), 128, 0, s>>>(w.partial, N, w.colsum);
-    MARS_LAUNCH_OK();
-    row_normalize_kernel<<<dim3((unsigned)N, E), 256, 0, s>>>(attn, ld_attn, N, w.colsum, k_pad, w.D, w.D_lo);
-    MARS_LAUNCH_OK();
-
+    if (stages & MARSB200_PIR_APPLY) {
+        const size_t smem = (size_t)6 * N * sizeof(int);
+        if (smem > 48 * 1024)
+            MARS_CUDA_OK(cudaFuncSetAttribute(box_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        box_mask_kernel<<<E, 256, smem, s>>>(prior, g, box_threshold, box_out, w.v, nullptr, nullptr);
+        MARS_LAUNCH_OK();
+    }
+    if (stages & MARSB200_PIR_NORMALISE) {
+        colsum_partial_kernel<<<dim3(ceil_div(N, 128), COLSUM_SPLITS, E), 128, 0, s>>>(attn, ld_attn, N, w.partial);
+        MARS_LAUNCH_OK();
+        colsum_final_kernel<<<dim3(ceil_div(N, 128), E), 128, 0, s>>>(w.partial, N, w.colsum);
+        MARS_LAUNCH_OK();
+        row_normalize_kernel<<<dim3((unsigned)N, E), 256, 0, s>>>(attn, ld_attn, N, w.colsum, k_pad, w.D, w.D_lo);
+        MARS_LAUNCH_OK();
+    }
+    if (stages & MARSB200_PIR_CONTRACT) {
     GemmEpilogue ep{};
     ep.out0 = w.R;
     ep.out1 = nullptr;
@@ -400,6 +412,8 @@ int marsb200_pir_refine(const float* prior, const float* attn, int64_t ld_attn, 
     else
         return fail(MARSB200_ERR_ARG, "%s: unknown backend %lld", "marsb200_pir_refine", backend);
     if (rc != MARSB200_OK) return rc;
+    }
+    if (!(stages & MARSB200_PIR_APPLY)) return MARSB200_OK;
 
     dim3 mv_grid(ceil_div(N, 8), E);
     matvec_kernel<<<mv_grid, 256, 0, s>>>(w.R, N, w.D, k_pad, N, w.v, w.t);

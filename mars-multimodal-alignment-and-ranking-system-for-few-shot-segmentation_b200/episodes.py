@@ -47,6 +47,9 @@ class RankingConfig:
     partition_pairwise_tail: int = 0   # intersections of the last chunks run on the `hbm` partition after the ingest
     partition_vta_on_hbm: bool = True  # vta refinement on the `hbm` partition after the ingest (else beside the vva chain)
     partition_pool_on_tensor: bool = False  # pooled bitmaps of a chunk on the `tensor` partition (the `hbm` one only packs)
+    # the streaming, prior-independent preparation (row normalisation of the features, Sinkhorn normalisation of both
+    # attention matrices) runs on the `hbm` partition in front of the ingest instead of on the `tensor` partition
+    partition_prep_on_hbm: bool = False
     partition_pool_side_stream: bool = False  # pooled bitmaps on a second stream of the `hbm` partition, beside the next chunk's pack
 
 
@@ -141,6 +144,7 @@ class RankingEngine:
         self._ev_join = torch.cuda.Event()
         self._ev_pack = torch.cuda.Event()
         self._ev_pool = torch.cuda.Event()
+        self._ev_prep = torch.cuda.Event()
         self._part = None
         self._capturing = False
         if cfg.tensor_partition_sms:
@@ -227,7 +231,18 @@ class RankingEngine:
         for st in streams:
             st.wait_event(self._ev_fork)
         masks = batch["masks"]
+        prep = cfg.partition_prep_on_hbm
         with torch.cuda.stream(hbm):
+            if prep:
+                # memory-streaming work that depends on the inputs only: it belongs with the ingest, not with the
+                # tensor-core chain (which then starts with the contractions)
+                ops.normalize_rows(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
+                ops.normalize_rows(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
+                ops.pir_refine(None, batch["attn_vva"], s.g, cfg.vva_box_threshold, workspace=self.pir_ws,
+                               stages=ops.PIR_NORMALISE)
+                ops.pir_refine(None, batch["attn_vta"], s.gt, cfg.vta_box_threshold, workspace=self.pir_ws_vta,
+                               stages=ops.PIR_NORMALISE)
+                self._ev_prep.record(hbm)
             for (lo, hi), ev in zip(self._chunks, self._ev_chunk):
                 if cfg.fused_pool and not cfg.partition_pool_on_tensor:
                     ops.pack_pool(masks[lo:hi], s.g, out_bits=self.bits[lo:hi], out_pool=tuple(t[lo:hi] for t in self.pool_out))
@@ -257,20 +272,27 @@ class RankingEngine:
         # the vta refinement is independent of everything else: it fills the `hbm` partition once the ingest is done
         # (the tensor partition is the longer chain) or runs beside the vva chain inside the tensor partition
         vta_stream = hbm if cfg.partition_vta_on_hbm else side
+        vta_stages = (ops.PIR_CONTRACT | ops.PIR_APPLY) if prep else ops.PIR_ALL
         with torch.cuda.stream(vta_stream):
+            if prep:
+                vta_stream.wait_event(self._ev_prep)
             ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
-                           backend=cfg.gemm_backend, workspace=self.pir_ws_vta, out=self.vta_ref)
+                           backend=cfg.gemm_backend, workspace=self.pir_ws_vta, out=self.vta_ref, stages=vta_stages)
             self._ev_vta.record(vta_stream)
         with torch.cuda.stream(ten):
-            ops.normalize_rows(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
-            ops.normalize_rows(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
+            if prep:
+                ten.wait_event(self._ev_prep)
+            else:
+                ops.normalize_rows(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
+                ops.normalize_rows(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
             ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
             ops.sim_contract(self.fs, self.fq, m, n, s.C, want_sim=cfg.want_sim,
                              want_cost=cfg.want_cost or cfg.emd_on_device, row_fg=self.row_fg, backend=cfg.gemm_backend,
                              out=self.gemm_out)
             ops.vva_finalize(self.gemm_out["colstats"], self.row_fg, m, n, out=self.prior)
             ops.pir_refine(self.prior, batch["attn_vva"], s.g, cfg.vva_box_threshold, apply_minmax=True,
-                           backend=cfg.gemm_backend, workspace=self.pir_ws, out=self.vva)
+                           backend=cfg.gemm_backend, workspace=self.pir_ws, out=self.vva,
+                           stages=(ops.PIR_CONTRACT | ops.PIR_APPLY) if prep else ops.PIR_ALL)
             ops.clip_scores(batch["clip_img"], batch["clip_txt"], out=self.clip)
             n_front = len(self._chunks) - len(tail)
             for k, ((lo, hi), ev) in enumerate(zip(self._chunks, self._ev_chunk)):

@@ -219,20 +219,37 @@ def pir_workspace(e: int, n: int, device) -> torch.Tensor:
     return torch.empty((nbytes + 255) // 256 * 256, device=device, dtype=torch.uint8)
 
 
-def pir_refine(prior: torch.Tensor, attn: torch.Tensor, g: int, box_threshold: float, apply_minmax=False,
-               want_box=False, backend=None, workspace=None, out=None):
-    """prior [E, g*g], attn [E, N, N] -> refined [E, N] (and the uint8 box mask when asked)."""
-    prior = _cuda(prior, torch.float32, "prior").reshape(-1, g * g)
-    e, n = prior.shape
-    attn = _cuda(attn, torch.float32, "attn").reshape(e, n, -1)
+PIR_NORMALISE, PIR_CONTRACT, PIR_APPLY, PIR_ALL = 1, 2, 4, 7
+
+
+def pir_refine(prior: Optional[torch.Tensor], attn: Optional[torch.Tensor], g: int, box_threshold: float, apply_minmax=False,
+               want_box=False, backend=None, workspace=None, out=None, stages: int = PIR_ALL, episodes: Optional[int] = None):
+    """prior [E, g*g], attn [E, N, N] -> refined [E, N] (and the uint8 box mask when asked).
+
+    `stages` selects parts of the refinement (include/marsb200.h): PIR_NORMALISE (attention -> operands in `workspace`,
+    needs only `attn`), PIR_CONTRACT (G = D D^T, needs only `workspace`), PIR_APPLY (box mask, mat-vecs, min-max; needs
+    `prior`).  A scheduler can run the first two before the prior exists; they must share `workspace` and keep the order."""
+    n = g * g
+    if prior is not None:
+        prior = _cuda(prior, torch.float32, "prior").reshape(-1, n)
+        e = prior.shape[0]
+    elif attn is not None:
+        e = attn.numel() // (attn.shape[-2] * attn.shape[-1])
+    else:
+        e = int(episodes)
+    ld = n
+    if attn is not None:
+        attn = _cuda(attn, torch.float32, "attn").reshape(e, n, -1)
+        ld = attn.stride(1)
+    dev = prior.device if prior is not None else (attn.device if attn is not None else workspace.device)
     if workspace is None:
-        workspace = pir_workspace(e, n, prior.device)
-    if out is None:
-        out = torch.empty((e, n), device=prior.device, dtype=torch.float32)
-    box = torch.empty((e, n), device=prior.device, dtype=torch.uint8) if want_box else None
-    check(lib.marsb200_pir_refine(prior.data_ptr(), attn.data_ptr(), attn.stride(1), e, g, float(box_threshold),
-                                  int(apply_minmax), out.data_ptr(), _ptr(box), workspace.data_ptr(),
-                                  workspace.numel(), DEFAULT_GEMM if backend is None else backend, _stream()))
+        workspace = pir_workspace(e, n, dev)
+    if out is None and (stages & PIR_APPLY):
+        out = torch.empty((e, n), device=dev, dtype=torch.float32)
+    box = torch.empty((e, n), device=dev, dtype=torch.uint8) if want_box else None
+    check(lib.marsb200_pir_stages(_ptr(prior), _ptr(attn), ld, e, g, float(box_threshold),
+                                  int(apply_minmax), _ptr(out), _ptr(box), workspace.data_ptr(),
+                                  workspace.numel(), DEFAULT_GEMM if backend is None else backend, int(stages), _stream()))
     return (out, box) if want_box else out
 
 
