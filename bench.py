@@ -451,6 +451,11 @@ def run_ours(args):
                 "traffic": ncu_traffic_bytes("pack_f32_vec_kernel" if md == torch.float32 else "pack_u8_vec_kernel",
                                              args.workload, E, args.mask_dtype),
                 "algorithmic_bytes_per_launch": pack_bytes, "ms_per_launch": pack_ms}
+    step_ms = elapsed_ms / args.steps
+    whole_step = {"input_bytes_per_step_per_gpu": bytes_per_step, "ms_per_step": step_ms,
+                  "input_gbs": bytes_per_step / (step_ms / 1e3) / 1e9, "frac_of_hbm_peak": bytes_per_step / (step_ms / 1e3) / 1e9 / peak,
+                  "note": "inputs only; the kernels of a step move ~1.22x the input bytes (packed bits, operands with their TF32 "
+                          "residuals, attention, G: profiles/r2_ncu_full_top_kernels.csv), so the step as a whole is HBM-bound"}
     pairwise = {"kernel": "pairwise_inter", "unordered_pairs_per_s": pairs / (pair_ms / 1e3), "ms_per_launch": pair_ms,
                 "word_ops_per_s": pairs * wpm / (pair_ms / 1e3)}
     fused_pool = {"kernel": "pack_pool (one pass: packed bits + pooled bitmaps)", "ms_per_launch": pack_pool_ms,
@@ -741,7 +746,7 @@ def run_ours(args):
                                         if pipe is not None else None)},
             "clocks": clocks, "value_variants": value_variants, "e2e": e2e, "e2e_variants": e2e_variants,
             "gpu_launches": marsb200.kernel_launches_per_run(cfg_main, E) * args.steps * world,
-            "roofline": roofline, "pairwise": pairwise, "fused_ingest": fused, "fused_pool": fused_pool, "full_scoring": full,
+            "roofline": roofline, "whole_step": whole_step, "pairwise": pairwise, "fused_ingest": fused, "fused_pool": fused_pool, "full_scoring": full,
             "single_episode_latency": lat, "cpu_baseline": cpu_baseline, "parity_checked": parity,
             "gather_verified": gather_check, "other_configs": other,
         }))
