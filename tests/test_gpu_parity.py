@@ -1428,16 +1428,24 @@ def test_stream_sm_count_follows_the_partition(mb):
         part.close()
 
 
-@pytest.mark.parametrize("chunks,vta_on_hbm,tail", [(1, True, 0), (2, False, 1), (3, True, 2)])
-def test_engine_partitioned_matches_one_timeline(mb, chunks, vta_on_hbm, tail):
-    """The two-partition schedule (ingest beside the contractions) is the same arithmetic: every output bit for bit."""
+@pytest.mark.parametrize("chunks,vta_on_hbm,tail,extra", [
+    (1, True, 0, {}), (2, False, 1, {}), (3, True, 2, {}),
+    (2, False, 0, dict(partition_prep_on_hbm=True)),          # streaming preparation (staged PIR) on the hbm partition
+    (3, True, 0, dict(partition_prep_on_hbm=True)),
+    (2, False, 0, dict(partition_pool_side_stream=True)),     # pooling beside the next chunk's ingest
+    (2, False, 0, dict(partition_pool_on_tensor=True)),
+    (2, False, 0, dict(fused_pool=True)),                     # one-pass pack + pool in the hbm partition
+])
+def test_engine_partitioned_matches_one_timeline(mb, chunks, vta_on_hbm, tail, extra):
+    """The two-partition schedule (ingest beside the contractions) and every optional placement of its pieces are the same
+    arithmetic: every output bit for bit."""
     shape = mb.EpisodeShape(ns=1, g=12, C=64, P=40, H=160, W=160, gt=9, D=32)
     eps = [mb.make_episode(shape, 300 + i) for i in range(5)]
     batch = mb.to_device(mb.stack_episodes(eps), dev())
     base = mb.RankingEngine(shape, 5, mb.RankingConfig(nms_iou_threshold=0.7), dev())
     ref = {k: v.clone() for k, v in base.run(batch).items() if v is not None}
     cfg = mb.RankingConfig(nms_iou_threshold=0.7, tensor_partition_sms=56, partition_chunks=chunks,
-                           partition_vta_on_hbm=vta_on_hbm, partition_pairwise_tail=tail)
+                           partition_vta_on_hbm=vta_on_hbm, partition_pairwise_tail=tail, **extra)
     eng = mb.RankingEngine(shape, 5, cfg, dev())
     try:
         for _ in range(2):
@@ -1447,6 +1455,22 @@ def test_engine_partitioned_matches_one_timeline(mb, chunks, vta_on_hbm, tail):
                 assert torch.equal(out[k], v), k
     finally:
         eng._part.close()
+
+
+def test_pir_stages_equal_the_single_call(mb):
+    """marsb200_pir_stages: normalise / contract / apply run separately (in that order, on one workspace) give the same
+    bits as marsb200_pir_refine."""
+    g, e = 12, 3
+    n = g * g
+    gen = torch.Generator().manual_seed(12)
+    attn = torch.softmax(2.0 * torch.randn(e, n, n, generator=gen), -1).to(dev())
+    prior = torch.rand(e, n, generator=gen).to(dev())
+    whole = mb.ops.pir_refine(prior, attn, g, 0.5, apply_minmax=True)
+    ws = mb.ops.pir_workspace(e, n, dev())
+    mb.ops.pir_refine(None, attn, g, 0.5, workspace=ws, stages=mb.ops.PIR_NORMALISE)
+    mb.ops.pir_refine(None, None, g, 0.5, workspace=ws, stages=mb.ops.PIR_CONTRACT, episodes=e)
+    staged = mb.ops.pir_refine(prior, None, g, 0.5, apply_minmax=True, workspace=ws, stages=mb.ops.PIR_APPLY)
+    assert torch.equal(whole, staged)
 
 
 def test_pack_inside_a_partition_is_bit_exact(mb):
