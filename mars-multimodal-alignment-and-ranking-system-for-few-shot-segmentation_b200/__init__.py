@@ -7,7 +7,7 @@ there is no CPU fallback.
 """
 from . import _lib, ops, synthetic  # noqa: F401  (loads libmarsb200.so)
 from ._lib import MarsB200Error  # noqa: F401
-from .episodes import (InterleavedRanking, PipelinedRanking, SpatialRanking, RankingConfig, RankingEngine, decode_records, gather_records,  # noqa: F401
+from .episodes import (InterleavedRanking, PipelinedRanking, RankingConfig, RankingEngine, decode_records, gather_records,  # noqa: F401
                        kernel_launches_per_run, shard_range)
 from .synthetic import CONFIGS, EpisodeShape, make_episode, masks_to_rle, stack_episodes, to_device  # noqa: F401
 from .components import (FilteringMergingModule, PriorInformationRefinementModule,  # noqa: F401

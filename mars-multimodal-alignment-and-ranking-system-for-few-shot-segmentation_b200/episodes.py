@@ -85,7 +85,7 @@ def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int
 
 class RankingEngine:
     def __init__(self, shape: EpisodeShape, episodes_per_batch: int, cfg: RankingConfig, device,
-                 mask_dtype=torch.float32, partition=None, side_streams=None):
+                 mask_dtype=torch.float32, partition=None):
         if torch.device(device).type != "cuda":
             raise RuntimeError("RankingEngine needs a CUDA device (marsb200 has no CPU path)")
         self.shape, self.E, self.cfg, self.device = shape, episodes_per_batch, cfg, torch.device(device)
@@ -136,12 +136,9 @@ class RankingEngine:
         self._graph = None
         self._static = None
         self._rle_ws = None
-        # the one-timeline schedule forks three side streams off the caller's stream; `side_streams` supplies them when the
-        # engine must stay inside one SM partition (streams of that green context: SpatialRanking)
-        mk = side_streams if side_streams is not None else (lambda: torch.cuda.Stream(device=dev))
-        self._side = mk() if cfg.overlap_streams else None
-        self._side2 = mk() if cfg.overlap_streams else None
-        self._side3 = mk() if cfg.overlap_streams else None
+        self._side = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
+        self._side2 = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
+        self._side3 = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
         self._ev_vta = torch.cuda.Event()
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
@@ -536,49 +533,6 @@ class InterleavedRanking:
 
     def close(self):
         pass
-
-
-class SpatialRanking:
-    """Two whole engines on two disjoint SM sets (CUDA green contexts), each running complete one-timeline steps; the steps
-    are handed to them in turn.  Spatial instead of temporal multiplexing for formats whose ingest is cheap: the
-    one-CTA-per-episode kernels of a step (box mask, fuse / rank / NMS, finalisation) leave most of a whole device idle,
-    but only most of HALF a device here, while the other half keeps working.  Same interface as `PipelinedRanking`."""
-
-    def __init__(self, shape: EpisodeShape, episodes_per_batch: int, cfg: RankingConfig, device, mask_dtype=torch.float32,
-                 first_sms: Optional[int] = None):
-        from .partition import SmPartition
-
-        if cfg.tensor_partition_sms:
-            raise ValueError("SpatialRanking partitions the device itself; pass a config without tensor_partition_sms")
-        total = torch.cuda.get_device_properties(device).multi_processor_count
-        self._part = SmPartition(device, first_sms or (total // 2 // 8 * 8))
-        self.streams = [self._part.tensor_stream, self._part.hbm_stream]
-        self.engines = [RankingEngine(shape, episodes_per_batch, cfg, device, mask_dtype,
-                                      side_streams=(lambda w=w: self._part.extra_stream(w))) for w in ("tensor", "hbm")]
-        self._fork = [torch.cuda.Event() for _ in range(2)]
-        self._done = [torch.cuda.Event() for _ in range(2)]
-        self._next = 0
-
-    def submit(self, batch: dict) -> int:
-        ticket = self._next
-        k = ticket % 2
-        self._fork[k].record(torch.cuda.current_stream())
-        self.streams[k].wait_event(self._fork[k])
-        with torch.cuda.stream(self.streams[k]):
-            self.engines[k].run(batch)
-            self._done[k].record(self.streams[k])
-        self._next += 1
-        return ticket
-
-    def engine(self, ticket: int) -> "RankingEngine":
-        return self.engines[ticket % 2]
-
-    def result(self, ticket: int) -> dict:
-        torch.cuda.current_stream().wait_event(self._done[ticket % 2])
-        return self.engine(ticket).outputs()
-
-    def close(self):
-        self._part.close()
 
 
 def decode_records(records: torch.Tensor, p: int) -> dict:
