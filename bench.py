@@ -473,7 +473,7 @@ def run_ours(args):
     rle_cache = {}
 
     def run_e2e(e2e_dtype, wire="dense", episodes=None, resident_backbone=False):
-        Ee = episodes or args.e2e_episodes_per_step
+        Ee = min(episodes or args.e2e_episodes_per_step, E)
         engs = [marsb200.RankingEngine(shape, Ee, cfg, dev, e2e_dtype) for _ in range(2)]
         host = {k: v[:Ee].cpu() for k, v in batches[0].items()}
         if wire == "rle":  # SAM's own output format: uncompressed COCO RLE, decoded on the device
@@ -562,11 +562,12 @@ def run_ours(args):
                        "host-to-device rate (H2D of step i + 1 overlaps the compute of step i)")
         if md == torch.float32:  # the same call with lighter proposal wire formats (PCIe carries far fewer bytes)
             Ev = min(E, 16)
-            e2e_variants = {"u8_host_masks": run_e2e(torch.uint8, episodes=4),
-                            "rle_host_masks": run_e2e(md, "rle", episodes=Ev),
+            e2e_variants = {"u8_host_masks": run_e2e(torch.uint8, episodes=min(4, E)),
                             "packed_host_masks": run_e2e(md, "bits", episodes=Ev),
-                            "rle_host_masks_backbone_resident": run_e2e(md, "rle", episodes=Ev, resident_backbone=True),
                             "packed_host_masks_backbone_resident": run_e2e(md, "bits", episodes=Ev, resident_backbone=True)}
+            if shape.H % 32 == 0 and shape.W % 32 == 0:  # the device RLE decoder needs word-aligned rows and columns
+                e2e_variants["rle_host_masks"] = run_e2e(md, "rle", episodes=Ev)
+                e2e_variants["rle_host_masks_backbone_resident"] = run_e2e(md, "rle", episodes=Ev, resident_backbone=True)
 
     # ---- single-episode latency (the reference ranks one episode at a time, main_MARS.py:54-94): eager launches
     # and one CUDA-graph replay of the same kernel sequence
