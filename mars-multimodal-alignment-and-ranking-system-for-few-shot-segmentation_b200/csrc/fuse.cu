@@ -187,45 +187,55 @@ __global__ void __launch_bounds__(FUSE_THREADS) fuse_rank_kernel(
         for (int p = tid; p < P; p += FUSE_THREADS) s_area[p] = im[(int64_t)p * P + p];
         __syncthreads();
         if (s_sup != nullptr) {
-            // (a) all threads: suppression bits in rank space, sup[ri] bit rj = IoU(order[ri], order[rj]) > thr
+            // (a) all warps: suppression bits in PROPOSAL space, sup[i] bit j = IoU(i, j) > thr (j != i).  A warp reads 32
+            // consecutive entries of row i of `inter` (one coalesced 128-byte request) and ballots them into one word; the
+            // rank order only enters in the scan below.  No "later ranks only" filter is needed: the relation is symmetric,
+            // so a kept proposal never overlaps an earlier kept one, and bits of earlier removed ones are set already.
             const int nw = (P + 31) >> 5;
-            for (int idx = tid; idx < P * nw; idx += FUSE_THREADS) {
-                const int ri = idx / nw, w = idx - ri * nw;
-                uint32_t bitsw = 0;
-                if (w * 32 + 31 > ri) {  // only later ranks can be suppressed by ri
-                    const int i = s_idx[ri];
-                    const int ai = s_area[i];
-                    const int32_t* row = im + (int64_t)i * P;
-#pragma unroll 8
-                    for (int b = 0; b < 32; ++b) {
-                        const int rj = w * 32 + b;
-                        if (rj > ri && rj < P) {
-                            const int j = s_idx[rj];
-                            const int in = row[j];
-                            const int un = ai + s_area[j] - in;
-                            // the IEEE division only where the quotient can exceed the threshold at all: 2 * in > thr * un
-                            // is implied by in / un > thr with a factor-two margin (float rounding is ~1e-7), and almost
-                            // every pair of proposals fails it (disjoint or barely touching masks)
-                            if (un > 0 && 2.f * (float)in > nms_thr * (float)un) {
-                                const float iou = __fdiv_rn((float)in, (float)un);
-                                if (iou > nms_thr) bitsw |= 1u << b;
-                            }
-                        }
-                    }
+            const int lane = tid & 31;
+            for (int idx0 = (tid >> 5) * 4; idx0 < P * nw; idx0 += (FUSE_THREADS / 32) * 4) {
+                int in[4], ii[4], jj[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int idx = idx0 + q;
+                    ii[q] = idx / nw;
+                    jj[q] = (idx - ii[q] * nw) * 32 + lane;
+                    in[q] = (idx < P * nw && jj[q] < P) ? im[(int64_t)ii[q] * P + jj[q]] : 0;
                 }
-                s_sup[idx] = bitsw;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int idx = idx0 + q;
+                    if (idx >= P * nw) break;  // warp-uniform
+                    bool over = false;
+                    if (jj[q] < P && jj[q] != ii[q]) {
+                        const int un = s_area[ii[q]] + s_area[jj[q]] - in[q];
+                        // the IEEE division only where the quotient can exceed the threshold at all: 2 * in > thr * un
+                        // is implied by in / un > thr with a factor-two margin (float rounding is ~1e-7), and almost
+                        // every pair of proposals fails it (disjoint or barely touching masks)
+                        if (un > 0 && 2.f * (float)in[q] > nms_thr * (float)un)
+                            over = __fdiv_rn((float)in[q], (float)un) > nms_thr;
+                    }
+                    const uint32_t bitsw = __ballot_sync(0xffffffffu, over);
+                    if (lane == 0) s_sup[idx] = bitsw;
+                }
             }
             __syncthreads();
-            // (b) one warp walks the ranks; lane w owns word w of the removed mask (P <= 1024)
+            // (b) one warp walks the ranks; lane w owns word w of the removed mask in proposal space (P <= 1024)
             if (tid < 32) {
                 uint32_t removed = 0;
+                int i = s_idx[0];
+                uint32_t sup = tid < nw ? s_sup[i * nw + tid] : 0u;
                 for (int r = 0; r < P; ++r) {
-                    const uint32_t word = __shfl_sync(0xffffffffu, removed, r >> 5);
-                    if (!((word >> (r & 31)) & 1u) && tid < nw) removed |= s_sup[r * nw + tid];
+                    const int i_next = r + 1 < P ? s_idx[r + 1] : 0;  // the loads of the next rank do not depend on `removed`
+                    const uint32_t sup_next = tid < nw ? s_sup[i_next * nw + tid] : 0u;
+                    const uint32_t word = __shfl_sync(0xffffffffu, removed, i >> 5);
+                    if (!((word >> (i & 31)) & 1u)) removed |= sup;
+                    i = i_next;
+                    sup = sup_next;
                 }
                 for (int b = 0; b < 32; ++b) {
-                    const int r = tid * 32 + b;
-                    if (tid < nw && r < P) s_removed[s_idx[r]] = (removed >> b) & 1u;
+                    const int p = tid * 32 + b;
+                    if (tid < nw && p < P) s_removed[p] = (removed >> b) & 1u;
                 }
             }
             __syncthreads();

@@ -231,6 +231,30 @@ def emd_exact(cost: np.ndarray) -> float:
     return float(res.fun)
 
 
+def emd_network_simplex(cost: np.ndarray) -> float:
+    """The same transport LP solved by a NETWORK SIMPLEX (networkx 3.x), the algorithm class POT's ``ot.emd2`` uses
+    (LEMON network simplex; FilteringMergingModule.py:160-166).  Integer arithmetic throughout: float32 costs in
+    [2^-5, 1) are exact multiples of 2^-29, supplies are M units and demands T units of mass 1/(T M), so the optimum
+    comes out exact.  Second, independent exact solver beside ``emd_exact`` (HiGHS); used by the tests only."""
+    import networkx as nx
+
+    c = np.asarray(cost, dtype=np.float64)
+    t, m = c.shape
+    if t == 0 or m == 0:
+        return 0.0
+    scale = float(1 << 29)
+    ci = c * scale
+    if not np.all(ci == np.rint(ci)):
+        raise ValueError("costs must be float32 values in [2^-5, 1) (exact multiples of 2^-29)")
+    ci = ci.astype(np.int64)
+    graph = nx.DiGraph()
+    graph.add_nodes_from(((0, i) for i in range(t)), demand=-m)
+    graph.add_nodes_from(((1, j) for j in range(m)), demand=t)
+    graph.add_weighted_edges_from(((0, i), (1, j), int(ci[i, j])) for i in range(t) for j in range(m))
+    total, _ = nx.network_simplex(graph)
+    return float(total) / scale / (t * m)
+
+
 def emd_score(pooled_support: torch.Tensor, pooled_proposal: torch.Tensor, cost_matrix: torch.Tensor) -> float:
     """``1 - emd`` on the cost sub-matrix (FilteringMergingModule.py:142-169)."""
     sub = cost_matrix[pooled_support.reshape(-1).bool(), :][:, pooled_proposal.reshape(-1).bool()]

@@ -1149,6 +1149,34 @@ def test_emd_rectangular_equals_expanded_assignment(mb, t, m):
     assert abs(got - want) < 1e-12
 
 
+def test_emd_c2_full_size_against_network_simplex(mb):
+    """Device EMD of a whole c2 episode (P = 256 LPs, T ~ 400 support patches) against a NETWORK SIMPLEX - the algorithm
+    class of the reference's ot.emd2 (FilteringMergingModule.py:162-166) - on the largest, the median and the smallest
+    non-empty proposals; integer arithmetic on the host side, so the comparison is exact up to float64 rounding."""
+    pytest.importorskip("networkx")
+    shape = mb.CONFIGS["c2"]
+    b = mb.stack_episodes([mb.make_episode(shape, 40, dev())])
+    n, g = shape.N, shape.g
+    fs = mb.ops.normalize_rows(b["feat_s"].reshape(1, n, shape.C))
+    fq = mb.ops.normalize_rows(b["feat_q"])
+    row_fg = mb.ops.pool_mask(b["support_mask"], g).reshape(1, n)
+    cost = mb.ops.sim_contract(fs, fq, n, n, shape.C, want_sim=False, want_cost=True)["cost"]
+    pooled, _, cnt = mb.ops.pool_packed(mb.ops.pack_masks(b["masks"]), shape.H, shape.W, g)
+    got = mb.ops.emd_scores(cost, row_fg, pooled)[0].cpu().numpy()
+    c_host = cost[0].cpu().numpy()
+    rows = row_fg[0].cpu().numpy().astype(bool)
+    order = np.argsort(-cnt[0].cpu().numpy(), kind="stable")
+    nonempty = [int(p) for p in order if int(cnt[0, p]) > 0]
+    picks = [nonempty[0], nonempty[1], nonempty[len(nonempty) // 2], nonempty[-1]]
+    words = pooled[0].cpu().numpy().view(np.uint32)
+    for p in picks:
+        cols = np.array([(words[p, j >> 5] >> np.uint32(j & 31)) & 1 for j in range(n)], dtype=bool)
+        sub = c_host[rows][:, cols]
+        assert sub.min() >= 2.0 ** -5 and sub.max() < 1.0
+        want = 1.0 - orc.emd_network_simplex(sub)
+        assert abs(got[p] - want) < 1e-9, (p, sub.shape, got[p], want)
+
+
 def test_emd_square_case_equals_assignment(mb):
     """T == M: the transport LP is an assignment problem; compare with scipy's exact LSAP at a larger size."""
     from scipy.optimize import linear_sum_assignment

@@ -248,3 +248,13 @@ def test_exact_emd_rectangular_cross_check(t, m):
     rs = np.random.RandomState(100 * t + m)
     cost = ((1 - rs.uniform(-0.2, 0.9, size=(t, m))) / 2).astype(np.float32)
     assert abs(orc.emd_exact(cost) - _emd_by_assignment(cost)) < 1e-12
+
+
+@pytest.mark.parametrize("t,m", [(40, 27), (64, 50), (120, 77), (90, 90), (33, 208), (245, 218)])
+def test_exact_emd_network_simplex_cross_check(t, m):
+    """HiGHS LP against a network simplex (the algorithm class of POT's ot.emd2, FilteringMergingModule.py:162-166; POT
+    itself cannot be installed here) at the sizes the c2 episodes produce: T ~ 245-402 support patches, M up to 650."""
+    pytest.importorskip("networkx")
+    rs = np.random.RandomState(100 * t + m)
+    cost = ((1 - rs.uniform(-0.2, 0.9, size=(t, m))) / 2).astype(np.float32)
+    assert abs(orc.emd_exact(cost) - orc.emd_network_simplex(cost)) < 1e-12
