@@ -237,12 +237,18 @@ int marsb200_clip_scores_f16(const void* img_f16, const void* txt_f16, int E, in
  * flags [E,P] uint8 by proposal index (bit0 = kept by NMS, bit1 = selected for the merge);
  * summary [E,4] int32 = {n_kept, n_selected, top_index, n_nonfinite}: n_nonfinite counts proposals whose fused score is
  * NaN / inf (a NaN input score); they rank last and the caller should treat the episode as failed.
- * record: optional [E, record_stride] bytes, see marsb200_record_bytes. */
+ * record: optional [E, record_stride] bytes, see marsb200_record_bytes.
+ * nms_bits: optional [E, P, ceil(P/32)] uint32 from marsb200_nms_bitmask (same inter, same threshold): the pairwise
+ * suppression relation does not depend on the ranking, so it can be computed by a many-CTA launch as soon as the
+ * intersections exist, off the critical path of the one-CTA-per-episode ranking kernel; NULL = built inside (same result). */
 int marsb200_fuse_rank(const double* emd, const float* clip, const int32_t* pooled_count, const float* sum_vva,
-                       const float* sum_vta, const int32_t* union_count, const int32_t* inter, int E, int P,
-                       double alpha, double static_threshold, double dynamic_threshold, float nms_iou_threshold,
-                       int clip_f16, double* scores, int32_t* order, uint8_t* flags, int32_t* summary, uint8_t* record,
-                       int64_t record_stride, void* stream);
+                       const float* sum_vta, const int32_t* union_count, const int32_t* inter, const uint32_t* nms_bits,
+                       int E, int P, double alpha, double static_threshold, double dynamic_threshold,
+                       float nms_iou_threshold, int clip_f16, double* scores, int32_t* order, uint8_t* flags,
+                       int32_t* summary, uint8_t* record, int64_t record_stride, void* stream);
+/* nms_bits[e, i] bit j = IoU(i, j) > nms_iou_threshold for j != i, IoU = inter[i][j] / (inter[i][i] + inter[j][j] -
+ * inter[i][j]) in float32 (builder-defined; torchvision-nms comparison semantics). */
+int marsb200_nms_bitmask(const int32_t* inter, int E, int P, float nms_iou_threshold, uint32_t* nms_bits, void* stream);
 /* Bytes of one episode's result record: order int32[P] | score float32[P] | flags uint8[P rounded up to 4] | summary
  * int32[4].  When `record` is given (row e at record + e * record_stride, 4-byte aligned) marsb200_fuse_rank writes the
  * record itself, so the rows can BE a rank's slice of the all-gather table (the only collective of the path

@@ -62,7 +62,7 @@ def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int
         if episodes_per_batch is not None:
             per = (episodes_per_batch + k - 1) // k
             k = (episodes_per_batch + per - 1) // per
-        n += (k - 1) * (2 + (1 if cfg.nms_iou_threshold is not None else 0))  # pack, pool_packed, pairwise
+        n += (k - 1) * (2 + (2 if cfg.nms_iou_threshold is not None else 0))  # pack, pool_packed, pairwise + suppression relation
     n += 2                     # normalize_rows x2
     n += 1                     # pool_mask
     n += 1                     # sim_contract
@@ -73,6 +73,8 @@ def kernel_launches_per_run(cfg: RankingConfig, episodes_per_batch: Optional[int
     n += 1                     # pack (memset not counted)
     if cfg.nms_iou_threshold is not None and not cfg.fused_ingest:
         n += 1                 # pairwise intersections (part of the pack kernel with fused_ingest)
+    if cfg.nms_iou_threshold is not None:
+        n += 1                 # suppression relation from the intersections (P <= 1024; larger P builds it while ranking)
     n += 1                     # pool_packed
     n += 1                     # region sums + union count (one launch)
     if cfg.emd_on_device:
@@ -123,6 +125,8 @@ class RankingEngine:
         self.pool_out = (new((e, s.P, npw), i32), new((e, s.P), i32), new((e, s.P), i32))
         self.region_out = (new((e, s.P), f32), new((e, s.P), f32), new((e,), i32))
         self.inter = new((e, s.P, s.P), i32) if cfg.nms_iou_threshold is not None else None
+        # pairwise suppression relation (proposal space), computed right behind the intersections: the ranking kernel only scans it
+        self.nms_bits = new((e, s.P, (s.P + 31) // 32), i32) if cfg.nms_iou_threshold is not None and s.P <= 1024 else None
         self.clip = new((e, s.P), f32)
         self.rank_out = dict(scores=new((e, s.P), torch.float64), order=new((e, s.P), i32),
                              flags=new((e, s.P), u8), summary=new((e, 4), i32))
@@ -180,12 +184,24 @@ class RankingEngine:
         else:
             ops.pack_masks(batch["masks"], out=self.bits)
 
+    def _pairwise(self, lo: int = 0, hi: Optional[int] = None):
+        """Intersections of the episodes [lo, hi) and, from them, the suppression relation the ranking kernel scans."""
+        hi = self.E if hi is None else hi
+        ops.pairwise_inter(self.bits[lo:hi], backend=self.cfg.pair_backend, out=self.inter[lo:hi])
+        self._relation(lo, hi)
+
+    def _relation(self, lo: int = 0, hi: Optional[int] = None):
+        if self.nms_bits is not None:
+            hi = self.E if hi is None else hi
+            ops.nms_bitmask(self.inter[lo:hi], self.cfg.nms_iou_threshold, out=self.nms_bits[lo:hi])
+
     def _mask_chain(self, batch: dict):
         """Ingest side: pack -> pooled bitmaps / areas -> pairwise intersections (depends on the masks only)."""
         s, cfg = self.shape, self.cfg
         if self.inter is not None and cfg.fused_ingest and "masks" in batch:
             # one pass over the masks: packed bits + intersections (falls back to two kernels when not fusable)
             ops.pack_pairwise(batch["masks"], backend=cfg.pair_backend, out=(self.bits, self.inter))
+            self._relation()
             ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
             return
         if "masks" in batch and cfg.fused_pool:
@@ -194,14 +210,14 @@ class RankingEngine:
             # by default
             ops.pack_pool(batch["masks"], s.g, out_bits=self.bits, out_pool=self.pool_out)
             if self.inter is not None:
-                ops.pairwise_inter(self.bits, backend=cfg.pair_backend, out=self.inter)
+                self._pairwise()
             return
         self._ingest(batch)
         if self.inter is None:
             ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
         elif self._side2 is None:
             ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
-            ops.pairwise_inter(self.bits, backend=cfg.pair_backend, out=self.inter)
+            self._pairwise()
         else:
             # pooling (re-reads the bits, HBM/issue-bound) runs beside the tensor-core pairwise kernel
             cur = torch.cuda.current_stream()
@@ -210,7 +226,7 @@ class RankingEngine:
             with torch.cuda.stream(self._side2):
                 ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
                 self._ev_pool.record(self._side2)
-            ops.pairwise_inter(self.bits, backend=cfg.pair_backend, out=self.inter)
+            self._pairwise()
             cur.wait_event(self._ev_pool)
 
     def _run_partitioned(self, batch: dict, wait: bool = True) -> dict:
@@ -264,7 +280,7 @@ class RankingEngine:
             tail = self._chunks[len(self._chunks) - cfg.partition_pairwise_tail:] if cfg.partition_pairwise_tail else []
             if self.inter is not None:
                 for lo, hi in tail:
-                    ops.pairwise_inter(self.bits[lo:hi], backend=cfg.pair_backend, out=self.inter[lo:hi])
+                    self._pairwise(lo, hi)
             if cfg.partition_pool_side_stream and not cfg.partition_pool_on_tensor:
                 self._ev_pack.record(part.hbm_side_stream)
                 hbm.wait_event(self._ev_pack)  # the pooled bitmaps of every chunk are done
@@ -302,7 +318,7 @@ class RankingEngine:
                 if cfg.partition_pool_on_tensor:
                     ops.pool_packed(self.bits[lo:hi], s.H, s.W, s.g, out=tuple(t[lo:hi] for t in self.pool_out))
                 if on_tensor:
-                    ops.pairwise_inter(self.bits[lo:hi], backend=cfg.pair_backend, out=self.inter[lo:hi])
+                    self._pairwise(lo, hi)
             ten.wait_event(self._ev_vta)
             ops.resize_minmax(self.vta_ref.reshape(e, s.gt, s.gt), s.g, True, out=self.vta)
             ten.wait_event(self._ev_pool)
@@ -314,7 +330,7 @@ class RankingEngine:
                                      check=False, status=self.emd_status)
             ops.fuse_rank(emd, self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
                           self.region_out[2], self.inter, cfg.alpha, cfg.static_threshold, cfg.dynamic_threshold,
-                          cfg.nms_iou_threshold, out=self.rank_out, record=self.record_buf)
+                          cfg.nms_iou_threshold, out=self.rank_out, record=self.record_buf, nms_bits=self.nms_bits)
             ops.merge_masks(self.bits, self.rank_out["flags"], s.H * s.W, want_bits=True,
                             want_f32=cfg.want_merged_f32, out=self.merge_out)
             self._ev_join.record(ten)
@@ -385,7 +401,7 @@ class RankingEngine:
                                  status=self.emd_status)
         ops.fuse_rank(emd, self.clip, self.pool_out[2], self.region_out[0], self.region_out[1],
                       self.region_out[2], self.inter, cfg.alpha, cfg.static_threshold, cfg.dynamic_threshold,
-                      cfg.nms_iou_threshold, out=self.rank_out, record=self.record_buf)
+                      cfg.nms_iou_threshold, out=self.rank_out, record=self.record_buf, nms_bits=self.nms_bits)
         ops.merge_masks(self.bits, self.rank_out["flags"], s.H * s.W, want_bits=True,
                         want_f32=cfg.want_merged_f32, out=self.merge_out)
         return self.outputs()

@@ -438,11 +438,22 @@ def clip_scores(img: torch.Tensor, txt: torch.Tensor, out=None) -> torch.Tensor:
     return out
 
 
+def nms_bitmask(inter: torch.Tensor, nms_iou_threshold: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Pairwise suppression relation [E, P, ceil(P/32)] int32 (bit j of row i: IoU(i, j) > threshold, j != i) from the
+    intersections [E, P, P]; independent of the ranking, so it can run as soon as `inter` exists (fuse_rank `nms_bits`)."""
+    e, p, _ = inter.shape
+    if out is None:
+        out = torch.empty((e, p, (p + 31) // 32), device=inter.device, dtype=torch.int32)
+    check(lib.marsb200_nms_bitmask(inter.data_ptr(), e, p, float(nms_iou_threshold), out.data_ptr(), _stream()))
+    return out
+
+
 def fuse_rank(emd, clip, pooled_count, sum_vva, sum_vta, union_count, inter, alpha, static_threshold,
-              dynamic_threshold, nms_iou_threshold=None, out=None, clip_f16=False, record=None):
+              dynamic_threshold, nms_iou_threshold=None, out=None, clip_f16=False, record=None, nms_bits=None):
     """Returns dict(scores [E,P] f64, order [E,P] i32, flags [E,P] u8, summary [E,4] i32).  `clip_f16`: `clip` holds
     float16 values and the fusion follows NumPy's float16 sequence (include/marsb200.h).  `record`: optional uint8
-    [E, >= record_bytes(P)] rows (may be a slice of a larger table) the kernel also writes the result records into."""
+    [E, >= record_bytes(P)] rows (may be a slice of a larger table) the kernel also writes the result records into.
+    `nms_bits`: the relation from `nms_bitmask(inter, nms_iou_threshold)` (else it is built inside the ranking kernel)."""
     e, p = clip.shape
     dev = clip.device
     emd = _cuda(emd, torch.float64, "emd").reshape(e, p)
@@ -453,7 +464,8 @@ def fuse_rank(emd, clip, pooled_count, sum_vva, sum_vta, union_count, inter, alp
                    summary=torch.empty((e, 4), device=dev, dtype=torch.int32))
     use_nms = inter is not None and nms_iou_threshold is not None and nms_iou_threshold >= 0
     check(lib.marsb200_fuse_rank(emd.data_ptr(), clip.data_ptr(), pooled_count.data_ptr(), sum_vva.data_ptr(),
-                                 sum_vta.data_ptr(), union_count.data_ptr(), _ptr(inter) if use_nms else None, e, p,
+                                 sum_vta.data_ptr(), union_count.data_ptr(), _ptr(inter) if use_nms else None,
+                                 _ptr(nms_bits) if use_nms and p <= 1024 else None, e, p,
                                  float(alpha), float(static_threshold), float(dynamic_threshold),
                                  float(nms_iou_threshold) if use_nms else -1.0, int(bool(clip_f16)), out["scores"].data_ptr(),
                                  out["order"].data_ptr(), out["flags"].data_ptr(), out["summary"].data_ptr(),

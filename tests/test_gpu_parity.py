@@ -405,8 +405,11 @@ def test_filtering_merging_host_emd_path(mb):
     np.testing.assert_allclose([s for _, s in ranked], z["scores"], rtol=RTOL)
 
 
-@pytest.mark.parametrize("p,thr", [(12, 0.5), (64, 0.7), (200, 0.3), (1, 0.7)])
-def test_nms_keep_set_bit_exact(mb, p, thr):
+@pytest.mark.parametrize("precomputed", [False, True])
+@pytest.mark.parametrize("p,thr", [(12, 0.5), (64, 0.7), (200, 0.3), (1, 0.7), (33, 0.0), (700, 0.5)])
+def test_nms_keep_set_bit_exact(mb, p, thr, precomputed):
+    """precomputed: the suppression relation comes from marsb200_nms_bitmask (the engine's path) instead of being built
+    inside the ranking kernel; both must give the oracle's keep-set."""
     h = 96
     masks = cases.blob_masks(p, h, h, seed=100 + p, min_frac=0.02, max_frac=0.3, dup_every=3)
     rs = np.random.RandomState(p)
@@ -424,8 +427,15 @@ def test_nms_keep_set_bit_exact(mb, p, thr):
     sv = torch.as_tensor(2 * scores, dtype=torch.float32, device=d).reshape(1, p)
     uc = torch.ones((1,), dtype=torch.int32, device=d)
     zero = torch.zeros((1, p), device=d)
+    rel = mb.ops.nms_bitmask(inter, thr) if precomputed else None
+    if precomputed:
+        # the relation itself against its definition (float32 quotient, strict comparison, no self-suppression)
+        want = (orc.iou_matrix(inter_ref, area_ref).numpy() > np.float32(thr)) & ~np.eye(p, dtype=bool)
+        words = rel[0].cpu().numpy().view(np.uint32)
+        got = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(p, -1)[:, :p].astype(bool)
+        np.testing.assert_array_equal(got, want)
     res = mb.ops.fuse_rank(zero.double(), zero, cnt, sv, sv, uc, inter, alpha=1.0, static_threshold=0.0,
-                           dynamic_threshold=0.0, nms_iou_threshold=thr)
+                           dynamic_threshold=0.0, nms_iou_threshold=thr, nms_bits=rel)
     order = res["order"][0].cpu().numpy()
     s32 = (2 * scores).astype(np.float32).astype(np.float64) / (1e-7 + 1)
     order_expected = orc.stable_rank((s32 + s32) / 4)

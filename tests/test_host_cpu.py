@@ -248,8 +248,8 @@ def test_launch_count_follows_the_schedule():
     from marsb200 import RankingConfig, kernel_launches_per_run
 
     base = kernel_launches_per_run(RankingConfig(nms_iou_threshold=0.7))
-    assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=0.7, tensor_partition_sms=56), 16) == base + 3 * 3
-    assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=0.7, tensor_partition_sms=56, partition_chunks=8), 2) == base + 3
+    assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=0.7, tensor_partition_sms=56), 16) == base + 3 * 4
+    assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=0.7, tensor_partition_sms=56, partition_chunks=8), 2) == base + 4
     assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=None, tensor_partition_sms=56), 16) == \
         kernel_launches_per_run(RankingConfig(nms_iou_threshold=None)) + 2 * 3
     assert kernel_launches_per_run(RankingConfig(nms_iou_threshold=0.7, emd_on_device=True)) == base + 6
