@@ -4,6 +4,8 @@
 // Shortest augmenting paths (Jonker-Volgenant) with dense reduced costs in float64: one CTA per problem,
 // block-wide arg-min over the sinks, parallel relaxation, sequential augmentation.  The smaller side is
 // always the set of sources, like scipy's rectangular solver every source gets assigned.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace marsb200 {
@@ -224,6 +226,353 @@ __global__ void __launch_bounds__(LSAP_THREADS) lsap_kernel(const float* __restr
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Near-square problems (the 5-shot forward matching, 1374 fg support rows x 1369 query patches): the per-source
+// Dijkstra above needs ~n searches of up to n steps each and runs at scipy's speed.  The transport solver's schedule
+// (emd.cu) is the better fit: a PHASE grows one shortest-path forest from ALL unmatched sources and augments along the
+// tree path of every free sink it settles; a WAVE settles every unscanned sink at the current minimum distance at
+// once.  With unit supplies the flow is a matching (two index arrays instead of flow lists) and a tree path is dead as
+// soon as one of its sources lies on a path augmented earlier in the phase (`used`).  Rows are the sources and columns
+// the sinks (a source relaxes a contiguous row of `sim`); the smaller side is padded with zero-cost dummy nodes to a
+// square problem, so both sides are equality-constrained and every dual may move freely - which nodes end up on the
+// dummies is exactly the rectangular optimum.  The dispatcher only takes this path when the padding is small.
+#ifdef MARSB200_LSQ_PROFILE
+#define LQ_TIC() long long lq_last = clock64(), lq0 = 0, lq1 = 0, lq2 = 0, lq3 = 0, lq4 = 0, lq5 = 0; int lq_ph = 0, lq_wv = 0
+#define LQ_LAP(x) do { const long long t = clock64(); x += t - lq_last; lq_last = t; } while (0)
+#define LQ_PRINT() do { if (threadIdx.x == 0 && blockIdx.x == 0) printf("lsq n=%d phases %d waves %d | init %lld argmin %lld settle %lld augment %lld relax %lld dual %lld\n", n, lq_ph, lq_wv, lq0, lq1, lq2, lq3, lq4, lq5); } while (0)
+#else
+#define LQ_TIC() do { } while (0)
+#define LQ_LAP(x) do { } while (0)
+#define LQ_PRINT() do { } while (0)
+#endif
+constexpr int LSQ_THREADS = 512;
+constexpr unsigned short LSQ_NONE = 0xffff;
+
+__host__ __device__ inline size_t lsq_smem_bytes(int n_cap) { return (size_t)n_cap * (4 * 8 + 8 * 2 + 3) + 64; }
+
+__global__ void __launch_bounds__(LSQ_THREADS) lsap_square_kernel(const float* __restrict__ sim, const uint8_t* __restrict__ row_sel,
+                                                                   const uint8_t* __restrict__ col_sel, int R, int Ccols,
+                                                                   int maximize, int n_cap, int32_t* __restrict__ row_to_col,
+                                                                   double* __restrict__ objective, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char lsq_smem_raw[];
+    double* u = reinterpret_cast<double*>(lsq_smem_raw);  // [n] source duals
+    double* dsrc = u + n_cap;                              // [n] distance at which a source was reached
+    double* v = dsrc + n_cap;                              // [n] sink duals
+    double* dist = v + n_cap;                              // [n] tentative / final sink distances
+    unsigned short* row_id = reinterpret_cast<unsigned short*>(dist + n_cap);  // [n] row of source i (dummy beyond nr)
+    unsigned short* col_id = row_id + n_cap;               // [n] column of sink j (dummy beyond nc)
+    unsigned short* src_sink = col_id + n_cap;             // [n] sink matched to source i, LSQ_NONE = unmatched
+    unsigned short* sink_src = src_sink + n_cap;           // [n] source matched to sink j, LSQ_NONE = free
+    unsigned short* pred_src = sink_src + n_cap;           // [n] source that gave sink j its distance
+    unsigned short* newlist = pred_src + n_cap;            // [n] sources reached in the current wave (roots at a phase start)
+    unsigned short* freelist = newlist + n_cap;            // [n] free sinks settled in the current wave
+    unsigned short* spare = freelist + n_cap;              // [n] (keeps the arrays 8-byte aligned in pairs)
+    unsigned char* scanned = reinterpret_cast<unsigned char*>(spare + n_cap);  // [n]
+    unsigned char* reached = scanned + n_cap;              // [n]
+    unsigned char* used = reached + n_cap;                 // [n] source lies on a path augmented in this phase
+    __shared__ double s_red[LSQ_THREADS / 32];
+    __shared__ int s_cnt[LSQ_THREADS / 32];
+    __shared__ int s_nr, s_nc, s_nnew, s_nfree, s_left, s_roots_left, s_free_unscanned;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t e = blockIdx.x;
+    const float* S = sim + e * (int64_t)R * Ccols;
+    int32_t* out = row_to_col + e * R;
+    (void)spare;
+
+    // ---- selected rows / columns in ascending order (ordered block compaction)
+    for (int r = tid; r < R; r += LSQ_THREADS) out[r] = -1;
+    auto compact = [&](int n, const uint8_t* sel, unsigned short* ids) -> int {
+        int base = 0;
+        for (int k0 = 0; k0 < n; k0 += LSQ_THREADS) {
+            const int k = k0 + tid;
+            const bool p = k < n && (!sel || sel[k]);
+            const unsigned bal = __ballot_sync(0xffffffffu, p);
+            if (lane == 0) s_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int off = base, total = base;
+            for (int w = 0; w < LSQ_THREADS / 32; ++w) {
+                if (w < warp) off += s_cnt[w];
+                total += s_cnt[w];
+            }
+            if (p) {
+                const int pos = off + __popc(bal & ((1u << lane) - 1u));
+                if (pos < n_cap) ids[pos] = (unsigned short)k;
+            }
+            base = total;
+            __syncthreads();
+        }
+        return base;
+    };
+    const int nr = compact(R, row_sel ? row_sel + e * R : nullptr, row_id);
+    const int nc = compact(Ccols, col_sel ? col_sel + e * Ccols : nullptr, col_id);
+    const int n = max(nr, nc);
+    if (nr == 0 || nc == 0) {
+        if (tid == 0) objective[e] = 0.0;
+        return;
+    }
+    if (n > n_cap) {
+        if (tid == 0) {
+            objective[e] = nan("");
+            atomicMax(status, n);
+        }
+        return;
+    }
+    const float sign = maximize ? -1.f : 1.f;
+    // cost of (source i, sink j): the signed similarity, 0 on the dummy rows / columns
+    // ---- initial duals: v_j = min_i c_ij (a thread per sink, coalesced over j), then u_i = min_j (c_ij - v_j) (a warp
+    // per source, contiguous row): every reduced cost is >= 0 and every row and column has a tight arc
+    for (int j = tid; j < n; j += LSQ_THREADS) {
+        double mn = nr < n ? 0.0 : 1e300;  // a dummy source is part of every column
+        if (j < nc) {
+            const float* colp = S + col_id[j];
+            int i = 0;
+            for (; i + 4 <= nr; i += 4) {
+                const float c0 = colp[(int64_t)row_id[i] * Ccols], c1 = colp[(int64_t)row_id[i + 1] * Ccols];
+                const float c2 = colp[(int64_t)row_id[i + 2] * Ccols], c3 = colp[(int64_t)row_id[i + 3] * Ccols];
+                mn = fmin(fmin(mn, (double)(sign * c0)), fmin((double)(sign * c1), fmin((double)(sign * c2), (double)(sign * c3))));
+            }
+            for (; i < nr; ++i) mn = fmin(mn, (double)(sign * colp[(int64_t)row_id[i] * Ccols]));
+        } else {
+            mn = 0.0;
+        }
+        v[j] = mn;
+        sink_src[j] = LSQ_NONE;
+    }
+    __syncthreads();
+    for (int i = warp; i < n; i += LSQ_THREADS / 32) {
+        double mn = 1e300;
+        if (i < nr) {
+            const float* row = S + (int64_t)row_id[i] * Ccols;
+            for (int j = lane; j < n; j += 32) mn = fmin(mn, (j < nc ? (double)(sign * row[col_id[j]]) : 0.0) - v[j]);
+        } else {
+            for (int j = lane; j < n; j += 32) mn = fmin(mn, -v[j]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (lane == 0) {
+            u[i] = mn;
+            src_sink[i] = LSQ_NONE;
+        }
+    }
+    if (tid == 0) s_left = n;
+    __syncthreads();
+
+    // relax the sinks owned by this thread against `cnt` listed sources reached at distance dsrc[.]
+    // (a thread owns the sinks tid, tid + 512, ...; four of them are processed together so that their gathers overlap)
+    auto relax = [&](const unsigned short* list, int cnt, bool init) {
+        for (int j0 = tid; j0 < n; j0 += 4 * LSQ_THREADS) {
+            bool live[4];
+            const float* colp[4];
+            double best[4], vj[4];
+            int best_i[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = j0 + t * LSQ_THREADS;
+                live[t] = j < n && (init || !scanned[j]);
+                const bool real_j = live[t] && j < nc;
+                colp[t] = real_j ? S + col_id[j] : nullptr;
+                best[t] = (init || !live[t]) ? 1e300 : dist[j];
+                best_i[t] = (init || !live[t]) ? 0 : pred_src[j];
+                vj[t] = live[t] ? v[j] : 0.0;
+            }
+            if (!(live[0] || live[1] || live[2] || live[3])) continue;
+            int k = 0;
+            for (; k + 2 <= cnt; k += 2) {  // two sources x four sinks of independent gathers in flight
+                const int ia = list[k], ib = list[k + 1];
+                const double base_a = dsrc[ia] - u[ia], base_b = dsrc[ib] - u[ib];
+                const int64_t ra = ia < nr ? (int64_t)row_id[ia] * Ccols : -1, rb = ib < nr ? (int64_t)row_id[ib] * Ccols : -1;
+                float ca[4], cb[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    ca[t] = (colp[t] != nullptr && ra >= 0) ? sign * colp[t][ra] : 0.f;
+                    cb[t] = (colp[t] != nullptr && rb >= 0) ? sign * colp[t][rb] : 0.f;
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double da = (base_a + (double)ca[t]) - vj[t];
+                    if (da < best[t]) {
+                        best[t] = da;
+                        best_i[t] = ia;
+                    }
+                    const double db = (base_b + (double)cb[t]) - vj[t];
+                    if (db < best[t]) {
+                        best[t] = db;
+                        best_i[t] = ib;
+                    }
+                }
+            }
+            for (; k < cnt; ++k) {
+                const int i = list[k];
+                const double base = dsrc[i] - u[i];
+                const int64_t roff = i < nr ? (int64_t)row_id[i] * Ccols : -1;
+                float cv[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) cv[t] = (colp[t] != nullptr && roff >= 0) ? sign * colp[t][roff] : 0.f;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double d = (base + (double)cv[t]) - vj[t];
+                    if (d < best[t]) {
+                        best[t] = d;
+                        best_i[t] = i;
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = j0 + t * LSQ_THREADS;
+                if (live[t]) {
+                    dist[j] = best[t];
+                    pred_src[j] = (unsigned short)best_i[t];
+                }
+            }
+        }
+    };
+
+    LQ_TIC();
+    while (s_left > 0) {  // uniform: shared state only changes between barriers
+        // ---- phase start: every unmatched source is a root at distance 0
+#ifdef MARSB200_LSQ_PROFILE
+        lq_ph++;
+#endif
+        if (tid == 0) {
+            s_nnew = 0;
+            s_nfree = 0;
+            s_free_unscanned = 0;
+        }
+        __syncthreads();
+        int free_local = 0;
+        for (int i = tid; i < n; i += LSQ_THREADS) {
+            const bool root = src_sink[i] == LSQ_NONE;
+            reached[i] = root ? 1 : 0;
+            used[i] = 0;
+            dsrc[i] = 0.0;
+            if (root) newlist[atomicAdd(&s_nnew, 1)] = (unsigned short)i;
+            scanned[i] = 0;  // (sinks: same index range)
+            free_local += sink_src[i] == LSQ_NONE ? 1 : 0;
+        }
+        free_local = warp_sum(free_local);
+        if (lane == 0 && free_local) atomicAdd(&s_free_unscanned, free_local);
+        __syncthreads();
+        const int nroots = s_nnew;
+        relax(newlist, nroots, true);
+        if (tid == 0) {
+            s_roots_left = nroots;
+            s_nnew = 0;
+        }
+        __syncthreads();
+
+        LQ_LAP(lq0);
+        double D = 0.0;
+        while (true) {
+#ifdef MARSB200_LSQ_PROFILE
+            lq_wv++;
+#endif
+            // ---- wave: settle every unscanned sink at the minimum distance
+            double mn = 1e300;
+            for (int j = tid; j < n; j += LSQ_THREADS)
+                if (!scanned[j]) mn = fmin(mn, dist[j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            if (lane == 0) s_red[warp] = mn;
+            __syncthreads();
+            mn = s_red[lane & (LSQ_THREADS / 32 - 1)];
+#pragma unroll
+            for (int o = LSQ_THREADS / 64; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            const double dmin = mn;
+            LQ_LAP(lq1);
+            if (dmin >= 1e300) break;  // every sink is scanned
+            D = dmin;
+            for (int j = tid; j < n; j += LSQ_THREADS)
+                if (!scanned[j] && dist[j] == dmin) {
+                    scanned[j] = 1;
+                    const unsigned short i = sink_src[j];
+                    if (i == LSQ_NONE) {
+                        freelist[atomicAdd(&s_nfree, 1)] = (unsigned short)j;
+                    } else {  // the matched source becomes reachable through the tight backward arc
+                        reached[i] = 1;
+                        dsrc[i] = dmin;
+                        newlist[atomicAdd(&s_nnew, 1)] = i;
+                    }
+                }
+            __syncthreads();
+            LQ_LAP(lq2);
+            const int nfree = s_nfree;
+            if (nfree > 0) {
+                if (tid == 0) {
+                    // ---- augment along the tree path of every settled free sink (sequential: the paths must be
+                    // vertex-disjoint); a path through a source used earlier in this phase, or ending in a spent root, is dead
+                    s_free_unscanned -= nfree;
+                    for (int b = 0; b < nfree; ++b) {
+                        const int j = freelist[b];
+                        int i = pred_src[j];
+                        bool ok = true;
+                        while (true) {
+                            if (used[i]) {
+                                ok = false;
+                                break;
+                            }
+                            const unsigned short m = src_sink[i];
+                            if (m == LSQ_NONE) break;  // an unmatched, unused source: the root
+                            i = pred_src[m];
+                        }
+                        if (!ok) continue;
+                        int jc = j;
+                        i = pred_src[jc];
+                        while (true) {
+                            const unsigned short prev = src_sink[i];
+                            src_sink[i] = (unsigned short)jc;
+                            sink_src[jc] = (unsigned short)i;
+                            used[i] = 1;
+                            if (prev == LSQ_NONE) break;
+                            jc = prev;
+                            i = pred_src[jc];
+                        }
+                        s_left -= 1;
+                        s_roots_left -= 1;
+                    }
+                    s_nfree = 0;
+                }
+                __syncthreads();
+                // the phase ends when everything is matched, no root is left to augment from, or no unscanned sink is free
+                if (s_left <= 0 || s_roots_left <= 0 || s_free_unscanned <= 0) break;
+            }
+            LQ_LAP(lq3);
+            const int nnew = s_nnew;
+            if (nnew > 0) relax(newlist, nnew, false);
+            __syncthreads();
+            if (tid == 0) s_nnew = 0;
+            LQ_LAP(lq4);
+        }
+        // ---- dual update: keeps every matched arc tight and all reduced costs non-negative
+        for (int i = tid; i < n; i += LSQ_THREADS) {
+            if (reached[i]) u[i] += D - dsrc[i];
+            if (scanned[i]) v[i] -= D - dist[i];
+        }
+        __syncthreads();
+        LQ_LAP(lq5);
+    }
+    LQ_PRINT();
+
+    double acc = 0.0;
+    for (int i = tid; i < nr; i += LSQ_THREADS) {
+        const int j = src_sink[i];
+        if (j < nc) {
+            out[row_id[i]] = col_id[j];
+            acc += (double)S[(int64_t)row_id[i] * Ccols + col_id[j]];
+        }
+    }
+    acc = warp_sum(acc);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double total = 0.0;
+        for (int w = 0; w < LSQ_THREADS / 32; ++w) total += s_red[w];
+        objective[e] = total;
+    }
+}
+
 }  // namespace marsb200
 
 using namespace marsb200;
@@ -237,11 +586,21 @@ extern "C" int marsb200_lsap(const float* sim, const uint8_t* row_sel, const uin
         t_cap = R < C ? R : C;
         m_cap = R < C ? C : R;
     }
+    cudaStream_t s = as_stream(stream);
+    MARS_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+    // near-square problems take the multi-source phase solver on the zero-padded square (see lsap_square_kernel)
+    const bool near_square = m_cap >= 64 && m_cap - t_cap <= std::max(8, m_cap / 16) && m_cap <= 65534 &&
+                             lsq_smem_bytes(m_cap) <= 220 * 1024;
+    if (near_square) {
+        const size_t smem = lsq_smem_bytes(m_cap);
+        MARS_CUDA_OK(cudaFuncSetAttribute(lsap_square_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lsap_square_kernel<<<E, LSQ_THREADS, smem, s>>>(sim, row_sel, col_sel, R, C, maximize, m_cap, row_to_col, objective, status);
+        MARS_LAUNCH_OK();
+        return MARSB200_OK;
+    }
     const size_t smem = lsap_smem_bytes(t_cap, m_cap);
     MARS_REQUIRE(smem <= 220 * 1024, "problem too large for the shared-memory state (28*min + 23*max bytes <= 220 KB)");
-    cudaStream_t s = as_stream(stream);
     MARS_CUDA_OK(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MARS_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
     lsap_kernel<<<E, LSAP_THREADS, smem, s>>>(sim, row_sel, col_sel, R, C, maximize, t_cap, m_cap, row_to_col, objective,
                                                status);
     MARS_LAUNCH_OK();

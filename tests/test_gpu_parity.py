@@ -1306,6 +1306,34 @@ def test_lsap_matches_scipy(mb, r, c, maximize):
         np.testing.assert_array_equal(got, expect)  # random costs: the optimum is unique
 
 
+@pytest.mark.parametrize("r,c,maximize,sel", [(130, 128, True, False), (128, 131, False, False), (300, 300, True, False),
+                                               (64, 64, True, False), (70, 66, True, True), (1374, 1369, True, False)])
+def test_lsap_near_square_matches_scipy(mb, r, c, maximize, sel):
+    """Near-square problems take the multi-source phase solver on the zero-padded square (lsap_square_kernel; the 5-shot
+    forward matching of Matcher.py:449 is 1374 x 1369): assignment and objective against scipy."""
+    from scipy.optimize import linear_sum_assignment
+
+    gen = torch.Generator().manual_seed(r * 11 + c)
+    sim = torch.rand(2, r, c, generator=gen)
+    row_sel = torch.ones(2, r, dtype=torch.uint8)
+    col_sel = torch.ones(2, c, dtype=torch.uint8)
+    if sel:
+        row_sel[:, 5] = 0
+        col_sel[:, 7] = 0
+        col_sel[1, 9] = 0
+    r2c, obj = mb.ops.lsap(sim.to(dev()), row_sel=row_sel.to(dev()), col_sel=col_sel.to(dev()), maximize=maximize)
+    r2c, obj = r2c.cpu().numpy(), obj.cpu().numpy()
+    for e in range(2):
+        rows = np.nonzero(row_sel[e].numpy())[0]
+        cols = np.nonzero(col_sel[e].numpy())[0]
+        sub = sim[e][rows][:, cols].double().numpy()
+        ri, ci = linear_sum_assignment(sub, maximize=maximize)
+        assert abs(obj[e] - sub[ri, ci].sum()) < 1e-9
+        expect = np.full(r, -1)
+        expect[rows[ri]] = cols[ci]
+        np.testing.assert_array_equal(r2c[e], expect)  # random costs: the optimum is unique
+
+
 def test_bidirectional_lsap_matching(mb):
     """Forward + reverse assignment and the retain rule of Matcher.patch_level_matching (Matcher.py:443-477)."""
     from scipy.optimize import linear_sum_assignment
