@@ -31,6 +31,10 @@ class RankingConfig:
     want_cost: bool = False            # export (1 - S) / 2 (the EMD cost)
     want_merged_f32: bool = True       # the float32 [H, W] map the reference returns
     overlap_streams: bool = True       # mask chain (HBM-bound) on a second stream beside the contractions
+    # the alignment chains on high-priority streams: their CTAs are placed before the pending CTAs of the ingest kernel
+    # (whose grid alone fills the device for the whole read of the masks): single-episode graph latency 0.43 -> 0.34 ms,
+    # one-timeline throughput +1.5 % (float32) ... +5 % (packed proposals)
+    priority_streams: bool = True
     fused_ingest: bool = False         # one-pass pack + pairwise kernel (owns all TMEM: cannot overlap the contractions)
     fused_pool: bool = False           # one-pass pack + pooled bitmaps (ops.pack_pool); measured slower than the two kernels
     emd_on_device: bool = False        # solve the P transport LPs per episode on the device instead of taking batch["emd"]
@@ -142,7 +146,10 @@ class RankingEngine:
         self._rle_ws = None
         self._side = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
         self._side2 = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
-        self._side3 = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
+        hi = dict(priority=-1) if cfg.priority_streams else {}
+        self._side3 = torch.cuda.Stream(device=dev, **hi) if cfg.overlap_streams else None
+        self._hi = torch.cuda.Stream(device=dev, priority=-1) if cfg.overlap_streams and cfg.priority_streams else None
+        self._ev_hi = torch.cuda.Event()
         self._ev_vta = torch.cuda.Event()
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
@@ -374,21 +381,31 @@ class RankingEngine:
                 ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
                                backend=cfg.gemm_backend, workspace=self.pir_ws_vta, out=self.vta_ref)
                 self._ev_vta.record(self._side3)
-        ops.normalize_rows(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
-        ops.normalize_rows(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
-        ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
-        ops.sim_contract(self.fs, self.fq, m, n, s.C, want_sim=cfg.want_sim, want_cost=cfg.want_cost or cfg.emd_on_device,
-                         row_fg=self.row_fg, backend=cfg.gemm_backend, out=self.gemm_out)
-        ops.vva_finalize(self.gemm_out["colstats"], self.row_fg, m, n, out=self.prior)
-        ops.pir_refine(self.prior, batch["attn_vva"], s.g, cfg.vva_box_threshold, apply_minmax=True,
-                       backend=cfg.gemm_backend, workspace=self.pir_ws, out=self.vva)
-        if self._side3 is not None:
-            main.wait_event(self._ev_vta)
-        else:
-            ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
-                           backend=cfg.gemm_backend, workspace=self.pir_ws_vta, out=self.vta_ref)
-        ops.resize_minmax(self.vta_ref.reshape(e, s.gt, s.gt), s.g, True, out=self.vta)
-        ops.clip_scores(batch["clip_img"], batch["clip_txt"], out=self.clip)
+        import contextlib
+
+        if self._hi is not None:
+            self._hi.wait_event(self._ev_fork)
+        with (torch.cuda.stream(self._hi) if self._hi is not None else contextlib.nullcontext()):
+            chain = torch.cuda.current_stream()
+            ops.normalize_rows(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
+            ops.normalize_rows(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
+            ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
+            ops.sim_contract(self.fs, self.fq, m, n, s.C, want_sim=cfg.want_sim, want_cost=cfg.want_cost or cfg.emd_on_device,
+                             row_fg=self.row_fg, backend=cfg.gemm_backend, out=self.gemm_out)
+            ops.vva_finalize(self.gemm_out["colstats"], self.row_fg, m, n, out=self.prior)
+            ops.pir_refine(self.prior, batch["attn_vva"], s.g, cfg.vva_box_threshold, apply_minmax=True,
+                           backend=cfg.gemm_backend, workspace=self.pir_ws, out=self.vva)
+            if self._side3 is not None:
+                chain.wait_event(self._ev_vta)
+            else:
+                ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
+                               backend=cfg.gemm_backend, workspace=self.pir_ws_vta, out=self.vta_ref)
+            ops.resize_minmax(self.vta_ref.reshape(e, s.gt, s.gt), s.g, True, out=self.vta)
+            ops.clip_scores(batch["clip_img"], batch["clip_txt"], out=self.clip)
+            if self._hi is not None:
+                self._ev_hi.record(self._hi)
+        if self._hi is not None:
+            main.wait_event(self._ev_hi)
         if self._side is not None:
             main.wait_event(self._ev_join)
         else:
