@@ -150,6 +150,7 @@ class RankingEngine:
         self._side3 = torch.cuda.Stream(device=dev, **hi) if cfg.overlap_streams else None
         self._hi = torch.cuda.Stream(device=dev, priority=-1) if cfg.overlap_streams and cfg.priority_streams else None
         self._ev_hi = torch.cuda.Event()
+        self._ev_rowfg = torch.cuda.Event()
         self._ev_vta = torch.cuda.Event()
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
@@ -158,6 +159,7 @@ class RankingEngine:
         self._ev_prep = torch.cuda.Event()
         self._part = None
         self._capturing = False
+        self._pool_ready = False
         if cfg.tensor_partition_sms:
             from .partition import SmPartition
 
@@ -205,6 +207,7 @@ class RankingEngine:
     def _mask_chain(self, batch: dict):
         """Ingest side: pack -> pooled bitmaps / areas -> pairwise intersections (depends on the masks only)."""
         s, cfg = self.shape, self.cfg
+        self._pool_ready = False
         if self.inter is not None and cfg.fused_ingest and "masks" in batch:
             # one pass over the masks: packed bits + intersections (falls back to two kernels when not fusable)
             ops.pack_pairwise(batch["masks"], backend=cfg.pair_backend, out=(self.bits, self.inter))
@@ -235,6 +238,7 @@ class RankingEngine:
                 self._ev_pool.record(self._side2)
             self._pairwise()
             cur.wait_event(self._ev_pool)
+            self._pool_ready = True  # _ev_pool marks the pooled bitmaps: the region sums need not wait for the intersections
 
     def _run_partitioned(self, batch: dict, wait: bool = True) -> dict:
         """The same kernel sequence on two disjoint SM sets.  `hbm` partition: pack (+ pooled bitmaps) of one episode
@@ -376,10 +380,15 @@ class RankingEngine:
         if self._side3 is not None:
             # the vta refinement depends on nothing of the vva chain: its small kernels (box mask, column sums, mat-vecs)
             # fill the gaps of the other chain's contractions
+            # ... and so do the pooled support mask and the AlphaCLIP scores: they ride on this (shorter) chain instead of
+            # lengthening the vva chain, which is on the critical path of a small batch
             self._side3.wait_event(self._ev_fork)
             with torch.cuda.stream(self._side3):
+                ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
+                self._ev_rowfg.record(self._side3)
                 ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
                                backend=cfg.gemm_backend, workspace=self.pir_ws_vta, out=self.vta_ref)
+                ops.clip_scores(batch["clip_img"], batch["clip_txt"], out=self.clip)
                 self._ev_vta.record(self._side3)
         import contextlib
 
@@ -389,7 +398,10 @@ class RankingEngine:
             chain = torch.cuda.current_stream()
             ops.normalize_rows(batch["feat_s"].reshape(e, m, s.C), True, out=self.fs)
             ops.normalize_rows(batch["feat_q"].reshape(e, n, s.C), True, out=self.fq)
-            ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
+            if self._side3 is not None:
+                chain.wait_event(self._ev_rowfg)
+            else:
+                ops.pool_mask(batch["support_mask"], s.g, out=self.row_fg)
             ops.sim_contract(self.fs, self.fq, m, n, s.C, want_sim=cfg.want_sim, want_cost=cfg.want_cost or cfg.emd_on_device,
                              row_fg=self.row_fg, backend=cfg.gemm_backend, out=self.gemm_out)
             ops.vva_finalize(self.gemm_out["colstats"], self.row_fg, m, n, out=self.prior)
@@ -401,16 +413,24 @@ class RankingEngine:
                 ops.pir_refine(batch["vta_raw"], batch["attn_vta"], s.gt, cfg.vta_box_threshold, apply_minmax=False,
                                backend=cfg.gemm_backend, workspace=self.pir_ws_vta, out=self.vta_ref)
             ops.resize_minmax(self.vta_ref.reshape(e, s.gt, s.gt), s.g, True, out=self.vta)
-            ops.clip_scores(batch["clip_img"], batch["clip_txt"], out=self.clip)
+            if self._side3 is None:
+                ops.clip_scores(batch["clip_img"], batch["clip_txt"], out=self.clip)
             if self._hi is not None:
                 self._ev_hi.record(self._hi)
         if self._hi is not None:
             main.wait_event(self._ev_hi)
-        if self._side is not None:
+        if self._side is not None and self._pool_ready:
+            # the region sums only need the pooled bitmaps; the intersections and the suppression relation are first
+            # read by the ranking kernel
+            main.wait_event(self._ev_pool)
+            ops.region_sums(self.pool_out[0], self.vva, self.vta, out=self.region_out)
             main.wait_event(self._ev_join)
         else:
-            self._mask_chain(batch)
-        ops.region_sums(self.pool_out[0], self.vva, self.vta, out=self.region_out)
+            if self._side is not None:
+                main.wait_event(self._ev_join)
+            else:
+                self._mask_chain(batch)
+            ops.region_sums(self.pool_out[0], self.vva, self.vta, out=self.region_out)
         emd = batch.get("emd")
         if cfg.emd_on_device:
             emd = ops.emd_scores(self.gemm_out["cost"], self.row_fg.reshape(e, m), self.pool_out[0], t_cap=self.emd_t_cap,
