@@ -8,8 +8,9 @@ dev = torch.device("cuda:0")
 shape = marsb200.CONFIGS["c2"]
 one = [marsb200.stack_episodes([marsb200.make_episode(shape, i, dev)]) for i in range(2)]
 ref = None
-for prio in (False, True, False, True):
-    eng = marsb200.RankingEngine(shape, 1, marsb200.RankingConfig(nms_iou_threshold=0.7, priority_streams=prio), dev)
+import itertools
+for prio, hoist in ((False, False), (True, False), (True, True), (True, False), (True, True)):
+    eng = marsb200.RankingEngine(shape, 1, marsb200.RankingConfig(nms_iou_threshold=0.7, priority_streams=prio, hoist_vva_contraction=hoist), dev)
     for i in range(4):
         eng.run(one[i % 2])
     torch.cuda.synchronize()
@@ -34,4 +35,4 @@ for prio in (False, True, False, True):
     t0 = time.perf_counter()
     for i in range(20):
         eng.replay(); torch.cuda.synchronize()
-    print(f"priority_streams={prio}: eager {eager:.4f} ms, graph {a.elapsed_time(b) / 20:.4f} ms, graph one at a time (host clock) {(time.perf_counter() - t0) / 20 * 1e3:.4f} ms, same outputs {same}", flush=True)
+    print(f"priority_streams={prio} hoist={hoist}: eager {eager:.4f} ms, graph {a.elapsed_time(b) / 20:.4f} ms, graph one at a time (host clock) {(time.perf_counter() - t0) / 20 * 1e3:.4f} ms, same outputs {same}", flush=True)

@@ -17,8 +17,8 @@ for b in batches:
     d["mask_bits"] = ops.pack_masks(b["masks"])
     packed.append(d)
 for name, data, md in (("f32", batches, torch.float32), ("u8", u8, torch.uint8), ("packed", packed, torch.float32)):
-    for prio in (False, True, False, True):
-        eng = marsb200.RankingEngine(shape, E, marsb200.RankingConfig(nms_iou_threshold=0.7, priority_streams=prio), dev, md)
+    for prio, hoist in ((False, False), (True, False), (True, True), (True, False), (True, True)):
+        eng = marsb200.RankingEngine(shape, E, marsb200.RankingConfig(nms_iou_threshold=0.7, priority_streams=prio, hoist_vva_contraction=hoist), dev, md)
         for i in range(4):
             eng.run(data[i % 2])
         torch.cuda.synchronize()
@@ -28,5 +28,5 @@ for name, data, md in (("f32", batches, torch.float32), ("u8", u8, torch.uint8),
             eng.run(data[i % 2])
         b_.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b_) / 20
-        print(f"{name:7s} priority_streams={prio}: {ms:.3f} ms per step = {E / ms * 1e3:.0f} episodes/s", flush=True)
+        print(f"{name:7s} priority_streams={prio} hoist={hoist}: {ms:.3f} ms per step = {E / ms * 1e3:.0f} episodes/s", flush=True)
         del eng

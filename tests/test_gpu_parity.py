@@ -481,6 +481,24 @@ def test_engine_small_episodes(mb, nms, mask_dtype):
         _check_episode(mb, shape, cfg, eps[e], out, e)
 
 
+@pytest.mark.parametrize("episodes", [1, 3])
+def test_engine_stream_options_are_bit_identical(mb, episodes):
+    """The one-timeline schedule's stream options (high-priority alignment streams, hoisted vva contraction, no side streams
+    at all) only move kernels between streams: every output must be bit-identical."""
+    shape = mb.EpisodeShape(ns=1, g=14, gt=12, C=64, D=32, P=40, H=96, W=96)
+    batch = mb.stack_episodes([mb.make_episode(shape, 70 + i, dev()) for i in range(episodes)])
+    outs = []
+    for kw in (dict(overlap_streams=False), dict(priority_streams=False, hoist_vva_contraction=False),
+               dict(priority_streams=True, hoist_vva_contraction=False), dict(priority_streams=True, hoist_vva_contraction=True)):
+        eng = mb.RankingEngine(shape, episodes, mb.RankingConfig(nms_iou_threshold=0.6, **kw), dev())
+        o = eng.run(batch)
+        torch.cuda.synchronize()
+        outs.append({k: o[k].clone() for k in ("vva", "vta", "inter", "scores", "order", "flags", "merged_bits", "clip", "row_fg")})
+    for o in outs[1:]:
+        for k, v in o.items():
+            assert torch.equal(v, outs[0][k]), k
+
+
 def test_engine_c1_shape_against_oracle(mb):
     """BASELINE config 1 (the reference's CPU-runnable case): N=1369, C=1024, P=128 at 518x518."""
     shape = mb.CONFIGS["c1"]
