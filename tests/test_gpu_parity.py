@@ -406,7 +406,7 @@ def test_filtering_merging_host_emd_path(mb):
 
 
 @pytest.mark.parametrize("precomputed", [False, True])
-@pytest.mark.parametrize("p,thr", [(12, 0.5), (64, 0.7), (200, 0.3), (1, 0.7), (33, 0.0), (700, 0.5)])
+@pytest.mark.parametrize("p,thr", [(12, 0.5), (64, 0.7), (200, 0.3), (1, 0.7), (33, 0.0), (700, 0.5), (1100, 0.5)])
 def test_nms_keep_set_bit_exact(mb, p, thr, precomputed):
     """precomputed: the suppression relation comes from marsb200_nms_bitmask (the engine's path) instead of being built
     inside the ranking kernel; both must give the oracle's keep-set."""
@@ -427,7 +427,7 @@ def test_nms_keep_set_bit_exact(mb, p, thr, precomputed):
     sv = torch.as_tensor(2 * scores, dtype=torch.float32, device=d).reshape(1, p)
     uc = torch.ones((1,), dtype=torch.int32, device=d)
     zero = torch.zeros((1, p), device=d)
-    rel = mb.ops.nms_bitmask(inter, thr) if precomputed else None
+    rel = mb.ops.nms_bitmask(inter, thr) if precomputed else None  # (P > 1024: the ranking kernel ignores it and walks the ranks itself)
     if precomputed:
         # the relation itself against its definition (float32 quotient, strict comparison, no self-suppression)
         want = (orc.iou_matrix(inter_ref, area_ref).numpy() > np.float32(thr)) & ~np.eye(p, dtype=bool)
