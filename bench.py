@@ -472,7 +472,14 @@ def run_ours(args):
     # produced on the GPU and only the proposals are loaded from disk, main_MARS.py:62).
     rle_cache = {}
 
-    def run_e2e(e2e_dtype, wire="dense", episodes=None, resident_backbone=False):
+    # host threads of the ingest: the ranks of one node share its cores; the raw share balances a 55 GB/s PCIe lane against
+    # the host threads (which share the host DRAM with the DMA engine): 0.26 with 16 threads, the flat optimum of profiles/r2_logs/e2e_host_pack_sweep.log
+    host_threads = max(1, (os.cpu_count() or 16) // world)
+    raw_share = round(55.0 / (55.0 + 10.0 * host_threads), 2)
+
+    def run_e2e(e2e_dtype, wire="dense", episodes=None, resident_backbone=False, host_pack=None):
+        """host_pack = share of every episode's proposals that crosses PCIe raw (packed by the device kernel); the rest is
+        packed by host threads in front of the copy (marsb200.HostMaskIngest).  None = everything raw (the plain path)."""
         Ee = min(episodes or args.e2e_episodes_per_step, E)
         engs = [marsb200.RankingEngine(shape, Ee, cfg, dev, e2e_dtype) for _ in range(2)]
         host = {k: v[:Ee].cpu() for k, v in batches[0].items()}
@@ -490,9 +497,16 @@ def run_ours(args):
         moved = mask_keys if resident_backbone else list(host)
         fixed = {k: host[k].to(dev) for k in host if k not in moved}  # produced on the device by the backbones
         host = {k: host[k].pin_memory() for k in moved}
+        ingests, host_masks = None, None
+        if host_pack is not None and wire == "dense":
+            host_masks = host.pop("masks")  # stays in pinned host memory; HostMaskIngest moves it in two lanes
+            ingests = [marsb200.HostMaskIngest(Ee, shape.P, shape.H, shape.W, dev, mask_dtype=e2e_dtype, raw_fraction=host_pack,
+                                               threads=host_threads) for _ in range(2)]
         dev_in = [dict({k: torch.empty_like(v, device=dev) for k, v in host.items()}, **fixed) for _ in range(2)]
         rec_host = [torch.empty((Ee, engs[0].record_bytes()), dtype=torch.uint8).pin_memory() for _ in range(2)]
         h2d = sum(v.numel() * v.element_size() for v in host.values())
+        if ingests:
+            h2d += ingests[0].h2d_bytes(host_masks.element_size())
         d2h = rec_host[0].numel()
         main = torch.cuda.current_stream()
         s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
@@ -506,7 +520,9 @@ def run_ours(args):
             with torch.cuda.stream(s_in):
                 for k in host:
                     dev_in[b][k].copy_(host[k], non_blocking=True)
-                ev_in[b].record(s_in)
+            if ingests:  # raw lane + device packing enqueued on s_in, the other lane packed by host threads meanwhile
+                dev_in[b]["mask_bits"] = ingests[b].upload(host_masks, s_in)
+            ev_in[b].record(s_in)
 
         def loop(n):
             for b in range(2):
@@ -514,8 +530,6 @@ def run_ours(args):
             upload(0)
             for i in range(n):
                 b = i % 2
-                if i + 1 < n:
-                    upload(i + 1)
                 main.wait_event(ev_in[b])
                 main.wait_event(ev_out[b])  # the records of the set's previous step have left the device
                 engs[b].run(dev_in[b])
@@ -526,6 +540,8 @@ def run_ours(args):
                     rec_host[b].copy_(rec, non_blocking=True)
                     ev_out[b].record(s_out)
                 rec.record_stream(s_out)
+                if i + 1 < n:
+                    upload(i + 1)  # the copies (and the host-side packing) of step i + 1 run while the device ranks step i
                 if i >= 1:
                     ev_out[(i - 1) % 2].synchronize()  # the caller reads step i - 1's result on the host
             ev_out[(n - 1) % 2].synchronize()
@@ -547,22 +563,42 @@ def run_ours(args):
             t = torch.tensor([ms2], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms2 = float(t.item())
-        return {"value": world * Ee * args.steps / (ms2 / 1e3), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
+        # what the loop produced against the device-resident engine on the same episodes (records: order, scores, flags)
+        out = {}
+        if e2e_dtype == md and wire == "dense":
+            engs[0].run({k: v[:Ee] for k, v in batches[0].items()})
+            out["records_equal_device_resident_run"] = bool(torch.equal(rec_host[(args.steps - 1) % 2], engs[0].records().cpu()))
+        if ingests:
+            out.update({"host_pack": {"raw_fraction": host_pack, "proposals_raw_over_pcie": ingests[0].p_raw,
+                                      "proposals_packed_by_host_threads": shape.P - ingests[0].p_raw,
+                                      "host_threads": host_threads or os.cpu_count()}})
+        out.update({"value": world * Ee * args.steps / (ms2 / 1e3), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "episodes_per_step": Ee, "ms_per_step": ms2 / args.steps,
                 "pcie_gbs": h2d * args.steps / (ms2 / 1e3) / 1e9,
                 "inputs_over_pcie": "proposals only (backbone tensors produced on the device)" if resident_backbone
                                     else "every input of the step",
                 "host_mask_format": {"dense": "f32" if e2e_dtype == torch.float32 else "u8", "rle": "uncompressed COCO RLE",
-                                     "bits": "packed bits"}[wire]}
+                                     "bits": "packed bits"}[wire]})
+        return out
 
     e2e, e2e_variants = None, None
     if not args.no_e2e:
-        e2e = run_e2e(md)
-        e2e["note"] = ("PCIe-bound: the reference's float32 wire format is 1.1 GB per episode; `pcie_gbs` is the achieved "
-                       "host-to-device rate (H2D of step i + 1 overlaps the compute of step i)")
+        # Host buffers in, records out.  A PCIe 5 link carries the reference's float32 proposals (1.07 GB per c2 episode) at
+        # 55 GB/s = 50 episodes/s; the host's cores read them at ~116 GB/s.  The ingest therefore runs two lanes at once
+        # (marsb200.HostMaskIngest): a share of every episode's proposals crosses PCIe raw and is packed by the device
+        # kernel, the rest is packed by host threads and only its bits are copied.  The share balances the two lanes.
+        e2e = run_e2e(md, host_pack=raw_share)
+        e2e["note"] = ("two-lane ingest of the reference's float32 host proposals: `proposals_raw_over_pcie` of every episode cross "
+                       "PCIe as float32 and are packed by the device kernel while host threads pack the others (a format "
+                       "conversion in front of the copy, bit-identical; nothing is scored on the host); every byte of the step's "
+                       "inputs still starts in pinned host memory inside the timed region.  `e2e_variants."
+                       "f32_host_masks_all_raw_over_pcie` is the single-lane path (PCIe-bound at ~55 GB/s)")
         if md == torch.float32:  # the same call with lighter proposal wire formats (PCIe carries far fewer bytes)
             Ev = min(E, 16)
-            e2e_variants = {"u8_host_masks": run_e2e(torch.uint8, episodes=min(4, E)),
+            e2e_variants = {"f32_host_masks_all_raw_over_pcie": run_e2e(md),
+                            "f32_host_masks_all_packed_by_host_threads": run_e2e(md, host_pack=0.0),
+                            "u8_host_masks": run_e2e(torch.uint8, episodes=min(4, E)),
+                            "u8_host_masks_two_lane_ingest": run_e2e(torch.uint8, episodes=min(4, E), host_pack=raw_share),
                             "packed_host_masks": run_e2e(md, "bits", episodes=Ev),
                             "packed_host_masks_backbone_resident": run_e2e(md, "bits", episodes=Ev, resident_backbone=True)}
             if shape.H % 32 == 0 and shape.W % 32 == 0:  # the device RLE decoder needs word-aligned rows and columns

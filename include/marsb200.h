@@ -218,6 +218,14 @@ int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t
                         int N, int t_cap, int m_cap, void* workspace, int64_t workspace_bytes, double* out,
                         int32_t* status, void* stream);
 
+/* ---- host side of the ingest ------------------------------------------------------------------------------------------
+ * The same packing for masks that are still in HOST memory (the reference's proposals are CPU tensors when they reach
+ * MARS.predict, main_MARS.py:62-69): a team of host threads (AVX2 when the CPU has it) writes the bit layout of
+ * marsb200_pack_masks into a host buffer, so that 1/32 of the bytes cross PCIe.  masks [n, HW] float32 / uint8 and bits
+ * [n, marsb200_words_per_mask(HW)] are HOST pointers (pinned or not); threads <= 0 = one per hardware thread.  Blocking; no
+ * CUDA call.  A format conversion in front of the copy - nothing is scored on the host. */
+int marsb200_host_pack_masks(const void* masks_host, int mask_dtype, int64_t n, int64_t HW, uint32_t* bits_host, int threads);
+
 /* ---- A8: AlphaCLIP cosine scores -----------------------------------------------------------
  * clip[e,p] = img[e,p,:] . txt[e,:].  Replaces img_feats @ text_feats.T, FilteringMergingModule.py:97. */
 int marsb200_clip_scores(const float* img, const float* txt, int E, int P, int D, float* out, void* stream);

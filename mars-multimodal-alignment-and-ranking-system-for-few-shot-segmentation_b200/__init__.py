@@ -16,5 +16,6 @@ from .MARS import MARS, build_MARS_fss  # noqa: F401
 from .matcher_scoring import MatcherScorer, PatchMatcher  # noqa: F401
 from .Matcher import Matcher, RobustPromptSampler  # noqa: F401
 from .evaluation import AverageMeter, Evaluator  # noqa: F401
+from .host_ingest import HostMaskIngest  # noqa: F401
 
 __version__ = "0.1.0"

@@ -63,6 +63,7 @@ SIGNATURES = {
     "marsb200_clip_scores_f16": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "marsb200_fuse_rank": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _d, _d, _d, _f, _i, _p, _p, _p, _p, _p, _l, _p]),
     "marsb200_nms_bitmask": (_i, [_p, _i, _i, _f, _p, _p]),
+    "marsb200_host_pack_masks": (_i, [_p, _i, _l, _l, _p, _i]),
     "marsb200_record_bytes": (_l, [_i]),
     "marsb200_merge_masks": (_i, [_p, _p, _i, _i, _l, _p, _p, _p]),
     "marsb200_points_in_masks": (_i, [_p, _l, _i, _i, _p, _i, _p, _p]),

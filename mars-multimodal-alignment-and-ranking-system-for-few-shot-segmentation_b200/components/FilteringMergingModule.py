@@ -114,10 +114,14 @@ class FilteringMergingModule:
     def _rank(self, query_img, mask_proposals, support_mask, cost_matrix, g, vva, vta, text, emd_scores,
               alphaclip_feats):
         dev = self.device
-        masks = mask_proposals.to(dev)
-        p, h, w = masks.shape
+        p, h, w = mask_proposals.shape
         n = g * g
-        bits = ops.pack_masks(masks)[None]
+        if not mask_proposals.is_cuda and mask_proposals.dtype in (torch.float32, torch.uint8, torch.bool):
+            # the reference's proposals are CPU tensors (main_MARS.py:62-69): host threads pack them and only the bits cross
+            # PCIe (1/32 of the float32 bytes; ops.host_pack_masks writes the device kernel's layout bit for bit)
+            bits = ops.host_pack_masks(mask_proposals).to(dev)[None]
+        else:
+            bits = ops.pack_masks(mask_proposals.to(dev))[None]
         pooled, area, cnt = ops.pool_packed(bits, h, w, g)
         sv, st, uc = ops.region_sums(pooled, vva.to(dev).reshape(1, n), vta.to(dev).reshape(1, n))
         if alphaclip_feats is None:

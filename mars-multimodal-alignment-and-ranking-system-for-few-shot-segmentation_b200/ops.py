@@ -438,6 +438,31 @@ def clip_scores(img: torch.Tensor, txt: torch.Tensor, out=None) -> torch.Tensor:
     return out
 
 
+def host_pack_masks(masks: torch.Tensor, out: Optional[torch.Tensor] = None, threads: int = 0) -> torch.Tensor:
+    """HOST tensors in, HOST tensor out: masks [..., H, W] float32 / uint8 / bool (CPU, contiguous; pinned or not) -> packed
+    bits [..., words_per_mask(H * W)] int32 in the layout of `pack_masks`, by a team of host threads.  The conversion in
+    front of the host->device copy (1/32 of the bytes); the only op of this module that takes CPU tensors."""
+    if masks.is_cuda:
+        raise ValueError("host_pack_masks packs HOST masks; device masks go through pack_masks")
+    if masks.dtype == torch.bool:
+        masks = masks.view(torch.uint8)
+    if masks.dtype not in (torch.float32, torch.uint8):
+        raise TypeError(f"masks must be float32, uint8 or bool, got {masks.dtype}")
+    if not masks.is_contiguous():
+        masks = masks.contiguous()
+    hw = masks.shape[-1] * masks.shape[-2]
+    n = masks.numel() // hw
+    wpm = words_per_mask(hw)
+    shape = tuple(masks.shape[:-2]) + (wpm,)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.int32)
+    if out.is_cuda or out.dtype != torch.int32 or out.numel() != n * wpm or not out.is_contiguous():
+        raise ValueError("out must be a contiguous CPU int32 tensor of n * words_per_mask(H * W) elements")
+    check(lib.marsb200_host_pack_masks(masks.data_ptr(), MASK_U8 if masks.dtype == torch.uint8 else MASK_F32, n, hw,
+                                       out.data_ptr(), int(threads)))
+    return out
+
+
 def nms_bitmask(inter: torch.Tensor, nms_iou_threshold: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Pairwise suppression relation [E, P, ceil(P/32)] int32 (bit j of row i: IoU(i, j) > threshold, j != i) from the
     intersections [E, P, P]; independent of the ranking, so it can run as soon as `inter` exists (fuse_rank `nms_bits`)."""

@@ -499,6 +499,24 @@ def test_engine_stream_options_are_bit_identical(mb, episodes):
             assert torch.equal(v, outs[0][k]), k
 
 
+@pytest.mark.parametrize("raw_fraction", [0.0, 0.3, 1.0])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.uint8])
+def test_host_mask_ingest_equals_device_packing(mb, raw_fraction, dtype):
+    """HostMaskIngest (a share of the proposals raw over PCIe + device kernel, the rest packed by host threads) lands the
+    same bits as packing the whole batch on the device, for every split."""
+    e, p, h, w = 2, 10, 96, 160
+    masks = cases.blob_masks(e * p, h, w, seed=5).reshape(e, p, h, w).to(dtype)
+    host = masks.pin_memory()
+    ing = mb.HostMaskIngest(e, p, h, w, dev(), mask_dtype=dtype, raw_fraction=raw_fraction, threads=3)
+    st = torch.cuda.Stream(device=dev())
+    for _ in range(2):  # the second upload reuses the pinned buffer
+        bits = ing.upload(host, st)
+        st.synchronize()
+    want = mb.ops.pack_masks(masks.to(dev()))
+    assert torch.equal(bits, want.reshape(bits.shape))
+    assert ing.h2d_bytes(masks.element_size()) == e * ing.p_raw * h * w * masks.element_size() + e * (p - ing.p_raw) * bits.shape[-1] * 4
+
+
 def test_engine_c1_shape_against_oracle(mb):
     """BASELINE config 1 (the reference's CPU-runnable case): N=1369, C=1024, P=128 at 518x518."""
     shape = mb.CONFIGS["c1"]

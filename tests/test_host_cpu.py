@@ -277,3 +277,35 @@ def test_record_layout_matches_the_header():
     for p in (1, 3, 4, 10, 256, 1000):
         assert ops.record_bytes(p) == 8 * p + (p + 3) // 4 * 4 + 16
         assert ops.record_bytes(p) % 4 == 0
+
+
+@pytest.mark.parametrize("n,h,w,dtype", [(5, 37, 41, "f32"), (3, 64, 64, "u8"), (2, 256, 512, "f32"), (4, 7, 5, "bool"), (1, 1, 1, "f32")])
+@pytest.mark.parametrize("threads", [1, 3, 0])
+def test_host_pack_masks_matches_the_packed_layout(n, h, w, dtype, threads):
+    """marsb200_host_pack_masks (host threads, no CUDA call) writes exactly the bit layout of the device ingest kernel:
+    bit k of word w = pixel 32 w + k is > 0 (NaN and negatives clear), rows padded with zero words to a multiple of 32."""
+    import numpy as np
+    import torch
+
+    from marsb200 import ops
+
+    gen = torch.Generator().manual_seed(100 * n + h)
+    m = torch.rand(n, h, w, generator=gen) < 0.3
+    if dtype == "f32":
+        x = m.float() * (0.1 + torch.rand(n, h, w, generator=gen))
+        x[0, 0, 0] = float("nan")
+        if w > 1:
+            x[0, 0, 1] = -1.0
+    else:
+        x = m.to(torch.uint8 if dtype == "u8" else torch.bool)
+        if dtype == "u8":
+            x = x * 255
+    bits = ops.host_pack_masks(x, threads=threads)
+    hw = h * w
+    wpm = ops.words_per_mask(hw)
+    assert tuple(bits.shape) == (n, wpm) and wpm % 32 == 0
+    ref = np.zeros((n, wpm * 32), dtype=np.uint8)
+    with np.errstate(invalid="ignore"):
+        ref[:, :hw] = x.reshape(n, -1).numpy() > 0
+    want = np.packbits(ref.reshape(n, wpm, 32), axis=-1, bitorder="little").view(np.uint32).reshape(n, wpm)
+    np.testing.assert_array_equal(bits.numpy().view(np.uint32), want)
