@@ -4,6 +4,7 @@
 // sixteen host cores read them at 116 GB/s.  This is a format conversion in front of the copy, not a scoring path: every
 // score, rank and merge still comes from the device kernels.
 #include <immintrin.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <condition_variable>
@@ -75,6 +76,10 @@ public:
         std::lock_guard<std::mutex> call(call_);
         {
             std::unique_lock<std::mutex> lk(m_);
+            if (owner_ != getpid()) {  // a forked child inherits the counters but none of the worker threads
+                owner_ = getpid();
+                spawned_ = 0;
+            }
             while ((int)spawned_ < threads - 1) {
                 const int index = ++spawned_;
                 std::thread([this, index] { worker(index); }).detach();
@@ -114,6 +119,7 @@ private:
     const std::function<void(int)>* job_ = nullptr;
     unsigned generation_ = 0;
     int spawned_ = 0, active_ = 0, pending_ = 0;
+    pid_t owner_ = 0;
 };
 
 static HostTeam& host_team() {
