@@ -58,7 +58,7 @@ __device__ inline void lsap_argmin(const double* dist, const unsigned char* scan
 
 // sim [E, R, C]; row_sel [E, R] / col_sel [E, C] choose the participating rows / columns (null = all).
 // row_to_col [E, R]: assigned column of each selected row or -1; objective [E]: sum of the assigned similarities.
-__global__ void __launch_bounds__(LSAP_THREADS) lsap_kernel(const float* __restrict__ sim, const uint8_t* __restrict__ row_sel,
+__global__ void __launch_bounds__(LSAP_THREADS, 1) lsap_kernel(const float* __restrict__ sim, const uint8_t* __restrict__ row_sel,
                                                              const uint8_t* __restrict__ col_sel, int R, int Ccols,
                                                              int maximize, int t_cap, int m_cap,
                                                              int32_t* __restrict__ row_to_col,
@@ -251,7 +251,7 @@ constexpr unsigned short LSQ_NONE = 0xffff;
 
 __host__ __device__ inline size_t lsq_smem_bytes(int n_cap) { return (size_t)n_cap * (4 * 8 + 8 * 2 + 3) + 64; }
 
-__global__ void __launch_bounds__(LSQ_THREADS) lsap_square_kernel(const float* __restrict__ sim, const uint8_t* __restrict__ row_sel,
+__global__ void __launch_bounds__(LSQ_THREADS, 1) lsap_square_kernel(const float* __restrict__ sim, const uint8_t* __restrict__ row_sel,
                                                                    const uint8_t* __restrict__ col_sel, int R, int Ccols,
                                                                    int maximize, int n_cap, int32_t* __restrict__ row_to_col,
                                                                    double* __restrict__ objective, int* __restrict__ status) {
