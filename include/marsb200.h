@@ -106,7 +106,7 @@ int marsb200_match_argmax(const float* sim, const uint8_t* row_mask, int E, int 
  * assigned similarities (fp64); *status: 0 or the size that exceeded the caps.  Shortest augmenting paths
  * (Jonker-Volgenant), one CTA per problem.  Near-square problems (m_cap - t_cap <= max(8, m_cap / 16), e.g. the 5-shot
  * forward matching 1374 x 1369) are padded with zero-cost dummy nodes to a square and solved by multi-source phases
- * with equal-distance waves instead of one search per row (54 bytes of state per node): 3x scipy at 1374 x 1369. */
+ * with equal-distance waves instead of one search per row (40 bytes of shared-memory state per node, n <= 2048): 3.5x scipy at 1374 x 1369. */
 int marsb200_lsap(const float* sim, const uint8_t* row_sel, const uint8_t* col_sel, int E, int R, int C, int maximize,
                   int t_cap, int m_cap, int32_t* row_to_col, double* objective, int32_t* status, void* stream);
 

@@ -249,36 +249,37 @@ __global__ void __launch_bounds__(LSAP_THREADS, 1) lsap_kernel(const float* __re
 constexpr int LSQ_THREADS = 512;  // measured at 1374 x 1369: 256 threads 76 ms, 512 threads 51 ms, 1024 threads 58 ms
 constexpr unsigned short LSQ_NONE = 0xffff;
 
-__host__ __device__ inline size_t lsq_smem_bytes(int n_cap) { return (size_t)n_cap * (4 * 8 + 8 * 2 + 3) + 64; }
+constexpr int LSQ_SLOTS = 4;  // sinks per thread, kept in registers: n <= LSQ_SLOTS * LSQ_THREADS = 2048
 
+__host__ __device__ inline size_t lsq_smem_bytes(int n_cap) { return (size_t)n_cap * (3 * 8 + 7 * 2 + 2) + 64; }
+
+// A thread owns the sinks tid, tid + 512, ... and keeps their distance, dual, column offset and scanned flag in REGISTERS for
+// the whole solve (the arg-min, the settle pass and the relaxation touch shared memory only for what other threads read:
+// the predecessor of a sink, the matching, the sources' duals).  One CTA per SM by design: no register cap.
 __global__ void __launch_bounds__(LSQ_THREADS, 1) lsap_square_kernel(const float* __restrict__ sim, const uint8_t* __restrict__ row_sel,
-                                                                   const uint8_t* __restrict__ col_sel, int R, int Ccols,
-                                                                   int maximize, int n_cap, int32_t* __restrict__ row_to_col,
-                                                                   double* __restrict__ objective, int* __restrict__ status) {
+                                                                      const uint8_t* __restrict__ col_sel, int R, int Ccols,
+                                                                      int maximize, int n_cap, int32_t* __restrict__ row_to_col,
+                                                                      double* __restrict__ objective, int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char lsq_smem_raw[];
     double* u = reinterpret_cast<double*>(lsq_smem_raw);  // [n] source duals
     double* dsrc = u + n_cap;                              // [n] distance at which a source was reached
-    double* v = dsrc + n_cap;                              // [n] sink duals
-    double* dist = v + n_cap;                              // [n] tentative / final sink distances
-    unsigned short* row_id = reinterpret_cast<unsigned short*>(dist + n_cap);  // [n] row of source i (dummy beyond nr)
+    double* v0 = dsrc + n_cap;                             // [n] sink duals after the column reduction (read by the row reduction only)
+    unsigned short* row_id = reinterpret_cast<unsigned short*>(v0 + n_cap);  // [n] row of source i (dummy beyond nr)
     unsigned short* col_id = row_id + n_cap;               // [n] column of sink j (dummy beyond nc)
     unsigned short* src_sink = col_id + n_cap;             // [n] sink matched to source i, LSQ_NONE = unmatched
     unsigned short* sink_src = src_sink + n_cap;           // [n] source matched to sink j, LSQ_NONE = free
     unsigned short* pred_src = sink_src + n_cap;           // [n] source that gave sink j its distance
     unsigned short* newlist = pred_src + n_cap;            // [n] sources reached in the current wave (roots at a phase start)
     unsigned short* freelist = newlist + n_cap;            // [n] free sinks settled in the current wave
-    unsigned short* spare = freelist + n_cap;              // [n] (keeps the arrays 8-byte aligned in pairs)
-    unsigned char* scanned = reinterpret_cast<unsigned char*>(spare + n_cap);  // [n]
-    unsigned char* reached = scanned + n_cap;              // [n]
+    unsigned char* reached = reinterpret_cast<unsigned char*>(freelist + n_cap);  // [n]
     unsigned char* used = reached + n_cap;                 // [n] source lies on a path augmented in this phase
     __shared__ double s_red[LSQ_THREADS / 32];
     __shared__ int s_cnt[LSQ_THREADS / 32];
-    __shared__ int s_nr, s_nc, s_nnew, s_nfree, s_left, s_roots_left, s_free_unscanned;
+    __shared__ int s_nnew, s_nfree, s_left, s_roots_left, s_free_unscanned;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t e = blockIdx.x;
     const float* S = sim + e * (int64_t)R * Ccols;
     int32_t* out = row_to_col + e * R;
-    (void)spare;
 
     // ---- selected rows / columns in ascending order (ordered block compaction)
     for (int r = tid; r < R; r += LSQ_THREADS) out[r] = -1;
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(LSQ_THREADS, 1) lsap_square_kernel(const float
         if (tid == 0) objective[e] = 0.0;
         return;
     }
-    if (n > n_cap) {
+    if (n > n_cap || n > LSQ_SLOTS * LSQ_THREADS) {
         if (tid == 0) {
             objective[e] = nan("");
             atomicMax(status, n);
@@ -319,34 +320,46 @@ __global__ void __launch_bounds__(LSQ_THREADS, 1) lsap_square_kernel(const float
         return;
     }
     const float sign = maximize ? -1.f : 1.f;
-    // cost of (source i, sink j): the signed similarity, 0 on the dummy rows / columns
-    // ---- initial duals: v_j = min_i c_ij (a thread per sink, coalesced over j), then u_i = min_j (c_ij - v_j) (a warp
-    // per source, contiguous row): every reduced cost is >= 0 and every row and column has a tight arc
-    for (int j = tid; j < n; j += LSQ_THREADS) {
-        double mn = nr < n ? 0.0 : 1e300;  // a dummy source is part of every column
-        if (j < nc) {
-            const float* colp = S + col_id[j];
+
+    // ---- the thread's own sinks: column pointer (null on a dummy sink), dual, distance, flags
+    const float* colp[LSQ_SLOTS];
+    double rv[LSQ_SLOTS], rd[LSQ_SLOTS];
+    bool exist[LSQ_SLOTS], scanned[LSQ_SLOTS];
+#pragma unroll
+    for (int t = 0; t < LSQ_SLOTS; ++t) {
+        const int j = tid + t * LSQ_THREADS;
+        exist[t] = j < n;
+        colp[t] = (exist[t] && j < nc) ? S + col_id[j] : nullptr;
+        scanned[t] = false;
+        rd[t] = 0.0;
+        // column reduction: v_j = min_i c_ij (0 on / through a dummy)
+        double mn = nr < n ? 0.0 : 1e300;
+        if (colp[t] != nullptr) {
             int i = 0;
             for (; i + 4 <= nr; i += 4) {
-                const float c0 = colp[(int64_t)row_id[i] * Ccols], c1 = colp[(int64_t)row_id[i + 1] * Ccols];
-                const float c2 = colp[(int64_t)row_id[i + 2] * Ccols], c3 = colp[(int64_t)row_id[i + 3] * Ccols];
+                const float c0 = colp[t][(int64_t)row_id[i] * Ccols], c1 = colp[t][(int64_t)row_id[i + 1] * Ccols];
+                const float c2 = colp[t][(int64_t)row_id[i + 2] * Ccols], c3 = colp[t][(int64_t)row_id[i + 3] * Ccols];
                 mn = fmin(fmin(mn, (double)(sign * c0)), fmin((double)(sign * c1), fmin((double)(sign * c2), (double)(sign * c3))));
             }
-            for (; i < nr; ++i) mn = fmin(mn, (double)(sign * colp[(int64_t)row_id[i] * Ccols]));
+            for (; i < nr; ++i) mn = fmin(mn, (double)(sign * colp[t][(int64_t)row_id[i] * Ccols]));
         } else {
             mn = 0.0;
         }
-        v[j] = mn;
-        sink_src[j] = LSQ_NONE;
+        rv[t] = mn;
+        if (exist[t]) {
+            v0[j] = mn;
+            sink_src[j] = LSQ_NONE;
+        }
     }
     __syncthreads();
+    // row reduction: u_i = min_j (c_ij - v_j) (a warp per source, contiguous row): every row and column has a tight arc
     for (int i = warp; i < n; i += LSQ_THREADS / 32) {
         double mn = 1e300;
         if (i < nr) {
             const float* row = S + (int64_t)row_id[i] * Ccols;
-            for (int j = lane; j < n; j += 32) mn = fmin(mn, (j < nc ? (double)(sign * row[col_id[j]]) : 0.0) - v[j]);
+            for (int j = lane; j < n; j += 32) mn = fmin(mn, (j < nc ? (double)(sign * row[col_id[j]]) : 0.0) - v0[j]);
         } else {
-            for (int j = lane; j < n; j += 32) mn = fmin(mn, -v[j]);
+            for (int j = lane; j < n; j += 32) mn = fmin(mn, -v0[j]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -358,75 +371,62 @@ __global__ void __launch_bounds__(LSQ_THREADS, 1) lsap_square_kernel(const float
     if (tid == 0) s_left = n;
     __syncthreads();
 
-    // relax the sinks owned by this thread against `cnt` listed sources reached at distance dsrc[.]
-    // (a thread owns the sinks tid, tid + 512, ...; four of them are processed together so that their gathers overlap)
-    auto relax = [&](const unsigned short* list, int cnt, bool init) {
-        for (int j0 = tid; j0 < n; j0 += 4 * LSQ_THREADS) {
-            bool live[4];
-            const float* colp[4];
-            double best[4], vj[4];
-            int best_i[4];
+    // relax the thread's unscanned sinks against `cnt` listed sources reached at distance dsrc[.]
+    auto relax = [&](const unsigned short* list, int cnt) {
+        bool live[LSQ_SLOTS];
+        int best_i[LSQ_SLOTS];
+        bool any = false;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int j = j0 + t * LSQ_THREADS;
-                live[t] = j < n && (init || !scanned[j]);
-                const bool real_j = live[t] && j < nc;
-                colp[t] = real_j ? S + col_id[j] : nullptr;
-                best[t] = (init || !live[t]) ? 1e300 : dist[j];
-                best_i[t] = (init || !live[t]) ? 0 : pred_src[j];
-                vj[t] = live[t] ? v[j] : 0.0;
-            }
-            if (!(live[0] || live[1] || live[2] || live[3])) continue;
-            int k = 0;
-            for (; k + 2 <= cnt; k += 2) {  // two sources x four sinks of independent gathers in flight
-                const int ia = list[k], ib = list[k + 1];
-                const double base_a = dsrc[ia] - u[ia], base_b = dsrc[ib] - u[ib];
-                const int64_t ra = ia < nr ? (int64_t)row_id[ia] * Ccols : -1, rb = ib < nr ? (int64_t)row_id[ib] * Ccols : -1;
-                float ca[4], cb[4];
+        for (int t = 0; t < LSQ_SLOTS; ++t) {
+            live[t] = exist[t] && !scanned[t];
+            best_i[t] = -1;
+            any |= live[t];
+        }
+        if (!any) return;
+        int k = 0;
+        for (; k + 2 <= cnt; k += 2) {  // two sources x four sinks of independent gathers in flight
+            const int ia = list[k], ib = list[k + 1];
+            const double base_a = dsrc[ia] - u[ia], base_b = dsrc[ib] - u[ib];
+            const int64_t ra = ia < nr ? (int64_t)row_id[ia] * Ccols : -1, rb = ib < nr ? (int64_t)row_id[ib] * Ccols : -1;
+            float ca[LSQ_SLOTS], cb[LSQ_SLOTS];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    ca[t] = (colp[t] != nullptr && ra >= 0) ? sign * colp[t][ra] : 0.f;
-                    cb[t] = (colp[t] != nullptr && rb >= 0) ? sign * colp[t][rb] : 0.f;
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const double da = (base_a + (double)ca[t]) - vj[t];
-                    if (da < best[t]) {
-                        best[t] = da;
-                        best_i[t] = ia;
-                    }
-                    const double db = (base_b + (double)cb[t]) - vj[t];
-                    if (db < best[t]) {
-                        best[t] = db;
-                        best_i[t] = ib;
-                    }
-                }
-            }
-            for (; k < cnt; ++k) {
-                const int i = list[k];
-                const double base = dsrc[i] - u[i];
-                const int64_t roff = i < nr ? (int64_t)row_id[i] * Ccols : -1;
-                float cv[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) cv[t] = (colp[t] != nullptr && roff >= 0) ? sign * colp[t][roff] : 0.f;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const double d = (base + (double)cv[t]) - vj[t];
-                    if (d < best[t]) {
-                        best[t] = d;
-                        best_i[t] = i;
-                    }
-                }
+            for (int t = 0; t < LSQ_SLOTS; ++t) {
+                ca[t] = (live[t] && colp[t] != nullptr && ra >= 0) ? sign * colp[t][ra] : 0.f;
+                cb[t] = (live[t] && colp[t] != nullptr && rb >= 0) ? sign * colp[t][rb] : 0.f;
             }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int j = j0 + t * LSQ_THREADS;
-                if (live[t]) {
-                    dist[j] = best[t];
-                    pred_src[j] = (unsigned short)best_i[t];
+            for (int t = 0; t < LSQ_SLOTS; ++t) {
+                const double da = (base_a + (double)ca[t]) - rv[t];
+                if (live[t] && da < rd[t]) {
+                    rd[t] = da;
+                    best_i[t] = ia;
+                }
+                const double db = (base_b + (double)cb[t]) - rv[t];
+                if (live[t] && db < rd[t]) {
+                    rd[t] = db;
+                    best_i[t] = ib;
                 }
             }
         }
+        for (; k < cnt; ++k) {
+            const int i = list[k];
+            const double base = dsrc[i] - u[i];
+            const int64_t roff = i < nr ? (int64_t)row_id[i] * Ccols : -1;
+            float cv[LSQ_SLOTS];
+#pragma unroll
+            for (int t = 0; t < LSQ_SLOTS; ++t) cv[t] = (live[t] && colp[t] != nullptr && roff >= 0) ? sign * colp[t][roff] : 0.f;
+#pragma unroll
+            for (int t = 0; t < LSQ_SLOTS; ++t) {
+                const double d = (base + (double)cv[t]) - rv[t];
+                if (live[t] && d < rd[t]) {
+                    rd[t] = d;
+                    best_i[t] = i;
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < LSQ_SLOTS; ++t)
+            if (best_i[t] >= 0) pred_src[tid + t * LSQ_THREADS] = (unsigned short)best_i[t];
     };
 
     LQ_TIC();
@@ -448,14 +448,19 @@ __global__ void __launch_bounds__(LSQ_THREADS, 1) lsap_square_kernel(const float
             used[i] = 0;
             dsrc[i] = 0.0;
             if (root) newlist[atomicAdd(&s_nnew, 1)] = (unsigned short)i;
-            scanned[i] = 0;  // (sinks: same index range)
-            free_local += sink_src[i] == LSQ_NONE ? 1 : 0;
+            free_local += sink_src[i] == LSQ_NONE ? 1 : 0;  // (sinks: same index range)
+        }
+#pragma unroll
+        for (int t = 0; t < LSQ_SLOTS; ++t) {
+            scanned[t] = false;
+            rd[t] = 1e300;
         }
         free_local = warp_sum(free_local);
         if (lane == 0 && free_local) atomicAdd(&s_free_unscanned, free_local);
         __syncthreads();
         const int nroots = s_nnew;
-        relax(newlist, nroots, true);
+        relax(newlist, nroots);
+        __syncthreads();  // everyone has read the root list
         if (tid == 0) {
             s_roots_left = nroots;
             s_nnew = 0;
@@ -470,8 +475,9 @@ __global__ void __launch_bounds__(LSQ_THREADS, 1) lsap_square_kernel(const float
 #endif
             // ---- wave: settle every unscanned sink at the minimum distance
             double mn = 1e300;
-            for (int j = tid; j < n; j += LSQ_THREADS)
-                if (!scanned[j]) mn = fmin(mn, dist[j]);
+#pragma unroll
+            for (int t = 0; t < LSQ_SLOTS; ++t)
+                if (exist[t] && !scanned[t]) mn = fmin(mn, rd[t]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
             if (lane == 0) s_red[warp] = mn;
@@ -483,9 +489,11 @@ __global__ void __launch_bounds__(LSQ_THREADS, 1) lsap_square_kernel(const float
             LQ_LAP(lq1);
             if (dmin >= 1e300) break;  // every sink is scanned
             D = dmin;
-            for (int j = tid; j < n; j += LSQ_THREADS)
-                if (!scanned[j] && dist[j] == dmin) {
-                    scanned[j] = 1;
+#pragma unroll
+            for (int t = 0; t < LSQ_SLOTS; ++t)
+                if (exist[t] && !scanned[t] && rd[t] == dmin) {
+                    scanned[t] = true;
+                    const int j = tid + t * LSQ_THREADS;
                     const unsigned short i = sink_src[j];
                     if (i == LSQ_NONE) {
                         freelist[atomicAdd(&s_nfree, 1)] = (unsigned short)j;
@@ -539,16 +547,17 @@ __global__ void __launch_bounds__(LSQ_THREADS, 1) lsap_square_kernel(const float
             }
             LQ_LAP(lq3);
             const int nnew = s_nnew;
-            if (nnew > 0) relax(newlist, nnew, false);
+            if (nnew > 0) relax(newlist, nnew);
             __syncthreads();
             if (tid == 0) s_nnew = 0;
             LQ_LAP(lq4);
         }
         // ---- dual update: keeps every matched arc tight and all reduced costs non-negative
-        for (int i = tid; i < n; i += LSQ_THREADS) {
+        for (int i = tid; i < n; i += LSQ_THREADS)
             if (reached[i]) u[i] += D - dsrc[i];
-            if (scanned[i]) v[i] -= D - dist[i];
-        }
+#pragma unroll
+        for (int t = 0; t < LSQ_SLOTS; ++t)
+            if (scanned[t]) rv[t] -= D - rd[t];
         __syncthreads();
         LQ_LAP(lq5);
     }
@@ -589,7 +598,7 @@ extern "C" int marsb200_lsap(const float* sim, const uint8_t* row_sel, const uin
     cudaStream_t s = as_stream(stream);
     MARS_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
     // near-square problems take the multi-source phase solver on the zero-padded square (see lsap_square_kernel)
-    const bool near_square = m_cap >= 64 && m_cap - t_cap <= std::max(8, m_cap / 16) && m_cap <= 65534 &&
+    const bool near_square = m_cap >= 64 && m_cap - t_cap <= std::max(8, m_cap / 16) && m_cap <= LSQ_SLOTS * LSQ_THREADS &&
                              lsq_smem_bytes(m_cap) <= 220 * 1024;
     if (near_square) {
         const size_t smem = lsq_smem_bytes(m_cap);
