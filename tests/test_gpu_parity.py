@@ -1370,6 +1370,32 @@ def test_lsap_near_square_matches_scipy(mb, r, c, maximize, sel):
         np.testing.assert_array_equal(r2c[e], expect)  # random costs: the optimum is unique
 
 
+@pytest.mark.parametrize("kind", ["all_equal", "few_levels", "duplicate_rows"])
+def test_lsap_near_square_with_ties(mb, kind):
+    """Ties everywhere (equal-distance waves settle many sinks at once, augmentation order is arbitrary): the near-square
+    solver must still return A valid optimal assignment - compared with scipy by objective, like any LSAP with ties."""
+    from scipy.optimize import linear_sum_assignment
+
+    r, c = 150, 146
+    gen = torch.Generator().manual_seed(3)
+    if kind == "all_equal":
+        sim = torch.full((1, r, c), 0.25)
+    elif kind == "few_levels":
+        sim = torch.randint(0, 4, (1, r, c), generator=gen).float() / 4
+    else:
+        base = torch.rand(1, 10, c, generator=gen)
+        sim = base[:, torch.randint(0, 10, (r,), generator=gen)]
+    r2c, obj = mb.ops.lsap(sim.to(dev()), maximize=True)
+    got = r2c[0].cpu().numpy()
+    assigned = got[got >= 0]
+    assert len(assigned) == min(r, c) and len(set(assigned.tolist())) == len(assigned)
+    ri, ci = linear_sum_assignment(sim[0].double().numpy(), maximize=True)
+    want = sim[0].double().numpy()[ri, ci].sum()
+    rows = np.nonzero(got >= 0)[0]
+    assert abs(sim[0].double().numpy()[rows, got[rows]].sum() - want) < 1e-9
+    assert abs(float(obj[0]) - want) < 1e-9
+
+
 def test_bidirectional_lsap_matching(mb):
     """Forward + reverse assignment and the retain rule of Matcher.patch_level_matching (Matcher.py:443-477)."""
     from scipy.optimize import linear_sum_assignment
