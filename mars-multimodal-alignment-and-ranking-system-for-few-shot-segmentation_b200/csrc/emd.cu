@@ -357,268 +357,22 @@ __global__ void __launch_bounds__(EMD_THREADS, EMD_MAX_CTAS) emd_kernel(const fl
                                                            int* __restrict__ status, int32_t* __restrict__ ovf_count,
                                                            int32_t* __restrict__ ovf_list, unsigned char* __restrict__ gstate,
                                                            size_t gstate_stride) {
-    extern __shared__ __align__(16) unsigned char emd_smem_raw[];
-    const bool GLOBAL_STATE = gstate != nullptr;  // (a runtime flag: nvcc 12.9 aborts on this kernel as a template)
-    // sources: the support rows (<= t_cap) or, transposed, a proposal with fewer than t_cap / 3 patches; sinks: either side
-    EmdSmem s = emd_carve(GLOBAL_STATE ? gstate + (size_t)blockIdx.x * gstate_stride : emd_smem_raw, t_cap, max(t_cap, m_cap));
-    __shared__ unsigned long long s_val[EMD_WARPS];
-    __shared__ double s_acc[EMD_WARPS];
-    __shared__ int s_warp[EMD_WARPS];
-    __shared__ int s_lp, s_ndef, s_nnew, s_left, s_free, s_fault, s_open;
-    const int tid = threadIdx.x;
-    const int pool = emd_pool_nodes(t_cap, max(t_cap, m_cap));
-    const int n_queue = GLOBAL_STATE ? *ovf_count : total_lps;  // written by the fast-path launch before this one starts
+#define EMD_GLOBAL_STATE 0
+#include "emd_solver_body.inc"
+#undef EMD_GLOBAL_STATE
+}
 
-    while (true) {
-        __syncthreads();
-        if (tid == 0) {
-            const int q = atomicAdd(counter, 1);
-            s_lp = q < n_queue ? (GLOBAL_STATE ? ovf_list[q] : order[q]) : -1;
-        }
-        __syncthreads();
-        const int64_t lp = s_lp;
-        if (lp < 0) return;
-        if (dup_of[lp] >= 0) continue;  // same pooled bitmap as an earlier proposal of the episode: copied afterwards
-#ifdef MARSB200_EMD_PROFILE
-        long long ep_acc[16] = {0};
-        long long ep_last = clock64();
-#endif
-        const int64_t e = lp / P;
-        const float* C = cost + e * m_rows * N;
-        const uint8_t* fg = row_fg + e * m_rows;
-        const uint32_t* pw = pooled + lp * npw;
-
-        // ---- index lists (ascending order, like boolean indexing in the reference), staged in two sink-sized arrays
-        const int k_cap = max(t_cap, m_cap);
-        const int T0 = block_compact((int)m_rows, k_cap, s.batch, [&](int r) { return fg[r] != 0; }, s_warp);
-        const int M0 = block_compact(N, k_cap, s.pred_src, [&](int b) { return ((pw[b >> 5] >> (b & 31)) & 1u) != 0; }, s_warp);
-        if (T0 == 0 || M0 == 0) {  // empty marginal: defined as zero transport cost
-            if (tid == 0) out[lp] = 1.0;
-            continue;
-        }
-        if (T0 > t_cap || M0 > m_cap) {
-            if (tid == 0) {
-                out[lp] = nan("");
-                if (GLOBAL_STATE) atomicMax(status, T0 > t_cap ? T0 : (1 << 24) + M0);  // beyond the 16-bit index range
-                else ovf_list[atomicAdd(ovf_count, 1)] = (int32_t)lp;                   // solved by the global-state launch
-            }
-            continue;
-        }
-        // ---- orientation: the smaller side plays the sources.  The EMD is symmetric in its marginals; with few
-        // sources the per-sink flow lists stay short (a sink of a basic solution is fed by ~ (T + M) / #sinks
-        // sources) and every list walk - settling, augmenting - is sequential.
-        const bool swapped = 3 * M0 < T0;  // the transposed gathers walk cost rows: only worth it when the lists would be long
-        const int T = swapped ? M0 : T0, M = swapped ? T0 : M0;  // T sources, M sinks from here on
-        for (int i = tid; i < T; i += EMD_THREADS) s.soff[i] = swapped ? (int)s.pred_src[i] : (int)s.batch[i] * N;
-        for (int j = tid; j < M; j += EMD_THREADS) s.koff[j] = swapped ? (int)s.batch[j] * N : (int)s.pred_src[j];
-        __syncthreads();
-
-        // ---- initial state: zero flow, u = 0, v_j = min_i c_ij (reduced costs stay >= 0)
-        for (int i = tid; i < T; i += EMD_THREADS) {
-            s.u[i] = 0.0;
-            s.supply[i] = (short)M;
-        }
-        for (int j = tid; j < M; j += EMD_THREADS) {
-            s.v[j] = 0.0;
-            s.demand[j] = (short)T;
-            s.head[j] = -1;
-        }
-        for (int k = tid; k < pool; k += EMD_THREADS) s.node_next[k] = (short)(k + 1 < pool ? k + 1 : -1);
-        if (tid == 0) {
-            s_left = T * M;
-            s_free = 0;
-            s_fault = 0;
-            s_ndef = 0;
-            s_nnew = 0;
-        }
-        int lanes = 1;  // threads per sink in the source scans
-        while (lanes < 32 && 2 * lanes * M <= EMD_THREADS) lanes *= 2;
-        __syncthreads();
-
-        bool first_phase = true;
-        EP_LAP(0);  // setup
-        while (s_left > 0 && !s_fault) {  // uniform: shared state only changes between barriers
-            EP_COUNT(8);
-            // ---- phase start: every source with supply left is a root at distance 0
-            const int nroots = block_compact(T, T, s.newlist, [&](int i) { return s.supply[i] > 0; }, s_warp);
-            for (int i = tid; i < T; i += EMD_THREADS) {
-                s.reached[i] = s.supply[i] > 0 ? 1 : 0;
-                s.dsrc[i] = 0.0;
-                s.pred_sink[i] = -1;
-            }
-            int open_local = 0;
-            for (int j = tid; j < M; j += EMD_THREADS) {
-                s.scanned[j] = 0;
-                open_local += s.demand[j] > 0 ? 1 : 0;
-            }
-            if (tid == 0) s_open = 0;
-            __syncthreads();
-            open_local = warp_sum(open_local);
-            if ((tid & 31) == 0 && open_local) atomicAdd(&s_open, open_local);  // unscanned sinks with open demand
-            scan_sources<true>(s, C, M, s.newlist, nroots, lanes, 0.0, first_phase);
-            if (first_phase) {
-                // row reduction: u_i = min_j (c_ij - v_j) >= 0 makes one more arc per source tight before the first
-                // forest is grown (about a fifth fewer waves on the larger problems); then the distances are redone
-                __syncthreads();
-                for (int i = tid >> 5; i < T; i += EMD_WARPS) {  // one warp per source, lanes stride over the sinks
-                    const float* row = C + s.soff[i];
-                    double best = EMD_INF;
-                    for (int j = tid & 31; j < M; j += 32) best = fmin(best, (double)row[s.koff[j]] - s.v[j]);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
-                    if ((tid & 31) == 0) s.u[i] = best;
-                }
-                __syncthreads();
-                scan_sources<true>(s, C, M, s.newlist, nroots, lanes, 0.0, false);
-            }
-            first_phase = false;
-            __syncthreads();
-            EP_LAP(1);  // phase init
-
-            double D = 0.0;
-            while (true) {
-                EP_COUNT(9);
-                // ---- wave: settle every unscanned sink at the minimum distance
-                const double dmin = block_min_key(s, M, s_val);
-                EP_LAP(2);  // argmin
-                if (dmin >= EMD_INF) break;  // every sink is scanned
-                D = dmin;
-                for (int j = tid; j < M; j += EMD_THREADS)
-                    if (!s.scanned[j] && s.dist[j] == dmin) {
-                        s.scanned[j] = 1;
-                        if (s.demand[j] > 0) s.batch[atomicAdd(&s_ndef, 1)] = (short)j;  // open demand: augment first
-                        else expand_feeders(s, j, dmin, &s_nnew);  // its flow arcs cannot change in this wave
-                    }
-                __syncthreads();
-                EP_LAP(3);  // settle
-                const int ndef = s_ndef;
-                if (ndef > 0) {
-                    // ---- augment along the tree path of every settled sink with open demand (sequential: paths share arcs).
-                    // Most attempts of the later phases find their root spent or a tree arc emptied: those are filtered
-                    // out in parallel first (capacities only shrink within a phase, so a dead path stays dead) and marked
-                    // by complementing the sink index.
-                    for (int b = tid; b < ndef; b += EMD_THREADS) {
-                        const int j = s.batch[b];
-                        int delta = s.demand[j];
-                        int i = s.pred_src[j];
-                        while (delta > 0 && s.pred_sink[i] >= 0) {
-                            delta = min(delta, (int)s.capflow[i]);
-                            i = s.pred_src[s.pred_sink[i]];
-                        }
-                        if (delta <= 0 || s.supply[i] <= 0) s.batch[b] = (short)~j;
-                    }
-                    __syncthreads();
-                    if (tid == 0) {
-                        s_open -= ndef;
-                        for (int b = 0; b < ndef; ++b) {
-                            const int j = s.batch[b];
-                            if (j < 0) continue;
-                            int delta = s.demand[j];
-                            int i = s.pred_src[j];
-                            while (s.pred_sink[i] >= 0) {
-                                delta = min(delta, (int)s.capflow[i]);
-                                i = s.pred_src[s.pred_sink[i]];
-                            }
-                            delta = min(delta, (int)s.supply[i]);
-                            if (delta <= 0) continue;  // the root is spent or a tree arc was emptied earlier in this phase
-                            s.supply[i] = (short)(s.supply[i] - delta);
-                            s.demand[j] = (short)(s.demand[j] - delta);
-                            s_left -= delta;
-                            int jj = j;
-                            while (true) {
-                                const int src = s.pred_src[jj];
-                                // forward arc src -> jj gains delta
-                                int n = s.head[jj];
-                                while (n >= 0 && s.node_src[n] != src) n = s.node_next[n];
-                                if (n >= 0) {
-                                    s.node_flow[n] = (short)(s.node_flow[n] + delta);
-                                } else {
-                                    n = s_free;
-                                    if (n < 0) {
-                                        s_fault = 1;  // flow-node pool exhausted (never seen: a basic solution has < T + M arcs)
-                                        break;
-                                    }
-                                    s_free = s.node_next[n];
-                                    s.node_src[n] = (short)src;
-                                    s.node_flow[n] = (short)delta;
-                                    s.node_next[n] = s.head[jj];
-                                    s.head[jj] = (short)n;
-                                }
-                                const int jp = s.pred_sink[src];
-                                if (jp < 0) break;
-                                // backward arc jp -> src loses delta
-                                s.capflow[src] = (short)(s.capflow[src] - delta);
-                                int prev = -1;
-                                n = s.head[jp];
-                                while (s.node_src[n] != src) {
-                                    prev = n;
-                                    n = s.node_next[n];
-                                }
-                                const int left = s.node_flow[n] - delta;
-                                if (left > 0) {
-                                    s.node_flow[n] = (short)left;
-                                } else {  // unlink the emptied arc
-                                    if (prev < 0) s.head[jp] = s.node_next[n];
-                                    else s.node_next[prev] = s.node_next[n];
-                                    s.node_next[n] = (short)s_free;
-                                    s_free = n;
-                                }
-                                jj = jp;
-                            }
-                            if (s_fault) break;
-                        }
-                    }
-                    __syncthreads();
-                    // the phase ends when the flow is complete or no unscanned sink has open demand left: later waves could
-                    // not augment anything (dual update with D = this wave's distance, unscanned nodes keep their duals)
-                    if (s_left <= 0 || s_fault || s_open <= 0) break;
-                    for (int b = tid; b < ndef; b += EMD_THREADS) {
-                        const int j = s.batch[b];
-                        expand_feeders(s, j < 0 ? ~j : j, dmin, &s_nnew);
-                    }
-                    __syncthreads();
-                }
-                EP_LAP(4);  // augment
-                const int nnew = s_nnew;
-                // ---- relax every unscanned sink against the newly reached sources
-                if (nnew > 0) scan_sources<false>(s, C, M, s.newlist, nnew, lanes, dmin, false);
-                __syncthreads();  // everyone has read the counters; the next wave's settle pass starts after another barrier
-                if (tid == 0) {
-                    s_ndef = 0;
-                    s_nnew = 0;
-                }
-                EP_LAP(6);  // relax
-            }
-            // ---- dual update: keeps every flow arc tight and all reduced costs non-negative
-            for (int i = tid; i < T; i += EMD_THREADS)
-                if (s.reached[i]) s.u[i] += D - s.dsrc[i];
-            for (int j = tid; j < M; j += EMD_THREADS)
-                if (s.scanned[j]) s.v[j] -= D - s.dist[j];
-            if (tid == 0) {
-                s_ndef = 0;
-                s_nnew = 0;
-            }
-            __syncthreads();
-        }
-
-        // ---- objective: sum f_ij c_ij / (T M), float64
-        double acc = 0.0;
-        for (int j = tid; j < M; j += EMD_THREADS)
-            for (int n = s.head[j]; n >= 0; n = s.node_next[n]) acc += (double)s.node_flow[n] * (double)C[s.soff[s.node_src[n]] + s.koff[j]];
-        acc = warp_sum(acc);
-        if ((tid & 31) == 0) s_acc[tid >> 5] = acc;
-        __syncthreads();
-        if (tid == 0) {
-            double total = 0.0;
-            for (int w = 0; w < EMD_WARPS; ++w) total += s_acc[w];
-            out[lp] = s_fault ? nan("") : 1.0 - total / ((double)T * (double)M);  // the reference's emd_score = 1 - emd
-            if (s_fault) atomicMin(status, -1);
-#ifdef MARSB200_EMD_PROFILE
-            EP_LAP(7);  // dual updates + objective (and everything not lapped)
-            for (int k = 0; k < 16; ++k) atomicAdd((unsigned long long*)&g_emd_prof[k], (unsigned long long)ep_acc[k]);
-#endif
-        }
-    }
+__global__ void __launch_bounds__(EMD_THREADS, 1) emd_global_state_kernel(const float* __restrict__ cost, const uint8_t* __restrict__ row_fg,
+                                                           const uint32_t* __restrict__ pooled, int P, int64_t m_rows,
+                                                           int N, int npw, int t_cap, int m_cap, int total_lps,
+                                                           const int32_t* __restrict__ order, int32_t* __restrict__ counter,
+                                                           const int32_t* __restrict__ dup_of, double* __restrict__ out,
+                                                           int* __restrict__ status, int32_t* __restrict__ ovf_count,
+                                                           int32_t* __restrict__ ovf_list, unsigned char* __restrict__ gstate,
+                                                           size_t gstate_stride) {
+#define EMD_GLOBAL_STATE 1
+#include "emd_solver_body.inc"
+#undef EMD_GLOBAL_STATE
 }
 
 }  // namespace marsb200
@@ -720,7 +474,7 @@ int marsb200_emd_scores(const float* cost, const uint8_t* row_fg, const uint32_t
     MARS_LAUNCH_OK();
     // problems beyond the fast path's caps (none in the usual case: the launch finds an empty list and returns)
     const int t_full = emd_full_t_cap(m_rows, N);
-    emd_kernel<<<EMD_GLOBAL_CTAS, EMD_THREADS, 0, s>>>(cost, row_fg, pooled, P, m_rows, N, npw, t_full, N, (int)lps, order,
+    emd_global_state_kernel<<<EMD_GLOBAL_CTAS, EMD_THREADS, 0, s>>>(cost, row_fg, pooled, P, m_rows, N, npw, t_full, N, (int)lps, order,
                                                             counter + 2, dup_of, out, status, counter + 1, ovf_list, gstate,
                                                             emd_gstate_stride(m_rows, N));
     MARS_LAUNCH_OK();
