@@ -21,8 +21,11 @@ stability score, torchvision box NMS, and the whole Matcher ancestry path -
 ``set_reference`` -> ``patch_level_matching`` -> ``mask_generation`` with its ``RobustPromptSampler`` - by executing the
 reference's own method bodies, cut out of matcher/Matcher.py with ``ast`` - and ``MARS.predict`` end to end through the
 reference's ``MARS``, ``VisualVisualAlignmentModule`` and ``FilteringMergingModule`` classes).  The builder-defined pieces
-(`pairwise_intersections`, `mask_nms`), the exact-EMD stand-in (POT is not
-installed anywhere we can run) and the Matcher assignment matching (scipy's
+(`pairwise_intersections`, `mask_nms`), the exact-EMD stand-in (POT 0.9.4 is not
+installed anywhere we can run; the optimum of the LP is solver-independent and three
+independent exact solvers agree on it: HiGHS here, a network simplex - POT's algorithm
+class - in `emd_network_simplex`, and the lcm-expanded assignment in the tests) and the
+Matcher assignment matching (scipy's
 LSAP tie-breaking is implementation-defined; compared by objective value) have
 no reference output to pin against: **parity unpinned** for those four, pinned
 for everything else.
