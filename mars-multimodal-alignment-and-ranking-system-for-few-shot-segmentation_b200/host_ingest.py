@@ -49,6 +49,8 @@ class HostMaskIngest:
         device tensor [E, P, wpm] the bits land in - valid once `stream` has drained."""
         if host_masks.is_cuda or tuple(host_masks.shape) != (self.E, self.P, self.H, self.W):
             raise ValueError(f"host_masks must be a CPU tensor of shape {(self.E, self.P, self.H, self.W)}")
+        if self.raw_dev is not None and host_masks.dtype != self.raw_dev.dtype:
+            raise TypeError(f"host_masks are {host_masks.dtype}, the ingest was built for {self.raw_dev.dtype}")
         p_raw = self.p_raw
         with torch.cuda.stream(stream):
             for e in range(self.E if p_raw else 0):  # the DMA of the raw lane runs while the host threads pack

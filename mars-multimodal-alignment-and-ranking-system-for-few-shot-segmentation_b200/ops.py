@@ -466,9 +466,14 @@ def host_pack_masks(masks: torch.Tensor, out: Optional[torch.Tensor] = None, thr
 def nms_bitmask(inter: torch.Tensor, nms_iou_threshold: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Pairwise suppression relation [E, P, ceil(P/32)] int32 (bit j of row i: IoU(i, j) > threshold, j != i) from the
     intersections [E, P, P]; independent of the ranking, so it can run as soon as `inter` exists (fuse_rank `nms_bits`)."""
+    inter = _cuda(inter, torch.int32, "inter")
+    if inter.dim() != 3 or inter.shape[1] != inter.shape[2]:
+        raise ValueError("inter must be [E, P, P]")
     e, p, _ = inter.shape
     if out is None:
         out = torch.empty((e, p, (p + 31) // 32), device=inter.device, dtype=torch.int32)
+    elif not out.is_cuda or out.dtype != torch.int32 or not out.is_contiguous() or out.numel() != e * p * ((p + 31) // 32):
+        raise ValueError("out must be a contiguous CUDA int32 tensor [E, P, ceil(P / 32)]")
     check(lib.marsb200_nms_bitmask(inter.data_ptr(), e, p, float(nms_iou_threshold), out.data_ptr(), _stream()))
     return out
 
