@@ -54,6 +54,12 @@ const char* marsb200_last_error(void);
  * mask ingest and the contractions disjoint SM partitions (no reference counterpart: the reference is single-stream,
  * main_MARS.py:54-94).  count_host is a HOST pointer. */
 int marsb200_stream_sm_count(void* stream, int* count_host);
+/* Caps what marsb200_stream_sm_count reports for `stream` at `cap` SMs (0 removes the cap; process-wide table keyed by
+ * the stream handle, thread-safe; remove the cap before destroying the stream).  A persistent kernel launched on a
+ * capped stream starts at most `cap` CTAs and leaves the other SMs to kernels of other streams: the single-episode
+ * schedule uses it so that the contractions do not displace the mask ingest running beside them (no reference
+ * counterpart, main_MARS.py:54-94 is single-stream). */
+int marsb200_stream_set_sm_cap(void* stream, int cap);
 /* words (uint32) per packed mask row for an H*W mask: ceil(HW/32) rounded up to 32 words (128 B) */
 int64_t marsb200_words_per_mask(int64_t hw);
 /* padded extents used by the contraction operands */

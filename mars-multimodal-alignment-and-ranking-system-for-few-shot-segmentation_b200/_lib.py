@@ -36,6 +36,7 @@ SIGNATURES = {
     "marsb200_version": (_i, []),
     "marsb200_last_error": (ctypes.c_char_p, []),
     "marsb200_stream_sm_count": (_i, [_p, ctypes.POINTER(_i)]),
+    "marsb200_stream_set_sm_cap": (_i, [_p, _i]),
     "marsb200_words_per_mask": (_l, [_l]),
     "marsb200_pad_rows": (_l, [_l]),
     "marsb200_pad_k": (_l, [_l]),

@@ -16,6 +16,7 @@ from typing import Optional
 import torch
 
 from . import ops
+from .partition import set_stream_sm_cap
 from .synthetic import EpisodeShape
 
 
@@ -39,6 +40,11 @@ class RankingConfig:
     # own stream beside normalise -> S -> prior instead of behind it: the alignment chain is the critical path of a small
     # batch (graph latency 0.33 -> 0.305 ms); at 16 episodes per step it is neutral to -3 %.  None = on for <= 2 episodes
     hoist_vva_contraction: Optional[bool] = None
+    # one-timeline schedule: CTAs the persistent contractions of the alignment streams may start (marsb200_stream_set_sm_cap).
+    # The ingest of ONE episode needs ~100 SMs to read its masks at the HBM rate; contractions that take the whole device
+    # stall it (graph latency 0.308 -> 0.294 ms at 40, profiles/r2_logs/latency_contraction_cap.log).  None = 40 for
+    # <= 2 episodes per step, no cap above; 0 = never
+    latency_contraction_sms: Optional[int] = None
     fused_ingest: bool = False         # one-pass pack + pairwise kernel (owns all TMEM: cannot overlap the contractions)
     fused_pool: bool = False           # one-pass pack + pooled bitmaps (ops.pack_pool); measured slower than the two kernels
     emd_on_device: bool = False        # solve the P transport LPs per episode on the device instead of taking batch["emd"]
@@ -157,6 +163,8 @@ class RankingEngine:
         self._ev_rowfg = torch.cuda.Event()
         hoist = cfg.hoist_vva_contraction if cfg.hoist_vva_contraction is not None else e <= 2
         self._side4 = torch.cuda.Stream(device=dev, **hi) if cfg.overlap_streams and hoist else None
+        cap = cfg.latency_contraction_sms if cfg.latency_contraction_sms is not None else (40 if e <= 2 else 0)
+        self._contraction_sms = cap if (cfg.overlap_streams and cfg.priority_streams) else 0
         self._ev_vva_g = torch.cuda.Event()
         self._ev_vta = torch.cuda.Event()
         self._ev_fork = torch.cuda.Event()
@@ -376,6 +384,18 @@ class RankingEngine:
         n, m = s.N, s.ns * s.N
         if self._part is not None and "masks" in batch and not cfg.fused_ingest and not self._capturing:
             return self._run_partitioned(batch, wait)
+        capped = [st for st in (self._hi, self._side3, self._side4) if st is not None] if self._contraction_sms else []
+        for st in capped:  # host-side launch parameter: read when the contractions are enqueued below
+            set_stream_sm_cap(st, self._contraction_sms)
+        try:
+            return self._run_one_timeline(batch)
+        finally:
+            for st in capped:  # torch hands out pooled stream handles: never leave a cap on one
+                set_stream_sm_cap(st, 0)
+
+    def _run_one_timeline(self, batch: dict) -> dict:
+        s, e, cfg = self.shape, self.E, self.cfg
+        n, m = s.N, s.ns * s.N
         main = torch.cuda.current_stream()
         if self._side is not None:
             # the mask chain is HBM-bound and the alignment chain tensor/L2-bound: let them share the SMs

@@ -34,6 +34,11 @@ def stream_sm_count(stream: torch.cuda.Stream) -> int:
     return n.value
 
 
+def set_stream_sm_cap(stream: torch.cuda.Stream, cap: int) -> None:
+    """Caps the SM count libmarsb200's persistent kernels see for `stream` (0 removes the cap)."""
+    _lib.check(_lib.lib.marsb200_stream_set_sm_cap(ctypes.c_void_p(stream.cuda_stream), int(cap)))
+
+
 class SmPartition:
     """Two disjoint SM sets of `device`: `.tensor_stream` (>= tensor_sms SMs) and `.hbm_stream` (the remainder)."""
 

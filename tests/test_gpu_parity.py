@@ -489,7 +489,8 @@ def test_engine_stream_options_are_bit_identical(mb, episodes):
     batch = mb.stack_episodes([mb.make_episode(shape, 70 + i, dev()) for i in range(episodes)])
     outs = []
     for kw in (dict(overlap_streams=False), dict(priority_streams=False, hoist_vva_contraction=False),
-               dict(priority_streams=True, hoist_vva_contraction=False), dict(priority_streams=True, hoist_vva_contraction=True)):
+               dict(priority_streams=True, hoist_vva_contraction=False), dict(priority_streams=True, hoist_vva_contraction=True),
+               dict(latency_contraction_sms=0), dict(latency_contraction_sms=1), dict(latency_contraction_sms=48)):
         eng = mb.RankingEngine(shape, episodes, mb.RankingConfig(nms_iou_threshold=0.6, **kw), dev())
         o = eng.run(batch)
         torch.cuda.synchronize()
@@ -1554,6 +1555,35 @@ def test_stream_sm_count_follows_the_partition(mb):
         assert stream_sm_count(part.extra_stream("tensor")) == part.tensor_sms
     finally:
         part.close()
+
+
+def test_stream_sm_cap(mb):
+    """marsb200_stream_set_sm_cap: a capped stream reports the cap (never more than the device), other streams are not
+    affected, 0 removes it; the engine leaves no cap behind on the (pooled) stream handles it used."""
+    from marsb200.partition import set_stream_sm_cap, stream_sm_count
+
+    total = torch.cuda.get_device_properties(dev()).multi_processor_count
+    a, b = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
+    set_stream_sm_cap(a, 48)
+    try:
+        assert stream_sm_count(a) == 48 and stream_sm_count(b) == total
+        set_stream_sm_cap(a, 32)
+        assert stream_sm_count(a) == 32
+        set_stream_sm_cap(a, 10 * total)
+        assert stream_sm_count(a) == total
+    finally:
+        set_stream_sm_cap(a, 0)
+    assert stream_sm_count(a) == total
+    with pytest.raises(mb.MarsB200Error):
+        set_stream_sm_cap(a, -1)
+    shape = mb.EpisodeShape(ns=1, g=14, gt=12, C=64, D=32, P=40, H=96, W=96)
+    eng = mb.RankingEngine(shape, 1, mb.RankingConfig(nms_iou_threshold=0.6), dev())
+    assert eng._contraction_sms == 40
+    eng.run(mb.stack_episodes([mb.make_episode(shape, 3, dev())]))
+    torch.cuda.synchronize()
+    for st in (eng._hi, eng._side3, eng._side4):
+        assert stream_sm_count(st) == total
+    assert mb.RankingEngine(shape, 4, mb.RankingConfig(), dev())._contraction_sms == 0
 
 
 @pytest.mark.parametrize("chunks,vta_on_hbm,tail,extra", [

@@ -309,3 +309,19 @@ def test_host_pack_masks_matches_the_packed_layout(n, h, w, dtype, threads):
         ref[:, :hw] = x.reshape(n, -1).numpy() > 0
     want = np.packbits(ref.reshape(n, wpm, 32), axis=-1, bitorder="little").view(np.uint32).reshape(n, wpm)
     np.testing.assert_array_equal(bits.numpy().view(np.uint32), want)
+
+
+def test_stream_sm_cap_table_is_host_side():
+    """marsb200_stream_set_sm_cap only edits a host table (no CUDA call): it accepts any handle, replaces and removes
+    entries, and refuses negative caps - the GPU suite checks what marsb200_stream_sm_count then reports."""
+    import ctypes
+
+    from marsb200 import _lib
+
+    h = ctypes.c_void_p(0x1234)
+    assert _lib.lib.marsb200_stream_set_sm_cap(h, 48) == 0
+    assert _lib.lib.marsb200_stream_set_sm_cap(h, 32) == 0
+    assert _lib.lib.marsb200_stream_set_sm_cap(h, 0) == 0
+    assert _lib.lib.marsb200_stream_set_sm_cap(h, 0) == 0  # removing a missing entry is not an error
+    assert _lib.lib.marsb200_stream_set_sm_cap(h, -1) != 0
+    assert b"cap" in _lib.lib.marsb200_last_error()
