@@ -170,6 +170,13 @@ int marsb200_resize_minmax(const float* src, int E, int gs, int gd, int apply_mi
  * bit k of word w = pixel 32*w + k; padding words are zero.  Replaces the per-proposal `m_p > 0`
  * views of FilteringMergingModule.py:77,104-108 and feeds every later mask kernel. */
 int marsb200_pack_masks(const void* masks, int mask_dtype, int64_t n, int64_t HW, uint32_t* bits, void* stream);
+/* The same for ONE pixel slice of every mask: packed words [word_begin, word_begin + word_count) of bits [n, wpm] from pixels
+ * [32 * word_begin, 32 * (word_begin + word_count)) of masks [n, HW] - whole 512-word blocks inside the mask's pixels,
+ * 16-byte aligned masks with HW % 4 == 0 (float32) / HW % 16 == 0 (uint8).  Slices that tile [0, wpm) produce exactly the bits
+ * of marsb200_pack_masks.  With marsb200_pairwise_inter_slice it lets a single episode's intersections start while most of
+ * its masks are still being read (no reference counterpart; the reference holds every mask as a dense tensor). */
+int marsb200_pack_masks_slice(const void* masks, int mask_dtype, int64_t n, int64_t HW, int64_t word_begin, int64_t word_count,
+                              uint32_t* bits, void* stream);
 
 /* Pooled patch bitmap, pixel area and pooled count of every packed mask.
  * Replaces F.adaptive_max_pool2d(m_p, (g, g)) > 0 in the hot loop, FilteringMergingModule.py:104-108.
@@ -196,6 +203,11 @@ int marsb200_region_sums(const uint32_t* pooled, int E, int P, int N, const floa
  * inter[e,i,j] = popcount(bits[e,i] & bits[e,j]) as int32 [E, P, P]; the diagonal is the area. */
 int marsb200_pairwise_inter(const uint32_t* bits, int E, int P, int64_t words_per_mask, int32_t* inter,
                             int backend, void* stream);
+/* The contribution of one pixel slice (packed words [word_begin, word_begin + word_count) of every mask, whole 256-pixel
+ * blocks): inter = (accumulate ? inter : 0) + popcount over the slice.  Integer additions: slices that tile the mask sum to
+ * exactly marsb200_pairwise_inter's counts in any order.  Tensor-core back ends only (AUTO / FP4 / MMA). */
+int marsb200_pairwise_inter_slice(const uint32_t* bits, int E, int P, int64_t words_per_mask, int64_t word_begin,
+                                  int64_t word_count, int accumulate, int32_t* inter, int backend, void* stream);
 
 /* Fused ingest: bits = pack(masks) AND inter = pairwise intersections in ONE pass over the masks
  * (float32 masks, P <= 256, tensor-core back end: the masks are read once at HBM rate and the int8 MMAs run

@@ -53,10 +53,12 @@ SIGNATURES = {
     "marsb200_scoremap_boxes": (_i, [_p, _i, _i, _d, _p, _p, _p]),
     "marsb200_resize_minmax": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "marsb200_pack_masks": (_i, [_p, _i, _l, _l, _p, _p]),
+    "marsb200_pack_masks_slice": (_i, [_p, _i, _l, _l, _l, _l, _p, _p]),
     "marsb200_pool_packed": (_i, [_p, _l, _i, _i, _i, _p, _p, _p, _p]),
     "marsb200_pack_pool_masks": (_i, [_p, _i, _l, _i, _i, _i, _p, _p, _p, _p, _p]),
     "marsb200_region_sums": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "marsb200_pairwise_inter": (_i, [_p, _i, _i, _l, _p, _i, _p]),
+    "marsb200_pairwise_inter_slice": (_i, [_p, _i, _i, _l, _l, _l, _i, _p, _i, _p]),
     "marsb200_pack_pairwise": (_i, [_p, _i, _i, _i, _l, _p, _p, _i, _p]),
     "marsb200_emd_workspace_bytes": (_l, [_i, _i, _i, _l, _i, _i]),
     "marsb200_emd_scores": (_i, [_p, _p, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p, _p, _p]),

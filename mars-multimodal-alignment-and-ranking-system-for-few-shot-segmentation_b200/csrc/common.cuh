@@ -127,7 +127,11 @@ int sms_for_stream(cudaStream_t s, int* out);
 
 // internal back ends shared between translation units
 int pairwise_popc(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s);
-int pairwise_mma(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s);
-int pairwise_fp4(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s);
+// word_begin / word_count: the pixel slice (packed words of every mask) the launch covers, -1 = to the end; accumulate: add to
+// `inter` instead of overwriting it (integer atomics: the slices of a mask may be summed in any order)
+int pairwise_mma(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s, int64_t word_begin = 0,
+                 int64_t word_count = -1, bool accumulate = false);
+int pairwise_fp4(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s, int64_t word_begin = 0,
+                 int64_t word_count = -1, bool accumulate = false);
 
 }  // namespace marsb200

@@ -727,6 +727,36 @@ int marsb200_pack_masks(const void* masks, int mask_dtype, int64_t n, int64_t HW
     return MARSB200_OK;
 }
 
+// Words [word_begin, word_begin + word_count) of every mask: the vector kernels on shifted base pointers (the row strides HW
+// and wpm are unchanged; a slice of whole 512-word blocks inside the mask's pixels never meets the tail handling).
+int marsb200_pack_masks_slice(const void* masks, int mask_dtype, int64_t n, int64_t HW, int64_t word_begin, int64_t word_count,
+                              uint32_t* bits, void* stream) {
+    MARS_REQUIRE(masks && bits, "null pointer");
+    MARS_CUDA_OK(per_device_once(g_ingest_carveouts, set_ingest_carveouts));
+    MARS_REQUIRE(n > 0 && HW > 0, "empty input");
+    MARS_REQUIRE(mask_dtype == MARSB200_MASK_F32 || mask_dtype == MARSB200_MASK_U8, "mask_dtype");
+    const int64_t wpm = marsb200_words_per_mask(HW);
+    MARS_REQUIRE(word_begin >= 0 && word_count > 0 && word_begin % 512 == 0 && word_count % 512 == 0,
+                 "slice must be whole 512-word blocks");
+    MARS_REQUIRE((word_begin + word_count) * 32 <= HW, "slice must lie inside the mask's pixels");
+    const int64_t esz = mask_dtype == MARSB200_MASK_F32 ? 4 : 1;
+    const char* src = static_cast<const char*>(masks) + word_begin * 32 * esz;
+    MARS_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && HW % (mask_dtype == MARSB200_MASK_F32 ? 4 : 16) == 0,
+                 "slices need 16-byte aligned masks with HW % 4 == 0 (float32) / HW % 16 == 0 (uint8)");
+    cudaStream_t s = as_stream(stream);
+    if (mask_dtype == MARSB200_MASK_F32) {
+        const int chunks = (int)(word_count * 32 / (PACK_THREADS * PACK_UNROLL_F32 * 4));
+        MARS_REQUIRE(n * chunks < (1ll << 31), "grid too large");
+        pack_f32_vec_kernel<<<(unsigned)(n * chunks), PACK_THREADS, 0, s>>>((const float*)src, n, HW, wpm, bits + word_begin, chunks);
+    } else {
+        const int chunks = (int)(word_count * 32 / (PACK_THREADS * PACK_UNROLL * 16));
+        MARS_REQUIRE(n * chunks < (1ll << 31), "grid too large");
+        pack_u8_vec_kernel<<<(unsigned)(n * chunks), PACK_THREADS, 0, s>>>((const uint8_t*)src, n, HW, wpm, bits + word_begin, chunks);
+    }
+    MARS_LAUNCH_OK();
+    return MARSB200_OK;
+}
+
 int marsb200_pool_mask(const void* masks, int mask_dtype, int64_t n, int H, int W, int g, uint8_t* out, void* stream) {
     MARS_REQUIRE(masks && out, "null pointer");
     MARS_REQUIRE(n > 0 && H > 0 && W > 0 && g > 0 && g <= H && g <= W, "shape");

@@ -69,7 +69,8 @@ __host__ __device__ constexpr uint32_t make_idesc_mxf4(uint32_t m, uint32_t n) {
 }
 
 __global__ void __launch_bounds__(PF_THREADS, 1)
-pairwise_fp4_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int kb_per_split, int32_t* __restrict__ inter) {
+pairwise_fp4_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int total_kb, int kb_per_split,
+                    int32_t* __restrict__ inter) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -82,7 +83,7 @@ pairwise_fp4_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int k
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t e = blockIdx.y;
-    const int total_kb = (int)(wpm / 8);  // 8 words = 256 pixels per k-block
+    // total_kb: k-blocks (8 words = 256 pixels) of the pixel slice this launch covers, starting at `bits`
     const int kb_begin = blockIdx.x * kb_per_split;
     const int kb_end = min(kb_begin + kb_per_split, total_kb);
     const int num_kb = kb_end - kb_begin;
@@ -203,12 +204,17 @@ pairwise_fp4_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int k
     if (warp == PF_PRODUCER_WARPS) tmem_dealloc(tmem_acc, 512);
 }
 
-int pairwise_fp4(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s) {
+int pairwise_fp4(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s, int64_t word_begin,
+                 int64_t word_count, bool accumulate) {
     if (reinterpret_cast<uintptr_t>(bits) & 15)
         return fail(MARSB200_ERR_ARG, "%s: packed masks must be 16-byte aligned", "pairwise_fp4");
     if (P > PF_ROWS) return fail(MARSB200_ERR_UNSUPPORTED, "%s: at most 256 proposals (%lld given)", "pairwise_fp4", P);
     if (wpm * 32 >= (1ll << 24)) return fail(MARSB200_ERR_UNSUPPORTED, "%s: masks of 2^24 pixels or more", "pairwise_fp4");
-    const int total_kb = (int)(wpm / 8);
+    if (word_count < 0) word_count = wpm - word_begin;
+    if (word_begin < 0 || word_begin % 8 || word_count <= 0 || word_count % 8 || word_begin + word_count > wpm)
+        return fail(MARSB200_ERR_ARG, "%s: pixel slice must be whole 256-pixel blocks inside the mask (%lld, %lld)", "pairwise_fp4",
+                    word_begin, word_count);
+    const int total_kb = (int)(word_count / 8);
     static PerDeviceOnce configured;  // the attribute is per device
     MARS_CUDA_OK(per_device_once(configured, [] {
         return cudaFuncSetAttribute(pairwise_fp4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BYTES);
@@ -219,8 +225,8 @@ int pairwise_fp4(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter
     int ksplit = std::max(1, std::min(total_kb, waves * num_sms / E));
     int kb_per_split = ceil_div(total_kb, ksplit);
     ksplit = ceil_div(total_kb, kb_per_split);
-    MARS_CUDA_OK(cudaMemsetAsync(inter, 0, sizeof(int32_t) * (size_t)E * P * P, s));
-    pairwise_fp4_kernel<<<dim3(ksplit, E), PF_THREADS, PF_SMEM_BYTES, s>>>(bits, P, wpm, kb_per_split, inter);
+    if (!accumulate) MARS_CUDA_OK(cudaMemsetAsync(inter, 0, sizeof(int32_t) * (size_t)E * P * P, s));
+    pairwise_fp4_kernel<<<dim3(ksplit, E), PF_THREADS, PF_SMEM_BYTES, s>>>(bits + word_begin, P, wpm, total_kb, kb_per_split, inter);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }

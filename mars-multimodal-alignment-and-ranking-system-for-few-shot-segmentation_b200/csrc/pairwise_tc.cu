@@ -44,7 +44,7 @@ __device__ __forceinline__ void expand_row(unsigned char* tile, int row, uint4 b
 }
 
 __global__ void __launch_bounds__(PM_THREADS, 1)
-pairwise_mma_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int blocks, int kb_per_split,
+pairwise_mma_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int blocks, int total_kb, int kb_per_split,
                     int32_t* __restrict__ inter) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -66,7 +66,7 @@ pairwise_mma_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int b
     const int bj = bi + t;
     const bool diagonal = (bi == bj);
     const int64_t e = blockIdx.z;
-    const int total_kb = (int)(wpm / 4);  // 4 words = 128 pixels per k-block
+    // total_kb: k-blocks (4 words = 128 pixels) of the pixel slice this launch covers, starting at `bits`
     const int kb_begin = blockIdx.y * kb_per_split;
     const int kb_end = min(kb_begin + kb_per_split, total_kb);
     const int num_kb = kb_end - kb_begin;
@@ -195,12 +195,17 @@ pairwise_mma_kernel(const uint32_t* __restrict__ bits, int P, int64_t wpm, int b
     if (warp == PM_PRODUCER_WARPS) tmem_dealloc(tmem_acc, 512);
 }
 
-int pairwise_mma(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s) {
+int pairwise_mma(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter, cudaStream_t s, int64_t word_begin,
+                 int64_t word_count, bool accumulate) {
     if (reinterpret_cast<uintptr_t>(bits) & 15)
         return fail(MARSB200_ERR_ARG, "%s: packed masks must be 16-byte aligned", "pairwise_mma");
+    if (word_count < 0) word_count = wpm - word_begin;
+    if (word_begin < 0 || word_begin % 4 || word_count <= 0 || word_count % 4 || word_begin + word_count > wpm)
+        return fail(MARSB200_ERR_ARG, "%s: pixel slice must be whole 128-pixel blocks inside the mask (%lld, %lld)", "pairwise_mma",
+                    word_begin, word_count);
     const int blocks = ceil_div(P, PM_ROWS);
     const int pairs = blocks * (blocks + 1) / 2;
-    const int total_kb = (int)(wpm / 4);
+    const int total_kb = (int)(word_count / 4);
     static PerDeviceOnce configured;  // the attribute is per device
     MARS_CUDA_OK(per_device_once(configured, [] {
         return cudaFuncSetAttribute(pairwise_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PM_SMEM_BYTES);
@@ -214,9 +219,9 @@ int pairwise_mma(const uint32_t* bits, int E, int P, int64_t wpm, int32_t* inter
     int ksplit = std::max(1, std::min(total_kb, waves * num_sms / units));
     int kb_per_split = ceil_div(total_kb, ksplit);
     ksplit = ceil_div(total_kb, kb_per_split);
-    MARS_CUDA_OK(cudaMemsetAsync(inter, 0, sizeof(int32_t) * (size_t)E * P * P, s));
+    if (!accumulate) MARS_CUDA_OK(cudaMemsetAsync(inter, 0, sizeof(int32_t) * (size_t)E * P * P, s));
     dim3 grid(pairs, ksplit, E);
-    pairwise_mma_kernel<<<grid, PM_THREADS, PM_SMEM_BYTES, s>>>(bits, P, wpm, blocks, kb_per_split, inter);
+    pairwise_mma_kernel<<<grid, PM_THREADS, PM_SMEM_BYTES, s>>>(bits + word_begin, P, wpm, blocks, total_kb, kb_per_split, inter);
     MARS_LAUNCH_OK();
     return MARSB200_OK;
 }

@@ -45,6 +45,12 @@ class RankingConfig:
     # stall it (graph latency 0.308 -> 0.294 ms at 40, profiles/r2_logs/latency_contraction_cap.log).  None = 40 for
     # <= 2 episodes per step, no cap above; 0 = never
     latency_contraction_sms: Optional[int] = None
+    # one-timeline schedule: pixel slices the ingest of a step is cut into so that the intersections of slice k run beside the
+    # read of slice k + 1 (marsb200_pack_masks_slice / marsb200_pairwise_inter_slice; masks whose pixels fill whole 512-word
+    # blocks).  Exact, but measured SLOWER on one c2 episode (graph latency 0.292 -> 0.317 / 0.373 ms with 2 / 4 slices; at best
+    # equal with the intersections capped at 64 SMs, profiles/r2_logs/latency_ingest_slices.log): an ingest CTA and a
+    # 197 KB tensor-core CTA do not share an SM, so the slices serialise and each pays the intersections' fixed cost.  Off.
+    latency_ingest_slices: int = 1
     fused_ingest: bool = False         # one-pass pack + pairwise kernel (owns all TMEM: cannot overlap the contractions)
     fused_pool: bool = False           # one-pass pack + pooled bitmaps (ops.pack_pool); measured slower than the two kernels
     emd_on_device: bool = False        # solve the P transport LPs per episode on the device instead of taking batch["emd"]
@@ -165,6 +171,15 @@ class RankingEngine:
         self._side4 = torch.cuda.Stream(device=dev, **hi) if cfg.overlap_streams and hoist else None
         cap = cfg.latency_contraction_sms if cfg.latency_contraction_sms is not None else (40 if e <= 2 else 0)
         self._contraction_sms = cap if (cfg.overlap_streams and cfg.priority_streams) else 0
+        # pixel-sliced ingest of a small batch (see _mask_chain): slices of whole 512-word blocks that tile the mask exactly
+        k = max(1, int(cfg.latency_ingest_slices))
+        sliceable = (cfg.overlap_streams and cfg.nms_iou_threshold is not None and not cfg.fused_ingest and not cfg.fused_pool
+                     and k > 1 and wpm * 32 == s.H * s.W and wpm % (512 * k) == 0 and s.H * s.W % 16 == 0
+                     and (cfg.pair_backend if cfg.pair_backend is not None else ops.DEFAULT_PAIR) != ops.PAIR_POPC)
+        self._slices = k if sliceable else 1
+        self._pair = torch.cuda.Stream(device=dev, **hi) if sliceable else None
+        self._ev_slice = [torch.cuda.Event() for _ in range(self._slices)]
+        self._ev_pair = torch.cuda.Event()
         self._ev_vva_g = torch.cuda.Event()
         self._ev_vta = torch.cuda.Event()
         self._ev_fork = torch.cuda.Event()
@@ -236,6 +251,25 @@ class RankingEngine:
             ops.pack_pool(batch["masks"], s.g, out_bits=self.bits, out_pool=self.pool_out)
             if self.inter is not None:
                 self._pairwise()
+            return
+        if "masks" in batch and self.inter is not None and self._pair is not None:
+            # small batch: the masks are packed one pixel slice after the other and the intersections of slice k are counted
+            # (high-priority stream, tensor cores) while slice k + 1 streams in from HBM; integer sums, any order
+            cur = torch.cuda.current_stream()
+            per = self.bits.shape[-1] // self._slices
+            for k in range(self._slices):
+                ops.pack_masks_slice(batch["masks"], k * per, per, out=self.bits)
+                self._ev_slice[k].record(cur)
+                self._pair.wait_event(self._ev_slice[k])
+                with torch.cuda.stream(self._pair):
+                    ops.pairwise_inter_slice(self.bits, k * per, per, k > 0, out=self.inter, backend=cfg.pair_backend)
+            with torch.cuda.stream(self._pair):
+                self._relation()
+                self._ev_pair.record(self._pair)
+            ops.pool_packed(self.bits, s.H, s.W, s.g, out=self.pool_out)
+            self._ev_pool.record(cur)
+            cur.wait_event(self._ev_pair)
+            self._pool_ready = True
             return
         self._ingest(batch)
         if self.inter is None:

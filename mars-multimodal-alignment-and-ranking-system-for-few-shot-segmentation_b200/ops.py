@@ -288,6 +288,26 @@ def pack_masks(masks: torch.Tensor, out=None) -> torch.Tensor:
     return out
 
 
+def pack_masks_slice(masks: torch.Tensor, word_begin: int, word_count: int, out: torch.Tensor) -> torch.Tensor:
+    """Packed words [word_begin, word_begin + word_count) of every mask into `out` [..., wpm] (whole 512-word blocks)."""
+    m, dt = _mask_tensor(masks)
+    h, w = m.shape[-2:]
+    check(lib.marsb200_pack_masks_slice(m.data_ptr(), dt, m.numel() // (h * w), h * w, word_begin, word_count, out.data_ptr(),
+                                        _stream()))
+    return out
+
+
+def pairwise_inter_slice(bits: torch.Tensor, word_begin: int, word_count: int, accumulate: bool, out: torch.Tensor,
+                         backend=None) -> torch.Tensor:
+    """Adds (or, with accumulate=False, writes) the intersections counted over one pixel slice of bits [E, P, wpm]."""
+    if bits.dim() == 2:
+        bits = bits[None]
+    e, p, wpm = bits.shape
+    check(lib.marsb200_pairwise_inter_slice(bits.data_ptr(), e, p, wpm, word_begin, word_count, int(bool(accumulate)),
+                                            out.data_ptr(), DEFAULT_PAIR if backend is None else backend, _stream()))
+    return out
+
+
 def pool_packed(bits: torch.Tensor, h: int, w: int, g: int, out=None):
     """bits [..., wpm] -> (pooled [..., ceil(g*g/32)] int32, area [...], pooled_count [...])."""
     lead = tuple(bits.shape[:-1])

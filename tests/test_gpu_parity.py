@@ -500,6 +500,81 @@ def test_engine_stream_options_are_bit_identical(mb, episodes):
             assert torch.equal(v, outs[0][k]), k
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.uint8, torch.bool])
+def test_pack_slices_tile_the_mask(mb, dtype):
+    """marsb200_pack_masks_slice: slices of whole 512-word blocks, in any order, land exactly the bits of the one-launch pack;
+    slices that are not whole blocks or leave the mask are refused."""
+    ops = mb.ops
+    n, h, w = 7, 256, 320  # 81920 pixels = 2560 words = 5 blocks of 512
+    masks = cases.blob_masks(n, h, w, seed=11).to(dtype).to(dev())
+    want = ops.pack_masks(masks)
+    got = torch.full_like(want, -1)
+    for k in (3, 0, 4, 1):
+        ops.pack_masks_slice(masks, 512 * k, 512, out=got)
+    assert not torch.equal(got, want)
+    ops.pack_masks_slice(masks, 1024, 512, out=got)
+    assert torch.equal(got, want)
+    got2 = torch.full_like(want, -1)
+    ops.pack_masks_slice(masks, 0, 1024, out=got2)
+    ops.pack_masks_slice(masks, 1024, 1536, out=got2)
+    assert torch.equal(got2, want)
+    for wb, wc in ((0, 256), (256, 512), (2048, 1024), (0, 0)):
+        with pytest.raises(mb.MarsB200Error):
+            ops.pack_masks_slice(masks, wb, wc, out=got)
+
+
+@pytest.mark.parametrize("p,backend", [(40, "PAIR_FP4"), (256, "PAIR_FP4"), (40, "PAIR_MMA"), (300, "PAIR_MMA"), (300, "PAIR_AUTO")])
+def test_pairwise_slices_sum_to_the_whole(mb, p, backend):
+    """marsb200_pairwise_inter_slice: the contributions of pixel slices that tile the mask add up (integer atomics) to the
+    one-launch intersections, bit for bit, whatever the order; the popcount back end has no slices."""
+    ops = mb.ops
+    backend = getattr(ops, backend)
+    e, h, w = 2, 128, 192  # 24576 pixels = 768 words
+    bits = ops.pack_masks(cases.blob_masks(e * p, h, w, seed=p).reshape(e, p, h, w).to(dev()))
+    want = ops.pairwise_inter(bits, backend=backend)
+    assert torch.equal(want, ops.pairwise_inter(bits, backend=ops.PAIR_POPC))
+    got = torch.full_like(want, 12345)
+    for i, (wb, wc) in enumerate(((512, 256), (0, 8), (8, 248), (256, 256))):
+        ops.pairwise_inter_slice(bits, wb, wc, i > 0, out=got, backend=backend)
+    assert torch.equal(got, want)
+    with pytest.raises(mb.MarsB200Error):
+        ops.pairwise_inter_slice(bits, 4, 8, False, out=got, backend=backend)
+    with pytest.raises(mb.MarsB200Error):
+        ops.pairwise_inter_slice(bits, 0, 776, False, out=got, backend=backend)
+    with pytest.raises(mb.MarsB200Error):
+        ops.pairwise_inter_slice(bits, 0, 256, False, out=got, backend=ops.PAIR_POPC)
+
+
+@pytest.mark.parametrize("episodes", [1, 2])
+@pytest.mark.parametrize("mask_dtype", [torch.float32, torch.uint8])
+def test_engine_sliced_ingest_is_bit_identical(mb, episodes, mask_dtype):
+    """Optional schedule: the masks are packed in pixel slices and the intersections of one slice counted beside the read of
+    the next.  Every output equals the unsliced schedule, eagerly and as a CUDA-graph replay; masks that do not tile into
+    512-word blocks keep one slice."""
+    shape = mb.EpisodeShape(ns=1, g=14, gt=12, C=64, D=32, P=40, H=256, W=256)
+    batch = mb.stack_episodes([mb.make_episode(shape, 90 + i, dev(), mask_dtype) for i in range(episodes)])
+    keys = ("vva", "vta", "inter", "scores", "order", "flags", "merged_bits", "clip", "pooled", "area")
+    outs = []
+    for k in (1, 2, 4):
+        eng = mb.RankingEngine(shape, episodes, mb.RankingConfig(nms_iou_threshold=0.6, latency_ingest_slices=k), dev(), mask_dtype)
+        assert eng._slices == k
+        o = eng.run(batch)
+        torch.cuda.synchronize()
+        outs.append({kk: o[kk].clone() for kk in keys})
+        eng.capture(batch)
+        eng.replay()
+        o = eng.replay()
+        torch.cuda.synchronize()
+        outs.append({kk: o[kk].clone() for kk in keys})
+    for o in outs[1:]:
+        for kk, v in o.items():
+            assert torch.equal(v, outs[0][kk]), kk
+    odd = mb.EpisodeShape(ns=1, g=14, gt=12, C=64, D=32, P=40, H=96, W=96)
+    assert mb.RankingEngine(odd, 1, mb.RankingConfig(nms_iou_threshold=0.6, latency_ingest_slices=4), dev())._slices == 1
+    assert mb.RankingEngine(shape, 1, mb.RankingConfig(nms_iou_threshold=0.6), dev())._slices == 1  # off by default (measured slower)
+    assert mb.RankingEngine(shape, 1, mb.RankingConfig(latency_ingest_slices=4), dev())._slices == 1  # no NMS, no intersections
+
+
 @pytest.mark.parametrize("raw_fraction", [0.0, 0.3, 1.0])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.uint8])
 def test_host_mask_ingest_equals_device_packing(mb, raw_fraction, dtype):
