@@ -108,6 +108,19 @@ class MatcherScorer:
         return merged, torch.as_tensor(final, device=self.device) if not torch.is_tensor(final) else final.to(self.device)
 
 
+_SIDE_STREAMS: Dict[torch.device, torch.cuda.Stream] = {}
+
+
+def _side_stream(device: torch.device) -> torch.cuda.Stream:
+    """One persistent side stream per device for the reverse assignment (Matcher builds a PatchMatcher per call)."""
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    if device not in _SIDE_STREAMS:
+        _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[device]
+
+
 class PatchMatcher:
     """Bidirectional patch matching of Matcher on the device.
 
@@ -118,11 +131,15 @@ class PatchMatcher:
     coordinates.  Prompt sampling / negative priors / SAM stay outside.
     """
 
-    def __init__(self, encoder_feat_size: int, patch_size: int, input_size, device="cuda"):
+    def __init__(self, encoder_feat_size: int, patch_size: int, input_size, device="cuda", concurrent_reverse: bool = True):
         self.encoder_feat_size = encoder_feat_size
         self.patch_size = patch_size
         self.input_size = tuple(input_size)  # (H, W)
         self.device = torch.device(device)
+        # With at least as many masked support patches as query patches (the multi-shot case) the forward assignment
+        # matches EVERY query patch, so the reverse problem - all query patches against all support patches - does not
+        # depend on the forward result: the two single-CTA solvers then run side by side on two streams.
+        self.concurrent_reverse = concurrent_reverse
 
     def match(self, ref_feats: torch.Tensor, tar_feat: torch.Tensor, ref_masks_pool: torch.Tensor):
         """ref_feats [ns*N, C] and tar_feat [N, C] (raw or normalised rows), ref_masks_pool [ns*N] (0/1).
@@ -139,15 +156,31 @@ class PatchMatcher:
         S, C = res["sim"][0], res["cost"][0]
         mask = ref_masks_pool.to(dev).flatten() != 0
         idx_mask = torch.nonzero(mask).flatten()
+        q2s = None
+        if self.concurrent_reverse and idx_mask.numel() >= n:
+            main, side = torch.cuda.current_stream(), _side_stream(dev)
+            St = S.t().contiguous()
+            # every buffer of the side launch comes from the main stream's pool (nothing is allocated under `side`)
+            rev_status = torch.zeros(1, device=dev, dtype=torch.int32)
+            rev_out = (torch.empty((1, n), device=dev, dtype=torch.int32), torch.empty((1,), device=dev, dtype=torch.float64))
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                q2s, _ = ops.lsap(St, status=rev_status, out=rev_out)  # no read-back: enqueued, then the forward problem
         # forward: masked support rows -> query patches
         r2c, _ = ops.lsap(S, row_sel=mask.to(torch.uint8))
         fwd_rows = idx_mask[r2c[0][idx_mask] >= 0]
         fwd_cols = r2c[0][fwd_rows].long()
         sim_f = S[fwd_rows, fwd_cols]
         # reverse: matched query patches -> all support rows
-        sel = torch.zeros(n, dtype=torch.uint8, device=dev)
-        sel[fwd_cols] = 1
-        q2s, _ = ops.lsap(S.t().contiguous(), row_sel=sel)
+        if q2s is not None:
+            main.wait_stream(side)
+            ops.raise_on_lsap_status(rev_status)
+            if fwd_cols.numel() != n:  # cannot happen for an exact solver; never trust it silently
+                raise ops.MarsB200Error("forward assignment left query patches unmatched although T >= N")
+        else:
+            sel = torch.zeros(n, dtype=torch.uint8, device=dev)
+            sel[fwd_cols] = 1
+            q2s, _ = ops.lsap(S.t().contiguous(), row_sel=sel)
         rev_rows = q2s[0][fwd_cols].long()
         retain = mask[rev_rows.clamp(min=0)] & (rev_rows >= 0)
         if bool(retain.any()):

@@ -15,6 +15,8 @@ import torch
 from . import _lib
 from ._lib import GEMM_SIMT, GEMM_TCGEN05, MASK_F32, MASK_U8, PAIR_AUTO, PAIR_FP4, PAIR_MMA, PAIR_POPC, check, lib
 
+MarsB200Error = _lib.MarsB200Error
+
 __all__ = [
     "words_per_mask", "pad_rows", "pad_k", "normalize_rows", "pool_mask", "sim_contract", "match_argmax", "mutual_matches", "lsap", "vva_finalize",
     "attn_mean", "pir_refine", "resize_minmax", "pack_masks", "pack_pairwise", "pool_packed", "region_sums", "pairwise_inter",
@@ -158,10 +160,12 @@ def mutual_matches(sim: torch.Tensor, row_fg: torch.Tensor):
 
 
 def lsap(sim: torch.Tensor, row_sel: Optional[torch.Tensor] = None, col_sel: Optional[torch.Tensor] = None,
-         maximize: bool = True, check_status: bool = True):
+         maximize: bool = True, check_status: bool = True, status: Optional[torch.Tensor] = None, out=None):
     """Exact assignment on sim [E, R, C] restricted to the selected rows / columns.
 
-    Returns (row_to_col [E, R] int32 with -1 for unassigned rows, objective [E] float64).
+    Returns (row_to_col [E, R] int32 with -1 for unassigned rows, objective [E] float64).  With a caller-owned `status`
+    ([1] int32, zeroed) nothing is read back here - the caller checks it (`raise_on_lsap_status`) once it has joined the
+    stream, so the launch does not synchronise.  `out` = (row_to_col, objective) buffers to fill instead of new ones.
     """
     sim = _cuda(sim, torch.float32, "sim")
     if sim.dim() == 2:
@@ -169,17 +173,28 @@ def lsap(sim: torch.Tensor, row_sel: Optional[torch.Tensor] = None, col_sel: Opt
     e, r, c = sim.shape
     rs = None if row_sel is None else _cuda(row_sel, torch.uint8, "row_sel").reshape(e, r)
     cs = None if col_sel is None else _cuda(col_sel, torch.uint8, "col_sel").reshape(e, c)
-    r2c = torch.empty((e, r), device=sim.device, dtype=torch.int32)
-    obj = torch.empty((e,), device=sim.device, dtype=torch.float64)
-    status = torch.zeros(1, device=sim.device, dtype=torch.int32)
+    if out is None:
+        r2c = torch.empty((e, r), device=sim.device, dtype=torch.int32)
+        obj = torch.empty((e,), device=sim.device, dtype=torch.float64)
+    else:
+        r2c, obj = out
+    own_status = status is None
+    if own_status:
+        status = torch.zeros(1, device=sim.device, dtype=torch.int32)
     # the solver's state is sized for the selected rows / columns (one small sync, like the reference's host call)
     nr = r if rs is None else max(1, int((rs != 0).sum(dim=1).max().item()))
     nc = c if cs is None else max(1, int((cs != 0).sum(dim=1).max().item()))
     check(lib.marsb200_lsap(sim.data_ptr(), _ptr(rs), _ptr(cs), e, r, c, int(maximize), min(nr, nc), max(nr, nc),
                             r2c.data_ptr(), obj.data_ptr(), status.data_ptr(), _stream()))
-    if check_status and int(status.item()):
-        raise _lib.MarsB200Error(f"lsap: a problem of size {int(status.item())} exceeds the shared-memory state")
+    if check_status and own_status:
+        raise_on_lsap_status(status)
     return r2c, obj
+
+
+def raise_on_lsap_status(status: torch.Tensor) -> None:
+    code = int(status.item())
+    if code:
+        raise _lib.MarsB200Error(f"lsap: a problem of size {code} exceeds the shared-memory state")
 
 
 def vva_finalize(colstats: torch.Tensor, row_fg: torch.Tensor, m: int, n: int, out=None) -> torch.Tensor:

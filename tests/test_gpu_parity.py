@@ -1613,6 +1613,43 @@ def test_patch_matcher_5shot_full_size(mb):
     assert sorted(map(tuple, res["points_discarded"].cpu().tolist())) == neg_ref
 
 
+@pytest.mark.parametrize("cover", [0.2, 0.6, 1.0])
+def test_patch_matcher_concurrent_reverse(mb, cover):
+    """With T >= N masked support patches the forward assignment matches every query patch, so PatchMatcher solves the reverse
+    problem beside the forward one on a second stream: same points as the sequential schedule and as the scipy restatement.
+    cover = 0.2 gives T < N (sequential either way)."""
+    g, ns, c = 12, 3, 48
+    n = g * g
+    gen = torch.Generator().manual_seed(int(cover * 100))
+    protos = torch.randn(6, c, generator=gen)
+    fs = orc.normalize_rows(0.6 * protos[torch.randint(0, 6, (ns * n,), generator=gen)] + 0.8 * torch.randn(ns * n, c, generator=gen))
+    fq = orc.normalize_rows(0.6 * protos[torch.randint(0, 6, (n,), generator=gen)] + 0.8 * torch.randn(n, c, generator=gen))
+    pool = (torch.rand(ns * n, generator=gen) < cover).float() if cover < 1.0 else torch.ones(ns * n)
+    t = int(pool.sum())
+    assert (t >= n) == (cover > 0.2)
+    pts_ref, neg_ref, reduced_ref = orc.matcher_patch_matching(fs, fq, pool, g, 14, (g * 14, g * 14))
+    res = [mb.PatchMatcher(g, 14, (g * 14, g * 14), dev(), concurrent_reverse=cr).match(fs, fq, pool) for cr in (True, False)]
+    for r in res:
+        assert r["reduced_points_num"] == reduced_ref
+        assert sorted(map(tuple, r["points"].cpu().tolist())) == pts_ref
+        assert sorted(map(tuple, r["points_discarded"].cpu().tolist())) == neg_ref
+    assert torch.equal(res[0]["retain"], res[1]["retain"])
+    assert torch.equal(res[0]["indices_forward"][1], res[1]["indices_forward"][1])
+
+
+def test_engine_check_status_raises_the_library_error(mb):
+    """RankingEngine.check_status reports non-finite fused scores as MarsB200Error (ops re-exports the error type)."""
+    assert mb.ops.MarsB200Error is mb.MarsB200Error
+    shape = mb.EpisodeShape(ns=1, g=10, C=32, P=8, H=64, W=64, gt=8, D=16)
+    batch = mb.stack_episodes([mb.make_episode(shape, 5, dev())])
+    batch["emd"] = batch["emd"].clone()
+    batch["emd"][0, 3] = float("nan")
+    eng = mb.RankingEngine(shape, 1, mb.RankingConfig(), dev())
+    eng.run(batch)
+    with pytest.raises(mb.MarsB200Error):
+        eng.check_status()
+
+
 # ------------------------------------------------------------------ SM partitions (CUDA green contexts)
 def test_stream_sm_count_follows_the_partition(mb):
     """Persistent kernels size their grids from the stream: whole device on a plain stream, the partition's SMs on a
