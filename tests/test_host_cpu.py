@@ -325,3 +325,22 @@ def test_stream_sm_cap_table_is_host_side():
     assert _lib.lib.marsb200_stream_set_sm_cap(h, 0) == 0  # removing a missing entry is not an error
     assert _lib.lib.marsb200_stream_set_sm_cap(h, -1) != 0
     assert b"cap" in _lib.lib.marsb200_last_error()
+
+
+@pytest.mark.parametrize("t,n,ns", [(150, 144, 3), (144, 144, 2), (400, 144, 3)])
+def test_reverse_assignment_is_independent_of_the_forward_one_when_t_ge_n(t, n, ns):
+    """The claim behind PatchMatcher.concurrent_reverse, pinned on the reference's own solver (scipy, Matcher.py:449,470):
+    with T >= N masked support patches the forward assignment matches EVERY query patch, so `S.t()[indices_forward[1]]` is a
+    row permutation of S.t() and its optimal assignment is the identity-order one gathered through that permutation."""
+    import numpy as np
+    from scipy.optimize import linear_sum_assignment
+
+    rng = np.random.default_rng(t * 1000 + n)
+    S = rng.standard_normal((ns * n, n)).astype(np.float32)  # tie-free with probability one
+    rows = np.sort(rng.choice(ns * n, size=t, replace=False))
+    fr, fc = linear_sum_assignment(S[rows], maximize=True)
+    assert len(fc) == n and sorted(fc.tolist()) == list(range(n))
+    rr, rc = linear_sum_assignment(S.T[fc], maximize=True)          # the reference's order of rows
+    ir, ic = linear_sum_assignment(S.T, maximize=True)              # identity order, solvable before the forward problem
+    assert np.array_equal(rr, np.arange(n)) and np.array_equal(ir, np.arange(n))
+    assert np.array_equal(rc, ic[fc])
