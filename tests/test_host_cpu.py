@@ -344,3 +344,21 @@ def test_reverse_assignment_is_independent_of_the_forward_one_when_t_ge_n(t, n, 
     ir, ic = linear_sum_assignment(S.T, maximize=True)              # identity order, solvable before the forward problem
     assert np.array_equal(rr, np.arange(n)) and np.array_equal(ir, np.arange(n))
     assert np.array_equal(rc, ic[fc])
+
+
+def test_roofline_traffic_is_tied_to_the_kernel_source(monkeypatch):
+    """bench.py reports `roofline.traffic` from the committed ncu capture only while the sha256 of the ingest kernel's source
+    still matches the one recorded with the capture: the committed capture is current, and any other
+    hash - a changed kernel - yields null instead of a stale number."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    got = bench.ncu_traffic_bytes("pack_f32_vec_kernel", "c2", 16, "f32")
+    algorithmic = 16 * 256 * (4 * 1024 * 1024 + 4 * 32768)
+    assert got is not None and 0.95 * algorithmic < got < 1.05 * algorithmic  # no re-reads: traffic = algorithmic bytes
+    assert bench.ncu_traffic_bytes("pack_f32_vec_kernel", "c2", 8, "f32") is None  # no capture of that launch shape
+    monkeypatch.setattr(bench, "kernel_source_sha16", lambda *a, **k: "0" * 16)
+    assert bench.ncu_traffic_bytes("pack_f32_vec_kernel", "c2", 16, "f32") is None
