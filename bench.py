@@ -220,6 +220,12 @@ def cpu_reference_episodes(shape, args, episodes):
     from oracle import mars_oracle as orc
 
     torch.set_num_threads(os.cpu_count() or 1)
+    try:  # torchrun exports OMP_NUM_THREADS=1: the host baseline gets every core in numpy's BLAS / OpenMP pools as well
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     cfg = oracle_cfg(shape, args)
     times, results = [], []
     for ep in episodes:
