@@ -43,7 +43,7 @@ class RankingConfig:
     # one-timeline schedule: CTAs the persistent contractions of the alignment streams may start (marsb200_stream_set_sm_cap).
     # The ingest of ONE episode needs ~100 SMs to read its masks at the HBM rate; contractions that take the whole device
     # stall it (graph latency 0.308 -> 0.294 ms at 40, profiles/r2_logs/latency_contraction_cap.log).  None = 40 for
-    # <= 2 episodes per step, no cap above; 0 = never
+    # <= 2 episodes per step of DENSE masks (packed / RLE proposals have no such read: never capped), no cap above; 0 = never
     latency_contraction_sms: Optional[int] = None
     # one-timeline schedule: pixel slices the ingest of a step is cut into so that the intersections of slice k run beside the
     # read of slice k + 1 (marsb200_pack_masks_slice / marsb200_pairwise_inter_slice; masks whose pixels fill whole 512-word
@@ -418,7 +418,9 @@ class RankingEngine:
         n, m = s.N, s.ns * s.N
         if self._part is not None and "masks" in batch and not cfg.fused_ingest and not self._capturing:
             return self._run_partitioned(batch, wait)
-        capped = [st for st in (self._hi, self._side3, self._side4) if st is not None] if self._contraction_sms else []
+        # the cap protects the dense-mask ingest; packed / RLE proposals have no such read and keep the whole device
+        capped = ([st for st in (self._hi, self._side3, self._side4) if st is not None]
+                  if self._contraction_sms and "masks" in batch else [])
         for st in capped:  # host-side launch parameter: read when the contractions are enqueued below
             set_stream_sm_cap(st, self._contraction_sms)
         try:
