@@ -22,9 +22,11 @@ stability score, torchvision box NMS, and the whole Matcher ancestry path -
 reference's own method bodies, cut out of matcher/Matcher.py with ``ast`` - and ``MARS.predict`` end to end through the
 reference's ``MARS``, ``VisualVisualAlignmentModule`` and ``FilteringMergingModule`` classes).  The builder-defined pieces
 (`pairwise_intersections`, `mask_nms`), the exact-EMD stand-in (POT 0.9.4 is not
-installed anywhere we can run; the optimum of the LP is solver-independent and three
+installed anywhere we can run; the optimum of the LP is solver-independent and four
 independent exact solvers agree on it: HiGHS here, a network simplex - POT's algorithm
-class - in `emd_network_simplex`, and the lcm-expanded assignment in the tests) and the
+class - from networkx in `emd_network_simplex`, a from-scratch C network simplex
+(`oracle/emd_netsimplex.c`, bound by `oracle/emd_c.py`; also the host EMD baseline of
+bench.py) and the lcm-expanded assignment in the tests) and the
 Matcher assignment matching (scipy's
 LSAP tie-breaking is implementation-defined; compared by objective value) have
 no reference output to pin against: **parity unpinned** for those four, pinned

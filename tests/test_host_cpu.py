@@ -362,3 +362,22 @@ def test_roofline_traffic_is_tied_to_the_kernel_source(monkeypatch):
     assert bench.ncu_traffic_bytes("pack_f32_vec_kernel", "c2", 8, "f32") is None  # no capture of that launch shape
     monkeypatch.setattr(bench, "kernel_source_sha16", lambda *a, **k: "0" * 16)
     assert bench.ncu_traffic_bytes("pack_f32_vec_kernel", "c2", 16, "f32") is None
+
+
+def test_bench_cpu_emd_leg_runs_both_host_solvers():
+    """bench.py's CPU EMD baseline: the sampled HiGHS LPs and every LP of the episode through the C network simplex (all host
+    threads), which must agree; the full-scoring host figure is built from the faster one."""
+    import importlib.util
+
+    import marsb200
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test_emd", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    shape = marsb200.EpisodeShape(ns=1, g=10, C=32, P=9, H=80, W=80, gt=8, D=16)
+    batch = marsb200.stack_episodes([marsb200.make_episode(shape, 3)])
+    res = bench.cpu_emd_sample(shape, batch, 2)
+    assert res["lps_per_s"] > 0 and res["cores"] == 1
+    ns = res["network_simplex"]
+    assert ns["lps"] == 9 and ns["lps_per_s"] > 0 and ns["agrees_with_highs"] is True
