@@ -24,6 +24,12 @@
 
 typedef long long ll;
 
+#ifdef MARS_ORACLE_STATS
+/* profiles/emd_netsimplex_stats.py: pivots, cycle arcs (sum, max), nodes cut off by the leaving arc (smaller side, sum),
+ * arcs priced, depth of the cut (sum) - the per-pivot work a CTA-parallel version would have to organise */
+ll mars_oracle_stats[8];
+#endif
+
 typedef struct {
     int T, M, n;
     const ll* c;   /* integer costs [T * M] */
@@ -133,6 +139,9 @@ int mars_oracle_emd_netsimplex(const double* cost, int T, int M, double* obj, do
                 ++next;
                 if (++nj == M) { nj = 0; if (++ni == T) { ni = 0; next = 0; } }
             }
+#ifdef MARS_ORACLE_STATS
+            mars_oracle_stats[4] += (ll)cnt;
+#endif
             if (best_d >= 0) { scanned_clean += cnt; continue; }
             scanned_clean = 0;
             const int ei = (int)(best_e / M), ej = (int)(best_e % M);
@@ -150,6 +159,21 @@ int mars_oracle_emd_netsimplex(const double* cost, int T, int M, double* obj, do
             if (theta <= 0) { rc = -5; goto done; }      /* non-degenerate by construction */
             for (int k = 0; k < na; ++k) t.flow[path[k]] += (k & 1) ? theta : -theta;
             if (t.flow[leave] != 0) { rc = -5; goto done; }
+#ifdef MARS_ORACLE_STATS
+            {
+                int child = -1, size = 0;
+                for (int v = 1; v < n; ++v) if (t.parc[v] == leave) child = v;
+                for (int v = 0; v < n; ++v) {  /* nodes below the leaving arc */
+                    int w = v;
+                    while (w != -1 && w != child) w = t.parent[w];
+                    size += (w == child);
+                }
+                mars_oracle_stats[0] += 1; mars_oracle_stats[1] += na + 1;
+                if (na + 1 > mars_oracle_stats[2]) mars_oracle_stats[2] = na + 1;
+                mars_oracle_stats[3] += size < n - size ? size : n - size;
+                mars_oracle_stats[5] += t.depth[child];
+            }
+#endif
             t.arc_i[leave] = ei; t.arc_j[leave] = ej; t.flow[leave] = theta;
             rebuild(&t);
             ++npiv;
