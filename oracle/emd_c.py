@@ -3,12 +3,14 @@ FilteringMergingModule.py:160-166).  Only tests/ and bench.py's CPU-baseline leg
 import ctypes
 import os
 import subprocess
+import threading
 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATH = os.path.join(_HERE, "_build", "libmarsoracle.so")
 _lib = None
+_lock = threading.Lock()  # bench.py calls from a thread pool: one thread builds / loads
 
 
 def available() -> bool:
@@ -17,7 +19,11 @@ def available() -> bool:
 
 def _load():
     global _lib
-    if _lib is None:
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
         if not os.path.exists(_PATH):  # built by __graft_entry__.build(); a checkout that skipped it builds on first use
             subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
         lib = ctypes.CDLL(_PATH)
@@ -25,7 +31,7 @@ def _load():
         lib.mars_oracle_emd_netsimplex.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                                    ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
         _lib = lib
-    return _lib
+        return _lib
 
 
 def emd_network_simplex_c(cost, details: bool = False):
