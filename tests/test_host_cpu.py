@@ -381,3 +381,45 @@ def test_bench_cpu_emd_leg_runs_both_host_solvers():
     assert res["lps_per_s"] > 0 and res["cores"] == 1
     ns = res["network_simplex"]
     assert ns["lps"] == 9 and ns["lps_per_s"] > 0 and ns["agrees_with_highs"] is True
+
+
+def _meter_all_reduce_worker(rank, world, port, nclass, q):
+    """A rank of a sharded evaluation: int64 area buffers filled from this rank's episodes, then AverageMeter.all_reduce."""
+    import types
+
+    import torch.distributed as dist
+
+    from marsb200.evaluation import AverageMeter
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rs = np.random.RandomState(7 + rank)
+    bufs = [torch.from_numpy(rs.randint(0, 2 ** 40, size=(2, nclass)).astype(np.int64)) for _ in range(4)]
+    meter = types.SimpleNamespace(intersection_buf=bufs[0], union_buf=bufs[1], intersection_buf_known_bad=bufs[2],
+                                  union_buf_known_bad=bufs[3])
+    AverageMeter.all_reduce(meter)  # the method only touches the four buffers; the class itself refuses CPU devices
+    q.put((rank, [b.numpy().copy() for b in bufs]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_all_reduce_of_the_evaluation_buffers():
+    """world_size-2 gloo run of the sharded evaluation: after AverageMeter.all_reduce every rank holds the
+    exact int64 sums of both ranks' intersection / union buffers (counts above 2^32: no float32 rounding as in logger.py)."""
+    import torch.multiprocessing as mp
+
+    nclass, world = 20, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 27500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_meter_all_reduce_worker, args=(r, world, port, nclass, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    want = [sum(np.random.RandomState(7 + r).randint(0, 2 ** 40, size=(4, 2, nclass)).astype(np.int64)[k] for r in range(world))
+            for k in range(4)]
+    for r in range(world):
+        for k in range(4):
+            np.testing.assert_array_equal(got[r][k], want[k])
